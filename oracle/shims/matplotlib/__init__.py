@@ -1,0 +1,1 @@
+"""Empty stand-in: only the reference visualisation helpers touch matplotlib."""
