@@ -1,0 +1,181 @@
+/* vmm.h -- C ABI of libvmm_sm100.so, the B200 (sm_100a) kernels behind the VideoMetamaterials hot path.
+ *
+ * The reference (jhbastek/VideoMetamaterials) is pure Python/PyTorch and has no FFI layer; the
+ * boundary a maintainer binds is therefore NEW.  Each entry point names the
+ * reference code it replaces as "VDDP:line" =
+ * denoising_diffusion_pytorch/video_denoising_diffusion_pytorch.py.
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes, no torch types.  The caller owns every buffer (including
+ *     workspaces); the library allocates nothing and never synchronises.
+ *   - every call is asynchronous on the `stream` argument (a cudaStream_t passed as void*).
+ *   - return value 0 = launched; negative = rejected (vmm_last_error() has the text; per thread).
+ *   - activations are channels-last: (b, f, h, w, c) row-major, 16-bit (fmt 0 = fp16, 1 = bf16)
+ *     unless stated; parameters and statistics are fp32 / fp64 as stated.
+ *   - there is NO CPU implementation behind this ABI: without a CUDA device every compute entry
+ *     point fails with VMM_ERR_CUDA.
+ */
+#ifndef VMM_H_
+#define VMM_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMM_OK 0
+#define VMM_ERR_ARG -1
+#define VMM_ERR_CUDA -2
+#define VMM_ERR_UNSUPPORTED -3
+
+#define VMM_FMT_F16 0
+#define VMM_FMT_BF16 1
+
+const char* vmm_last_error(void);
+int vmm_abi_version(void);
+/* number of kernel launches issued through this library by the calling process (for bench.py) */
+uint64_t vmm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ *
+ *   out[pix, n] = epilogue( sum_{tap} sum_{c} A_tap[pix + (dy,dx), c] * W[n, tap.kofs + c] )
+ *
+ * replaces: Block.proj  nn.Conv3d(Cin,Cout,(1,3,3))                VDDP:271,278   (9 taps)
+ *           ResnetBlock.res_conv / final 1x1x1 conv                VDDP:297,311,708 (1 tap)
+ *           Attention.to_qkv / to_out nn.Linear                    VDDP:413,421,437,535
+ *           SpatialLinearAttention.to_qkv / to_out 1x1 Conv2d      VDDP:319,325,336,377
+ *           Downsample nn.Conv3d (1,4,4)/(1,2,2)                   VDDP:241  (16 taps over 4 parity views)
+ *           Upsample nn.ConvTranspose3d (1,4,4)/(1,2,2)            VDDP:155  (4 output phases x 4 taps)
+ *           init_conv (1,7,7) on an 8-channel padded input         VDDP:626  (7 taps of 8 px x 8 ch)
+ *           and every data-gradient of the above (same kernel, transformed weights).
+ *
+ * A operand: up to 4 strided 4-D views (c, w, h, bf) of 16-bit activations, read by TMA with
+ * out-of-range coordinates zero-filled (that IS the 'zeros' padding mode).  W: packed 16-bit
+ * [N_pad, Ktot] K-major.  The GEMM-M space is the output grid (BF, OH, OW), cut into tiles of
+ * TF x TH x TW = 128 positions (powers of two).
+ * Epilogue (all optional): + bias[n]; + residual[pix, n]; per-(sample, group) sum / sum-of-squares
+ * for GroupNorm accumulated in fp64 (VDDP:274); store 16-bit or fp32; columns >= nsplit go to out2.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* ptr;    /* 16-bit elements */
+  int32_t dims[4];    /* {C, W, H, BF}, innermost first */
+  int64_t strides[3]; /* element strides of W, H, BF (C is contiguous); multiples of 8 */
+} vmm_view4;
+
+typedef struct {
+  int32_t src;  /* index into a[] */
+  int32_t dy, dx; /* offsets added to the tile origin (y, x) in that view's coordinates */
+  int32_t kofs; /* first K column of this tap in W; multiple of 64 */
+  int32_t c;    /* channels read from the view for this tap (rounded up to 64 with zero fill) */
+} vmm_tap;
+
+#define VMM_MAX_VIEWS 4
+#define VMM_MAX_PHASES 4
+#define VMM_MAX_TAPS 20
+
+typedef struct {
+  int32_t fmt; /* VMM_FMT_* of A, W, residual and 16-bit outputs */
+  int32_t n_views;
+  vmm_view4 a[VMM_MAX_VIEWS];
+  int32_t n_phases; /* 1, or 4 for the transposed conv */
+  int32_t n_taps[VMM_MAX_PHASES];
+  vmm_tap taps[VMM_MAX_PHASES][VMM_MAX_TAPS];
+  int32_t phase_oy[VMM_MAX_PHASES], phase_ox[VMM_MAX_PHASES]; /* output offsets of each phase */
+  const void* w; /* [n_pad][ktot] 16-bit, n_pad = N rounded up to 16 */
+  int32_t n, ktot;
+  int32_t bf, oh, ow; /* GEMM-M grid */
+  int32_t tf, th, tw; /* tile, tf*th*tw == 128 */
+  /* output pixel index = ((bf * ohs) + y * sy + oy) * ows + x * sx + ox ; element offset = index * ldo + n */
+  void* out;
+  int64_t ldo;
+  int32_t out_fp32;
+  int32_t ohs, ows, sy, sx;
+  void* out2; /* columns >= nsplit (multiple of 16) are written to out2[:, n - nsplit]; may be NULL */
+  int64_t ldo2;
+  int32_t nsplit;
+  const float* bias;  /* [n] or NULL */
+  const void* res;    /* 16-bit residual with the output's pixel indexing, or NULL */
+  int64_t ldr;
+  double* gn_stats;   /* [samples][n / gn_group][2] (sum, sum of squares), accumulated atomically; or NULL */
+  int32_t gn_group;   /* channels per group */
+  int32_t frames_per_sample;
+} vmm_cgemm_params;
+
+int vmm_cgemm(const vmm_cgemm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm apply (+ time-embedding scale/shift + SiLU).  replaces Block.norm / scale_shift / act
+ * VDDP:279-285.  x, y: [B][pix][C] 16-bit.  stats: fp64 (sum, sumsq) per (sample, group) as
+ * accumulated by vmm_cgemm.  scale_shift: [B][2C] fp32 (scale | shift, ResnetBlock.mlp output
+ * VDDP:304-306) or NULL.  act: 1 = SiLU, 0 = identity.  res (may be NULL) is added after the
+ * activation: the identity skip of ResnetBlock (VDDP:311) when dim == dim_out.
+ * The backward also accumulates dgamma/dbeta (+=) and writes d(scale_shift) [B][2C] (may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+int vmm_gn_silu_fwd(const void* x, const void* res, void* y, int fmt, int B, long long pix, int C, int groups, const double* stats,
+                    const float* gamma, const float* beta, const float* scale_shift, float eps, int act, void* stream);
+size_t vmm_gn_silu_bwd_workspace(int B, int C, int groups);
+int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt, int B, long long pix, int C, int groups,
+                    const double* stats, const float* gamma, const float* beta, const float* scale_shift, float eps, int act,
+                    float* dgamma, float* dbeta, float* dscale_shift, void* workspace, size_t workspace_bytes, void* stream);
+
+/* channel LayerNorm with gain only (VDDP:245-254) over rows of C 16-bit values.
+ * backward: dx = LN'(dy) (+ dres if non-NULL, the Residual skip VDDP:137); dgamma accumulated (+=). */
+int vmm_ln_fwd(const void* x, void* y, int fmt, long long rows, int C, const float* gamma, float eps, float* mean_rstd,
+               void* stream);
+int vmm_ln_bwd(const void* x, const void* dy, const void* dres, void* dx, int fmt, long long rows, int C, const float* gamma,
+               float eps, float* dgamma, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention cores.  qkv rows: [position][3 * heads * 32] 16-bit (q | k | v, each (head, 32)); out rows:
+ * [position][heads * 32].  ekv: fp32 conditioning keys | values, [B][T][2 * heads * 32].
+ *
+ * vmm_tattn_*: temporal attention, one sequence per pixel over `frames` tokens, rotary on q and k,
+ *   relative position bias [heads][frames][frames] added to the cond half and the frame half (VDDP:425-535,
+ *   503-510); ekv (keys already rotated) may be NULL (init_temporal_attn VDDP:743).  rot: [frames][16][2] cos,sin.
+ *   positions are ordered (b, f, pixel).
+ * vmm_lattn_*: SpatialLinearAttention VDDP:331-378, positions ordered (bf, pixel); T cond tokens prepended
+ *   to every frame; ctx [BF][heads][32][32] and kstat [BF][heads][32][2] are outputs kept for the backward.
+ * vmm_sattn_*: quadratic spatial attention of the bottleneck VDDP:687-689: one cond token per frame
+ *   (ekv row bf), no rotary, no bias; lse [BF][heads][HW] kept for the backward.
+ * ------------------------------------------------------------------------------------------ */
+int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bias, const float* rot, void* out, int fmt, int B, int frames,
+                  int HW, int heads, float scale, void* stream);
+int vmm_lattn_fwd(const void* qkv, const float* ekv, int T, void* out, float* ctx, float* kstat, int fmt, int BF, int frames,
+                  int HW, int heads, float scale, void* stream);
+int vmm_sattn_fwd(const void* qkv, const float* ekv, void* out, float* lse, int fmt, int BF, int frames, int HW, int heads,
+                  float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Around the network (fp32 tensors in the reference (B, C, F, H, W) layout unless stated).
+ * vmm_prep_input : value = a[b]*x + c[b] + s[b]*noise -> 16-bit [BF][H][W+6][8] init_conv operand
+ *                  (q_sample VDDP:1036-1042, normalize_img VDDP:1109); the buffer needs 8 trailing zero elements.
+ * vmm_loss       : F.l1_loss / F.mse_loss (VDDP:1053-1056) of pred (fp32 channels-last [pix][C]) against
+ *                  target; adds the mean to *loss_sum and writes dpred [pix][8] 16-bit (x grad_scale).
+ * vmm_cfg_x0     : eps = null + (cond - null) * w (VDDP:728), x0 = sr*x - srm1*eps (VDDP:920-924);
+ *                  eps_cl is fp32 channels-last [(2)B][F*H*W][C].
+ * vmm_abs_quantile: s[b] = max(quantile(|v_b|), floor) with torch.quantile's linear interpolation between the
+ *                  k-th and (k+1)-th order statistics (VDDP:941-947); exact radix select, one CTA per sample.
+ * vmm_posterior_step: clamp(x0,-s,s)/s (skipped when s == NULL), posterior mean (VDDP:926-933), + sig[b]*noise (VDDP:963).
+ * vmm_axpby      : out = ca*a + cb*b + cc  (DDIM update VDDP:1014-1016, unnormalize_img VDDP:1112).
+ * vmm_adam_ema_step: torch.optim.Adam (VDDP:1481) over a flat arena + EMA (VDDP:121-129); ema_mode 0 none,
+ *                  1 copy (step < step_start_ema, VDDP:1501-1503), 2 update.
+ * ------------------------------------------------------------------------------------------ */
+int vmm_prep_input(const float* x, const float* noise, const float* a, const float* c, const float* s, void* xin, int fmt, int B,
+                   int C, int F, int H, int W, void* stream);
+int vmm_loss(const float* pred, const float* target, float* loss_sum, void* dpred, int fmt, int B, int C, int F, int H, int W,
+             int l2, float grad_scale, void* stream);
+int vmm_cfg_x0(const float* x, const float* eps_cl, int has_null, float w, const float* sr, const float* srm1, float* x0,
+               float* eps_out, int B, int C, int F, int H, int W, void* stream);
+int vmm_abs_quantile(const float* v, int B, long long n, long long k, float frac, float floor_val, float* s_out, void* stream);
+int vmm_posterior_step(const float* x0, const float* x, const float* noise, const float* s, const float* c1, const float* c2,
+                       const float* sig, float* out, int B, long long per, void* stream);
+int vmm_axpby(const float* a, const float* b, float ca, float cb, float cc, float* out, long long n, void* stream);
+int vmm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long long n, float lr, float beta1, float beta2,
+                      float eps, int step, float grad_scale, int ema_mode, float ema_beta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMM_H_ */

@@ -1,0 +1,226 @@
+"""Parity of each CUDA kernel (called through the C ABI) against the CPU oracle / plain fp32 torch math.
+
+Tolerances: activations are stored in 16 bit, so a kernel whose output is bf16 is checked to 6e-3 relative
+L2 (bf16 has 8 mantissa bits: 2^-9 rounding ~ 2e-3 per element) and fp16 to 1e-3; fp32 outputs to 1e-5.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DT = [torch.bfloat16, torch.float16]
+TOL = {torch.bfloat16: 6e-3, torch.float16: 1e-3}
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from videometamaterials_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(2, 11 * 16 * 16, 64, True), (3, 11 * 8 * 8, 16, False), (2, 11 * 12 * 12, 512, True)])
+def test_gn_silu_fwd(ops, dt, shape):
+    B, pix, C, with_ss = shape
+    torch.manual_seed(0)
+    x = (torch.randn(B, pix, C, device="cuda") * 2 + 0.5).to(dt)
+    gamma = torch.randn(C, device="cuda")
+    beta = torch.randn(C, device="cuda")
+    ss = torch.randn(B, 2 * C, device="cuda") if with_ss else None
+    res = torch.randn(B, pix, C, device="cuda").to(dt)
+    xf = x.double().view(B, pix, 8, C // 8)
+    stats = torch.stack((xf.sum(dim=(1, 3)), (xf * xf).sum(dim=(1, 3))), dim=-1).contiguous()
+    y = torch.empty_like(x)
+    ops.gn_silu_fwd(x, y, stats, gamma, beta, ss, B, pix, C, 8, res=res)
+    want = F.group_norm(x.float().transpose(1, 2), 8, gamma, beta, eps=1e-5).transpose(1, 2)
+    if with_ss:
+        want = want * (ss[:, None, :C] + 1) + ss[:, None, C:]
+    want = F.silu(want) + res.float()
+    assert rel(y, want) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("C", [16, 64, 128, 256, 512])
+def test_layernorm_fwd(ops, dt, C):
+    torch.manual_seed(1)
+    rows = 1000
+    x = (torch.randn(rows, C, device="cuda") * 3 + 1).to(dt)
+    gamma = torch.randn(C, device="cuda")
+    y = torch.empty_like(x)
+    ops.ln_fwd(x, y, gamma)
+    xf = x.float()
+    want = (xf - xf.mean(1, keepdim=True)) / (xf.var(1, unbiased=False, keepdim=True) + 1e-5).sqrt() * gamma
+    assert rel(y, want) < TOL[dt]
+
+
+def _attn_inputs(B, Fr, H, W, heads, dt, seed):
+    torch.manual_seed(seed)
+    hd = heads * 32
+    qkv = torch.randn(B, Fr, H, W, 3 * hd, device="cuda").to(dt)
+    ekv = torch.randn(B, 11, 2 * hd, device="cuda")
+    return qkv, ekv
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("with_cond", [True, False])
+def test_temporal_attention_core(ops, dt, with_cond):
+    from oracle import vdm_oracle as O
+    B, Fr, H, W, heads = 2, 11, 5, 7, 8
+    hd = heads * 32
+    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 2)
+    bias = torch.randn(heads, Fr, Fr, device="cuda")
+    freqs = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32)).cuda()
+    ang = torch.arange(Fr, device="cuda").float()[:, None] * freqs[None, :]
+    rot = torch.stack((ang.cos(), ang.sin()), -1).contiguous()
+    out = torch.empty(B, Fr, H, W, hd, device="cuda", dtype=dt)
+    ops.tattn_fwd(qkv, ekv if with_cond else None, bias, rot, out, B, Fr, H * W, heads)
+    # oracle: identity projections; the oracle rotates cond keys itself, the kernel takes them pre-rotated
+    q, k, v = (t.float().permute(0, 2, 3, 1, 4).reshape(B, H * W, Fr, heads, 32).transpose(2, 3) for t in qkv.chunk(3, dim=-1))
+    k = O.rotary(k, freqs)
+    if with_cond:
+        ek = ekv[..., :hd].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
+        ev = ekv[..., hd:].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
+        k = torch.cat((ek, k), -2)
+        v = torch.cat((ev, v), -2)
+    qq = O.rotary(q * 32 ** -0.5, freqs)
+    sim = torch.einsum("...id,...jd->...ij", qq, k)
+    sim = sim + (torch.cat((bias, bias), -1) if with_cond else bias)
+    want = torch.einsum("...ij,...jd->...id", sim.softmax(-1), v).transpose(2, 3).reshape(B, H, W, Fr, hd).permute(0, 3, 1, 2, 4)
+    assert rel(out, want) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("hw", [(6, 7), (24, 24)])
+def test_linear_attention_core(ops, dt, hw):
+    H, W = hw
+    B, Fr, heads = 2, 11, 8
+    hd = heads * 32
+    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 3)
+    n = H * W
+    out = torch.empty(B, Fr, H, W, hd, device="cuda", dtype=dt)
+    ctx = torch.empty(B * Fr, heads, 32, 32, device="cuda")
+    kstat = torch.empty(B * Fr, heads, 32, 2, device="cuda")
+    ops.lattn_fwd(qkv, ekv, 11, out, ctx, kstat, B * Fr, Fr, n, heads)
+    q, k, v = (t.float().reshape(B * Fr, n, heads, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=-1))   # (bf, h, d, n)
+    ek = ekv[..., :hd].reshape(B, 1, 11, heads, 32).expand(B, Fr, 11, heads, 32).permute(0, 1, 3, 4, 2).reshape(B * Fr, heads, 32, 11)
+    ev = ekv[..., hd:].reshape(B, 1, 11, heads, 32).expand(B, Fr, 11, heads, 32).permute(0, 1, 3, 4, 2).reshape(B * Fr, heads, 32, 11)
+    k = torch.cat((ek, k), -1).softmax(-1)
+    v = torch.cat((ev, v), -1) / n
+    q = q.softmax(-2) * 32 ** -0.5
+    c = torch.einsum("bhdn,bhen->bhde", k, v)
+    want = torch.einsum("bhde,bhdn->bhen", c, q).permute(0, 3, 1, 2).reshape(B, Fr, H, W, hd)
+    assert rel(ctx, c) < 1e-4
+    assert rel(out, want) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_spatial_attention_core(ops, dt):
+    B, Fr, H, W, heads = 2, 11, 12, 12, 8
+    hd = heads * 32
+    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 4)
+    n = H * W
+    out = torch.empty(B, Fr, H, W, hd, device="cuda", dtype=dt)
+    lse = torch.empty(B * Fr, heads, n, device="cuda")
+    ops.sattn_fwd(qkv, ekv, out, lse, B * Fr, Fr, n, heads)
+    q, k, v = (t.float().reshape(B * Fr, n, heads, 32).transpose(1, 2) for t in qkv.chunk(3, dim=-1))      # (bf, h, n, d)
+    ek = ekv[..., :hd].reshape(B * Fr, 1, heads, 32).transpose(1, 2)
+    ev = ekv[..., hd:].reshape(B * Fr, 1, heads, 32).transpose(1, 2)
+    k = torch.cat((ek, k), -2)
+    v = torch.cat((ev, v), -2)
+    sim = torch.einsum("bhid,bhjd->bhij", q * 32 ** -0.5, k)
+    want = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), v).transpose(1, 2).reshape(B, Fr, H, W, hd)
+    assert rel(out, want) < TOL[dt]
+    assert rel(lse, torch.logsumexp(sim, -1)) < 1e-5
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("C", [16, 64, 128])
+def test_down_up_convs(ops, dt, C):
+    torch.manual_seed(5)
+    bf, H, W = 5, 16, 16
+    x = torch.randn(bf, H, W, C, device="cuda").to(dt)
+    wd = (torch.randn(C, C, 4, 4, device="cuda") / (16 * C) ** 0.5).to(dt)
+    b = torch.randn(C, device="cuda")
+    out = torch.empty(bf, H // 2, W // 2, C, device="cuda", dtype=dt)
+    ops.conv_down(x, ops.pack_conv_taps(wd.float(), [C], dt), C, out, bias=b)
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), wd.float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert rel(out, want) < TOL[dt]
+    wu = (torch.randn(C, C, 1, 4, 4, device="cuda") / (4 * C) ** 0.5).to(dt)
+    out2 = torch.empty(bf, 2 * H, 2 * W, C, device="cuda", dtype=dt)
+    ops.conv_up(x, ops.pack_conv_up(wu.float(), dt), C, out2, bias=b)
+    want2 = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wu[:, :, 0].float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert rel(out2, want2) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_init_conv_with_q_sample(ops, dt):
+    torch.manual_seed(6)
+    B, C, Fr, H, W, N = 2, 3, 11, 16, 16, 64
+    x = torch.rand(B, C, Fr, H, W, device="cuda")
+    noise = torch.randn_like(x)
+    a = torch.tensor([0.9, 0.3], device="cuda")
+    c = torch.tensor([0.1, -0.2], device="cuda")
+    s = torch.tensor([0.4, 0.95], device="cuda")
+    w = (torch.randn(N, C, 1, 7, 7, device="cuda") / (49 * C) ** 0.5)
+    bias = torch.randn(N, device="cuda")
+    xin = torch.zeros(B * Fr * H * (W + 6) * 8 + 8, device="cuda", dtype=dt)
+    ops.prep_input(x, noise, a, c, s, xin, B, C, Fr, H, W)
+    out = torch.empty(B * Fr, H, W, N, device="cuda", dtype=dt)
+    ops.init_conv(xin, B * Fr, H, W, ops.pack_init_conv(w, dt), N, out, bias=bias)
+    xt = (a.view(-1, 1, 1, 1, 1) * x + c.view(-1, 1, 1, 1, 1) + s.view(-1, 1, 1, 1, 1) * noise).to(dt).float()
+    want = F.conv2d(xt.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, H, W), w[:, :, 0].to(dt).float(), bias, padding=3).permute(0, 2, 3, 1)
+    assert rel(out, want) < TOL[dt]
+
+
+def test_sampler_elementwise_and_quantile(ops):
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200.diffusion import quantile_rank
+    torch.manual_seed(7)
+    B, C, Fr, H, W = 3, 3, 11, 96, 96
+    S = {k: v.cuda() for k, v in O.schedule(256).items()}
+    x = torch.randn(B, C, Fr, H, W, device="cuda")
+    eps_cl = torch.randn(2 * B, Fr, H, W, C, device="cuda")
+    noise = torch.randn_like(x)
+    t = torch.tensor([255, 17, 0], device="cuda")
+    x0 = torch.empty_like(x)
+    eps = torch.empty_like(x)
+    ops.cfg_x0(x, eps_cl, True, 5.0, S["sqrt_recip_alphas_cumprod"][t].contiguous(), S["sqrt_recipm1_alphas_cumprod"][t].contiguous(),
+               x0, eps, B, C, Fr, H, W)
+    ec, en = (e.permute(0, 4, 1, 2, 3) for e in (eps_cl[:B], eps_cl[B:]))
+    eps_want = en + (ec - en) * 5.0
+    assert torch.equal(eps, eps_want)
+    x0_want = O.predict_x0(S, x, t, eps_want)
+    assert rel(x0, x0_want) < 1e-6
+    per = C * Fr * H * W
+    k, frac = quantile_rank(per, 0.9)
+    s = torch.empty(B, device="cuda")
+    ops.abs_quantile(x0, B, per, k, frac, 1.0, s)
+    s_want = torch.quantile(x0.flatten(1).abs(), 0.9, dim=-1).clamp(min=1.0)
+    assert torch.equal(s, s_want), (s, s_want)     # order statistics + the same lerp: bit exact
+    out = torch.empty_like(x)
+    c1 = S["posterior_mean_coef1"][t].contiguous()
+    c2 = S["posterior_mean_coef2"][t].contiguous()
+    sig = ((t != 0).float() * (0.5 * S["posterior_log_variance_clipped"][t]).exp()).contiguous()
+    ops.posterior_step(x0, x, noise, s, c1, c2, sig, out, B, per)
+    want = O.p_sample_from_eps(S, x, t, eps_want, noise, dynamic=True)
+    assert rel(out, want) < 1e-6
+
+
+def test_quantile_edge_cases(ops):
+    from videometamaterials_b200.diffusion import quantile_rank
+    for n in (1, 2, 10, 1000, 4097):
+        torch.manual_seed(n)
+        v = torch.randn(2, n, device="cuda")
+        v[1] = torch.round(v[1] * 2) / 2          # many ties
+        k, frac = quantile_rank(n, 0.9)
+        s = torch.empty(2, device="cuda")
+        ops.abs_quantile(v, 2, n, k, frac, 0.0, s)
+        want = torch.quantile(v.abs(), 0.9, dim=-1)
+        assert torch.equal(s, want), (n, s, want)

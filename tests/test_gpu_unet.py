@@ -1,0 +1,122 @@
+"""Whole-network parity on the GPU against the committed golden fixtures (reference outputs, fp32 CPU).
+
+Tolerances (relative L2, stated per SURVEY.md section 0 D5): the network stores activations in 16 bit, so one
+forward is expected at ~1e-3 (fp16) / ~6e-3 (bf16) of the fp32 reference; guided outputs amplify the
+difference of two forwards by w=5.  The post-network sampler arithmetic is fp32 and adds nothing measurable.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = {torch.float16: 3e-3, torch.bfloat16: 2e-2}
+
+
+def rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm().clamp_min(1e-30))
+
+
+def build(cfg_dim, mults, T, size, sampling_T, dtype, seed):
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import GaussianDiffusion, Unet3D
+    model = Unet3D(dim=cfg_dim, dim_mults=mults, channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True,
+                   resnet_groups=8, cond_bias=True, cond_attention='self-stacked', cond_attention_tokens=16,
+                   use_temporal_attention_cond=True, cond_to_time='add', per_frame_cond=True, padding_mode='zeros')
+    sd = O.synthetic_state_dict(O.UnetCfg(dim=cfg_dim, dim_mults=mults), seed=seed)
+    model.load_state_dict(sd, strict=True)
+    model.set_compute_dtype(dtype)
+    gd = GaussianDiffusion(model, image_size=size, channels=3, num_frames=11, timesteps=T, loss_type='l1', use_dynamic_thres=True,
+                           sampling_timesteps=sampling_T).cuda()
+    return model, gd, sd
+
+
+class Replay:
+    def __init__(self, tensors):
+        self.tensors, self.i = list(tensors), 0
+
+    def __enter__(self):
+        self._a, self._b = torch.randn, torch.randn_like
+
+        def nxt(*a, **k):
+            t = self.tensors[self.i]
+            self.i += 1
+            return t.clone().cuda()
+
+        torch.randn, torch.randn_like = nxt, nxt
+        return self
+
+    def __exit__(self, *e):
+        torch.randn, torch.randn_like = self._a, self._b
+
+
+@pytest.fixture(scope="module")
+def gold_small(golden_dir):
+    return torch.load(os.path.join(golden_dir, "small_unet.pt"))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_small_unet_forward(gold_small, dtype):
+    g = gold_small
+    model, gd, _ = build(16, (1, 2), g["T"], g["size"], g["T"], dtype, g["seed"])
+    x, t, cond = g["x"].cuda(), g["t"].cuda(), g["cond"].cuda()
+    with torch.no_grad():
+        y_cond = model(x, t, cond=cond, null_cond_prob=0.0)
+        y_null = model(x, t, cond=cond, null_cond_prob=1.0)
+        y_g = model.forward_with_guidance_scale(x, t, cond=cond, guidance_scale=5.0)
+    e = [rel(y_cond, g["y_cond"]), rel(y_null, g["y_null"]), rel(y_g, g["y_guided"])]
+    print("small forward rel-L2 (cond, null, guided):", dtype, e)
+    assert e[0] < FWD_TOL[dtype] and e[1] < FWD_TOL[dtype] and e[2] < 5 * FWD_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16])
+def test_small_sampling(gold_small, dtype):
+    g = gold_small
+    model, gd, _ = build(16, (1, 2), g["T"], g["size"], g["T"], dtype, g["seed"])
+    x, t, cond = g["x"].cuda(), g["t"].cuda(), g["cond"].cuda()
+    noises = list(g["step_noise"])
+    with Replay([noises[0]]):
+        p1 = gd.p_sample(x, t, cond=cond, guidance_scale=5.0)
+    with Replay([noises[0]]):
+        p0 = gd.p_sample(x, torch.zeros_like(t), cond=cond, guidance_scale=5.0)
+    with Replay(noises):
+        loop = gd.sample(cond=cond, guidance_scale=5.0)
+    _, gd4, _ = build(16, (1, 2), g["T"], g["size"], 4, dtype, g["seed"])
+    with Replay(noises):
+        ddim = gd4.sample(cond=cond, guidance_scale=5.0)
+    e = dict(p_sample_t=rel(p1, g["p_sample_t"]), p_sample_t0=rel(p0, g["p_sample_t0"]), loop=rel(loop, g["loop"]),
+             ddim4=rel(ddim, g["ddim4"]))
+    print("small sampling rel-L2:", e)
+    assert e["p_sample_t"] < 1e-2 and e["p_sample_t0"] < 1e-2
+    assert e["loop"] < 5e-2 and e["ddim4"] < 5e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_full_unet_forward_slices(golden_dir, dtype):
+    """Shipped 96x96x11 configuration, b=1, t=128: compare against the strided slices of the reference output."""
+    g = torch.load(os.path.join(golden_dir, "full_unet_slices.pt"))
+    model, gd, _ = build(64, (1, 2, 4, 8), 256, 96, 256, dtype, g["seed"])
+    gen = torch.Generator().manual_seed(g["data_seed"])
+    x = torch.randn(1, 3, 11, 96, 96, generator=gen)
+    cond = torch.rand(1, 11, generator=gen) * 2 - 1
+    noise = torch.randn(1, 3, 11, 96, 96, generator=gen)
+    t = torch.tensor([g["t"]])
+    sl = (slice(None), slice(None), slice(None, None, 2), slice(None, None, 8), slice(None, None, 8))
+    with torch.no_grad():
+        yc = model(x.cuda(), t.cuda(), cond=cond.cuda(), null_cond_prob=0.0)
+        yn = model(x.cuda(), t.cuda(), cond=cond.cuda(), null_cond_prob=1.0)
+    with Replay([noise]):
+        ps = gd.p_sample(x.cuda(), t.cuda(), cond=cond.cuda(), guidance_scale=5.0)
+    e = dict(cond=rel(yc[sl], g["y_cond_slice"]), null=rel(yn[sl], g["y_null_slice"]), p_sample=rel(ps[sl], g["p_sample_slice"]),
+             norm=abs(float(yc.norm()) - g["y_cond_norm"]) / g["y_cond_norm"])
+    print("full forward rel-L2:", dtype, e)
+    assert e["cond"] < FWD_TOL[dtype] and e["null"] < FWD_TOL[dtype] and e["norm"] < FWD_TOL[dtype]
+    assert e["p_sample"] < 10 * FWD_TOL[dtype]
+
+
+def test_forward_needs_cuda():
+    from videometamaterials_b200 import Unet3D
+    m = Unet3D(dim=16, dim_mults=(1, 2), per_frame_cond=True, use_temporal_attention_cond=True, cond_attention='self-stacked')
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 11, 16, 16), torch.zeros(1, dtype=torch.long), cond=torch.zeros(1, 11))

@@ -1,0 +1,101 @@
+"""ctypes binding of libvmm_sm100.so (the C ABI declared in include/vmm.h).
+
+The library is the product's only compute path.  If it is missing it is built with nvcc when a
+toolkit is present; otherwise import fails loudly.  There is no Python / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvmm_sm100.so")
+
+MAX_VIEWS, MAX_PHASES, MAX_TAPS = 4, 4, 20
+FMT_F16, FMT_BF16 = 0, 1
+
+
+class View4(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dims", C.c_int32 * 4), ("strides", C.c_int64 * 3)]
+
+
+class Tap(C.Structure):
+    _fields_ = [("src", C.c_int32), ("dy", C.c_int32), ("dx", C.c_int32), ("kofs", C.c_int32), ("c", C.c_int32)]
+
+
+class CgemmParams(C.Structure):
+    _fields_ = [
+        ("fmt", C.c_int32), ("n_views", C.c_int32), ("a", View4 * MAX_VIEWS),
+        ("n_phases", C.c_int32), ("n_taps", C.c_int32 * MAX_PHASES), ("taps", (Tap * MAX_TAPS) * MAX_PHASES),
+        ("phase_oy", C.c_int32 * MAX_PHASES), ("phase_ox", C.c_int32 * MAX_PHASES),
+        ("w", C.c_void_p), ("n", C.c_int32), ("ktot", C.c_int32),
+        ("bf", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32),
+        ("tf", C.c_int32), ("th", C.c_int32), ("tw", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_fp32", C.c_int32),
+        ("ohs", C.c_int32), ("ows", C.c_int32), ("sy", C.c_int32), ("sx", C.c_int32),
+        ("out2", C.c_void_p), ("ldo2", C.c_int64), ("nsplit", C.c_int32),
+        ("bias", C.c_void_p), ("res", C.c_void_p), ("ldr", C.c_int64),
+        ("gn_stats", C.c_void_p), ("gn_group", C.c_int32), ("frames_per_sample", C.c_int32),
+    ]
+
+
+class VmmError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise ImportError(
+                f"libvmm_sm100.so is missing at {LIB_PATH} and could not be built ({e}). "
+                "This package has no CPU or PyTorch fallback: build it with "
+                "`python -m videometamaterials_b200.build` where nvcc is available.") from e
+    lib = C.CDLL(LIB_PATH)
+    lib.vmm_last_error.restype = C.c_char_p
+    lib.vmm_abi_version.restype = C.c_int
+    lib.vmm_launch_count.restype = C.c_uint64
+    return lib
+
+
+lib = _load()
+
+_P, _I, _L, _F, _Z = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
+# name -> argtypes (restype int unless listed in _RESTYPES); mirrors include/vmm.h one to one
+_SIGNATURES = {
+    "vmm_cgemm": [C.POINTER(CgemmParams), _P],
+    "vmm_gn_silu_fwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P],
+    "vmm_gn_silu_bwd_workspace": [_I, _I, _I],
+    "vmm_gn_silu_bwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _Z, _P],
+    "vmm_ln_fwd": [_P, _P, _I, _L, _I, _P, _F, _P, _P],
+    "vmm_ln_bwd": [_P, _P, _P, _P, _I, _L, _I, _P, _F, _P, _P],
+    "vmm_tattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "vmm_lattn_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "vmm_sattn_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "vmm_prep_input": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "vmm_loss": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "vmm_cfg_x0": [_P, _P, _I, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "vmm_abs_quantile": [_P, _I, _L, _L, _F, _F, _P, _P],
+    "vmm_posterior_step": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _P],
+    "vmm_axpby": [_P, _P, _F, _F, _F, _P, _L, _P],
+    "vmm_adam_ema_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _I, _F, _P],
+}
+_RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t}
+for _name, _args in _SIGNATURES.items():
+    _fn = getattr(lib, _name)     # AttributeError here == the .so is stale: rebuild it
+    _fn.argtypes = _args
+    _fn.restype = _RESTYPES.get(_name, C.c_int)
+
+# every symbol include/vmm.h declares; tests assert that the library exports all of them
+EXPORTS = ["vmm_last_error", "vmm_abi_version", "vmm_launch_count", *_SIGNATURES.keys()]
+
+
+def check(rc: int, what: str = "vmm call") -> None:
+    if rc != 0:
+        raise VmmError(f"{what} failed ({rc}): {lib.vmm_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib.vmm_launch_count())

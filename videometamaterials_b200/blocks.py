@@ -1,0 +1,345 @@
+"""Block-level forward (and, in blocks_bwd.py, backward) of Unet3D issued on the C ABI.
+
+Every function takes channels-last 16-bit activations `(b, f, h, w, c)` and launches a fixed sequence of
+`vmm_*` kernels; nothing here does arithmetic on activations in PyTorch.  The conditioning path (R10 of
+SURVEY.md section 8a: tensors of at most b*11*256 elements, 0.004 GFLOP) is plain fp32 torch ops on the GPU.
+Each *_fwd returns `(out, saved)`; `saved` is what the matching backward needs.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+def prob_mask_like(shape, prob, device):
+    """VDDP:55-61, including its RNG consumption (a draw only when 0 < prob < 1)."""
+    if prob == 1:
+        return torch.ones(shape, device=device, dtype=torch.bool)
+    if prob == 0:
+        return torch.zeros(shape, device=device, dtype=torch.bool)
+    return torch.zeros(shape, device=device).float().uniform_(0, 1) < prob
+
+
+# ------------------------------------------------------------------------------------------------
+# model walk helpers
+# ------------------------------------------------------------------------------------------------
+def resnet_names(model) -> List[str]:
+    L = len(model.dim_mults)
+    names = []
+    for i in range(L):
+        names += [f"downs.{i}.0.", f"downs.{i}.1."]
+    names += ["mid_block1.", "mid_block2."]
+    for i in range(L):
+        names += [f"ups.{i}.0.", f"ups.{i}.1."]
+    return names          # final_conv.0. has no time mlp
+
+
+def attn_names(model) -> List[Tuple[str, str]]:
+    """(prefix of the Attention module, kind) for every attention with conditioning tokens."""
+    L = len(model.dim_mults)
+    out = []
+    for i in range(L):
+        out += [(f"downs.{i}.2.fn.fn.", "linear"), (f"downs.{i}.3.fn.fn.fn.", "temporal")]
+    out += [("mid_spatial_attn.fn.fn.fn.", "spatial"), ("mid_temporal_attn.fn.fn.fn.", "temporal")]
+    for i in range(L):
+        out += [(f"ups.{i}.2.fn.fn.", "linear"), (f"ups.{i}.3.fn.fn.fn.", "temporal")]
+    return out
+
+
+def level_dims(model) -> List[int]:
+    return [model.dim] + [model.dim * m for m in model.dim_mults]
+
+
+def resnet_splits(model) -> Dict[str, List[int]]:
+    dims = level_dims(model)
+    io = list(zip(dims[:-1], dims[1:]))
+    sp: Dict[str, List[int]] = {}
+    for i, (ci, co) in enumerate(io):
+        sp[f"downs.{i}.0."] = [ci]
+        sp[f"downs.{i}.1."] = [co]
+    sp["mid_block1."] = [dims[-1]]
+    sp["mid_block2."] = [dims[-1]]
+    for i, (ci, co) in enumerate(reversed(io)):
+        sp[f"ups.{i}.0."] = [co, co]
+        sp[f"ups.{i}.1."] = [ci]
+    sp["final_conv.0."] = [model.dim, model.dim]
+    return sp
+
+
+def pack_all(model, dtype) -> Dict[str, Tensor]:
+    """fp32 master parameters -> 16-bit K-major GEMM operands (forward and data-gradient forms)."""
+    sd = dict(model.named_parameters())
+    P: Dict[str, Tensor] = {}
+    sp = resnet_splits(model)
+    for pre, splits in sp.items():
+        w1 = sd[pre + "block1.proj.weight"][:, :, 0]
+        w2 = sd[pre + "block2.proj.weight"][:, :, 0]
+        cout = w1.shape[0]
+        P[pre + "block1.w"] = ops.pack_conv_taps(w1, splits, dtype)
+        P[pre + "block2.w"] = ops.pack_conv_taps(w2, [cout], dtype)
+        # data gradients: dx[q] = sum_t dy[q - d_t] W_t^T  -> flipped taps, (cin, cout) transposed
+        P[pre + "block1.wd"] = ops.pack_conv_taps(w1.flip(2, 3).permute(1, 0, 2, 3), [cout], dtype)
+        P[pre + "block2.wd"] = ops.pack_conv_taps(w2.flip(2, 3).permute(1, 0, 2, 3), [cout], dtype)
+        if (pre + "res_conv.weight") in sd:
+            wr = sd[pre + "res_conv.weight"][:, :, 0]          # (cout, cin, 1, 1)
+            P[pre + "res.w"] = ops.pack_conv_taps(wr, splits, dtype)
+            P[pre + "res.wd"] = ops.pack_linear(wr[:, :, 0, 0].t(), dtype)
+    for pre, kind in attn_names(model) + [("init_temporal_attn.fn.fn.fn.", "temporal")]:
+        wq = sd[pre + "to_qkv.weight"]
+        wo = sd[pre + "to_out.weight"]
+        if kind == "linear":
+            wq, wo = wq[:, :, 0, 0], wo[:, :, 0, 0]
+        P[pre + "qkv.w"] = ops.pack_linear(wq, dtype)
+        P[pre + "out.w"] = ops.pack_linear(wo, dtype)
+        P[pre + "qkv.wd"] = ops.pack_linear(wq.t(), dtype)
+        P[pre + "out.wd"] = ops.pack_linear(wo.t(), dtype)
+    L = len(model.dim_mults)
+    for i in range(L - 1):
+        wd = sd[f"downs.{i}.4.weight"][:, :, 0]                 # (cout, cin, 4, 4)
+        P[f"downs.{i}.4.w"] = ops.pack_conv_taps(wd, [wd.shape[1]], dtype)
+        # d/dx of the strided conv is a transposed conv with the same weight viewed as (cin_t = cout, cout_t = cin)
+        P[f"downs.{i}.4.wd"] = ops.pack_conv_taps(wd.permute(1, 0, 2, 3), [wd.shape[0]], dtype)
+        wu = sd[f"ups.{i}.4.weight"]                            # ConvTranspose3d: (cin, cout, 1, 4, 4)
+        P[f"ups.{i}.4.w"] = ops.pack_conv_up(wu, dtype)
+        # d/dx of the transposed conv is the strided conv with weight (cout_s = cin, cin_s = cout)
+        P[f"ups.{i}.4.wd"] = ops.pack_conv_taps(wu[:, :, 0], [wu.shape[1]], dtype)
+    P["init_conv.w"] = ops.pack_init_conv(sd["init_conv.weight"], dtype)
+    wf = sd["final_conv.1.weight"][:, :, 0, 0, 0]              # (channels, dim)
+    P["final.w"] = ops.pack_linear(wf, dtype)
+    wfd = wf.new_zeros(8, wf.shape[0])                          # dpred rows carry 8 (zero padded) channels
+    P["final.wd"] = ops.pack_linear(torch.cat((wf.t(), wf.new_zeros(wf.shape[1], 8 - wf.shape[0])), dim=1), dtype)
+    del wfd
+    return P
+
+
+# ------------------------------------------------------------------------------------------------
+# conditioning path (fp32 torch ops; differentiable through torch autograd)      VDDP:741-788
+# ------------------------------------------------------------------------------------------------
+_BUCKET_CACHE: Dict[Tuple[int, str], Tensor] = {}
+
+
+def rel_pos_buckets(n: int, device) -> Tensor:
+    """T5-style bucket index of (k - q), num_buckets=32, max_distance=32.  VDDP:82-106."""
+    key = (n, str(device))
+    if key not in _BUCKET_CACHE:
+        q = torch.arange(n)[:, None]
+        k = torch.arange(n)[None, :]
+        neg = q - k
+        ret = (neg < 0).long() * 16
+        dist = neg.abs()
+        large = (8 + (torch.log(dist.float() / 8) / math.log(32 / 8) * 8).long()).clamp(max=15)
+        _BUCKET_CACHE[key] = (ret + torch.where(dist < 8, dist, large)).to(device)
+    return _BUCKET_CACHE[key]
+
+
+def sinusoidal(t: Tensor, dim: int) -> Tensor:
+    half = dim // 2
+    rate = math.log(10000) / (half - 1)
+    freq = torch.exp(torch.arange(half, device=t.device) * -rate)
+    arg = t[:, None] * freq[None, :]
+    return torch.cat((arg.sin(), arg.cos()), dim=-1)
+
+
+def rotate_pairs(x: Tensor, freqs: Tensor) -> Tensor:
+    """rotary_embedding_torch rotate_queries_or_keys on (..., n, d): position = index along dim -2."""
+    n = x.shape[-2]
+    ang = torch.arange(n, device=x.device, dtype=freqs.dtype)[:, None] * freqs[None, :]
+    c, s = ang.cos(), ang.sin()
+    xe, xo = x[..., 0::2], x[..., 1::2]
+    return torch.stack((xe * c - xo * s, xo * c + xe * s), dim=-1).flatten(-2)
+
+
+def conditioning(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: int):
+    """Returns (scale_shift per resnet block, ekv per attention block, bias (h,f,f), rot (f,16,2))."""
+    sd = dict(model.named_parameters())
+    heads = model.heads
+    e = sinusoidal(time, model.dim)
+    e = F.gelu(F.linear(e, sd["time_mlp.1.weight"], sd["time_mlp.1.bias"]))
+    t = F.linear(e, sd["time_mlp.3.weight"], sd["time_mlp.3.bias"])
+    tok = F.linear(cond[..., None].float(), sd["sign_emb.weight"], sd["sign_emb.bias"])
+    hid = tok.mean(dim=-2)
+    hid = F.layer_norm(hid, hid.shape[-1:], sd["cond_token_to_hidden.0.weight"], sd["cond_token_to_hidden.0.bias"])
+    hid = F.linear(hid, sd["cond_token_to_hidden.1.weight"], sd["cond_token_to_hidden.1.bias"])
+    hid = F.linear(F.silu(hid), sd["cond_token_to_hidden.3.weight"], sd["cond_token_to_hidden.3.bias"])
+    tok = torch.where(null_mask[:, None, None], sd["null_text_token"], tok)
+    hid = torch.where(null_mask[:, None], sd["null_text_hidden"], hid)
+    t = t + hid
+    # every ResnetBlock.mlp in one GEMM
+    rn = resnet_names(model)
+    wm = torch.cat([sd[p + "mlp.1.weight"] for p in rn], dim=0)
+    bm = torch.cat([sd[p + "mlp.1.bias"] for p in rn], dim=0)
+    ss_all = F.linear(F.silu(t), wm, bm)
+    ss, o = {}, 0
+    for p in rn:
+        n = sd[p + "mlp.1.bias"].shape[0]
+        ss[p] = ss_all[:, o:o + n].contiguous()
+        o += n
+    # every to_k / to_v on the tokens in one GEMM
+    an = attn_names(model)
+    wkv = torch.cat([torch.cat((sd[p + "to_k.weight"], sd[p + "to_v.weight"]), dim=0) for p, _ in an], dim=0)
+    kv_all = F.linear(tok, wkv)                                   # (b, T, n_attn * 2 * hd)
+    hd = heads * 32
+    freqs = sd["init_temporal_attn.fn.fn.fn.rotary_emb.freqs"]
+    ekv = {}
+    for j, (p, kind) in enumerate(an):
+        ek = kv_all[..., j * 2 * hd: j * 2 * hd + hd]
+        ev = kv_all[..., j * 2 * hd + hd: (j + 1) * 2 * hd]
+        if kind == "temporal":                                   # VDDP:470-471: cond keys are rotated by token index
+            b, T, _ = ek.shape
+            ek = rotate_pairs(ek.reshape(b, T, heads, 32).transpose(1, 2), freqs).transpose(1, 2).reshape(b, T, hd)
+        ekv[p] = torch.cat((ek, ev), dim=-1).contiguous()
+    table = sd["time_rel_pos_bias.relative_attention_bias.weight"]
+    bias = table[rel_pos_buckets(frames, table.device)].permute(2, 0, 1).contiguous()      # (h, f, f)
+    ang = torch.arange(frames, device=freqs.device, dtype=freqs.dtype)[:, None] * freqs[None, :]
+    rot = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous()                          # (f, 16, 2)
+    return ss, ekv, bias, rot
+
+
+# ------------------------------------------------------------------------------------------------
+# blocks (forward)
+# ------------------------------------------------------------------------------------------------
+def _flat(x: Tensor) -> Tensor:
+    return x.reshape(-1, x.shape[-1])
+
+
+def resnet_fwd(P, sd, pre: str, xs: Sequence[Tensor], ss: Optional[Tensor], groups: int):
+    """ResnetBlock VDDP:299-311 on an implicit channel-concat of xs."""
+    B, Fr, H, W, _ = xs[0].shape
+    cout = sd[pre + "block1.proj.bias"].shape[0]
+    dt, dev = xs[0].dtype, xs[0].device
+    xv = [ops.as_bfhwc(x) for x in xs]
+    pix = Fr * H * W
+    h1 = torch.empty(B, Fr, H, W, cout, dtype=dt, device=dev)
+    st1 = torch.zeros(B, groups, 2, dtype=torch.float64, device=dev)
+    ops.conv3x3(xv, P[pre + "block1.w"], cout, h1, bias=sd[pre + "block1.proj.bias"], gn_stats=st1, gn_group=cout // groups,
+                frames_per_sample=Fr)
+    a1 = torch.empty_like(h1)
+    ops.gn_silu_fwd(h1, a1, st1, sd[pre + "block1.norm.weight"], sd[pre + "block1.norm.bias"], ss, B, pix, cout, groups)
+    h2 = torch.empty_like(h1)
+    st2 = torch.zeros(B, groups, 2, dtype=torch.float64, device=dev)
+    ops.conv3x3([ops.as_bfhwc(a1)], P[pre + "block2.w"], cout, h2, bias=sd[pre + "block2.proj.bias"], gn_stats=st2,
+                gn_group=cout // groups, frames_per_sample=Fr)
+    out = torch.empty_like(h1)
+    if (pre + "res.w") in P:
+        a2 = torch.empty_like(h1)
+        ops.gn_silu_fwd(h2, a2, st2, sd[pre + "block2.norm.weight"], sd[pre + "block2.norm.bias"], None, B, pix, cout, groups)
+        ops.linear_rows([_flat(x) for x in xs], P[pre + "res.w"], cout, _flat(out), bias=sd[pre + "res_conv.bias"], res=_flat(a2))
+    else:
+        ops.gn_silu_fwd(h2, out, st2, sd[pre + "block2.norm.weight"], sd[pre + "block2.norm.bias"], None, B, pix, cout, groups,
+                        res=xs[0])
+    return out, (h1, st1, a1, h2, st2)
+
+
+def attn_block_fwd(P, sd, pre: str, kind: str, x: Tensor, ekv: Optional[Tensor], bias: Optional[Tensor], rot: Optional[Tensor],
+                   heads: int):
+    """Residual(PreNorm(attention)) for the three attention flavours.  VDDP:131-137, 256-264, 313-535."""
+    B, Fr, H, W, Cc = x.shape
+    dt, dev = x.dtype, x.device
+    hd = heads * 32
+    norm_pre = pre[: pre.index("fn.fn.") + 3]                     # "....fn."  -> PreNorm owns `norm`
+    gamma = sd[norm_pre + "norm.gamma"].reshape(-1)
+    x2 = _flat(x)
+    xn = torch.empty_like(x2)
+    ops.ln_fwd(x2, xn, gamma)
+    qkv = torch.empty(x2.shape[0], 3 * hd, dtype=dt, device=dev)
+    ops.linear_rows([xn], P[pre + "qkv.w"], 3 * hd, qkv)
+    ao = torch.empty(x2.shape[0], hd, dtype=dt, device=dev)
+    extra = None
+    if kind == "temporal":
+        ops.tattn_fwd(qkv, ekv, bias, rot, ao, B, Fr, H * W, heads)
+    elif kind == "linear":
+        ctx = torch.empty(B * Fr, heads, 32, 32, dtype=torch.float32, device=dev)
+        kstat = torch.empty(B * Fr, heads, 32, 2, dtype=torch.float32, device=dev)
+        ops.lattn_fwd(qkv, ekv, ekv.shape[1], ao, ctx, kstat, B * Fr, Fr, H * W, heads)
+        extra = (ctx, kstat)
+    else:
+        lse = torch.empty(B * Fr, heads, H * W, dtype=torch.float32, device=dev)
+        ops.sattn_fwd(qkv, ekv, ao, lse, B * Fr, Fr, H * W, heads)
+        extra = (lse,)
+    out = torch.empty_like(x)
+    ob = sd.get(pre + "to_out.bias")
+    ops.linear_rows([ao], P[pre + "out.w"], Cc, _flat(out), bias=ob, res=x2)
+    return out, (xn, qkv, ao, extra)
+
+
+def down_fwd(P, sd, pre: str, x: Tensor):
+    B, Fr, H, W, Cc = x.shape
+    out = torch.empty(B, Fr, H // 2, W // 2, Cc, dtype=x.dtype, device=x.device)
+    ops.conv_down(ops.as_bfhwc(x), P[pre + "w"], Cc, out, bias=sd[pre + "bias"])
+    return out
+
+
+def up_fwd(P, sd, pre: str, x: Tensor):
+    B, Fr, H, W, Cc = x.shape
+    out = torch.empty(B, Fr, 2 * H, 2 * W, Cc, dtype=x.dtype, device=x.device)
+    ops.conv_up(ops.as_bfhwc(x), P[pre + "w"], Cc, out, bias=sd[pre + "bias"])
+    return out
+
+
+def init_fwd(P, sd, model, x: Tensor, noise: Optional[Tensor], qcoef):
+    """prep (q_sample fused) + init_conv.  x fp32 (b, c, f, h, w)."""
+    B, Cc, Fr, H, W = x.shape
+    dt = model.compute_dtype
+    xin = torch.zeros(B * Fr * H * (W + 6) * 8 + 8, dtype=dt, device=x.device)
+    a, c, s = qcoef if qcoef is not None else (None, None, None)
+    ops.prep_input(x.contiguous(), noise, a, c, s, xin, B, Cc, Fr, H, W)
+    out = torch.empty(B, Fr, H, W, model.dim, dtype=dt, device=x.device)
+    ops.init_conv(xin, B * Fr, H, W, P["init_conv.w"], model.dim, out, bias=sd["init_conv.bias"])
+    return out, xin
+
+
+def final_fwd(P, sd, model, x: Tensor):
+    B, Fr, H, W, Cc = x.shape
+    out = torch.empty(B, Fr, H, W, model.channels, dtype=torch.float32, device=x.device)
+    ops.linear_rows([_flat(x)], P["final.w"], model.channels, _flat(out), bias=sd["final_conv.1.bias"])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# whole network, inference form (no autograd)      VDDP:730-821
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor, cond: Tensor, null_mask: Tensor) -> Tensor:
+    """x fp32 (b, c, f, h, w) -> eps fp32 channels-last (b, f, h, w, c)."""
+    if not x.is_cuda:
+        raise RuntimeError("videometamaterials_b200 has no CPU path: move the model and inputs to a CUDA device")
+    P = model.packed()
+    sd = dict(model.named_parameters())
+    L = len(model.dim_mults)
+    g, heads = model.groups, model.heads
+    frames = x.shape[2]
+    ss, ekv, bias, rot = conditioning(model, time, cond, null_mask, frames)
+    h, _ = init_fwd(P, sd, model, x.float(), noise, qcoef)
+    h, _ = attn_block_fwd(P, sd, "init_temporal_attn.fn.fn.fn.", "temporal", h, None, bias, rot, heads)
+    r = h
+    skips = []
+    for i in range(L):
+        p = f"downs.{i}."
+        h, _ = resnet_fwd(P, sd, p + "0.", [h], ss[p + "0."], g)
+        h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g)
+        h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads)
+        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads)
+        skips.append(h)
+        if i < L - 1:
+            h = down_fwd(P, sd, p + "4.", h)
+    h, _ = resnet_fwd(P, sd, "mid_block1.", [h], ss["mid_block1."], g)
+    h, _ = attn_block_fwd(P, sd, "mid_spatial_attn.fn.fn.fn.", "spatial", h, ekv["mid_spatial_attn.fn.fn.fn."], None, None, heads)
+    h, _ = attn_block_fwd(P, sd, "mid_temporal_attn.fn.fn.fn.", "temporal", h, ekv["mid_temporal_attn.fn.fn.fn."], bias, rot, heads)
+    h, _ = resnet_fwd(P, sd, "mid_block2.", [h], ss["mid_block2."], g)
+    for i in range(L):
+        p = f"ups.{i}."
+        h, _ = resnet_fwd(P, sd, p + "0.", [h, skips.pop()], ss[p + "0."], g)
+        h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g)
+        h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads)
+        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads)
+        if i < L - 1:
+            h = up_fwd(P, sd, p + "4.", h)
+    h, _ = resnet_fwd(P, sd, "final_conv.0.", [h, r], None, g)
+    return final_fwd(P, sd, model, h)

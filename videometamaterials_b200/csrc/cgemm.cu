@@ -1,0 +1,537 @@
+// vmm_cgemm: persistent, warp-specialised implicit-GEMM convolution for sm_100a.
+//
+//   warp 0      TMA producer   (one lane): per K block, one 4-D box of A (shifted by the tap) + one 2-D box of W
+//   warp 1      MMA issuer     (one lane): tcgen05.mma kind::f16, M=128, N=BN, K=16 x4 per 64-wide block
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue: tcgen05.ld -> bias / residual / GroupNorm partial sums -> global stores
+//
+// Two TMEM accumulators (double buffer) let the epilogue of tile i overlap the main loop of tile i+1.
+// The ring of smem stages is shared across tiles (the producer runs ahead of the MMA warp).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace vmm {
+
+struct TapDev {
+  int16_t src, dy, dx, nk;
+  int32_t kofs;
+};
+
+struct CgemmDev {
+  CUtensorMap amap[VMM_MAX_VIEWS];
+  CUtensorMap bmap;
+  TapDev taps[VMM_MAX_PHASES][VMM_MAX_TAPS];
+  int n_taps[VMM_MAX_PHASES];
+  int phase_oy[VMM_MAX_PHASES], phase_ox[VMM_MAX_PHASES];
+  int n_phases;
+  int N, BN, n_ntiles;
+  int BF, OH, OW;
+  int tf_log, th_log, tw_log;
+  int tiles_f, tiles_y, tiles_x;
+  int total_tiles;
+  int stages;
+  uint32_t stage_bytes, tx_bytes, acc_stride, tmem_cols;
+  uint32_t idesc;
+  void* out;
+  long long ldo;
+  int out_fp32;
+  int OHs, OWs, sy, sx;
+  void* out2;
+  long long ldo2;
+  int nsplit;
+  const float* bias;
+  const void* res;
+  long long ldr;
+  double* gn_stats;
+  int gn_gs, gn_groups, fps;
+  int fmt;
+};
+
+constexpr int kMaxStages = 8;
+constexpr int kABytes = 128 * 128;   // 128 rows x 64 16-bit elements
+
+struct __align__(8) CgemmSmemCtl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  float gn_acc[2][16][2];   // [sample slot][group in n-tile][sum, sumsq], kept across tiles of one (sample, n-tile)
+};
+
+__device__ __forceinline__ void decode_tile(const CgemmDev& p, int t, int& phase, int& bf0, int& y0, int& x0, int& n0) {
+  int nt = t % p.n_ntiles;
+  int r = t / p.n_ntiles;
+  int xt = r % p.tiles_x;
+  r /= p.tiles_x;
+  int yt = r % p.tiles_y;
+  r /= p.tiles_y;
+  int ft = r % p.tiles_f;
+  phase = r / p.tiles_f;
+  bf0 = ft << p.tf_log;
+  y0 = yt << p.th_log;
+  x0 = xt << p.tw_log;
+  n0 = nt * p.BN;
+}
+
+// Add the shared-memory GroupNorm partial sums of (first sample smp0, n-tile n0) to the global fp64 statistics
+// and clear them.  Called by all 128 epilogue threads between two named-barrier syncs.
+__device__ __forceinline__ void gn_flush(const CgemmDev& p, CgemmSmemCtl* ctl, int ethread, int smp0, int n0) {
+  if (ethread < 2 * 16 * 2) {
+    const int sl = ethread >> 5, gl = (ethread >> 1) & 15, w = ethread & 1;
+    const int g = n0 / p.gn_gs + gl;
+    const float val = ctl->gn_acc[sl][gl][w];
+    const int nsamp = (p.BF + p.fps - 1) / p.fps;
+    if (g < p.gn_groups && smp0 + sl < nsamp && val != 0.f)
+      atomicAdd(p.gn_stats + (static_cast<long long>(smp0 + sl) * p.gn_groups + g) * 2 + w, static_cast<double>(val));
+    ctl->gn_acc[sl][gl][w] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ CgemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  CgemmSmemCtl* ctl = reinterpret_cast<CgemmSmemCtl*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < VMM_MAX_VIEWS; ++i) tma_prefetch_desc(&p.amap[i]);
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&ctl->tfull[a], 1);
+      mbar_init(&ctl->tempty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&ctl->tmem_base, p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == 3) {
+    float* g = &ctl->gn_acc[0][0][0];
+    for (int i = lane; i < 2 * 16 * 2; i += 32) g[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int phase, bf0, y0, x0, n0;
+        decode_tile(p, t, phase, bf0, y0, x0, n0);
+        const int nt = p.n_taps[phase];
+        for (int tap = 0; tap < nt; ++tap) {
+          const TapDev T = p.taps[phase][tap];
+          for (int kb = 0; kb < T.nk; ++kb) {
+            mbar_wait(&ctl->empty[s], ph ^ 1);
+            uint8_t* a_s = smem + static_cast<size_t>(s) * p.stage_bytes;
+            mbar_expect_tx(&ctl->full[s], p.tx_bytes);
+            tma_load_4d(a_s, &p.amap[T.src], &ctl->full[s], kb * 64, x0 + T.dx, y0 + T.dy, bf0);
+            tma_load_2d(a_s + kABytes, &p.bmap, &ctl->full[s], T.kofs + kb * 64, n0);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      int phase, bf0, y0, x0, n0;
+      decode_tile(p, t, phase, bf0, y0, x0, n0);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&ctl->tempty[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+      const int nt = p.n_taps[phase];
+      uint32_t accumulate = 0;
+      for (int tap = 0; tap < nt; ++tap) {
+        const int nk = p.taps[phase][tap].nk;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&ctl->full[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
+            const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), p.idesc,
+                       accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&ctl->empty[s]);   // frees the stage once these MMAs have read it
+          }
+          __syncwarp();
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+      if (lane == 0) umma_commit(&ctl->tfull[acc]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;       // row of the 128-row tile == TMEM lane
+    const int ethread = threadIdx.x - 128;
+    int it = 0;
+    int gn_key_smp = -1, gn_key_n0 = -1;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      int phase, bf0, y0, x0, n0;
+      decode_tile(p, t, phase, bf0, y0, x0, n0);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+
+      const int xl = row & ((1 << p.tw_log) - 1);
+      const int yl = (row >> p.tw_log) & ((1 << p.th_log) - 1);
+      const int fl = row >> (p.tw_log + p.th_log);
+      const int bf = bf0 + fl, y = y0 + yl, x = x0 + xl;
+      const bool valid = (bf < p.BF) && (y < p.OH) && (x < p.OW);
+      const long long pix =
+          (static_cast<long long>(bf) * p.OHs + (y * p.sy + p.phase_oy[phase])) * p.OWs + (x * p.sx + p.phase_ox[phase]);
+
+      // GroupNorm bookkeeping.  Partial sums stay in shared memory while consecutive tiles of this CTA belong
+      // to the same (first sample, n-tile); they go to global memory (fp64 atomics) only when that key changes,
+      // which keeps the number of same-address atomics per launch at O(CTAs x samples) instead of O(tiles).
+      int slot = 0;
+      bool two_samples = false;
+      if (p.gn_stats) {
+        const int smp0 = bf0 / p.fps;
+        const int last_bf = min(bf0 + (1 << p.tf_log), p.BF) - 1;
+        two_samples = (last_bf / p.fps) != smp0;
+        slot = valid ? (bf / p.fps - smp0) : 0;
+        if (smp0 != gn_key_smp || n0 != gn_key_n0) {
+          if (gn_key_smp >= 0) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            gn_flush(p, ctl, ethread, gn_key_smp, gn_key_n0);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+          gn_key_smp = smp0;
+          gn_key_n0 = n0;
+        }
+      }
+      float(*gacc)[16][2] = ctl->gn_acc;
+
+      mbar_wait(&ctl->tfull[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.acc_stride;
+
+      const int nchunks = p.BN >> 4;
+      float gs1 = 0.f, gs2 = 0.f;   // running sums of the current group (group size >= 16 case)
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t r[16];
+        tmem_ld16(t_addr + c * 16, r);
+        tmem_ld_wait();
+        const int ncol = n0 + c * 16;
+        if (ncol >= p.N) continue;   // uniform: padded columns of the last n-tile
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full_chunk = (ncol + 16 <= p.N);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (full_chunk || ncol + j < p.N) v[j] += __ldg(p.bias + ncol + j);
+        }
+        if (p.res && valid) {
+          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldr + ncol;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
+            const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+            const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = unpack2_h16(w[j], p.fmt);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
+            }
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (ncol + j < p.N) v[j] += h16_to_f(rp[j], p.fmt);
+          }
+        }
+        // choose destination (column split for fused concat gradients)
+        void* obase = p.out;
+        long long ld = p.ldo;
+        int ocol = ncol;
+        if (p.out2 && ncol >= p.nsplit) {
+          obase = p.out2;
+          ld = p.ldo2;
+          ocol = ncol - p.nsplit;
+        }
+        if (p.out_fp32) {
+          if (valid) {
+            float* op = reinterpret_cast<float*>(obase) + pix * ld + ocol;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (ncol + j < p.N) op[j] = v[j];
+            }
+          }
+        } else {
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = pack2_h16(v[2 * j], v[2 * j + 1], p.fmt);
+          if (p.gn_stats) {
+            // statistics of the values as stored (rounded to 16 bit), like GroupNorm on the fp16 conv output
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = unpack2_h16(w[j], p.fmt);
+              v[2 * j] = f.x;
+              v[2 * j + 1] = f.y;
+            }
+          }
+          if (valid) {
+            uint16_t* op = reinterpret_cast<uint16_t*>(obase) + pix * ld + ocol;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+              reinterpret_cast<uint4*>(op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              reinterpret_cast<uint4*>(op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (ncol + j < p.N) op[j] = static_cast<uint16_t>((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
+            }
+          }
+        }
+        if (p.gn_stats) {
+          const int gs = p.gn_gs;
+          if (gs >= 16) {
+            // whole chunk lies in one group; flush when the group ends
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                gs1 += v[j];
+                gs2 += v[j] * v[j];
+              }
+            }
+            if (((ncol + 16) % gs) == 0) {
+              const int gl = (ncol - n0) / gs;
+              for (int sl = 0; sl < (two_samples ? 2 : 1); ++sl) {
+                float a = (slot == sl) ? gs1 : 0.f, b = (slot == sl) ? gs2 : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  a += __shfl_xor_sync(0xffffffffu, a, o);
+                  b += __shfl_xor_sync(0xffffffffu, b, o);
+                }
+                if (lane == 0) {
+                  atomicAdd(&gacc[sl][gl][0], a);
+                  atomicAdd(&gacc[sl][gl][1], b);
+                }
+              }
+              gs1 = gs2 = 0.f;
+            }
+          } else {
+            // several groups per chunk (small channel counts): gs in {1,2,4,8}
+            for (int g0 = 0; g0 < 16; g0 += gs) {
+              float a0 = 0.f, b0 = 0.f;
+              if (valid)
+                for (int j = g0; j < g0 + gs; ++j)
+                  if (ncol + j < p.N) {
+                    a0 += v[j];
+                    b0 += v[j] * v[j];
+                  }
+              const int gl = (ncol - n0 + g0) / gs;
+              if (ncol + g0 >= p.N || gl >= 16) continue;
+              for (int sl = 0; sl < (two_samples ? 2 : 1); ++sl) {
+                float a = (slot == sl) ? a0 : 0.f, b = (slot == sl) ? b0 : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  a += __shfl_xor_sync(0xffffffffu, a, o);
+                  b += __shfl_xor_sync(0xffffffffu, b, o);
+                }
+                if (lane == 0) {
+                  atomicAdd(&gacc[sl][gl][0], a);
+                  atomicAdd(&gacc[sl][gl][1], b);
+                }
+              }
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&ctl->tempty[acc]);
+
+    }
+    if (p.gn_stats && gn_key_smp >= 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      gn_flush(p, ctl, ethread, gn_key_smp, gn_key_n0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return ((1 << l) == v) ? l : -1;
+}
+
+}  // namespace vmm
+
+using namespace vmm;
+
+extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
+  if (!hp) return set_error(VMM_ERR_ARG, "vmm_cgemm: null params");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const vmm_cgemm_params& h = *hp;
+  if (h.fmt != VMM_FMT_F16 && h.fmt != VMM_FMT_BF16) return set_error(VMM_ERR_ARG, "vmm_cgemm: bad fmt");
+  if (h.n_views < 1 || h.n_views > VMM_MAX_VIEWS) return set_error(VMM_ERR_ARG, "vmm_cgemm: n_views");
+  if (h.n_phases < 1 || h.n_phases > VMM_MAX_PHASES) return set_error(VMM_ERR_ARG, "vmm_cgemm: n_phases");
+  const int tfl = ilog2_exact(h.tf), thl = ilog2_exact(h.th), twl = ilog2_exact(h.tw);
+  if (tfl < 0 || thl < 0 || twl < 0 || h.tf * h.th * h.tw != 128)
+    return set_error(VMM_ERR_ARG, "vmm_cgemm: tile must be powers of two with tf*th*tw == 128");
+  if (h.n < 1 || h.ktot < 64 || (h.ktot % 64) != 0) return set_error(VMM_ERR_ARG, "vmm_cgemm: n / ktot");
+  if (!h.out || !h.w) return set_error(VMM_ERR_ARG, "vmm_cgemm: null out / w");
+  if (h.out2 && (h.nsplit % 16) != 0) return set_error(VMM_ERR_ARG, "vmm_cgemm: nsplit must be a multiple of 16");
+  if (h.gn_stats) {
+    if (h.out_fp32) return set_error(VMM_ERR_ARG, "vmm_cgemm: gn_stats needs a 16-bit output");
+    if (h.gn_group < 1 || (h.n % h.gn_group) != 0 || h.frames_per_sample < 1)
+      return set_error(VMM_ERR_ARG, "vmm_cgemm: gn_group / frames_per_sample");
+    if (h.gn_group < 16 && (16 % h.gn_group) != 0) return set_error(VMM_ERR_ARG, "vmm_cgemm: gn_group < 16 must divide 16");
+    if (h.gn_group >= 16 && (h.gn_group % 16) != 0) return set_error(VMM_ERR_ARG, "vmm_cgemm: gn_group must be a multiple of 16");
+    if (h.tf > h.frames_per_sample) return set_error(VMM_ERR_ARG, "vmm_cgemm: tile spans more than two samples");
+  }
+
+  CgemmDev d;
+  memset(&d, 0, sizeof(d));
+  const int n_pad = (h.n + 15) / 16 * 16;
+  int BN = n_pad <= 256 ? n_pad : 256;
+  if (n_pad > 256) {
+    // prefer an even split for the common 512-wide case, else 256 + remainder
+    BN = 256;
+  }
+  if (h.gn_stats && h.gn_group >= 16 && (BN % h.gn_group) != 0) {
+    // keep groups inside one n-tile
+    BN = (BN / h.gn_group) * h.gn_group;
+    if (BN == 0) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: gn_group larger than an n-tile");
+  }
+  if (h.gn_stats && h.gn_group < 16 && BN / h.gn_group > 16) BN = 16 * h.gn_group;
+  d.N = h.n;
+  d.BN = BN;
+  d.n_ntiles = (n_pad + BN - 1) / BN;
+  d.BF = h.bf;
+  d.OH = h.oh;
+  d.OW = h.ow;
+  d.tf_log = tfl;
+  d.th_log = thl;
+  d.tw_log = twl;
+  d.tiles_f = (h.bf + h.tf - 1) / h.tf;
+  d.tiles_y = (h.oh + h.th - 1) / h.th;
+  d.tiles_x = (h.ow + h.tw - 1) / h.tw;
+  d.n_phases = h.n_phases;
+  const long long total = 1LL * d.n_phases * d.tiles_f * d.tiles_y * d.tiles_x * d.n_ntiles;
+  if (total <= 0 || total > 0x7fffffffLL) return set_error(VMM_ERR_ARG, "vmm_cgemm: tile count");
+  d.total_tiles = static_cast<int>(total);
+  d.stage_bytes = kABytes + BN * 128;
+  d.tx_bytes = d.stage_bytes;
+  const int smem_budget = 200 * 1024;
+  int stages = smem_budget / static_cast<int>(d.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile too large for shared memory");
+  d.stages = stages;
+  d.acc_stride = (BN + 31) / 32 * 32;
+  uint32_t cols = 32;
+  while (cols < 2 * d.acc_stride) cols <<= 1;
+  d.tmem_cols = cols;
+  d.idesc = make_idesc_f16(128, BN, h.fmt, 0, 0);
+  d.out = h.out;
+  d.ldo = h.ldo;
+  d.out_fp32 = h.out_fp32;
+  d.OHs = h.ohs;
+  d.OWs = h.ows;
+  d.sy = h.sy;
+  d.sx = h.sx;
+  d.out2 = h.out2;
+  d.ldo2 = h.ldo2;
+  d.nsplit = h.nsplit;
+  d.bias = h.bias;
+  d.res = h.res;
+  d.ldr = h.ldr;
+  d.gn_stats = h.gn_stats;
+  d.gn_gs = h.gn_group > 0 ? h.gn_group : 1;
+  d.gn_groups = h.gn_stats ? h.n / h.gn_group : 1;
+  d.fps = h.frames_per_sample > 0 ? h.frames_per_sample : 1;
+  d.fmt = h.fmt;
+
+  for (int ph = 0; ph < h.n_phases; ++ph) {
+    if (h.n_taps[ph] < 1 || h.n_taps[ph] > VMM_MAX_TAPS) return set_error(VMM_ERR_ARG, "vmm_cgemm: n_taps");
+    d.n_taps[ph] = h.n_taps[ph];
+    d.phase_oy[ph] = h.phase_oy[ph];
+    d.phase_ox[ph] = h.phase_ox[ph];
+    for (int t = 0; t < h.n_taps[ph]; ++t) {
+      const vmm_tap& T = h.taps[ph][t];
+      if (T.src < 0 || T.src >= h.n_views || T.c < 1 || (T.kofs % 64) != 0 || T.kofs + (T.c + 63) / 64 * 64 > h.ktot)
+        return set_error(VMM_ERR_ARG, "vmm_cgemm: bad tap");
+      d.taps[ph][t].src = static_cast<int16_t>(T.src);
+      d.taps[ph][t].dy = static_cast<int16_t>(T.dy);
+      d.taps[ph][t].dx = static_cast<int16_t>(T.dx);
+      d.taps[ph][t].nk = static_cast<int16_t>((T.c + 63) / 64);
+      d.taps[ph][t].kofs = T.kofs;
+    }
+  }
+
+  const CUtensorMapDataType dt = h.fmt == VMM_FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  for (int i = 0; i < VMM_MAX_VIEWS; ++i) {
+    const vmm_view4& v = h.a[i < h.n_views ? i : 0];
+    if (!v.ptr) return set_error(VMM_ERR_ARG, "vmm_cgemm: null view");
+    uint64_t gdim[4] = {(uint64_t)v.dims[0], (uint64_t)v.dims[1], (uint64_t)v.dims[2], (uint64_t)v.dims[3]};
+    uint64_t gstr[3] = {(uint64_t)v.strides[0] * 2, (uint64_t)v.strides[1] * 2, (uint64_t)v.strides[2] * 2};
+    uint32_t box[4] = {64, (uint32_t)h.tw, (uint32_t)h.th, (uint32_t)h.tf};
+    int rc = encode_tensor_map(&d.amap[i], dt, 4, v.ptr, gdim, gstr, box, /*l2_256=*/false);
+    if (rc) return rc;
+  }
+  {
+    uint64_t gdim[2] = {(uint64_t)h.ktot, (uint64_t)n_pad};
+    uint64_t gstr[1] = {(uint64_t)h.ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    int rc = encode_tensor_map(&d.bmap, dt, 2, h.w, gdim, gstr, box, /*l2_256=*/true);
+    if (rc) return rc;
+  }
+
+  const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + sizeof(CgemmSmemCtl) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, "vmm_cgemm: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  const int grid = d.total_tiles < num_sms() ? d.total_tiles : num_sms();
+  cgemm_kernel<<<grid, 256, smem, stream>>>(d);
+  count_launch();
+  return check_launch("vmm_cgemm");
+}

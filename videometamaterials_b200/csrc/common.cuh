@@ -1,0 +1,29 @@
+// Host-side helpers shared by every translation unit of libvmm_sm100.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vmm.h"
+
+namespace vmm {
+
+// error text of the last failing call on this thread (vmm_last_error)
+char* error_buffer();
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* where);
+int check_launch(const char* where);
+void count_launch();
+int num_sms();
+
+// cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency, so the
+// library also loads on a machine without a driver).  128-byte swizzle, zero fill out of bounds.
+int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* gdim,
+                      const uint64_t* gstride_bytes, const uint32_t* box, bool l2_256);
+
+static inline unsigned int ceil_div(long long a, long long b) { return static_cast<unsigned int>((a + b - 1) / b); }
+static inline long long min64(long long a, long long b) { return a < b ? a : b; }
+
+}  // namespace vmm

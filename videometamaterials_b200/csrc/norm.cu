@@ -1,0 +1,530 @@
+// GroupNorm (+ time scale/shift + SiLU) and channel LayerNorm, forward and backward.
+// All tensors are channels-last [sample, pixel, C] 16-bit; statistics / parameters are fp32 or fp64.
+// These kernels are HBM-bound: 16-byte vector accesses, one read (+ one write) of the activation.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace vmm {
+
+__device__ __forceinline__ float silu_f(float u) { return u / (1.f + __expf(-u)); }
+__device__ __forceinline__ float dsilu_f(float u) {
+  const float s = 1.f / (1.f + __expf(-u));
+  return s * (1.f + u * (1.f - s));
+}
+
+__device__ __forceinline__ void load8(const uint16_t* p, int fmt, float* v) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack2_h16(w[j], fmt);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(uint16_t* p, int fmt, const float* v) {
+  uint4 q;
+  q.x = pack2_h16(v[0], v[1], fmt);
+  q.y = pack2_h16(v[2], v[3], fmt);
+  q.z = pack2_h16(v[4], v[5], fmt);
+  q.w = pack2_h16(v[6], v[7], fmt);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm apply:  y = silu( ((x - mean) * rstd * gamma + beta) * (scale + 1) + shift )     VDDP:279-285
+// statistics come from the conv epilogue as fp64 (sum, sum of squares) per (sample, group).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_silu_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ res,
+                                                          uint16_t* __restrict__ y, int fmt,
+                                                          long long pix, int C, int groups, const double* __restrict__ stats,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ scale_shift, float eps, int act) {
+  extern __shared__ float coef[];   // [2][C]
+  const int b = blockIdx.y;
+  const int gs = C / groups;
+  const double n = static_cast<double>(pix) * gs;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / gs;
+    const double s1 = stats[(static_cast<long long>(b) * groups + g) * 2];
+    const double s2 = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
+    const double mean = s1 / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    float a = rstd * gamma[c];
+    float d = beta[c] - static_cast<float>(mean) * a;
+    if (scale_shift) {
+      const float sc = scale_shift[static_cast<long long>(b) * 2 * C + c] + 1.f;
+      const float sh = scale_shift[static_cast<long long>(b) * 2 * C + C + c];
+      a *= sc;
+      d = d * sc + sh;
+    }
+    coef[c] = a;
+    coef[C + c] = d;
+  }
+  __syncthreads();
+  const long long nvec = pix * C / 8;
+  const uint16_t* xb = x + static_cast<long long>(b) * pix * C;
+  const uint16_t* rb = res ? res + static_cast<long long>(b) * pix * C : nullptr;
+  uint16_t* yb = y + static_cast<long long>(b) * pix * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>((i * 8) % C);
+    float v[8];
+    load8(xb + i * 8, fmt, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float u = v[j] * coef[c0 + j] + coef[C + c0 + j];
+      v[j] = act ? silu_f(u) : u;
+    }
+    if (rb) {   // identity skip of a ResnetBlock whose dim == dim_out (VDDP:297,311)
+      float r8[8];
+      load8(rb + i * 8, fmt, r8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r8[j];
+    }
+    store8(yb + i * 8, fmt, v);
+  }
+}
+
+// Backward pass 1: per (sample, channel)  S1 = sum_pix du,  S2 = sum_pix du * xhat   with du = dy * silu'(u).
+// part: [B][C][2] fp32, accumulated atomically (zeroed by the caller).
+__global__ void __launch_bounds__(256) gn_silu_bwd_reduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dy,
+                                                                 int fmt, long long pix, int C, int groups,
+                                                                 const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, const float* __restrict__ scale_shift,
+                                                                 float eps, int act, float* __restrict__ part, int pix_per_cta) {
+  extern __shared__ float sm[];   // coef a[C], d[C], mean_rstd: m[C], r[C]; then reduction scratch [rows][C][2]
+  float* ca = sm;
+  float* cd = sm + C;
+  float* cm = sm + 2 * C;
+  float* cr = sm + 3 * C;
+  float* red = sm + 4 * C;
+  const int b = blockIdx.y;
+  const int gs = C / groups;
+  const double n = static_cast<double>(pix) * gs;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / gs;
+    const double s1 = stats[(static_cast<long long>(b) * groups + g) * 2];
+    const double s2 = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
+    const double mean = s1 / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    float a = rstd * gamma[c];
+    float d = beta[c] - static_cast<float>(mean) * a;
+    if (scale_shift) {
+      const float sc = scale_shift[static_cast<long long>(b) * 2 * C + c] + 1.f;
+      const float sh = scale_shift[static_cast<long long>(b) * 2 * C + C + c];
+      a *= sc;
+      d = d * sc + sh;
+    }
+    ca[c] = a;
+    cd[c] = d;
+    cm[c] = static_cast<float>(mean);
+    cr[c] = rstd;
+  }
+  __syncthreads();
+  const int vpr = C / 8;                 // 16-byte vectors per pixel row
+  const int rows = blockDim.x / vpr;     // pixel rows processed per step (blockDim is a multiple of vpr)
+  const int vc = threadIdx.x % vpr;
+  const int vr = threadIdx.x / vpr;
+  const int c0 = vc * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_cta;
+  const long long p1 = min(p0 + pix_per_cta, pix);
+  const uint16_t* xb = x + static_cast<long long>(b) * pix * C;
+  const uint16_t* db = dy + static_cast<long long>(b) * pix * C;
+  if (vr < rows) {
+    for (long long pp = p0 + vr; pp < p1; pp += rows) {
+      float xv[8], dv[8];
+      load8(xb + pp * C + c0, fmt, xv);
+      load8(db + pp * C + c0, fmt, dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float u = xv[j] * ca[c0 + j] + cd[c0 + j];
+        const float du = act ? dv[j] * dsilu_f(u) : dv[j];
+        const float xh = (xv[j] - cm[c0 + j]) * cr[c0 + j];
+        s1[j] += du;
+        s2[j] += du * xh;
+      }
+    }
+  }
+  // reduce over the `rows` thread rows through shared memory
+  if (vr < rows) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[(vr * C + c0 + j) * 2] = s1[j];
+      red[(vr * C + c0 + j) * 2 + 1] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < rows; ++r) a += red[r * 2 * C + i];
+    atomicAdd(part + static_cast<long long>(b) * 2 * C + i, a);
+  }
+}
+
+// Backward finalize (tiny): from part[B][C][2] produce
+//   coefficients for pass 2:  k1[b][c] = rstd*gamma*(1+sc),  m1[b][g], m2[b][g]  (group means of dxhat and dxhat*xhat)
+//   parameter grads: dgamma[c] += sum_b (1+sc) S2, dbeta[c] += sum_b (1+sc) S1, d(scale_shift)[b][c] = gamma*S2 + beta*S1, [b][C+c] = S1
+__global__ void gn_silu_bwd_finalize_kernel(const float* __restrict__ part, int B, long long pix, int C, int groups,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            const float* __restrict__ scale_shift, float* __restrict__ gm /*[B][groups][2]*/,
+                                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dss) {
+  const int gs = C / groups;
+  const float inv_n = 1.f / (static_cast<float>(pix) * gs);
+  // group means
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * groups; i += gridDim.x * blockDim.x) {
+    const int b = i / groups, g = i % groups;
+    float a1 = 0.f, a2 = 0.f;
+    for (int c = g * gs; c < (g + 1) * gs; ++c) {
+      const float sc = scale_shift ? scale_shift[static_cast<long long>(b) * 2 * C + c] + 1.f : 1.f;
+      const float k = gamma[c] * sc;
+      a1 += k * part[(static_cast<long long>(b) * C + c) * 2];
+      a2 += k * part[(static_cast<long long>(b) * C + c) * 2 + 1];
+    }
+    gm[i * 2] = a1 * inv_n;
+    gm[i * 2 + 1] = a2 * inv_n;
+  }
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float dg = 0.f, db = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float sc = scale_shift ? scale_shift[static_cast<long long>(b) * 2 * C + c] + 1.f : 1.f;
+      const float S1 = part[(static_cast<long long>(b) * C + c) * 2];
+      const float S2 = part[(static_cast<long long>(b) * C + c) * 2 + 1];
+      dg += sc * S2;
+      db += sc * S1;
+      if (dss) {
+        dss[static_cast<long long>(b) * 2 * C + c] = gamma[c] * S2 + beta[c] * S1;
+        dss[static_cast<long long>(b) * 2 * C + C + c] = S1;
+      }
+    }
+    dgamma[c] += dg;
+    dbeta[c] += db;
+  }
+}
+
+// Backward pass 2: dx = rstd * ( gamma*(1+sc)*du - m1_g - xhat * m2_g )
+__global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dy,
+                                                                uint16_t* __restrict__ dx, int fmt, long long pix, int C, int groups,
+                                                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, const float* __restrict__ scale_shift,
+                                                                float eps, int act, const float* __restrict__ gm) {
+  extern __shared__ float sm[];   // a[C], d[C], mean[C], rstd[C], k[C], m1[C], m2[C]
+  float* ca = sm;
+  float* cd = sm + C;
+  float* cm = sm + 2 * C;
+  float* cr = sm + 3 * C;
+  float* ck = sm + 4 * C;
+  float* c1 = sm + 5 * C;
+  float* c2 = sm + 6 * C;
+  const int b = blockIdx.y;
+  const int gs = C / groups;
+  const double n = static_cast<double>(pix) * gs;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / gs;
+    const double s1 = stats[(static_cast<long long>(b) * groups + g) * 2];
+    const double s2 = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
+    const double mean = s1 / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    float a = rstd * gamma[c];
+    float d = beta[c] - static_cast<float>(mean) * a;
+    float sc = 1.f;
+    if (scale_shift) {
+      sc = scale_shift[static_cast<long long>(b) * 2 * C + c] + 1.f;
+      const float sh = scale_shift[static_cast<long long>(b) * 2 * C + C + c];
+      a *= sc;
+      d = d * sc + sh;
+    }
+    ca[c] = a;
+    cd[c] = d;
+    cm[c] = static_cast<float>(mean);
+    cr[c] = rstd;
+    ck[c] = gamma[c] * sc;
+    c1[c] = gm[(static_cast<long long>(b) * groups + g) * 2];
+    c2[c] = gm[(static_cast<long long>(b) * groups + g) * 2 + 1];
+  }
+  __syncthreads();
+  const long long nvec = pix * C / 8;
+  const uint16_t* xb = x + static_cast<long long>(b) * pix * C;
+  const uint16_t* db = dy + static_cast<long long>(b) * pix * C;
+  uint16_t* ob = dx + static_cast<long long>(b) * pix * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>((i * 8) % C);
+    float xv[8], dv[8], o[8];
+    load8(xb + i * 8, fmt, xv);
+    load8(db + i * 8, fmt, dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float u = xv[j] * ca[c] + cd[c];
+      const float du = act ? dv[j] * dsilu_f(u) : dv[j];
+      const float xh = (xv[j] - cm[c]) * cr[c];
+      o[j] = cr[c] * (ck[c] * du - c1[c] - xh * c2[c]);
+    }
+    store8(ob + i * 8, fmt, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel LayerNorm (gain only, biased variance)  VDDP:245-254, rows = every (b, f, h, w) position
+// ------------------------------------------------------------------------------------------------
+template <int VPT>   // 16-byte vectors per thread (C = 8 * VPT * tpr)
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int fmt,
+                                                     long long rows, int C, int tpr, const float* __restrict__ gamma, float eps,
+                                                     float* __restrict__ mean_rstd) {
+  const int rpb = blockDim.x / tpr;
+  const int lr = threadIdx.x / tpr, lc = threadIdx.x % tpr;
+  const float inv_c = 1.f / C;
+  // the row loop is block-uniform so that the sub-warp shuffles always run with all lanes present
+  for (long long rb = static_cast<long long>(blockIdx.x) * rpb; rb < rows; rb += static_cast<long long>(gridDim.x) * rpb) {
+    const long long r = rb + lr;
+    const bool live = r < rows;
+    float v[VPT][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      if (live) {
+        load8(x + r * C + (k * tpr + lc) * 8, fmt, v[k]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[k][j];
+    }
+    for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[k][j] - mean;
+        q += d * d;
+      }
+    for (int o = tpr >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + eps);
+    if (!live) continue;
+    if (mean_rstd && lc == 0) {
+      mean_rstd[r * 2] = mean;
+      mean_rstd[r * 2 + 1] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int c0 = (k * tpr + lc) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[k][j] = (v[k][j] - mean) * rstd * __ldg(gamma + c0 + j);
+      store8(y + r * C + c0, fmt, v[k]);
+    }
+  }
+}
+
+// backward: dx = rstd * (g*dy - mean_c(g*dy) - xhat * mean_c(g*dy*xhat)) (+ dres),  dgamma[c] += sum_rows dy*xhat
+template <int VPT>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dy,
+                                                     const uint16_t* __restrict__ dres, uint16_t* __restrict__ dx, int fmt,
+                                                     long long rows, int C, int tpr, const float* __restrict__ gamma, float eps,
+                                                     float* __restrict__ dgamma) {
+  extern __shared__ float sdg[];   // [C] block partial of dgamma
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sdg[c] = 0.f;
+  __syncthreads();
+  const int rpb = blockDim.x / tpr;
+  const int lr = threadIdx.x / tpr, lc = threadIdx.x % tpr;
+  const float inv_c = 1.f / C;
+  float dg[VPT][8];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[k][j] = 0.f;
+  for (long long rb = static_cast<long long>(blockIdx.x) * rpb; rb < rows; rb += static_cast<long long>(gridDim.x) * rpb) {
+    const long long r = rb + lr;
+    const bool live = r < rows;
+    float v[VPT][8], d[VPT][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      if (live) {
+        load8(x + r * C + (k * tpr + lc) * 8, fmt, v[k]);
+        load8(dy + r * C + (k * tpr + lc) * 8, fmt, d[k]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = d[k][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[k][j];
+    }
+    for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[k][j] -= mean;
+        q += v[k][j] * v[k][j];
+      }
+    for (int o = tpr >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + eps);
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int c0 = (k * tpr + lc) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = v[k][j] * rstd;
+        dg[k][j] += d[k][j] * xh;
+        const float gd = d[k][j] * __ldg(gamma + c0 + j);
+        v[k][j] = xh;
+        d[k][j] = gd;
+        a1 += gd;
+        a2 += gd * xh;
+      }
+    }
+    for (int o = tpr >> 1; o > 0; o >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    a1 *= inv_c;
+    a2 *= inv_c;
+    if (!live) continue;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int c0 = (k * tpr + lc) * 8;
+      float o8[8];
+      if (dres) load8(dres + r * C + c0, fmt, o8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = rstd * (d[k][j] - a1 - v[k][j] * a2);
+        o8[j] = dres ? o8[j] + g : g;
+      }
+      store8(dx + r * C + c0, fmt, o8);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VPT; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sdg[(k * tpr + lc) * 8 + j], dg[k][j]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dgamma + c, sdg[c]);
+}
+
+static int ln_shape(int C, int& tpr, int& vpt) {
+  if (C % 8) return -1;
+  const int vec = C / 8;
+  tpr = 1;
+  while (tpr < 32 && tpr * 2 <= vec && (vec % (tpr * 2)) == 0) tpr *= 2;
+  vpt = vec / tpr;
+  if (vpt > 4) return -1;
+  return 0;
+}
+
+}  // namespace vmm
+
+using namespace vmm;
+
+extern "C" int vmm_gn_silu_fwd(const void* x, const void* res, void* y, int fmt, int B, long long pix, int C, int groups, const double* stats,
+                               const float* gamma, const float* beta, const float* scale_shift, float eps, int act, void* stream) {
+  if (!x || !y || !stats || !gamma || !beta) return set_error(VMM_ERR_ARG, "vmm_gn_silu_fwd: null pointer");
+  if (C % 8 || C % groups || C > 4096) return set_error(VMM_ERR_ARG, "vmm_gn_silu_fwd: C must be a multiple of 8 and of groups");
+  const long long nvec = pix * C / 8;
+  int gx = static_cast<int>(min64((nvec + 255) / 256, (4LL * num_sms() + B - 1) / B * 2));
+  if (gx < 1) gx = 1;
+  gn_silu_fwd_kernel<<<dim3(gx, B), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(res), static_cast<uint16_t*>(y), fmt, pix, C, groups, stats, gamma,
+      beta, scale_shift, eps, act);
+  count_launch();
+  return check_launch("vmm_gn_silu_fwd");
+}
+
+extern "C" size_t vmm_gn_silu_bwd_workspace(int B, int C, int groups) {
+  return (static_cast<size_t>(B) * C * 2 + static_cast<size_t>(B) * groups * 2) * sizeof(float);
+}
+
+extern "C" int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt, int B, long long pix, int C, int groups,
+                               const double* stats, const float* gamma, const float* beta, const float* scale_shift, float eps,
+                               int act, float* dgamma, float* dbeta, float* dscale_shift, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+  if (!x || !dy || !dx || !stats || !gamma || !beta || !dgamma || !dbeta || !workspace)
+    return set_error(VMM_ERR_ARG, "vmm_gn_silu_bwd: null pointer");
+  if (C % 8 || C % groups || C > 2048) return set_error(VMM_ERR_ARG, "vmm_gn_silu_bwd: bad C");
+  if (workspace_bytes < vmm_gn_silu_bwd_workspace(B, C, groups)) return set_error(VMM_ERR_ARG, "vmm_gn_silu_bwd: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* part = static_cast<float*>(workspace);
+  float* gm = part + static_cast<size_t>(B) * C * 2;
+  cudaError_t e = cudaMemsetAsync(part, 0, static_cast<size_t>(B) * C * 2 * sizeof(float), stream);
+  if (e != cudaSuccess) return set_cuda_error(e, "vmm_gn_silu_bwd: memset");
+  const int vpr = C / 8;
+  int threads = 256;
+  if (threads % vpr) threads = (256 / vpr) * vpr;
+  if (threads < vpr) threads = vpr;
+  if (threads > 1024) return set_error(VMM_ERR_UNSUPPORTED, "vmm_gn_silu_bwd: C too large");
+  const int rows = threads / vpr;
+  int ctas = (2 * num_sms() + B - 1) / B;
+  int ppc = static_cast<int>((pix + ctas - 1) / ctas);
+  if (ppc < rows * 4) ppc = rows * 4;
+  ctas = static_cast<int>((pix + ppc - 1) / ppc);
+  const size_t sm1 = (4 * C + static_cast<size_t>(rows) * C * 2) * sizeof(float);
+  if (sm1 > 48 * 1024) {
+    cudaFuncSetAttribute(gn_silu_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  }
+  gn_silu_bwd_reduce_kernel<<<dim3(ctas, B), threads, sm1, stream>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(dy),
+                                                                      fmt, pix, C, groups, stats, gamma, beta, scale_shift, eps, act,
+                                                                      part, ppc);
+  count_launch();
+  gn_silu_bwd_finalize_kernel<<<4, 256, 0, stream>>>(part, B, pix, C, groups, gamma, beta, scale_shift, gm, dgamma, dbeta, dscale_shift);
+  count_launch();
+  const long long nvec = pix * C / 8;
+  int gx = static_cast<int>(min64((nvec + 255) / 256, (4LL * num_sms() + B - 1) / B * 2));
+  if (gx < 1) gx = 1;
+  gn_silu_bwd_apply_kernel<<<dim3(gx, B), 256, 7 * C * sizeof(float), stream>>>(
+      static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(dy), static_cast<uint16_t*>(dx), fmt, pix, C, groups, stats, gamma,
+      beta, scale_shift, eps, act, gm);
+  count_launch();
+  return check_launch("vmm_gn_silu_bwd");
+}
+
+#define LN_DISPATCH(KERNEL, ...)                                  \
+  switch (vpt) {                                                  \
+    case 1: KERNEL<1> __VA_ARGS__; break;                         \
+    case 2: KERNEL<2> __VA_ARGS__; break;                         \
+    case 4: KERNEL<4> __VA_ARGS__; break;                         \
+    default: return set_error(VMM_ERR_UNSUPPORTED, "layernorm: unsupported channel count"); \
+  }
+
+extern "C" int vmm_ln_fwd(const void* x, void* y, int fmt, long long rows, int C, const float* gamma, float eps, float* mean_rstd,
+                          void* stream_) {
+  if (!x || !y || !gamma) return set_error(VMM_ERR_ARG, "vmm_ln_fwd: null pointer");
+  int tpr, vpt;
+  if (ln_shape(C, tpr, vpt)) return set_error(VMM_ERR_UNSUPPORTED, "vmm_ln_fwd: unsupported channel count");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int rpb = 256 / tpr;
+  const int grid = static_cast<int>(min64((rows + rpb - 1) / rpb, 8LL * num_sms()));
+  LN_DISPATCH(ln_fwd_kernel, <<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), fmt, rows, C, tpr,
+                                                        gamma, eps, mean_rstd));
+  count_launch();
+  return check_launch("vmm_ln_fwd");
+}
+
+extern "C" int vmm_ln_bwd(const void* x, const void* dy, const void* dres, void* dx, int fmt, long long rows, int C,
+                          const float* gamma, float eps, float* dgamma, void* stream_) {
+  if (!x || !dy || !dx || !gamma || !dgamma) return set_error(VMM_ERR_ARG, "vmm_ln_bwd: null pointer");
+  int tpr, vpt;
+  if (ln_shape(C, tpr, vpt)) return set_error(VMM_ERR_UNSUPPORTED, "vmm_ln_bwd: unsupported channel count");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int rpb = 256 / tpr;
+  const int grid = static_cast<int>(min64((rows + rpb - 1) / rpb, 4LL * num_sms()));
+  LN_DISPATCH(ln_bwd_kernel, <<<grid, 256, C * sizeof(float), stream>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(dy),
+                                                                        static_cast<const uint16_t*>(dres), static_cast<uint16_t*>(dx), fmt,
+                                                                        rows, C, tpr, gamma, eps, dgamma));
+  count_launch();
+  return check_launch("vmm_ln_bwd");
+}

@@ -1,0 +1,252 @@
+"""GaussianDiffusion on the B200 kernels, keeping the reference's constructor / method surface.
+
+Reference: VDDP:841-1067 (`GaussianDiffusion`), `cosine_beta_schedule` VDDP:829-839.
+The network call, the guidance lerp + x0 prediction, the dynamic-threshold quantile and the posterior /
+DDIM updates are each one kernel launch of libvmm_sm100.so; a whole `p_sample` step can be captured in a
+CUDA graph and replayed (sampling is launch-latency bound otherwise).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import blocks, blocks_bwd, ops
+
+
+def extract(a, t, x_shape):
+    """VDDP:824-827."""
+    b, *_ = t.shape
+    out = a.gather(-1, t)
+    return out.reshape(b, *((1,) * (len(x_shape) - 1)))
+
+
+def cosine_beta_schedule(timesteps, s=0.008):
+    """VDDP:829-839."""
+    steps = timesteps + 1
+    x = torch.linspace(0, timesteps, steps, dtype=torch.float64)
+    alphas_cumprod = torch.cos(((x / timesteps) + s) / (1 + s) * torch.pi * 0.5) ** 2
+    alphas_cumprod = alphas_cumprod / alphas_cumprod[0]
+    betas = 1 - (alphas_cumprod[1:] / alphas_cumprod[:-1])
+    return torch.clip(betas, 0, 0.9999)
+
+
+def normalize_img(t):
+    return t * 2 - 1
+
+
+def unnormalize_img(t):
+    return (t + 1) * 0.5
+
+
+def quantile_rank(n: int, q: float):
+    """(k, frac) exactly as torch.quantile computes them for a float32 input: rank = q * (n - 1) in fp32."""
+    rank = np.float32(q) * np.float32(n - 1)
+    k = int(np.floor(rank))
+    return k, float(np.float32(rank - np.float32(k)))
+
+
+class GaussianDiffusion(nn.Module):
+    def __init__(self, denoise_fn, *, image_size, num_frames, channels=4, timesteps=1000, loss_type='l1', use_dynamic_thres=False,
+                 dynamic_thres_percentile=0.9, sampling_timesteps=1000, ddim_sampling_eta=0.):
+        super().__init__()
+        self.channels = channels
+        self.image_size = image_size
+        self.num_frames = num_frames
+        self.denoise_fn = denoise_fn
+
+        betas = cosine_beta_schedule(timesteps)
+        alphas = 1. - betas
+        alphas_cumprod = torch.cumprod(alphas, axis=0)
+        alphas_cumprod_prev = F.pad(alphas_cumprod[:-1], (1, 0), value=1.)
+        timesteps, = betas.shape
+        self.num_timesteps = int(timesteps)
+        self.loss_type = loss_type
+        reg = lambda name, val: self.register_buffer(name, val.to(torch.float32))
+        reg('betas', betas)
+        reg('alphas_cumprod', alphas_cumprod)
+        reg('alphas_cumprod_prev', alphas_cumprod_prev)
+        reg('sqrt_alphas_cumprod', torch.sqrt(alphas_cumprod))
+        reg('sqrt_one_minus_alphas_cumprod', torch.sqrt(1. - alphas_cumprod))
+        reg('log_one_minus_alphas_cumprod', torch.log(1. - alphas_cumprod))
+        reg('sqrt_recip_alphas_cumprod', torch.sqrt(1. / alphas_cumprod))
+        reg('sqrt_recipm1_alphas_cumprod', torch.sqrt(1. / alphas_cumprod - 1))
+        posterior_variance = betas * (1. - alphas_cumprod_prev) / (1. - alphas_cumprod)
+        reg('posterior_variance', posterior_variance)
+        reg('posterior_log_variance_clipped', torch.log(posterior_variance.clamp(min=1e-20)))
+        reg('posterior_mean_coef1', betas * torch.sqrt(alphas_cumprod_prev) / (1. - alphas_cumprod))
+        reg('posterior_mean_coef2', (1. - alphas_cumprod_prev) * torch.sqrt(alphas) / (1. - alphas_cumprod))
+        self.use_dynamic_thres = use_dynamic_thres
+        self.dynamic_thres_percentile = dynamic_thres_percentile
+        self.sampling_timesteps = sampling_timesteps if sampling_timesteps is not None else timesteps
+        assert self.sampling_timesteps <= timesteps
+        self.is_ddim_sampling = self.sampling_timesteps < timesteps
+        self.ddim_sampling_eta = ddim_sampling_eta
+        if ddim_sampling_eta != 0.:
+            raise NotImplementedError("ddim_sampling_eta != 0 is not implemented (the reference default is 0)")
+        if loss_type not in ('l1', 'l2'):
+            raise NotImplementedError()
+        self.use_cuda_graph = False        # bench / Trainer turn this on; parity tests run eagerly
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ pieces kept for API parity
+    def q_mean_variance(self, x_start, t):
+        mean = extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+        variance = extract(1. - self.alphas_cumprod, t, x_start.shape)
+        log_variance = extract(self.log_one_minus_alphas_cumprod, t, x_start.shape)
+        return mean, variance, log_variance
+
+    def predict_start_from_noise(self, x_t, t, noise):
+        return extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t - extract(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * noise
+
+    def q_posterior(self, x_start, x_t, t):
+        mean = extract(self.posterior_mean_coef1, t, x_t.shape) * x_start + extract(self.posterior_mean_coef2, t, x_t.shape) * x_t
+        return mean, extract(self.posterior_variance, t, x_t.shape), extract(self.posterior_log_variance_clipped, t, x_t.shape)
+
+    def q_sample(self, x_start, t, noise=None):
+        noise = noise if noise is not None else torch.randn_like(x_start)
+        return extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start + extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise
+
+    # ------------------------------------------------------------------ sampling
+    def _eps_channels_last(self, x, t, cond, guidance_scale):
+        """Network output for the guided step: fp32 channels-last [(2)b, f, h, w, c]; cond rows first, null rows second."""
+        b = x.shape[0]
+        if guidance_scale == 1:
+            mask = torch.zeros(b, dtype=torch.bool, device=x.device)
+            return blocks.unet_forward(self.denoise_fn, x, None, None, t, cond, mask), False
+        mask = torch.cat((torch.zeros(b, dtype=torch.bool, device=x.device), torch.ones(b, dtype=torch.bool, device=x.device)))
+        eps = blocks.unet_forward(self.denoise_fn, torch.cat((x, x)), None, None, torch.cat((t, t)), torch.cat((cond, cond)), mask)
+        return eps, True
+
+    def _p_sample_core(self, x, t, cond, guidance_scale, noise, clip_denoised=True):
+        b, c, f, h, w = x.shape
+        eps_cl, has_null = self._eps_channels_last(x, t, cond, guidance_scale)
+        sr = self.sqrt_recip_alphas_cumprod[t].contiguous()
+        srm1 = self.sqrt_recipm1_alphas_cumprod[t].contiguous()
+        x0 = torch.empty_like(x)
+        ops.cfg_x0(x, eps_cl, has_null, guidance_scale, sr, srm1, x0, None, b, c, f, h, w)
+        per = c * f * h * w
+        s = None
+        if clip_denoised:
+            s = torch.ones(b, dtype=torch.float32, device=x.device)
+            if self.use_dynamic_thres:
+                k, frac = quantile_rank(per, self.dynamic_thres_percentile)
+                ops.abs_quantile(x0, b, per, k, frac, 1.0, s)
+        c1 = self.posterior_mean_coef1[t].contiguous()
+        c2 = self.posterior_mean_coef2[t].contiguous()
+        sig = ((t != 0).float() * (0.5 * self.posterior_log_variance_clipped[t]).exp()).contiguous()
+        out = torch.empty_like(x)
+        ops.posterior_step(x0, x, noise, s, c1, c2, sig, out, b, per)
+        return out
+
+    @torch.inference_mode()
+    def p_sample(self, x, t, cond=None, clip_denoised=True, guidance_scale=1.):
+        """VDDP:956-963.  Draws its noise with torch.randn_like exactly where the reference does."""
+        x = x.contiguous().float()
+        noise = torch.randn_like(x)
+        return self._p_sample_core(x, t, cond, guidance_scale, noise, clip_denoised)
+
+    @torch.inference_mode()
+    def p_sample_loop(self, shape, cond=None, guidance_scale=1.):
+        """VDDP:965-975."""
+        device = self.betas.device
+        b = shape[0]
+        img = torch.randn(shape, device=device)
+        if self.use_cuda_graph:
+            return unnormalize_img(self._graph_loop(img, cond, guidance_scale))
+        for i in reversed(range(0, self.num_timesteps)):
+            img = self.p_sample(img, torch.full((b,), i, device=device, dtype=torch.long), cond=cond, guidance_scale=guidance_scale)
+        return unnormalize_img(img)
+
+    def _graph_loop(self, img, cond, guidance_scale):
+        """The ancestral loop with one CUDA graph per step shape: t, x and the noise live in static buffers."""
+        key = (tuple(img.shape), float(guidance_scale), str(self.denoise_fn.compute_dtype))
+        g = self._graphs.get(key)
+        b = img.shape[0]
+        if g is None:
+            st = dict(x=img.clone(), t=torch.zeros(b, dtype=torch.long, device=img.device), cond=cond.clone().float(),
+                      noise=torch.zeros_like(img))
+            self.denoise_fn.packed()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    st["out"] = self._p_sample_core(st["x"], st["t"], st["cond"], guidance_scale, st["noise"])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["out"] = self._p_sample_core(st["x"], st["t"], st["cond"], guidance_scale, st["noise"])
+            g = (graph, st)
+            self._graphs[key] = g
+        graph, st = g
+        st["x"].copy_(img)
+        st["cond"].copy_(cond)
+        for i in reversed(range(0, self.num_timesteps)):
+            st["t"].fill_(i)
+            st["noise"].normal_()
+            graph.replay()
+            st["x"].copy_(st["out"])
+        return st["x"].clone()
+
+    @torch.inference_mode()
+    def sample(self, cond=None, batch_size=16, guidance_scale=1.):
+        """VDDP:977-984."""
+        batch_size = cond.shape[0] if cond is not None else batch_size
+        fn = self.p_sample_loop if not self.is_ddim_sampling else self.ddim_sample
+        return fn((batch_size, self.channels, self.num_frames, self.image_size, self.image_size), cond=cond, guidance_scale=guidance_scale)
+
+    @torch.inference_mode()
+    def ddim_sample(self, shape, cond=None, guidance_scale=1.):
+        """VDDP:986-1018 (eta = 0: no clamp, no dynamic threshold, the drawn noise is multiplied by sigma = 0)."""
+        batch, device, total, steps = shape[0], self.betas.device, self.num_timesteps, self.sampling_timesteps
+        times = torch.linspace(-1, total - 1, steps=steps + 1)
+        times = list(reversed(times.int().tolist()))
+        pairs = list(zip(times[:-1], times[1:]))
+        img = torch.randn(shape, device=device)
+        b, c, f, h, w = shape
+        for time, time_next in pairs:
+            t = torch.full((batch,), time, device=device, dtype=torch.long)
+            eps_cl, has_null = self._eps_channels_last(img, t, cond, guidance_scale)
+            x0 = torch.empty_like(img)
+            eps = torch.empty_like(img)
+            ops.cfg_x0(img, eps_cl, has_null, guidance_scale, self.sqrt_recip_alphas_cumprod[t].contiguous(),
+                       self.sqrt_recipm1_alphas_cumprod[t].contiguous(), x0, eps, b, c, f, h, w)
+            if time_next < 0:
+                img = x0
+                continue
+            an = float(self.alphas_cumprod[time_next])
+            torch.randn_like(img)                       # the reference draws (and discards, sigma = 0) one noise per step
+            out = torch.empty_like(img)
+            ops.axpby(x0, eps, an ** 0.5, (1 - an) ** 0.5, 0.0, out)
+            img = out
+        return unnormalize_img(img)
+
+    @torch.inference_mode()
+    def interpolate(self, x1, x2, t=None, lam=0.5):
+        """VDDP:1020-1034 (unconditional p_sample calls, as in the reference)."""
+        raise NotImplementedError("interpolate() calls p_sample without cond, which the per_frame_cond network cannot serve "
+                                  "(the reference fails the same way at VDDP:753)")
+
+    # ------------------------------------------------------------------ training
+    def p_losses(self, x_start, t, cond=None, noise=None, **kwargs):
+        """VDDP:1044-1060: loss between the drawn noise and the network's prediction on q_sample(x_start, t, noise)."""
+        noise = noise if noise is not None else torch.randn_like(x_start)
+        null_cond_prob = kwargs.pop('null_cond_prob', 0.)
+        kwargs.pop('prob_focus_present', None)
+        kwargs.pop('focus_present_mask', None)
+        b = x_start.shape[0]
+        mask = blocks.prob_mask_like((b,), null_cond_prob, x_start.device)
+        a = self.sqrt_alphas_cumprod[t].contiguous()
+        s = self.sqrt_one_minus_alphas_cumprod[t].contiguous()
+        return blocks_bwd.training_loss(self.denoise_fn, x_start.contiguous().float(), noise.contiguous().float(), (a, None, s), t, cond,
+                                        mask, l2=(self.loss_type == 'l2'))
+
+    def forward(self, x, *args, **kwargs):
+        """VDDP:1062-1067."""
+        b, device, img_size = x.shape[0], x.device, self.image_size
+        if tuple(x.shape[1:]) != (self.channels, self.num_frames, img_size, img_size):
+            raise ValueError(f"expected input of shape (b, {self.channels}, {self.num_frames}, {img_size}, {img_size}), got {tuple(x.shape)}")
+        t = torch.randint(0, self.num_timesteps, (b,), device=device).long()
+        x = normalize_img(x)
+        return self.p_losses(x, t, *args, **kwargs)

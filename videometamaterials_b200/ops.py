@@ -1,0 +1,355 @@
+"""Python-side launch helpers over the C ABI (include/vmm.h).
+
+Tensors are torch CUDA tensors used purely as device memory: every function turns them into raw
+pointers + sizes and calls one `vmm_*` entry point on torch's current stream.  Activations are
+channels-last `(b, f, h, w, c)` 16-bit.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import CgemmParams, FMT_BF16, FMT_F16, check, lib
+
+
+def fmt_of(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return FMT_F16
+    if t.dtype == torch.bfloat16:
+        return FMT_BF16
+    raise TypeError(f"expected a 16-bit activation tensor, got {t.dtype}")
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ceil64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def _require_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("videometamaterials_b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+# ------------------------------------------------------------------------------------------------
+# tile choice for the implicit GEMM
+# ------------------------------------------------------------------------------------------------
+def choose_tile(bf: int, oh: int, ow: int, max_tf: int = 8) -> Tuple[int, int, int]:
+    """(tf, th, tw), powers of two with product 128, minimising zero-padded work; ties -> wider rows."""
+    best = None
+    for tw_l in range(8):
+        tw = 1 << tw_l
+        for th_l in range(8 - tw_l):
+            th = 1 << th_l
+            tf = 128 // (tw * th)
+            if tf > max_tf:
+                continue
+            pad = (-(-bf // tf) * tf) * (-(-oh // th) * th) * (-(-ow // tw) * tw)
+            key = (pad, -tw, -th)
+            if best is None or key < best[0]:
+                best = (key, (tf, th, tw))
+    assert best is not None
+    return best[1]
+
+
+def _view_bfhwc(p: CgemmParams, idx: int, t: torch.Tensor) -> None:
+    """Fill view idx from a (bf, h, w, c) tensor whose channel stride is 1."""
+    assert t.dim() == 4 and t.stride(3) == 1, "view must be (bf, h, w, c) with contiguous channels"
+    v = p.a[idx]
+    v.ptr = t.data_ptr()
+    bf, h, w, c = t.shape
+    v.dims[0], v.dims[1], v.dims[2], v.dims[3] = c, w, h, bf
+    sw, sh, sb = t.stride(2), t.stride(1), t.stride(0)
+    # size-1 dims may carry arbitrary strides; give TMA something legal
+    v.strides[0] = sw if w > 1 else max(8, c)
+    v.strides[1] = sh if h > 1 else max(8, v.strides[0] * w)
+    v.strides[2] = sb if bf > 1 else max(8, v.strides[1] * h)
+
+
+def as_bfhwc(x: torch.Tensor) -> torch.Tensor:
+    """(b, f, h, w, c) -> (b*f, h, w, c) view (no copy)."""
+    b, f, h, w, c = x.shape
+    return x.reshape(b * f, h, w, c) if x.is_contiguous() else x.view(b * f, h, w, c)
+
+
+def cgemm(views: Sequence[torch.Tensor], taps: Sequence[Sequence[Tuple[int, int, int, int, int]]], w: torch.Tensor, n: int,
+          out: torch.Tensor, grid: Tuple[int, int, int], *, out_geom: Optional[Tuple[int, int, int, int]] = None,
+          phase_off: Optional[Sequence[Tuple[int, int]]] = None, bias: Optional[torch.Tensor] = None,
+          res: Optional[torch.Tensor] = None, gn_stats: Optional[torch.Tensor] = None, gn_group: int = 0,
+          frames_per_sample: int = 1, out2: Optional[torch.Tensor] = None, nsplit: int = 0,
+          tile: Optional[Tuple[int, int, int]] = None) -> None:
+    """Launch vmm_cgemm.
+
+    views : list of (bf, h, w, c) 16-bit tensors (A operand sources)
+    taps  : per phase, list of (src, dy, dx, kofs, c)
+    w     : packed weights [n_pad16, ktot] (same 16-bit dtype)
+    out   : tensor whose last dim is the channel dim; rows are addressed by the pixel index formula
+    grid  : (BF, OH, OW) of the GEMM-M space;  out_geom = (ohs, ows, sy, sx) (default: same grid, unit stride)
+    """
+    _require_cuda(w, out, *views)
+    p = CgemmParams()
+    p.fmt = fmt_of(views[0])
+    p.n_views = len(views)
+    for i, t in enumerate(views):
+        assert t.dtype == views[0].dtype
+        _view_bfhwc(p, i, t)
+    p.n_phases = len(taps)
+    for ph, tl in enumerate(taps):
+        p.n_taps[ph] = len(tl)
+        for i, (src, dy, dx, kofs, c) in enumerate(tl):
+            T = p.taps[ph][i]
+            T.src, T.dy, T.dx, T.kofs, T.c = src, dy, dx, kofs, c
+        oy, ox = phase_off[ph] if phase_off is not None else (0, 0)
+        p.phase_oy[ph], p.phase_ox[ph] = oy, ox
+    assert w.dtype == views[0].dtype and w.is_contiguous() and w.dim() == 2
+    p.w = w.data_ptr()
+    p.n = n
+    p.ktot = w.shape[1]
+    assert w.shape[0] >= (n + 15) // 16 * 16
+    bf, oh, ow = grid
+    p.bf, p.oh, p.ow = bf, oh, ow
+    p.tf, p.th, p.tw = tile if tile is not None else choose_tile(bf, oh, ow, max_tf=min(8, frames_per_sample) if gn_stats is not None else 8)
+    p.out = out.data_ptr()
+    assert out.stride(-1) == 1
+    p.ldo = out.stride(-2)
+    p.out_fp32 = 1 if out.dtype == torch.float32 else 0
+    if not p.out_fp32:
+        assert out.dtype == views[0].dtype
+    ohs, ows, sy, sx = out_geom if out_geom is not None else (oh, ow, 1, 1)
+    p.ohs, p.ows, p.sy, p.sx = ohs, ows, sy, sx
+    if out2 is not None:
+        p.out2 = out2.data_ptr()
+        p.ldo2 = out2.stride(-2)
+        p.nsplit = nsplit
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() >= n
+        p.bias = bias.data_ptr()
+    if res is not None:
+        assert res.dtype == views[0].dtype and res.stride(-1) == 1
+        p.res = res.data_ptr()
+        p.ldr = res.stride(-2)
+    if gn_stats is not None:
+        assert gn_stats.dtype == torch.float64 and gn_stats.is_contiguous()
+        p.gn_stats = gn_stats.data_ptr()
+        p.gn_group = gn_group
+        p.frames_per_sample = frames_per_sample
+    check(lib.vmm_cgemm(C.byref(p), stream_ptr()), "vmm_cgemm")
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing (fp32 master weights -> 16-bit K-major GEMM operands)
+# ------------------------------------------------------------------------------------------------
+def _pad_rows16(w2d: torch.Tensor) -> torch.Tensor:
+    n = w2d.shape[0]
+    n_pad = (n + 15) // 16 * 16
+    if n_pad != n:
+        w2d = torch.cat((w2d, w2d.new_zeros(n_pad - n, w2d.shape[1])), dim=0)
+    return w2d.contiguous()
+
+
+def pack_linear(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """(N, K) -> [N_pad16, ceil64(K)]."""
+    n, k = w.shape
+    out = w.new_zeros(n, ceil64(k))
+    out[:, :k] = w
+    return _pad_rows16(out.to(dtype))
+
+
+def pack_conv_taps(w: torch.Tensor, splits: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+    """(N, Cin, kh, kw) with Cin = sum(splits) -> [N_pad16, kh*kw*sum(ceil64(split))], tap-major then source-major."""
+    n, cin, kh, kw = w.shape
+    assert sum(splits) == cin
+    blocks = []
+    for ky in range(kh):
+        for kx in range(kw):
+            c0 = 0
+            for c in splits:
+                blk = w.new_zeros(n, ceil64(c))
+                blk[:, :c] = w[:, c0:c0 + c, ky, kx]
+                blocks.append(blk)
+                c0 += c
+    return _pad_rows16(torch.cat(blocks, dim=1).to(dtype))
+
+
+def taps_conv(kh: int, kw: int, splits: Sequence[int], pad: int) -> Tuple[List[Tuple[int, int, int, int, int]], int]:
+    taps, kofs = [], 0
+    for ky in range(kh):
+        for kx in range(kw):
+            for s, c in enumerate(splits):
+                taps.append((s, ky - pad, kx - pad, kofs, c))
+                kofs += ceil64(c)
+    return taps, kofs
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution front-ends over cgemm (forward geometry; the same helpers serve the data gradients)
+# ------------------------------------------------------------------------------------------------
+def rows_view(x2d: torch.Tensor) -> torch.Tensor:
+    """[M, C] (row stride may exceed C) -> (1, 1, M, C) view for the 'rows' GEMM."""
+    return x2d.as_strided((1, 1, x2d.shape[0], x2d.shape[1]), (x2d.stride(0) * x2d.shape[0], x2d.stride(0) * x2d.shape[0], x2d.stride(0), 1))
+
+
+def linear_rows(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch.Tensor, *, bias=None, res=None,
+                gn_stats=None, gn_group=0, frames_per_sample=1, out2=None, nsplit=0) -> None:
+    """out[m, :n] = cat(xs, dim=1)[m] @ W^T  for 2-D operands [M, C_i]; wp = pack_linear / pack_conv_taps(1x1)."""
+    taps, kofs = [], 0
+    for s, x in enumerate(xs):
+        taps.append((s, 0, 0, kofs, x.shape[1]))
+        kofs += ceil64(x.shape[1])
+    m = xs[0].shape[0]
+    cgemm([rows_view(x) for x in xs], [taps], wp, n, out, (1, 1, m), bias=bias, res=res, gn_stats=gn_stats,
+          gn_group=gn_group, frames_per_sample=frames_per_sample, out2=out2, nsplit=nsplit)
+
+
+def conv3x3(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch.Tensor, **kw) -> None:
+    """xs: list of (bf, h, w, c_i) sources (implicit channel concat); 'zeros' padding 1."""
+    taps, _ = taps_conv(3, 3, [x.shape[3] for x in xs], 1)
+    bf, h, w, _ = xs[0].shape
+    cgemm(list(xs), [taps], wp, n, out, (bf, h, w), **kw)
+
+
+def down_taps(c: int):
+    taps = []
+    for ky in range(4):
+        for kx in range(4):
+            py, px = (ky + 1) % 2, (kx + 1) % 2
+            taps.append((py * 2 + px, (ky - 1) // 2, (kx - 1) // 2, (ky * 4 + kx) * ceil64(c), c))
+    return taps
+
+
+def parity_views(x: torch.Tensor):
+    return [x[:, py::2, px::2, :] for py in range(2) for px in range(2)]
+
+
+def conv_down(x: torch.Tensor, wp: torch.Tensor, n: int, out: torch.Tensor, **kw) -> None:
+    """(1,4,4) stride (1,2,2) pad (0,1,1) conv, VDDP:241.  x (bf, h, w, c) -> out (bf, h/2, w/2, n)."""
+    bf, h, w, c = x.shape
+    cgemm(parity_views(x), [down_taps(c)], wp, n, out, (bf, h // 2, w // 2), **kw)
+
+
+def up_taps(c: int):
+    phases, offs = [], []
+    for py in range(2):
+        for px in range(2):
+            taps = []
+            for ky, dy in (((1, 0), (3, -1)) if py == 0 else ((0, 1), (2, 0))):
+                for kx, dx in (((1, 0), (3, -1)) if px == 0 else ((0, 1), (2, 0))):
+                    taps.append((0, dy, dx, (ky * 4 + kx) * ceil64(c), c))
+            phases.append(taps)
+            offs.append((py, px))
+    return phases, offs
+
+
+def conv_up(x: torch.Tensor, wp: torch.Tensor, n: int, out: torch.Tensor, **kw) -> None:
+    """ConvTranspose (1,4,4)/(1,2,2)/(0,1,1), VDDP:155, as 4 output phases of 2x2 taps.  out (bf, 2h, 2w, n)."""
+    bf, h, w, c = x.shape
+    phases, offs = up_taps(c)
+    cgemm([x], phases, wp, n, out, (bf, h, w), out_geom=(2 * h, 2 * w, 2, 2), phase_off=offs, **kw)
+
+
+def pack_conv_up(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """ConvTranspose3d weight (Cin, Cout, 1, 4, 4) -> [Cout_pad, 16*ceil64(Cin)]."""
+    return pack_conv_taps(w[:, :, 0].permute(1, 0, 2, 3), [w.shape[0]], dtype)
+
+
+def pack_init_conv(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """(N, C<=8, 1, 7, 7) -> [N_pad, 7*64]: per ky a block of 8 px x 8 ch (px 7 and ch >= C are zero)."""
+    n, c, _, kh, kw = w.shape
+    assert kw <= 8 and c <= 8
+    out = w.new_zeros(n, kh, 8, 8)
+    out[:, :, :kw, :c] = w[:, :, 0].permute(0, 2, 3, 1)
+    return _pad_rows16(out.reshape(n, kh * 64).to(dtype))
+
+
+def init_conv(xin: torch.Tensor, bf: int, h: int, w: int, wp: torch.Tensor, n: int, out: torch.Tensor, ksize: int = 7, **kw) -> None:
+    """xin: flat 16-bit buffer [bf][h][w+6][8] (+8 slack) from prep_input; (1,7,7) conv VDDP:626."""
+    assert ksize == 7
+    view = xin.as_strided((bf, h, w, 64), (h * (w + 6) * 8, (w + 6) * 8, 8, 1))
+    taps = [(0, ky - 3, 0, ky * 64, 64) for ky in range(7)]
+    cgemm([view], [taps], wp, n, out, (bf, h, w), **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# norms / attention cores / sampler wrappers
+# ------------------------------------------------------------------------------------------------
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def gn_silu_fwd(x, y, stats, gamma, beta, scale_shift, B, pix, C_, groups, act=True, eps=1e-5, res=None):
+    check(lib.vmm_gn_silu_fwd(_p(x), _p(res), _p(y), fmt_of(x), B, pix, C_, groups, _p(stats), _p(gamma), _p(beta), _p(scale_shift),
+                              eps, 1 if act else 0, stream_ptr()), "vmm_gn_silu_fwd")
+
+
+def gn_silu_bwd(x, dy, dx, stats, gamma, beta, scale_shift, B, pix, C_, groups, dgamma, dbeta, dss, act=True, eps=1e-5):
+    nbytes = int(lib.vmm_gn_silu_bwd_workspace(B, C_, groups))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(lib.vmm_gn_silu_bwd(_p(x), _p(dy), _p(dx), fmt_of(x), B, pix, C_, groups, _p(stats), _p(gamma), _p(beta),
+                              _p(scale_shift), eps, 1 if act else 0, _p(dgamma), _p(dbeta), _p(dss), _p(ws), nbytes,
+                              stream_ptr()), "vmm_gn_silu_bwd")
+
+
+def ln_fwd(x2d, y2d, gamma, eps=1e-5):
+    rows, C_ = x2d.shape
+    check(lib.vmm_ln_fwd(_p(x2d), _p(y2d), fmt_of(x2d), rows, C_, _p(gamma), eps, None, stream_ptr()), "vmm_ln_fwd")
+
+
+def ln_bwd(x2d, dy2d, dres2d, dx2d, gamma, dgamma, eps=1e-5):
+    rows, C_ = x2d.shape
+    check(lib.vmm_ln_bwd(_p(x2d), _p(dy2d), _p(dres2d), _p(dx2d), fmt_of(x2d), rows, C_, _p(gamma), eps, _p(dgamma),
+                         stream_ptr()), "vmm_ln_bwd")
+
+
+def tattn_fwd(qkv, ekv, bias, rot, out, B, frames, HW, heads):
+    check(lib.vmm_tattn_fwd(_p(qkv), _p(ekv), _p(bias), _p(rot), _p(out), fmt_of(qkv), B, frames, HW, heads, 32 ** -0.5,
+                            stream_ptr()), "vmm_tattn_fwd")
+
+
+def lattn_fwd(qkv, ekv, T, out, ctx, kstat, BF, frames, HW, heads):
+    check(lib.vmm_lattn_fwd(_p(qkv), _p(ekv), T, _p(out), _p(ctx), _p(kstat), fmt_of(qkv), BF, frames, HW, heads, 32 ** -0.5,
+                            stream_ptr()), "vmm_lattn_fwd")
+
+
+def sattn_fwd(qkv, ekv, out, lse, BF, frames, HW, heads):
+    check(lib.vmm_sattn_fwd(_p(qkv), _p(ekv), _p(out), _p(lse), fmt_of(qkv), BF, frames, HW, heads, 32 ** -0.5, stream_ptr()),
+          "vmm_sattn_fwd")
+
+
+def prep_input(x, noise, a, c, s, xin, B, C_, F_, H, W):
+    fmt = FMT_F16 if xin.dtype == torch.float16 else FMT_BF16
+    check(lib.vmm_prep_input(_p(x), _p(noise), _p(a), _p(c), _p(s), _p(xin), fmt, B, C_, F_, H, W, stream_ptr()), "vmm_prep_input")
+
+
+def loss_fwd_bwd(pred, target, loss_sum, dpred, B, C_, F_, H, W, l2=False, grad_scale=1.0):
+    fmt = FMT_BF16 if (dpred is None or dpred.dtype == torch.bfloat16) else FMT_F16
+    check(lib.vmm_loss(_p(pred), _p(target), _p(loss_sum), _p(dpred), fmt, B, C_, F_, H, W, 1 if l2 else 0, grad_scale,
+                       stream_ptr()), "vmm_loss")
+
+
+def cfg_x0(x, eps_cl, has_null, w, sr, srm1, x0, eps_out, B, C_, F_, H, W):
+    check(lib.vmm_cfg_x0(_p(x), _p(eps_cl), 1 if has_null else 0, float(w), _p(sr), _p(srm1), _p(x0), _p(eps_out), B, C_, F_, H, W,
+                         stream_ptr()), "vmm_cfg_x0")
+
+
+def abs_quantile(v, B, n, k, frac, floor_val, s_out):
+    check(lib.vmm_abs_quantile(_p(v), B, n, k, frac, floor_val, _p(s_out), stream_ptr()), "vmm_abs_quantile")
+
+
+def posterior_step(x0, x, noise, s, c1, c2, sig, out, B, per):
+    check(lib.vmm_posterior_step(_p(x0), _p(x), _p(noise), _p(s), _p(c1), _p(c2), _p(sig), _p(out), B, per, stream_ptr()),
+          "vmm_posterior_step")
+
+
+def axpby(a, b, ca, cb, cc, out):
+    check(lib.vmm_axpby(_p(a), _p(b), float(ca), float(cb), float(cc), _p(out), out.numel(), stream_ptr()), "vmm_axpby")
+
+
+def adam_ema_step(p, g, m, v, ema, lr, beta1, beta2, eps, step, grad_scale, ema_mode, ema_beta):
+    check(lib.vmm_adam_ema_step(_p(p), _p(g), _p(m), _p(v), _p(ema), p.numel(), lr, beta1, beta2, eps, step, grad_scale, ema_mode,
+                                ema_beta, stream_ptr()), "vmm_adam_ema_step")
