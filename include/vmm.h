@@ -55,7 +55,7 @@ uint64_t vmm_launch_count(void);
  * out-of-range coordinates zero-filled (that IS the 'zeros' padding mode).  W: packed 16-bit
  * [N_pad, Ktot] K-major.  The GEMM-M space is the output grid (BF, OH, OW), cut into tiles of
  * TF x TH x TW = 128 positions (powers of two).
- * Epilogue (all optional): + bias[n]; + residual[pix, n]; per-(sample, group) sum / sum-of-squares
+ * Epilogue (all optional): x alpha; + bias[n]; + residual[pix, n]; per-(sample, group) sum / sum-of-squares
  * for GroupNorm accumulated in fp64 (VDDP:274); store 16-bit or fp32; columns >= nsplit go to out2.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -98,6 +98,9 @@ typedef struct {
   const float* bias;  /* [n] or NULL */
   const void* res;    /* 16-bit residual with the output's pixel indexing, or NULL */
   int64_t ldr;
+  const void* res2;   /* residual for the columns >= nsplit (required when res and out2 are both set) */
+  int64_t ldr2;
+  float alpha;        /* accumulator scale applied before bias / residual; 0 means 1 */
   double* gn_stats;   /* [samples][n / gn_group][2] (sum, sum of squares), accumulated atomically; or NULL */
   int32_t gn_group;   /* channels per group */
   int32_t frames_per_sample;
@@ -147,6 +150,16 @@ int vmm_lattn_fwd(const void* qkv, const float* ekv, int T, void* out, float* ct
 int vmm_sattn_fwd(const void* qkv, const float* ekv, void* out, float* lse, int fmt, int BF, int frames, int HW, int heads,
                   float scale, void* stream);
 
+/* Backward of the attention cores: gradients w.r.t. the qkv rows (dqkv, same layout as qkv), the conditioning
+ * keys|values (dekv, fp32, ACCUMULATED with atomics except vmm_sattn_bwd which overwrites its rows) and, for the
+ * temporal attention, the relative position bias (dbias, accumulated).  vscale = 1 / (h*w) of VDDP:371. */
+int vmm_tattn_bwd(const void* qkv, const float* ekv, const float* bias, const float* rot, const void* dout, void* dqkv, float* dekv,
+                  float* dbias, int fmt, int B, int frames, int HW, int heads, float scale, void* stream);
+int vmm_lattn_bwd(const void* qkv, const float* ekv, int T, const void* dout, const float* ctx, const float* kstat, float* dctx,
+                  void* dqkv, float* dekv, int fmt, int BF, int frames, int HW, int heads, float scale, float vscale, void* stream);
+int vmm_sattn_bwd(const void* qkv, const float* ekv, const void* aout, const void* dout, const float* lse, void* dqkv, float* dekv,
+                  int fmt, int BF, int HW, int heads, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Around the network (fp32 tensors in the reference (B, C, F, H, W) layout unless stated).
  * vmm_prep_input : value = a[b]*x + c[b] + s[b]*noise -> 16-bit [BF][H][W+6][8] init_conv operand
@@ -174,6 +187,40 @@ int vmm_posterior_step(const float* x0, const float* x, const float* noise, cons
 int vmm_axpby(const float* a, const float* b, float ca, float cb, float cc, float* out, long long n, void* stream);
 int vmm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long long n, float lr, float beta1, float beta2,
                       float eps, int step, float grad_scale, int ema_mode, float ema_beta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight gradients on tcgen05 tensor cores:  dW[n, tap, c] += sum_pix dY[pix, n] * X[pix + d_tap, c].
+ * The gradient of every layer vmm_cgemm runs forward (VDDP:271,297,319,325,413,421,241,155,626,708).
+ * a[]: views of the output gradient (one, or the 4 parity views for the transposed conv);
+ * b[]: views of the layer input (one or two concat sources, or 4 parity views for the strided conv).
+ * Partial sums are added atomically into the fp32 master-layout gradient:
+ *   dw[tap.wofs + n * s_m + (c % cmod) * s_c + (c / cmod) * s_c2]      (cmod <= 0: plain c * s_c)
+ * vmm_colsum: out[n] += sum_rows x[row][n]  (bias gradients).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t a_src, b_src; /* view indices */
+  int32_t dy, dx;       /* shift of the b view relative to the a view */
+  int32_t c;            /* channels of the b view used by this tap */
+  int64_t wofs;         /* element offset of this tap in dw */
+} vmm_wgrad_tap;
+
+typedef struct {
+  int32_t fmt;
+  int32_t n_a_views, n_b_views;
+  vmm_view4 a[VMM_MAX_VIEWS];
+  vmm_view4 b[VMM_MAX_VIEWS];
+  int32_t n_taps;
+  vmm_wgrad_tap taps[VMM_MAX_TAPS];
+  int32_t n;            /* channels of dY = rows of dW */
+  int32_t bf, oh, ow;   /* pixel grid of the a views (the reduction axis) */
+  int32_t tf, th, tw;   /* pixel tile, tf*th*tw == 128 */
+  float* dw;
+  int64_t s_m, s_c, s_c2;
+  int32_t cmod, c_valid, k_valid;
+} vmm_wgrad_params;
+
+int vmm_wgrad(const vmm_wgrad_params* p, void* stream);
+int vmm_colsum(const void* x, long long rows, int n, long long ld, int fmt, float* out, void* stream);
 
 #ifdef __cplusplus
 }

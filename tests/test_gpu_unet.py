@@ -120,3 +120,34 @@ def test_forward_needs_cuda():
     m = Unet3D(dim=16, dim_mults=(1, 2), per_frame_cond=True, use_temporal_attention_cond=True, cond_attention='self-stacked')
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 11, 16, 16), torch.zeros(1, dtype=torch.long), cond=torch.zeros(1, 11))
+
+
+@pytest.mark.parametrize("dtype,scale", [(torch.bfloat16, 1.0), (torch.float16, 4096.0)])
+def test_small_training_loss_and_gradients(gold_small, dtype, scale):
+    """loss + every parameter gradient of p_losses().backward() against the reference's (fp32 CPU autograd).
+    fp16 needs a loss scale (the reference trains under a GradScaler); bf16 does not."""
+    g = gold_small
+    model, gd, _ = build(16, (1, 2), g["T"], g["size"], g["T"], dtype, g["seed"])
+    x01, t, cond, noise = g["x01"].cuda(), g["t"].cuda(), g["cond"].cuda(), g["noise"].cuda()
+    loss = gd.p_losses(x01 * 2 - 1, t, cond=cond, noise=noise, null_cond_prob=0.0)
+    (loss * scale).backward()
+    torch.cuda.synchronize()
+    tol = 2e-3 if dtype == torch.float16 else 1e-2
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < tol, (float(loss), float(g["loss"]))
+    params = dict(model.named_parameters())
+    worst = []
+    for k, want in g["grad_norms"].items():
+        got = float(params[k].grad.norm()) / scale
+        worst.append((abs(got - want) / max(want, 1e-12), k, got, want))
+    worst.sort(reverse=True)
+    print("worst grad-norm deviations:", dtype, [(round(w, 4), k) for w, k, _, _ in worst[:6]])
+    gtol = 0.05 if dtype == torch.float16 else 0.15
+    assert worst[0][0] < gtol, worst[:5]
+    for k in g["grad_none"]:
+        assert float(params[k].grad.abs().max()) == 0.0, k       # never-used parameters keep a zero gradient
+    errs = {}
+    for k, want in g["grad_samples"].items():
+        got = params[k].grad.flatten()[:64].float().cpu() / scale
+        errs[k] = float((got - want).norm() / want.norm().clamp_min(1e-30))
+    print("grad sample rel-L2:", dtype, {k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) < (0.05 if dtype == torch.float16 else 0.2), errs

@@ -34,8 +34,26 @@ class CgemmParams(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int64), ("out_fp32", C.c_int32),
         ("ohs", C.c_int32), ("ows", C.c_int32), ("sy", C.c_int32), ("sx", C.c_int32),
         ("out2", C.c_void_p), ("ldo2", C.c_int64), ("nsplit", C.c_int32),
-        ("bias", C.c_void_p), ("res", C.c_void_p), ("ldr", C.c_int64),
+        ("bias", C.c_void_p), ("res", C.c_void_p), ("ldr", C.c_int64), ("res2", C.c_void_p), ("ldr2", C.c_int64),
+        ("alpha", C.c_float),
         ("gn_stats", C.c_void_p), ("gn_group", C.c_int32), ("frames_per_sample", C.c_int32),
+    ]
+
+
+class WgradTap(C.Structure):
+    _fields_ = [("a_src", C.c_int32), ("b_src", C.c_int32), ("dy", C.c_int32), ("dx", C.c_int32), ("c", C.c_int32),
+                ("wofs", C.c_int64)]
+
+
+class WgradParams(C.Structure):
+    _fields_ = [
+        ("fmt", C.c_int32), ("n_a_views", C.c_int32), ("n_b_views", C.c_int32),
+        ("a", View4 * MAX_VIEWS), ("b", View4 * MAX_VIEWS),
+        ("n_taps", C.c_int32), ("taps", WgradTap * MAX_TAPS),
+        ("n", C.c_int32), ("bf", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32),
+        ("tf", C.c_int32), ("th", C.c_int32), ("tw", C.c_int32),
+        ("dw", C.c_void_p), ("s_m", C.c_int64), ("s_c", C.c_int64), ("s_c2", C.c_int64),
+        ("cmod", C.c_int32), ("c_valid", C.c_int32), ("k_valid", C.c_int32),
     ]
 
 
@@ -66,6 +84,8 @@ _P, _I, _L, _F, _Z = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 # name -> argtypes (restype int unless listed in _RESTYPES); mirrors include/vmm.h one to one
 _SIGNATURES = {
     "vmm_cgemm": [C.POINTER(CgemmParams), _P],
+    "vmm_wgrad": [C.POINTER(WgradParams), _P],
+    "vmm_colsum": [_P, _L, _I, _L, _I, _P, _P],
     "vmm_gn_silu_fwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P],
     "vmm_gn_silu_bwd_workspace": [_I, _I, _I],
     "vmm_gn_silu_bwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _Z, _P],
@@ -74,6 +94,9 @@ _SIGNATURES = {
     "vmm_tattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vmm_lattn_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vmm_sattn_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "vmm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "vmm_lattn_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P],
+    "vmm_sattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "vmm_prep_input": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vmm_loss": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "vmm_cfg_x0": [_P, _P, _I, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) lattn_out_kernel(const uint16_t* __restri
 #pragma unroll
   for (int k = 0; k < DH; ++k) o[k] = 0.f;
   const float* ch = cs + h * DH * DH;
-#pragma unroll 4
+#pragma unroll
   for (int dd = 0; dd < DH; ++dd) {
     const float w = q[dd] * inv;
 #pragma unroll

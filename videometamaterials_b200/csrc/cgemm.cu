@@ -42,6 +42,9 @@ struct CgemmDev {
   const float* bias;
   const void* res;
   long long ldr;
+  const void* res2;
+  long long ldr2;
+  float alpha;
   double* gn_stats;
   int gn_gs, gn_groups, fps;
   int fmt;
@@ -57,7 +60,6 @@ struct __align__(8) CgemmSmemCtl {
   uint64_t tempty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  float gn_acc[2][16][2];   // [sample slot][group in n-tile][sum, sumsq], kept across tiles of one (sample, n-tile)
 };
 
 __device__ __forceinline__ void decode_tile(const CgemmDev& p, int t, int& phase, int& bf0, int& y0, int& x0, int& n0) {
@@ -75,22 +77,42 @@ __device__ __forceinline__ void decode_tile(const CgemmDev& p, int t, int& phase
   n0 = nt * p.BN;
 }
 
+constexpr int kBiasSmem = 1024;
+
 // Add the shared-memory GroupNorm partial sums of (first sample smp0, n-tile n0) to the global fp64 statistics
 // and clear them.  Called by all 128 epilogue threads between two named-barrier syncs.
-__device__ __forceinline__ void gn_flush(const CgemmDev& p, CgemmSmemCtl* ctl, int ethread, int smp0, int n0) {
+__device__ __forceinline__ void gn_flush(const CgemmDev& p, float (*gacc)[16][2], int ethread, int smp0, int n0) {
   if (ethread < 2 * 16 * 2) {
     const int sl = ethread >> 5, gl = (ethread >> 1) & 15, w = ethread & 1;
     const int g = n0 / p.gn_gs + gl;
-    const float val = ctl->gn_acc[sl][gl][w];
+    const float val = gacc[sl][gl][w];
     const int nsamp = (p.BF + p.fps - 1) / p.fps;
     if (g < p.gn_groups && smp0 + sl < nsamp && val != 0.f)
       atomicAdd(p.gn_stats + (static_cast<long long>(smp0 + sl) * p.gn_groups + g) * 2 + w, static_cast<double>(val));
-    ctl->gn_acc[sl][gl][w] = 0.f;
+    gacc[sl][gl][w] = 0.f;
+  }
+}
+
+// warp-reduce one group's (sum, sumsq) and add it to the CTA accumulators (shared-memory atomics)
+__device__ __forceinline__ void gn_warp_add(float (*gacc)[16][2], int gl, int slot, bool two_samples, float a1, float a2, int lane) {
+  for (int sl = 0; sl < (two_samples ? 2 : 1); ++sl) {
+    float a = (slot == sl) ? a1 : 0.f, b = (slot == sl) ? a2 : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&gacc[sl][gl][0], a);
+      atomicAdd(&gacc[sl][gl][1], b);
+    }
   }
 }
 
 __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ CgemmDev p) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_gn[2][16][2];        // [sample slot][group in n-tile][sum, sumsq], kept across tiles of one (sample, n-tile)
+  __shared__ __align__(16) float s_bias[kBiasSmem];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   CgemmSmemCtl* ctl = reinterpret_cast<CgemmSmemCtl*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
 
@@ -117,7 +139,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
     tmem_relinquish();
   }
   if (warp == 3) {
-    float* g = &ctl->gn_acc[0][0][0];
+    float* g = &s_gn[0][0][0];
     for (int i = lane; i < 2 * 16 * 2; i += 32) g[i] = 0.f;
   }
   tc_fence_before();
@@ -197,6 +219,13 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
     const int q = warp & 3;              // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;       // row of the 128-row tile == TMEM lane
     const int ethread = threadIdx.x - 128;
+    // bias lives in shared memory for the whole kernel (global loads in the column loop were the bottleneck)
+    const bool bias_smem = p.bias != nullptr && p.N <= kBiasSmem;
+    if (bias_smem) {
+      for (int i = ethread; i < p.N; i += 128) s_bias[i] = __ldg(p.bias + i);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const int nsteps = (p.BN + 31) >> 5;
     int it = 0;
     int gn_key_smp = -1, gn_key_n0 = -1;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -226,147 +255,189 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
         if (smp0 != gn_key_smp || n0 != gn_key_n0) {
           if (gn_key_smp >= 0) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            gn_flush(p, ctl, ethread, gn_key_smp, gn_key_n0);
+            gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0);
             asm volatile("bar.sync 1, 128;" ::: "memory");
           }
           gn_key_smp = smp0;
           gn_key_n0 = n0;
         }
       }
-      float(*gacc)[16][2] = ctl->gn_acc;
+
+      // residual rows are known before the accumulator is: fetch the first 32 columns while the MMAs still run.
+      // With a column split (out2), columns >= nsplit read res2 (same split as the outputs).
+      const bool split = p.out2 != nullptr;
+      const uint16_t* rrow1 = (p.res && valid) ? reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldr : nullptr;
+      const uint16_t* rrow2 = (p.res && valid && split) ? reinterpret_cast<const uint16_t*>(p.res2) + pix * p.ldr2 - p.nsplit : nullptr;
+      const bool res_al = ((p.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0) &&
+                          (!split || (((p.ldr2 & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.res2) & 15) == 0)));
+      uint4 rq[4];
+      auto res_ptr = [&](int col) -> const uint16_t* { return (split && col >= p.nsplit) ? rrow2 + col : rrow1 + col; };
+      auto straddles = [&](int col) -> bool { return split && col < p.nsplit && col + 32 > p.nsplit; };
+      if (rrow1 && res_al && n0 + 32 <= p.N && !straddles(n0)) {
+        const uint4* rp = reinterpret_cast<const uint4*>(res_ptr(n0));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rq[j] = __ldg(rp + j);
+      }
 
       mbar_wait(&ctl->tfull[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.acc_stride;
 
-      const int nchunks = p.BN >> 4;
-      float gs1 = 0.f, gs2 = 0.f;   // running sums of the current group (group size >= 16 case)
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t r[16];
-        tmem_ld16(t_addr + c * 16, r);
+      float gs1 = 0.f, gs2 = 0.f;   // running sums of the current GroupNorm group
+      for (int st = 0; st < nsteps; ++st) {
+        const int ncol = n0 + st * 32;
+        uint32_t r[32];
+        tmem_ld16(t_addr + st * 32, r);
+        tmem_ld16(t_addr + st * 32 + 16, r + 16);
         tmem_ld_wait();
-        const int ncol = n0 + c * 16;
         if (ncol >= p.N) continue;   // uniform: padded columns of the last n-tile
-        float v[16];
+        const bool full = (ncol + 32 <= p.N);
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        const bool full_chunk = (ncol + 16 <= p.N);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (p.bias) {
+          if (bias_smem && full) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (full_chunk || ncol + j < p.N) v[j] += __ldg(p.bias + ncol + j);
-        }
-        if (p.res && valid) {
-          const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldr + ncol;
-          if (full_chunk && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-            const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-            const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 f = unpack2_h16(w[j], p.fmt);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[ncol + j]);
+              v[j] += b4.x;
+              v[j + 1] += b4.y;
+              v[j + 2] += b4.z;
+              v[j + 3] += b4.w;
             }
           } else {
-            for (int j = 0; j < 16; ++j)
-              if (ncol + j < p.N) v[j] += h16_to_f(rp[j], p.fmt);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ncol + j < p.N) v[j] += bias_smem ? s_bias[ncol + j] : __ldg(p.bias + ncol + j);
           }
         }
-        // choose destination (column split for fused concat gradients)
+        const bool strad = straddles(ncol);
+        if (p.alpha != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+        }
+        if (rrow1) {
+          if (res_al && full && !strad) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w4[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack2_h16(w4[k], p.fmt);
+                v[j * 8 + 2 * k] += f.x;
+                v[j * 8 + 2 * k + 1] += f.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ncol + j < p.N) v[j] += h16_to_f(*res_ptr(ncol + j), p.fmt);
+          }
+          // prefetch the next 32 columns
+          if (res_al && st + 1 < nsteps && ncol + 64 <= p.N && !straddles(ncol + 32)) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res_ptr(ncol + 32));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rq[j] = __ldg(rp + j);
+          }
+        }
+        // destination (column split for fused concat gradients)
         void* obase = p.out;
         long long ld = p.ldo;
         int ocol = ncol;
-        if (p.out2 && ncol >= p.nsplit) {
+        if (split && ncol >= p.nsplit) {
           obase = p.out2;
           ld = p.ldo2;
           ocol = ncol - p.nsplit;
         }
+        const bool vec_ok = full && !strad;
         if (p.out_fp32) {
           if (valid) {
             float* op = reinterpret_cast<float*>(obase) + pix * ld + ocol;
-            if (full_chunk && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
+              for (int j = 0; j < 8; ++j)
                 reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             } else {
-              for (int j = 0; j < 16; ++j)
-                if (ncol + j < p.N) op[j] = v[j];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ncol + j < p.N) {
+                  if (split && ncol + j >= p.nsplit)
+                    (reinterpret_cast<float*>(p.out2) + pix * p.ldo2)[ncol + j - p.nsplit] = v[j];
+                  else
+                    (reinterpret_cast<float*>(p.out) + pix * p.ldo)[ncol + j] = v[j];
+                }
             }
           }
         } else {
-          uint32_t w[8];
+          uint32_t w[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = pack2_h16(v[2 * j], v[2 * j + 1], p.fmt);
-          if (p.gn_stats) {
-            // statistics of the values as stored (rounded to 16 bit), like GroupNorm on the fp16 conv output
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 f = unpack2_h16(w[j], p.fmt);
-              v[2 * j] = f.x;
-              v[2 * j + 1] = f.y;
-            }
-          }
+          for (int j = 0; j < 16; ++j) w[j] = pack2_h16(v[2 * j], v[2 * j + 1], p.fmt);
           if (valid) {
             uint16_t* op = reinterpret_cast<uint16_t*>(obase) + pix * ld + ocol;
-            if (full_chunk && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-              reinterpret_cast<uint4*>(op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-              reinterpret_cast<uint4*>(op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(op)[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
             } else {
-              for (int j = 0; j < 16; ++j)
-                if (ncol + j < p.N) op[j] = static_cast<uint16_t>((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ncol + j < p.N) {
+                  const uint16_t hv = static_cast<uint16_t>((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
+                  if (split && ncol + j >= p.nsplit)
+                    (reinterpret_cast<uint16_t*>(p.out2) + pix * p.ldo2)[ncol + j - p.nsplit] = hv;
+                  else
+                    (reinterpret_cast<uint16_t*>(p.out) + pix * p.ldo)[ncol + j] = hv;
+                }
             }
           }
-        }
-        if (p.gn_stats) {
-          const int gs = p.gn_gs;
-          if (gs >= 16) {
-            // whole chunk lies in one group; flush when the group ends
-            if (valid) {
+          if (p.gn_stats) {
+            // statistics of the values as stored (rounded to 16 bit), like GroupNorm on the fp16 conv output:
+            // per 8-column block sums first (static indexing), then group them
+            float b1[4], b2[4];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                gs1 += v[j];
-                gs2 += v[j] * v[j];
-              }
-            }
-            if (((ncol + 16) % gs) == 0) {
-              const int gl = (ncol - n0) / gs;
-              for (int sl = 0; sl < (two_samples ? 2 : 1); ++sl) {
-                float a = (slot == sl) ? gs1 : 0.f, b = (slot == sl) ? gs2 : 0.f;
+            for (int b = 0; b < 4; ++b) {
+              float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  a += __shfl_xor_sync(0xffffffffu, a, o);
-                  b += __shfl_xor_sync(0xffffffffu, b, o);
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack2_h16(w[b * 4 + k], p.fmt);
+                const bool in0 = full || (ncol + b * 8 + 2 * k < p.N), in1 = full || (ncol + b * 8 + 2 * k + 1 < p.N);
+                if (in0) {
+                  a1 += f.x;
+                  a2 += f.x * f.x;
                 }
-                if (lane == 0) {
-                  atomicAdd(&gacc[sl][gl][0], a);
-                  atomicAdd(&gacc[sl][gl][1], b);
+                if (in1) {
+                  a1 += f.y;
+                  a2 += f.y * f.y;
                 }
               }
-              gs1 = gs2 = 0.f;
+              b1[b] = valid ? a1 : 0.f;
+              b2[b] = valid ? a2 : 0.f;
             }
-          } else {
-            // several groups per chunk (small channel counts): gs in {1,2,4,8}
-            for (int g0 = 0; g0 < 16; g0 += gs) {
-              float a0 = 0.f, b0 = 0.f;
-              if (valid)
-                for (int j = g0; j < g0 + gs; ++j)
-                  if (ncol + j < p.N) {
-                    a0 += v[j];
-                    b0 += v[j] * v[j];
-                  }
-              const int gl = (ncol - n0 + g0) / gs;
-              if (ncol + g0 >= p.N || gl >= 16) continue;
-              for (int sl = 0; sl < (two_samples ? 2 : 1); ++sl) {
-                float a = (slot == sl) ? a0 : 0.f, b = (slot == sl) ? b0 : 0.f;
+            const int gs = p.gn_gs;
+            if (gs >= 8) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  a += __shfl_xor_sync(0xffffffffu, a, o);
-                  b += __shfl_xor_sync(0xffffffffu, b, o);
+              for (int b = 0; b < 4; ++b) {
+                gs1 += b1[b];
+                gs2 += b2[b];
+                const int cend = ncol + 8 * (b + 1);
+                if ((cend % gs) == 0 && cend - gs < p.N) {   // group complete (uniform across the warp)
+                  gn_warp_add(s_gn, (cend - gs - n0) / gs, slot, two_samples, gs1, gs2, lane);
+                  gs1 = gs2 = 0.f;
                 }
-                if (lane == 0) {
-                  atomicAdd(&gacc[sl][gl][0], a);
-                  atomicAdd(&gacc[sl][gl][1], b);
+              }
+            } else {
+              // tiny channel counts (tests): groups of 1, 2 or 4 columns; fully unrolled so that w[] stays in registers
+#pragma unroll
+              for (int cj = 0; cj < 32; ++cj) {
+                if (ncol + cj < p.N && valid) {
+                  const float f = h16_to_f(static_cast<uint16_t>((w[cj >> 1] >> ((cj & 1) * 16)) & 0xFFFF), p.fmt);
+                  gs1 += f;
+                  gs2 += f * f;
+                }
+                if (((cj + 1) % gs) == 0) {
+                  const int c0g = ncol + cj + 1 - gs;
+                  const int gl = (c0g - n0) / gs;
+                  if (c0g < p.N && gl < 16) gn_warp_add(s_gn, gl, slot, two_samples, gs1, gs2, lane);
+                  gs1 = gs2 = 0.f;
                 }
               }
             }
@@ -376,11 +447,10 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       mbar_arrive(&ctl->tempty[acc]);
-
     }
     if (p.gn_stats && gn_key_smp >= 0) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      gn_flush(p, ctl, ethread, gn_key_smp, gn_key_n0);
+      gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0);
     }
   }
 
@@ -459,7 +529,7 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   d.total_tiles = static_cast<int>(total);
   d.stage_bytes = kABytes + BN * 128;
   d.tx_bytes = d.stage_bytes;
-  const int smem_budget = 200 * 1024;
+  const int smem_budget = 196 * 1024;
   int stages = smem_budget / static_cast<int>(d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile too large for shared memory");
@@ -482,6 +552,10 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   d.bias = h.bias;
   d.res = h.res;
   d.ldr = h.ldr;
+  d.res2 = h.res2;
+  d.ldr2 = h.ldr2;
+  d.alpha = h.alpha == 0.f ? 1.f : h.alpha;
+  if (h.res && h.out2 && !h.res2) return set_error(VMM_ERR_ARG, "vmm_cgemm: res2 is required when both res and out2 are given");
   d.gn_stats = h.gn_stats;
   d.gn_gs = h.gn_group > 0 ? h.gn_group : 1;
   d.gn_groups = h.gn_stats ? h.n / h.gn_group : 1;
@@ -523,10 +597,10 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     if (rc) return rc;
   }
 
-  const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + sizeof(CgemmSmemCtl) + 1024;
+  const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + sizeof(CgemmSmemCtl) + 1024;   // + ~4.4 KB static
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "vmm_cgemm: cudaFuncSetAttribute");
     attr_set = true;
   }

@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import CgemmParams, FMT_BF16, FMT_F16, check, lib
+from ._lib import CgemmParams, FMT_BF16, FMT_F16, WgradParams, check, lib
 
 
 def fmt_of(t: torch.Tensor) -> int:
@@ -83,7 +83,7 @@ def cgemm(views: Sequence[torch.Tensor], taps: Sequence[Sequence[Tuple[int, int,
           phase_off: Optional[Sequence[Tuple[int, int]]] = None, bias: Optional[torch.Tensor] = None,
           res: Optional[torch.Tensor] = None, gn_stats: Optional[torch.Tensor] = None, gn_group: int = 0,
           frames_per_sample: int = 1, out2: Optional[torch.Tensor] = None, nsplit: int = 0,
-          tile: Optional[Tuple[int, int, int]] = None) -> None:
+          tile: Optional[Tuple[int, int, int]] = None, res2: Optional[torch.Tensor] = None, alpha: float = 1.0) -> None:
     """Launch vmm_cgemm.
 
     views : list of (bf, h, w, c) 16-bit tensors (A operand sources)
@@ -134,6 +134,11 @@ def cgemm(views: Sequence[torch.Tensor], taps: Sequence[Sequence[Tuple[int, int,
         assert res.dtype == views[0].dtype and res.stride(-1) == 1
         p.res = res.data_ptr()
         p.ldr = res.stride(-2)
+        if res2 is not None:
+            assert res2.dtype == views[0].dtype and res2.stride(-1) == 1
+            p.res2 = res2.data_ptr()
+            p.ldr2 = res2.stride(-2)
+    p.alpha = alpha
     if gn_stats is not None:
         assert gn_stats.dtype == torch.float64 and gn_stats.is_contiguous()
         p.gn_stats = gn_stats.data_ptr()
@@ -196,7 +201,7 @@ def rows_view(x2d: torch.Tensor) -> torch.Tensor:
 
 
 def linear_rows(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch.Tensor, *, bias=None, res=None,
-                gn_stats=None, gn_group=0, frames_per_sample=1, out2=None, nsplit=0) -> None:
+                gn_stats=None, gn_group=0, frames_per_sample=1, out2=None, nsplit=0, res2=None, alpha=1.0) -> None:
     """out[m, :n] = cat(xs, dim=1)[m] @ W^T  for 2-D operands [M, C_i]; wp = pack_linear / pack_conv_taps(1x1)."""
     taps, kofs = [], 0
     for s, x in enumerate(xs):
@@ -204,7 +209,7 @@ def linear_rows(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch
         kofs += ceil64(x.shape[1])
     m = xs[0].shape[0]
     cgemm([rows_view(x) for x in xs], [taps], wp, n, out, (1, 1, m), bias=bias, res=res, gn_stats=gn_stats,
-          gn_group=gn_group, frames_per_sample=frames_per_sample, out2=out2, nsplit=nsplit)
+          gn_group=gn_group, frames_per_sample=frames_per_sample, out2=out2, nsplit=nsplit, res2=res2, alpha=alpha)
 
 
 def conv3x3(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch.Tensor, **kw) -> None:
@@ -353,3 +358,126 @@ def axpby(a, b, ca, cb, cc, out):
 def adam_ema_step(p, g, m, v, ema, lr, beta1, beta2, eps, step, grad_scale, ema_mode, ema_beta):
     check(lib.vmm_adam_ema_step(_p(p), _p(g), _p(m), _p(v), _p(ema), p.numel(), lr, beta1, beta2, eps, step, grad_scale, ema_mode,
                                 ema_beta, stream_ptr()), "vmm_adam_ema_step")
+
+
+# ------------------------------------------------------------------------------------------------
+# weight gradients
+# ------------------------------------------------------------------------------------------------
+def _fill_view(v, t: torch.Tensor) -> None:
+    assert t.dim() == 4 and t.stride(3) == 1
+    v.ptr = t.data_ptr()
+    bf, h, w, c = t.shape
+    v.dims[0], v.dims[1], v.dims[2], v.dims[3] = c, w, h, bf
+    sw, sh, sb = t.stride(2), t.stride(1), t.stride(0)
+    v.strides[0] = sw if w > 1 else max(8, c)
+    v.strides[1] = sh if h > 1 else max(8, v.strides[0] * w)
+    v.strides[2] = sb if bf > 1 else max(8, v.strides[1] * h)
+
+
+def wgrad(a_views: Sequence[torch.Tensor], b_views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int, int, int, int]],
+          n: int, dw: torch.Tensor, s_m: int, s_c: int, grid: Tuple[int, int, int], *, s_c2: int = 0, cmod: int = 0,
+          c_valid: int = 0, k_valid: int = 0, tile: Optional[Tuple[int, int, int]] = None) -> None:
+    """dw (fp32, master layout, accumulated) += dY^T X.  taps: (a_src, b_src, dy, dx, c, wofs)."""
+    _require_cuda(dw, *a_views, *b_views)
+    assert dw.dtype == torch.float32
+    p = WgradParams()
+    p.fmt = fmt_of(a_views[0])
+    p.n_a_views, p.n_b_views = len(a_views), len(b_views)
+    for i, t in enumerate(a_views):
+        _fill_view(p.a[i], t)
+    for i, t in enumerate(b_views):
+        assert t.dtype == a_views[0].dtype
+        _fill_view(p.b[i], t)
+    p.n_taps = len(taps)
+    for i, (a_src, b_src, dy, dx, c, wofs) in enumerate(taps):
+        T = p.taps[i]
+        T.a_src, T.b_src, T.dy, T.dx, T.c, T.wofs = a_src, b_src, dy, dx, c, wofs
+    p.n = n
+    bf, oh, ow = grid
+    p.bf, p.oh, p.ow = bf, oh, ow
+    p.tf, p.th, p.tw = tile if tile is not None else choose_tile(bf, oh, ow)
+    p.dw = dw.data_ptr()
+    p.s_m, p.s_c, p.s_c2 = s_m, s_c, s_c2
+    p.cmod, p.c_valid, p.k_valid = cmod, c_valid, k_valid
+    check(lib.vmm_wgrad(C.byref(p), stream_ptr()), "vmm_wgrad")
+
+
+def colsum(x2d: torch.Tensor, out: torch.Tensor) -> None:
+    """out[n] (fp32, accumulated) += sum over rows of x2d[:, n]."""
+    rows, n = x2d.shape
+    check(lib.vmm_colsum(_p(x2d), rows, n, x2d.stride(0), fmt_of(x2d), _p(out), stream_ptr()), "vmm_colsum")
+
+
+def wgrad_conv3x3(dy: torch.Tensor, xs: Sequence[torch.Tensor], dw: torch.Tensor) -> None:
+    """dw: (Cout, Cin_total, 1, 3, 3) fp32.  dy (bf,h,w,Cout); xs: concat sources (bf,h,w,c_i)."""
+    cout, cin_tot = dw.shape[0], dw.shape[1]
+    taps, coff = [], 0
+    for s, x in enumerate(xs):
+        for ky in range(3):
+            for kx in range(3):
+                taps.append((0, s, ky - 1, kx - 1, x.shape[3], coff * 9 + ky * 3 + kx))
+        coff += x.shape[3]
+    bf, h, w, _ = dy.shape
+    wgrad([dy], list(xs), taps, cout, dw, cin_tot * 9, 9, (bf, h, w))
+
+
+def wgrad_linear(dy2d: torch.Tensor, xs2d: Sequence[torch.Tensor], dw: torch.Tensor) -> None:
+    """dw: (N, K_total) fp32 (any trailing singleton dims);  dy2d [M, N]; xs2d concat sources [M, K_i]."""
+    n = dw.shape[0]
+    ktot = dw.numel() // n
+    taps, coff = [], 0
+    for s, x in enumerate(xs2d):
+        taps.append((0, s, 0, 0, x.shape[1], coff))
+        coff += x.shape[1]
+    m = dy2d.shape[0]
+    wgrad([rows_view(dy2d)], [rows_view(x) for x in xs2d], taps, n, dw, ktot, 1, (1, 1, m))
+
+
+def wgrad_down(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
+    """Strided (1,4,4) conv: dw (Cout, Cin, 1, 4, 4); dy (bf, h/2, w/2, Cout); x (bf, h, w, Cin)."""
+    cout, cin = dw.shape[0], dw.shape[1]
+    taps = []
+    for ky in range(4):
+        for kx in range(4):
+            py, px = (ky + 1) % 2, (kx + 1) % 2
+            taps.append((0, py * 2 + px, (ky - 1) // 2, (kx - 1) // 2, cin, ky * 4 + kx))
+    bf, h2, w2, _ = dy.shape
+    wgrad([dy], parity_views(x), taps, cout, dw, cin * 16, 16, (bf, h2, w2))
+
+
+def wgrad_up(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
+    """Transposed conv: dw (Cin, Cout, 1, 4, 4); dy (bf, 2h, 2w, Cout); x (bf, h, w, Cin)."""
+    cin, cout = dw.shape[0], dw.shape[1]
+    taps = []
+    for py in range(2):
+        for px in range(2):
+            for ky, ddy in (((1, 0), (3, -1)) if py == 0 else ((0, 1), (2, 0))):
+                for kx, ddx in (((1, 0), (3, -1)) if px == 0 else ((0, 1), (2, 0))):
+                    taps.append((py * 2 + px, 0, ddy, ddx, cin, ky * 4 + kx))
+    bf, h, w, _ = x.shape
+    wgrad(parity_views(dy), [x], taps, cout, dw, 16, cout * 16, (bf, h, w))
+
+
+def wgrad_init_conv(dy: torch.Tensor, xin: torch.Tensor, dw: torch.Tensor, channels: int) -> None:
+    """init_conv: dw (N, C, 1, 7, 7); dy (bf, h, w, N); xin the padded 8-channel buffer of prep_input."""
+    n = dw.shape[0]
+    bf, h, w, _ = dy.shape
+    view = xin.as_strided((bf, h, w, 64), (h * (w + 6) * 8, (w + 6) * 8, 8, 1))
+    taps = [(0, 0, ky - 3, 0, 64, ky * 7) for ky in range(7)]
+    # column j of the 64-wide window = (kx = j // 8, ch = j % 8) -> dw[n][ch][ky][kx]
+    wgrad([dy], [view], taps, n, dw, channels * 49, 49, (bf, h, w), s_c2=1, cmod=8, c_valid=channels, k_valid=7)
+
+
+def tattn_bwd(qkv, ekv, bias, rot, dout, dqkv, dekv, dbias, B, frames, HW, heads):
+    check(lib.vmm_tattn_bwd(_p(qkv), _p(ekv), _p(bias), _p(rot), _p(dout), _p(dqkv), _p(dekv), _p(dbias), fmt_of(qkv), B, frames, HW,
+                            heads, 32 ** -0.5, stream_ptr()), "vmm_tattn_bwd")
+
+
+def lattn_bwd(qkv, ekv, T, dout, ctx, kstat, dctx, dqkv, dekv, BF, frames, HW, heads):
+    check(lib.vmm_lattn_bwd(_p(qkv), _p(ekv), T, _p(dout), _p(ctx), _p(kstat), _p(dctx), _p(dqkv), _p(dekv), fmt_of(qkv), BF, frames,
+                            HW, heads, 32 ** -0.5, 1.0 / HW, stream_ptr()), "vmm_lattn_bwd")
+
+
+def sattn_bwd(qkv, ekv, aout, dout, lse, dqkv, dekv, BF, HW, heads):
+    check(lib.vmm_sattn_bwd(_p(qkv), _p(ekv), _p(aout), _p(dout), _p(lse), _p(dqkv), _p(dekv), fmt_of(qkv), BF, HW, heads, 32 ** -0.5,
+                            stream_ptr()), "vmm_sattn_bwd")
