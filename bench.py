@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the VideoMetamaterials hot path (driver contract: see the repository task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]         own arm: B200 kernels
+  python bench.py --impl reference [...]                       reference arm: the CPU oracle port of the reference algorithm
+
+Metric (BASELINE.json): UNet3D fwd+bwd video-clips/s at 96x96x11 (+ p_sample steps/s as an extra key).
+Workload at every N: configs[1] = "Unet3D fwd+bwd bf16, batch=8, 96x96x11" per GPU (weak scaling, global batch 8N);
+a step is one full optimisation step of the Trainer (forward, backward, NCCL gradient all-reduce when N > 1, fused
+Adam + EMA + weight repack) on synthetic clips of the Dataset's value range.
+  value : device-timed (CUDA events), inputs resident in HBM, max over ranks.
+  e2e   : the same step through the public API (`Trainer.train_step`) with pinned HOST buffers copied to the device
+          and the loss read back to the host inside the timed region.
+  roofline : the implicit-GEMM tcgen05 kernel (vmm_cgemm), tensor bound: algorithmic FLOPs of every launch in two
+          profiled steps / their summed CUDA-event durations, against MEASURED_PEAKS.json bf16_tflops_sustained.
+  cpu_baseline : the oracle port (fp32 torch on the host cores), one clip forward+backward.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "UNet3D fwd+bwd video-clips/sec (96x96x11)"
+UNIT = "clips/s"
+FWD_BWD_GFLOP_PER_CLIP = 1159.87      # SURVEY.md section 8d (torch flop counter on the reference)
+FWD_GFLOP_PER_CLIP = 387.26
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tflops=d.get("bf16_tflops", 1590.0), tflops_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    source="measured")
+    return dict(hbm=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def oracle_step_fn():
+    import torch
+    from oracle import vdm_oracle as O
+    cfg = O.UnetCfg()
+    sd = O.synthetic_state_dict(cfg, seed=0)
+    P = {k: v.clone().requires_grad_(v.is_floating_point() and "freqs" not in k) for k, v in sd.items()}
+    S = O.schedule(256)
+    g = torch.Generator().manual_seed(1)
+    x01 = torch.rand(1, 3, 11, 96, 96, generator=g)
+    cond = torch.rand(1, 11, generator=g) * 2 - 1
+    noise = torch.randn(1, 3, 11, 96, 96, generator=g)
+    t = torch.randint(0, 256, (1,), generator=g)
+    mask = torch.zeros(1, dtype=torch.bool)
+
+    def step():
+        for p in P.values():
+            p.grad = None
+        loss = O.p_losses(P, cfg, S, x01, t, cond, noise, mask)
+        loss.backward()
+        return float(loss)
+
+    return step
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = oracle_step_fn()
+    t0 = time.perf_counter()
+    step()                                   # first warm-up also gives the per-step cost
+    est = time.perf_counter() - t0
+    warm = max(args.warmup - 1, 0)
+    budget = 170.0
+    steps = args.steps
+    if est * (warm + steps) > budget:        # keep the whole run within a few minutes
+        warm = 0
+        steps = max(1, int(budget / est))
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = 1.0 / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Unet3D fwd+bwd, 96x96x11, reference algorithm (oracle port) on host CPU", "sample": "1 clip per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": "1 clip forward+backward per step, fp32"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_bounded():
+    """One clip forward+backward of the oracle port on all host cores (~10-30 s of CPU work)."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = oracle_step_fn()
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": "1 clip (b=1) forward+backward, fp32, single run"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace('.', '').isdigit())
+        mx = max(int(float(r[1])) for r in self.rows if r[1].replace('.', '').isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from videometamaterials_b200 import Accelerator, GaussianDiffusion, Trainer, Unet3D, _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    acc = Accelerator(mixed_precision="bf16")
+    dev = acc.device
+    B = 8
+    torch.manual_seed(0)
+    model = Unet3D(dim=64, dim_mults=(1, 2, 4, 8), channels=3, attn_heads=8, attn_dim_head=32, init_dim=None, init_kernel_size=7,
+                   use_sparse_linear_attn=True, resnet_groups=8, cond_bias=True, cond_attention='self-stacked', cond_attention_tokens=16,
+                   cond_att_GRU=False, use_temporal_attention_cond=True, cond_to_time='add', per_frame_cond=True, padding_mode='zeros')
+    gd = GaussianDiffusion(model, image_size=96, channels=3, num_frames=11, timesteps=256, loss_type='l1', use_dynamic_thres=True,
+                           sampling_timesteps=256)
+    trainer = Trainer(gd, folder=None, validation_folder=None, selected_channels=[0, 1, 3], train_batch_size=B, test_batch_size=4,
+                      train_lr=1e-4, train_num_steps=10 ** 9, results_folder=os.path.join(ROOT, "gpurun_out", "bench_run"), log=False,
+                      null_cond_prob=0.1, per_frame_cond=True, reference_frame='lagrangian', accelerator=acc)
+    torch.manual_seed(1 + rank)
+    x_host = torch.rand(B, 3, 11, 96, 96).pin_memory()
+    c_host = (torch.rand(B, 11) * 2 - 1).pin_memory()
+    x_dev, c_dev = x_host.to(dev), c_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        trainer.step += 1
+        return trainer.train_step(x_dev, c_dev)
+
+    def step_e2e():
+        trainer.step += 1
+        xd = x_host.to(dev, non_blocking=True)
+        cd = c_host.to(dev, non_blocking=True)
+        return float(trainer.train_step(xd, cd).item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = e0.elapsed_time(e1) / args.steps
+    # e2e leg: host buffers in, loss out
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank != 0:
+        return
+    pk = peaks()
+    # roofline of the dominant kernel (vmm_cgemm): profile two more steps with per-launch events
+    ops.PROFILE = []
+    for _ in range(2):
+        step_resident()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    by = {}
+    for name, flops, a, b in prof:
+        d = by.setdefault(name, [0.0, 0.0, 0])
+        d[0] += flops
+        d[1] += a.elapsed_time(b) * 1e-3
+        d[2] += 1
+    cg = by.get("cgemm", [0.0, 1.0, 1])
+    achieved = cg[0] / cg[1] / 1e12
+    roof = {"bound": "tensor", "kernel": "vmm::cgemm_kernel", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (bf16_tflops_sustained)",
+            "launches_per_step": cg[2] // 2, "share_of_step": (cg[1] / 2) / (ms * 1e-3),
+            "wgrad": {"achieved": by["wgrad"][0] / by["wgrad"][1] / 1e12 if "wgrad" in by else None,
+                      "share_of_step": (by["wgrad"][1] / 2) / (ms * 1e-3) if "wgrad" in by else None}}
+    # sampling metric (second half of BASELINE.json's metric): ancestral p_sample with guidance, b=4, CUDA graph
+    ps = None
+    try:
+        ema = trainer.ema_model
+        ema.denoise_fn.set_compute_dtype(torch.float16)
+        ema.use_cuda_graph = True
+        condp = torch.rand(4, 11, device=dev) * 2 - 1
+        T = ema.num_timesteps
+        ema.num_timesteps = 8
+        ema.sample(cond=condp, guidance_scale=5.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ema.sample(cond=condp, guidance_scale=5.0)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 8
+        ema.num_timesteps = T
+        ps = {"value": 1.0 / dt, "unit": "p_sample steps/s", "batch": 4, "guidance_scale": 5.0, "dtype": "f16", "steps_timed": 8,
+              "tflops": 4 * 2 * FWD_GFLOP_PER_CLIP / dt / 1e3}
+    except Exception as e:  # noqa: BLE001
+        ps = {"error": str(e)[:200]}
+    cpu = cpu_baseline_bounded() if world == 1 and not args.no_cpu_baseline else None
+    value = world * B / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Unet3D fwd+bwd bf16, batch=8 per GPU, 96x96x11 (BASELINE configs[1]); step = forward + backward + "
+                               "gradient all-reduce + fused Adam/EMA + weight repack", "global_batch": world * B,
+                   "l2": "activation working set per step (>20 GB) is far larger than the 126 MB L2; no explicit flush",
+                   "parallelism": f"dp{world}", "model_tflops_per_gpu": B * FWD_BWD_GFLOP_PER_CLIP / ms},
+        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + c_host.numel() * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "p_sample": ps,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,26 @@ from . import _lib
 from ._lib import CgemmParams, FMT_BF16, FMT_F16, WgradParams, check, lib
 
 
+# bench.py sets PROFILE = [] to collect (kernel, algorithmic flops, start event, end event) per GEMM launch
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(name: str, flops: float, e0) -> None:
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILE.append((name, flops, e0, e1))
+
+
 def fmt_of(t: torch.Tensor) -> int:
     if t.dtype == torch.float16:
         return FMT_F16
@@ -144,7 +164,10 @@ def cgemm(views: Sequence[torch.Tensor], taps: Sequence[Sequence[Tuple[int, int,
         p.gn_stats = gn_stats.data_ptr()
         p.gn_group = gn_group
         p.frames_per_sample = frames_per_sample
+    e0 = _prof_begin()
     check(lib.vmm_cgemm(C.byref(p), stream_ptr()), "vmm_cgemm")
+    if e0 is not None:
+        _prof_end("cgemm", 2.0 * bf * oh * ow * n * sum(c for tl in taps for (_, _, _, _, c) in tl), e0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -399,7 +422,10 @@ def wgrad(a_views: Sequence[torch.Tensor], b_views: Sequence[torch.Tensor], taps
     p.dw = dw.data_ptr()
     p.s_m, p.s_c, p.s_c2 = s_m, s_c, s_c2
     p.cmod, p.c_valid, p.k_valid = cmod, c_valid, k_valid
+    e0 = _prof_begin()
     check(lib.vmm_wgrad(C.byref(p), stream_ptr()), "vmm_wgrad")
+    if e0 is not None:
+        _prof_end("wgrad", 2.0 * bf * oh * ow * n * sum(tp[4] for tp in taps), e0)
 
 
 def colsum(x2d: torch.Tensor, out: torch.Tensor) -> None:

@@ -1,0 +1,361 @@
+"""Trainer with the reference's constructor / method surface (VDDP:1400-1919) on the B200 kernels.
+
+What is kept verbatim in meaning: the training loop bookkeeping (step counting, EMA every `update_ema_every`
+steps with the `step_start_ema` copy phase, checkpoint at the final step only, resume semantics VDDP:1605-1617),
+the checkpoint file layout (`<run>/model/step_<n>/checkpoint.pt` with keys model / optimizer / steps / ema), the
+contiguous split of conditionings over ranks (`cond_to_gpu` VDDP:1506-1532) and the output files of
+`eval_target` (VDDP:1755-1919).  What changes underneath: forward/backward are the `vmm_*` kernels, the
+optimizer + EMA are one fused kernel over a flat parameter arena, gradients are all-reduced once per step over
+NCCL, and the per-step `loss.item()` host sync of VDDP:1635 is replaced by logging every `log_every` steps.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import time
+from pathlib import Path
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch.utils import data
+
+from . import ops
+from .accel import Accelerator, broadcast_object_list
+from .blocks_bwd import get_arena
+from .dataset import Dataset, SyntheticLagrangianDataset, clean_pred, video_tensor_to_gif
+
+
+def cycle(dl):
+    while True:
+        for d in dl:
+            yield d
+
+
+def num_to_groups(num, divisor):
+    groups, rem = divmod(num, divisor)
+    arr = [divisor] * groups
+    if rem > 0:
+        arr.append(rem)
+    return arr
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8) over a GradArena, one kernel launch per step, with the
+    EMA update of VDDP:116-129 folded in.  state_dict() is laid out like torch.optim.Adam's."""
+
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.step_count = 0
+        self.arena = None
+        self.m = self.v = None
+
+    def _ensure(self):
+        if self.arena is None:
+            self.arena = get_arena(self.model)
+            self.m = torch.zeros_like(self.arena.flat_param)
+            self.v = torch.zeros_like(self.arena.flat_param)
+
+    def zero_grad(self, set_to_none: bool = False):
+        self._ensure()
+        self.arena.zero_grad()
+
+    def step(self, ema_flat: Optional[torch.Tensor] = None, ema_mode: int = 0, ema_beta: float = 0.995, grad_scale: float = 1.0):
+        self._ensure()
+        self.step_count += 1
+        ops.adam_ema_step(self.arena.flat_param, self.arena.flat_grad, self.m, self.v, ema_flat, self.lr, self.betas[0], self.betas[1],
+                          self.eps, self.step_count, grad_scale, ema_mode, ema_beta)
+        self.model.repack()
+
+    def state_dict(self):
+        self._ensure()
+        state, o = {}, 0
+        for i, p in enumerate(self.arena.params):
+            k = p.numel()
+            state[i] = dict(step=torch.tensor(float(self.step_count)), exp_avg=self.m[o:o + k].view(p.shape).clone(),
+                            exp_avg_sq=self.v[o:o + k].view(p.shape).clone())
+            o += k
+        group = dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=0, amsgrad=False, params=list(range(len(self.arena.params))))
+        return dict(state=state, param_groups=[group])
+
+    def load_state_dict(self, sd):
+        self._ensure()
+        o = 0
+        for i, p in enumerate(self.arena.params):
+            k = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                self.step_count = int(st["step"])
+            o += k
+        self.lr = sd["param_groups"][0]["lr"]
+
+
+class Trainer(object):
+    def __init__(self, diffusion_model, folder, validation_folder, selected_channels, *, ema_decay=0.995, train_batch_size=4,
+                 test_batch_size=2, train_lr=1.e-4, train_num_steps=100000, step_start_ema=2000, update_ema_every=10,
+                 save_and_sample_every=1000, results_folder='./', max_grad_norm=None, log=True, null_cond_prob=0., per_frame_cond=False,
+                 reference_frame='eulerian', run_name=None, accelerator=None, wandb_username=None, log_every=50):
+        super().__init__()
+        self.accelerator = accelerator if accelerator is not None else Accelerator()
+        if log:
+            self.accelerator.init_trackers(project_name='metamaterial_diffusion',
+                                           init_kwargs={'wandb': {'name': run_name, 'entity': wandb_username}})
+            self.log_fn = self.accelerator.log
+        else:
+            self.log_fn = lambda *a, **k: None
+        self.log_every = log_every
+        self.results_folder = Path(results_folder)
+        self.results_folder.mkdir(exist_ok=True, parents=True)
+        self.step = 0
+        self.model = self.accelerator.prepare(diffusion_model)
+        self.device = self.accelerator.device
+        self.ema_decay = ema_decay
+        self.ema_model = copy.deepcopy(self.model)
+        self.ema_model.denoise_fn._vmm_arena = None
+        self.update_ema_every = update_ema_every
+        self.step_start_ema = step_start_ema
+        self.save_and_sample_every = save_and_sample_every
+        self.batch_size = train_batch_size
+        self.test_batch_size = max(test_batch_size // 2, 1)      # VDDP:1460
+        self.train_num_steps = train_num_steps
+        image_size = diffusion_model.image_size
+        num_frames = diffusion_model.num_frames
+        self.num_frames = num_frames
+        self.selected_channels = selected_channels
+        self.per_frame_cond = per_frame_cond
+        self.reference_frame = reference_frame
+        if folder is not None and os.path.isdir(str(folder)):
+            self.ds = Dataset(folder, image_size, labels_scaling=None, selected_channels=selected_channels, num_frames=num_frames,
+                              per_frame_cond=per_frame_cond, reference_frame=reference_frame)
+        else:
+            self.ds = SyntheticLagrangianDataset(1024, image_size, len(selected_channels), num_frames)
+        self.dl = cycle(self.accelerator.prepare(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=True, pin_memory=True)))
+        self.accelerator.print(f'found {len(self.ds)} videos in {folder}')
+        assert len(self.ds) > 0, 'could not find any gif files in folder'
+        if validation_folder is not None and os.path.isdir(str(validation_folder)):
+            self.ds_test = Dataset(validation_folder, image_size, labels_scaling=self.ds.labels_scaling, selected_channels=selected_channels,
+                                   num_frames=num_frames, per_frame_cond=per_frame_cond, reference_frame=reference_frame)
+        else:
+            self.ds_test = SyntheticLagrangianDataset(8, image_size, len(selected_channels), num_frames, seed=1)
+        self.dl_test = self.accelerator.prepare(data.DataLoader(self.ds_test, batch_size=self.test_batch_size, shuffle=False, pin_memory=True))
+        self.opt = FusedAdam(self.model.denoise_fn, lr=train_lr)
+        self.max_grad_norm = max_grad_norm
+        self.null_cond_prob = null_cond_prob
+        self.reset_parameters()
+        self.num_processes = self.accelerator.num_processes
+        self.folder = folder
+
+    # ------------------------------------------------------------------ EMA
+    def reset_parameters(self):
+        self.ema_model.load_state_dict(self.model.state_dict())
+
+    def _ema_flat(self) -> torch.Tensor:
+        return get_arena(self.ema_model.denoise_fn).flat_param
+
+    def step_ema(self):
+        """Kept for API parity; train() fuses the EMA into the optimizer kernel."""
+        arena, ema = get_arena(self.model.denoise_fn), self._ema_flat()
+        if self.step < self.step_start_ema:
+            ema.copy_(arena.flat_param)
+        else:
+            ema.mul_(self.ema_decay).add_(arena.flat_param, alpha=1 - self.ema_decay)
+        self.ema_model.denoise_fn.repack()
+
+    # ------------------------------------------------------------------ conditioning fan-out (VDDP:1506-1532)
+    def cond_to_gpu(self, cond):
+        idx, nproc = self.accelerator.process_index, self.accelerator.num_processes
+        per = len(cond) // nproc
+        start = idx * per
+        end = (idx + 1) * per if idx != nproc - 1 else cond.shape[0]
+        local = cond[start:end, :]
+        out, s = [], 0
+        for bs in num_to_groups(local.shape[0], self.test_batch_size):
+            out.append(local[s:s + bs, :])
+            s += bs
+        return out
+
+    # ------------------------------------------------------------------ checkpoints (VDDP:1534-1592)
+    def save(self, step=None):
+        step = self.step if step is None else step
+        save_dir = str(self.results_folder) + '/model/step_' + str(step)
+        if self.accelerator.is_main_process:
+            os.makedirs(save_dir, exist_ok=True)
+        self.accelerator.wait_for_everyone()
+        if self.accelerator.is_main_process:      # the reference lets every rank write the same file
+            obj = dict(model=self.model.state_dict(), optimizer=self.opt.state_dict(), steps=self.step, ema=self.ema_model.state_dict())
+            with open(save_dir + '/checkpoint.pt', 'wb') as f:
+                torch.save(obj, f)
+        self.accelerator.print(f'checkpoint saved to {save_dir}/checkpoint.pt')
+
+    def load(self, strict=True):
+        path = str(self.results_folder) + '/model/step_' + str(self.step) + '/checkpoint.pt'
+        if not os.path.isfile(path):
+            raise FileNotFoundError(f'trainer checkpoint not found at {str(path)}. Please check path or run load_model_step = None')
+        with open(path, 'rb') as f:
+            obj = torch.load(f, map_location='cpu')
+        strip = lambda sd: {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in sd.items()}   # DDP-saved checkpoints
+        try:
+            self.model.load_state_dict(strip(obj['model']), strict=strict)
+        except RuntimeError:
+            print("Failed loading state dict.")
+        try:
+            self.opt.load_state_dict(obj['optimizer'])
+        except Exception:
+            self.accelerator.print('resuming with new optimizer')
+        try:
+            self.ema_model.load_state_dict(strip(obj['ema']), strict=strict)
+        except RuntimeError:
+            print("Failed loading state dict.")
+        self.model.denoise_fn.repack()
+        self.ema_model.denoise_fn.repack()
+        self.accelerator.print(f'checkpoint loaded from {path}')
+        return obj
+
+    # ------------------------------------------------------------------ training (VDDP:1594-1672)
+    def train_step(self, x, cond):
+        """One optimisation step on a device batch: forward, backward, gradient all-reduce, fused Adam (+EMA)."""
+        self.opt.zero_grad()
+        loss = self.model(x=x, cond=cond, null_cond_prob=self.null_cond_prob)
+        self.accelerator.backward(loss)
+        if self.max_grad_norm is not None:
+            self.accelerator.clip_grad_norm_(get_arena(self.model.denoise_fn).params, self.max_grad_norm)
+        ema_mode = 0
+        if self.step % self.update_ema_every == 0:
+            ema_mode = 1 if self.step < self.step_start_ema else 2
+        self.opt.step(ema_flat=self._ema_flat() if ema_mode else None, ema_mode=ema_mode, ema_beta=self.ema_decay)
+        if ema_mode:
+            self.ema_model.denoise_fn.repack()
+        return loss
+
+    def train(self, prob_focus_present=0., focus_present_mask=None, load_model_step=None, num_samples=1, num_preds=1):
+        assert callable(self.log_fn)
+        if load_model_step is not None:
+            self.step = load_model_step
+            self.load()
+        start_time = time.time()
+        while self.step <= self.train_num_steps:
+            if load_model_step is not None:
+                if load_model_step >= self.train_num_steps:
+                    break
+                self.step += 1
+            x, cond = next(self.dl)
+            loss = self.train_step(x, cond)
+            if self.step % self.log_every == 0:
+                self.log_fn({'training loss': loss.item()}, step=self.step)
+            if 0 < self.step and self.step % self.save_and_sample_every == 0:
+                self.accelerator.wait_for_everyone()
+                steps = self.accelerator.gather(torch.tensor(self.step).to(self.accelerator.device))
+                if steps.numel() > 1:
+                    assert torch.all(steps == steps[0])
+                self.accelerator.print(f'current step: {self.step}, total time elapsed: {time.strftime("%H:%M:%S", time.gmtime(time.time() - start_time))}')
+                self.eval_network(prob_focus_present, focus_present_mask, num_samples=num_samples, num_preds=num_preds)
+            if self.step != self.train_num_steps:
+                self.step += 1
+            else:
+                self.accelerator.wait_for_everyone()
+                self.save(step=self.step)
+                break
+        self.accelerator.print('training completed')
+        self.accelerator.end_training()
+
+    # ------------------------------------------------------------------ evaluation (VDDP:1674-1919)
+    def _sample_and_gather(self, cond_full, guidance_scale, num_samples, mode):
+        cond_full = broadcast_object_list([cond_full])[0].to(self.device)
+        chunks = self.cond_to_gpu(cond_full)
+        ema_model = self.accelerator.unwrap_model(self.ema_model)
+        vids = [ema_model.sample(cond=c, guidance_scale=guidance_scale) for c in chunks if c.shape[0] > 0]
+        self.accelerator.wait_for_everyone()
+        vids = torch.cat(vids, dim=0) if vids else torch.zeros(0, ema_model.channels, self.num_frames, ema_model.image_size, ema_model.image_size,
+                                                               device=self.device)
+        padded = self.accelerator.pad_across_processes(vids, dim=0)
+        max_length = padded.shape[0]
+        gathered = self.accelerator.gather(padded)
+        lengths = self.accelerator.gather(torch.tensor(vids.shape[0]).to(vids.device))
+        if self.accelerator.is_main_process:
+            self.save_preds(gathered, lengths, max_length, num_samples=num_samples, mode=mode)
+        return gathered
+
+    def eval_network(self, prob_focus_present, focus_present_mask, guidance_scale=5., num_samples=1, num_preds=1):
+        mode = 'training'
+        if self.accelerator.is_main_process:
+            os.makedirs('./' + str(self.results_folder) + '/' + mode + '/step_' + str(self.step) + '/gifs', exist_ok=True)
+        losses, conds = [], []
+        with torch.no_grad():
+            for x, cond in self.dl_test:
+                loss = self.model(x=x, cond=cond, null_cond_prob=self.null_cond_prob)
+                losses.append(self.accelerator.gather_for_metrics(loss.detach()).mean().item())
+                conds.append(cond.clone())
+        cond_full = None
+        if self.accelerator.is_main_process:
+            self.log_fn({'validation loss': float(np.mean(losses))}, step=self.step)
+            if num_samples > 0:
+                cond_full = torch.cat(conds, dim=0)[:num_samples, :].repeat_interleave(num_preds, dim=0)
+        self.accelerator.wait_for_everyone()
+        if num_samples > 0:
+            self._sample_and_gather(cond_full, guidance_scale, num_samples, mode)
+
+    def eval_target(self, target_labels_dir, guidance_scale=5., num_preds=1):
+        self.accelerator.wait_for_everyone()
+        mode = 'eval_target_w_' + str(guidance_scale)
+        cond_full, num_samples = None, 0
+        if self.accelerator.is_main_process:
+            eval_idx = 0
+            while os.path.exists('./' + str(self.results_folder) + '/' + mode + '_' + str(eval_idx) + '/step_' + str(self.step)):
+                eval_idx += 1
+            mode = mode + '_' + str(eval_idx)
+            os.makedirs('./' + str(self.results_folder) + '/' + mode + '/step_' + str(self.step) + '/gifs', exist_ok=True)
+            target = np.genfromtxt(target_labels_dir, delimiter=',')
+            if target.ndim == 1:
+                target = target[np.newaxis, :]
+            if self.per_frame_cond and self.num_frames != target.shape[1]:
+                strain = 0.2
+                given = np.linspace(0., strain, num=target.shape[1])
+                ev = np.linspace(0., strain, num=self.num_frames)
+                ev[0] = 0.01 * strain
+                target = np.array([np.interp(ev, given, target[i, :]) for i in range(target.shape[0])])
+            elif not self.per_frame_cond:
+                target = target[:, 1:]
+            cond = self.ds.labels_scaling.normalize(torch.tensor(target).float())
+            num_samples = len(cond)
+            cond_full = cond.repeat_interleave(num_preds, dim=0)
+        mode = broadcast_object_list([mode])[0]
+        num_samples = broadcast_object_list([num_samples])[0]
+        self.accelerator.wait_for_everyone()
+        return self._sample_and_gather(cond_full, guidance_scale, num_samples, mode)
+
+    def remove_padding(self, gathered, original_lengths, max_length):
+        if original_lengths.dim() == 0:
+            original_lengths = original_lengths.unsqueeze(0)
+        out, s = [], 0
+        for n in original_lengths:
+            out.append(gathered[s:s + int(n)])
+            s += max_length
+        return torch.cat(out, dim=0)
+
+    def save_preds(self, gathered, original_lengths, max_length, num_samples, mode='training'):
+        vids = self.remove_padding(gathered, original_lengths, max_length)
+        save_dir = './' + str(self.results_folder) + '/' + mode + '/step_' + str(self.step) + '/'
+        os.makedirs(save_dir + 'gifs', exist_ok=True)
+        padded = F.pad(vids, (2, 2, 2, 2))
+        n, c, f, h, w = padded.shape
+        i = max(num_samples, 1)
+        j = n // i
+        one = padded[: i * j].reshape(i, j, c, f, h, w).permute(2, 3, 0, 4, 1, 5).reshape(c, f, i * h, j * w)     # '(i j) c f h w -> c f (i h) (j w)'
+        for k, ch in enumerate(self.selected_channels):
+            video_tensor_to_gif(one[None, k].float().cpu(), save_dir + 'gifs/prediction_channel_' + str(ch) + '.gif')
+        pixels = vids.shape[-1]
+        if self.reference_frame == 'lagrangian' and self.num_frames != 1:
+            red = vids[:, :, :, :pixels // 2, :pixels // 2].detach().clone().flip(-2)
+            zero_u2 = self.ds.zero_u_2.to(red.device)
+            close = torch.isclose(red[:, 1], zero_u2, atol=0.02)           # (n, f, h, w)
+            topologies = torch.logical_not(close.all(dim=1)).float()
+        else:
+            red = vids[:, :, :, pixels // 2:, :pixels // 2].detach().clone()
+            topologies = red[:, 0, 0, :, :]
+        geom = topologies.permute(0, 2, 1).cpu().numpy()
+        np.savetxt(save_dir + 'geometries.csv', clean_pred(geom, geom.shape[1]), delimiter=',', comments='')
+        self.accelerator.print(f'generated samples saved to {save_dir}')
