@@ -185,6 +185,8 @@ int vmm_abs_quantile(const float* v, int B, long long n, long long k, float frac
 int vmm_posterior_step(const float* x0, const float* x, const float* noise, const float* s, const float* c1, const float* c2,
                        const float* sig, float* out, int B, long long per, void* stream);
 int vmm_axpby(const float* a, const float* b, float ca, float cb, float cc, float* out, long long n, void* stream);
+/* dst[i] = idx[i] < 0 ? 0 : (16-bit) src[idx[i]]: rebuilds every packed GEMM operand from the fp32 parameter arena. */
+int vmm_gather_cast(const float* src, const int* idx, void* dst, long long n, int fmt, void* stream);
 int vmm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long long n, float lr, float beta1, float beta2,
                       float eps, int step, float grad_scale, int ema_mode, float ema_beta, void* stream);
 

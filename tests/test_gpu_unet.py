@@ -151,3 +151,20 @@ def test_small_training_loss_and_gradients(gold_small, dtype, scale):
         errs[k] = float((got - want).norm() / want.norm().clamp_min(1e-30))
     print("grad sample rel-L2:", dtype, {k: round(v, 4) for k, v in errs.items()})
     assert max(errs.values()) < (0.05 if dtype == torch.float16 else 0.2), errs
+
+
+def test_gather_repack_equals_slicing_pack(gold_small):
+    """After a training step the packed GEMM operands come from the one-launch gather; they must equal the reference
+    slicing pack of the updated parameters bit for bit."""
+    from videometamaterials_b200 import blocks
+    from videometamaterials_b200.blocks_bwd import get_arena
+    g = gold_small
+    model, gd, _ = build(16, (1, 2), g["T"], g["size"], g["T"], torch.bfloat16, g["seed"])
+    get_arena(model)
+    model.repack()
+    assert getattr(model, "_pack_plan", None) is not None
+    want = blocks.pack_all(model, torch.bfloat16)
+    got = model.packed()
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k

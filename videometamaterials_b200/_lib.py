@@ -103,6 +103,7 @@ _SIGNATURES = {
     "vmm_abs_quantile": [_P, _I, _L, _L, _F, _F, _P, _P],
     "vmm_posterior_step": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _P],
     "vmm_axpby": [_P, _P, _F, _F, _F, _P, _L, _P],
+    "vmm_gather_cast": [_P, _P, _P, _L, _I, _P],
     "vmm_adam_ema_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _I, _F, _P],
 }
 _RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t}

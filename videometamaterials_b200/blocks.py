@@ -73,9 +73,10 @@ def resnet_splits(model) -> Dict[str, List[int]]:
     return sp
 
 
-def pack_all(model, dtype) -> Dict[str, Tensor]:
-    """fp32 master parameters -> 16-bit K-major GEMM operands (forward and data-gradient forms)."""
-    sd = dict(model.named_parameters())
+def pack_all(model, dtype, sd=None) -> Dict[str, Tensor]:
+    """fp32 master parameters -> K-major GEMM operands (forward and data-gradient forms).  `sd` overrides the
+    parameter values (pack_plan() runs this once on tensors holding their own arena indices)."""
+    sd = dict(model.named_parameters()) if sd is None else sd
     P: Dict[str, Tensor] = {}
     sp = resnet_splits(model)
     for pre, splits in sp.items():
@@ -117,6 +118,33 @@ def pack_all(model, dtype) -> Dict[str, Tensor]:
     P["final.wd"] = ops.pack_linear(torch.cat((wf.t(), wf.new_zeros(wf.shape[1], 8 - wf.shape[0])), dim=1), dtype)
     del wfd
     return P
+
+
+def pack_plan(model, arena):
+    """The packing as ONE gather: run pack_all on tensors that hold (their own arena index + 1) and read the layout
+    back.  Returns (int32 gather index over the arena, -1 = structural zero; {name: (offset, shape)})."""
+    sd, o = {}, 0
+    index_of = {}
+    for p in arena.params:
+        k = p.numel()
+        index_of[id(p)] = (o, k)
+        o += k
+    for name, p in model.named_parameters():
+        if id(p) in index_of:
+            o0, k = index_of[id(p)]
+            sd[name] = (torch.arange(o0 + 1, o0 + k + 1, dtype=torch.float64, device=p.device)).view(p.shape)
+        else:
+            sd[name] = torch.zeros(p.shape, dtype=torch.float64, device=p.device)
+    packed = pack_all(model, torch.float64, sd=sd)
+    layout, chunks, off = {}, [], 0
+    for name, t in packed.items():
+        n = t.numel()
+        assert n % 8 == 0
+        layout[name] = (off, tuple(t.shape))
+        chunks.append(t.reshape(-1))
+        off += n
+    idx = (torch.cat(chunks).round().to(torch.int64) - 1).to(torch.int32)
+    return idx, layout
 
 
 # ------------------------------------------------------------------------------------------------

@@ -330,3 +330,37 @@ extern "C" int vmm_adam_ema_step(float* p, const float* g, float* m, float* v, f
   count_launch();
   return check_launch("vmm_adam_ema_step");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Weight repack: every 16-bit GEMM operand of the network (forward and data-gradient forms, ~2x the parameter
+// count) is a fixed gather of the flat fp32 parameter arena.  dst[i] = idx[i] < 0 ? 0 : cast(src[idx[i]]).
+// One launch per optimisation step instead of ~4000 slicing kernels.
+// ------------------------------------------------------------------------------------------------
+namespace vmm {
+__global__ void gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ idx, uint16_t* __restrict__ dst, long long n,
+                                   int fmt) {
+  const long long nvec = n / 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(idx) + 2 * i);
+    const int4 b = __ldg(reinterpret_cast<const int4*>(idx) + 2 * i + 1);
+    const int id[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = id[j] < 0 ? 0.f : __ldg(src + id[j]);
+    uint4 q;
+    q.x = pack2_h16(v[0], v[1], fmt);
+    q.y = pack2_h16(v[2], v[3], fmt);
+    q.z = pack2_h16(v[4], v[5], fmt);
+    q.w = pack2_h16(v[6], v[7], fmt);
+    reinterpret_cast<uint4*>(dst)[i] = q;
+  }
+}
+}  // namespace vmm
+
+extern "C" int vmm_gather_cast(const float* src, const int* idx, void* dst, long long n, int fmt, void* stream) {
+  if (!src || !idx || !dst || (n % 8) != 0) return vmm::set_error(VMM_ERR_ARG, "vmm_gather_cast: bad arguments (n must be a multiple of 8)");
+  vmm::gather_cast_kernel<<<vmm::grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, idx, static_cast<uint16_t*>(dst), n, fmt);
+  vmm::count_launch();
+  return vmm::check_launch("vmm_gather_cast");
+}

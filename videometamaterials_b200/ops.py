@@ -507,3 +507,8 @@ def lattn_bwd(qkv, ekv, T, dout, ctx, kstat, dctx, dqkv, dekv, BF, frames, HW, h
 def sattn_bwd(qkv, ekv, aout, dout, lse, dqkv, dekv, BF, HW, heads):
     check(lib.vmm_sattn_bwd(_p(qkv), _p(ekv), _p(aout), _p(dout), _p(lse), _p(dqkv), _p(dekv), fmt_of(qkv), BF, HW, heads, 32 ** -0.5,
                             stream_ptr()), "vmm_sattn_bwd")
+
+
+def gather_cast(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> None:
+    assert src.dtype == torch.float32 and idx.dtype == torch.int32 and idx.numel() == dst.numel()
+    check(lib.vmm_gather_cast(_p(src), _p(idx), _p(dst), dst.numel(), fmt_of(dst), stream_ptr()), "vmm_gather_cast")

@@ -209,9 +209,26 @@ class Unet3D(nn.Module):
             self._packed = None
 
     def repack(self) -> None:
-        """Rebuild every packed weight (call after an optimizer step or a load_state_dict)."""
+        """Rebuild every packed weight (call after an optimizer step or a load_state_dict).  With a parameter
+        arena (training) this is ONE gather+cast launch over the arena; otherwise the torch slicing path."""
         with torch.no_grad():
-            self._packed = blocks.pack_all(self, self.compute_dtype)
+            arena = getattr(self, "_vmm_arena", None)
+            dev = next(self.parameters()).device
+            if arena is not None and arena.flat_param.device == dev and dev.type == "cuda":
+                plan = getattr(self, "_pack_plan", None)
+                if plan is None or plan[0].device != dev or plan[3] is not arena:
+                    idx, layout = blocks.pack_plan(self, arena)
+                    plan = (idx, layout, {}, arena)
+                    self._pack_plan = plan
+                idx, layout, bufs, _ = plan
+                buf = bufs.get(self.compute_dtype)
+                if buf is None:
+                    buf = torch.empty(idx.numel(), dtype=self.compute_dtype, device=dev)
+                    bufs[self.compute_dtype] = buf
+                ops.gather_cast(arena.flat_param, idx, buf)
+                self._packed = {k: buf[o:o + int(torch.Size(shp).numel())].view(shp) for k, (o, shp) in layout.items()}
+            else:
+                self._packed = blocks.pack_all(self, self.compute_dtype)
             self._packed_key = self._param_fingerprint()
 
     def _param_fingerprint(self):
