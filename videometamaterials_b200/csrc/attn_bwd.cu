@@ -29,277 +29,6 @@ __device__ __forceinline__ void bst8f(uint16_t* p, int fmt, const float* v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// temporal attention backward.  grid = (ctas_per_sample, B); each CTA walks pixel groups of PX pixels.
-// phase 1: thread = (pixel, head, query i)  -> dq, and P / dS rows into shared memory
-// phase 2: thread = (pixel, head, key j)    -> dk, dv of the frame keys; cond-key gradients kept in registers
-// ------------------------------------------------------------------------------------------------
-template <int NF>
-__global__ void __launch_bounds__(192, 1) tattn_bwd_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv,
-                                                           const float* __restrict__ bias, const float* __restrict__ rot,
-                                                           const uint16_t* __restrict__ dout, uint16_t* __restrict__ dqkv,
-                                                           float* __restrict__ dekv, float* __restrict__ dbias, int fmt, int HW,
-                                                           int heads, float scale, int PX) {
-  extern __shared__ float sm[];
-  const int HD = heads * BDH;
-  const int HS = heads * BDHP;
-  const int NK2 = 2 * NF;
-  float* Ks = sm;                              // [PX][NF][HS]  rotated keys
-  float* Vs = Ks + PX * NF * HS;
-  float* Qs = Vs + PX * NF * HS;               // rotated, scaled queries
-  float* Ds = Qs + PX * NF * HS;               // dO
-  float* Ps = Ds + PX * NF * HS;               // [PX][heads][NF][2NF]
-  float* Ss = Ps + PX * heads * NF * NK2;      // dS
-  float* EK = Ss + PX * heads * NF * NK2;      // [NF][HS]
-  float* EV = EK + NF * HS;
-  float* RT = EV + NF * HS;                    // [NF][16][2]
-  float* BS = RT + NF * 32;                    // [heads][NF][NF]
-  float* GA = BS + heads * NF * NF;            // [64][nth]  cond-key gradients of (head, token) = this thread's (th, ti), summed over pixels
-  float* GB = GA + 64 * blockDim.x;            // [NF][nth]  bias gradient row (th, ti, :)
-  const int b = blockIdx.y;
-  const int tid = threadIdx.x, nth = blockDim.x;
-  const bool cond = ekv != nullptr;
-  const int NK = cond ? NK2 : NF;
-
-  for (int i = tid; i < NF * 32; i += nth) RT[i] = rot[i];
-  for (int i = tid; i < heads * NF * NF; i += nth) BS[i] = bias[i];
-  if (cond) {
-    for (int i = tid; i < NF * HD; i += nth) {
-      const int j = i / HD, c = i % HD;
-      EK[j * HS + (c / BDH) * BDHP + (c % BDH)] = ekv[(static_cast<long long>(b) * NF + j) * 2 * HD + c];
-      EV[j * HS + (c / BDH) * BDHP + (c % BDH)] = ekv[(static_cast<long long>(b) * NF + j) * 2 * HD + HD + c];
-    }
-  }
-  const int ti = tid % NF;                      // query index (phase 1) / key index (phase 2)
-  const int th = (tid / NF) % heads;
-  const int tp = tid / (NF * heads);
-  const bool tlive = tp < PX;
-  for (int k = 0; k < 64; ++k) GA[k * nth + tid] = 0.f;     // thread-private columns: no synchronisation needed
-  for (int k = 0; k < NF; ++k) GB[k * nth + tid] = 0.f;
-  __syncthreads();
-
-  const int groups = (HW + PX - 1) / PX;
-  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-    const int p0 = grp * PX;
-    // ---- stage K (rotated) and V
-    const int vec_per_row = HD / 8;
-    for (int i = tid; i < PX * NF * vec_per_row; i += nth) {
-      const int c8 = i % vec_per_row;
-      const int f = (i / vec_per_row) % NF;
-      const int p = i / (vec_per_row * NF);
-      float kv[8], vv[8];
-      if (p0 + p < HW) {
-        const uint16_t* row = qkv + ((static_cast<long long>(b) * NF + f) * HW + p0 + p) * 3 * HD;
-        bld8f(row + HD + c8 * 8, fmt, kv);
-        bld8f(row + 2 * HD + c8 * 8, fmt, vv);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) kv[j] = vv[j] = 0.f;
-      }
-      const int c = c8 * 8;
-      const int h = c / BDH, d0 = c % BDH;
-      float* kd = Ks + (p * NF + f) * HS + h * BDHP + d0;
-      float* vd = Vs + (p * NF + f) * HS + h * BDHP + d0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float cs = RT[(f * 16 + d0 / 2 + j) * 2], sn = RT[(f * 16 + d0 / 2 + j) * 2 + 1];
-        kd[2 * j] = kv[2 * j] * cs - kv[2 * j + 1] * sn;
-        kd[2 * j + 1] = kv[2 * j + 1] * cs + kv[2 * j] * sn;
-        vd[2 * j] = vv[2 * j];
-        vd[2 * j + 1] = vv[2 * j + 1];
-      }
-    }
-    __syncthreads();
-    const bool live = tlive && (p0 + tp < HW);
-    // ---- phase 1: query ti
-    if (live) {
-      const int i = ti, h = th, p = tp;
-      float q[BDH], dO[BDH];
-      const long long rowi = (static_cast<long long>(b) * NF + i) * HW + p0 + p;
-      {
-        const uint16_t* row = qkv + rowi * 3 * HD + h * BDH;
-        const uint16_t* drow = dout + rowi * HD + h * BDH;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          bld8f(row + k * 8, fmt, q + k * 8);
-          bld8f(drow + k * 8, fmt, dO + k * 8);
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float cs = RT[(i * 16 + k) * 2], sn = RT[(i * 16 + k) * 2 + 1];
-          const float a = q[2 * k] * scale, c = q[2 * k + 1] * scale;
-          q[2 * k] = a * cs - c * sn;
-          q[2 * k + 1] = c * cs + a * sn;
-        }
-        float* qd = Qs + (p * NF + i) * HS + h * BDHP;
-        float* dd = Ds + (p * NF + i) * HS + h * BDHP;
-#pragma unroll
-        for (int k = 0; k < BDH; ++k) {
-          qd[k] = q[k];
-          dd[k] = dO[k];
-        }
-      }
-      // scores and dP rows live in shared memory (prow / srow), not in registers: the fully unrolled version
-      // spilled ~3 KB per thread
-      float* prow = Ps + ((p * heads + h) * NF + i) * NK2;
-      float* srow = Ss + ((p * heads + h) * NF + i) * NK2;
-      float mx = -1e30f;
-#pragma unroll 1
-      for (int j = 0; j < NK; ++j) {
-        const int jf = cond ? j - NF : j;
-        const float* kr = (cond && j < NF) ? (EK + j * HS + h * BDHP) : (Ks + (p * NF + jf) * HS + h * BDHP);
-        const float* vr = (cond && j < NF) ? (EV + j * HS + h * BDHP) : (Vs + (p * NF + jf) * HS + h * BDHP);
-        float acc = 0.f, accv = 0.f;
-#pragma unroll
-        for (int k = 0; k < BDH; k += 4) {
-          const float4 kk = *reinterpret_cast<const float4*>(kr + k);
-          const float4 vv = *reinterpret_cast<const float4*>(vr + k);
-          acc += q[k] * kk.x + q[k + 1] * kk.y + q[k + 2] * kk.z + q[k + 3] * kk.w;
-          accv += dO[k] * vv.x + dO[k + 1] * vv.y + dO[k + 2] * vv.z + dO[k + 3] * vv.w;
-        }
-        const int jb = (j < NF) ? j : j - NF;
-        acc += BS[(h * NF + i) * NF + jb];
-        prow[j] = acc;
-        srow[j] = accv;
-        mx = fmaxf(mx, acc);
-      }
-      float sum = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < NK; ++j) {
-        const float e = __expf(prow[j] - mx);
-        prow[j] = e;
-        sum += e;
-      }
-      const float inv = 1.f / sum;
-      float Dsum = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < NK; ++j) {
-        const float pj = prow[j] * inv;
-        prow[j] = pj;
-        Dsum += pj * srow[j];
-      }
-      float dq[BDH];
-#pragma unroll
-      for (int k = 0; k < BDH; ++k) dq[k] = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < NK; ++j) {
-        const float ds = prow[j] * (srow[j] - Dsum);
-        srow[j] = ds;
-        const int jb = (j < NF) ? j : j - NF;
-        GB[jb * nth + tid] += ds;
-        const int jf = cond ? j - NF : j;
-        const float* kr = (cond && j < NF) ? (EK + j * HS + h * BDHP) : (Ks + (p * NF + jf) * HS + h * BDHP);
-#pragma unroll
-        for (int k = 0; k < BDH; k += 4) {
-          const float4 kk = *reinterpret_cast<const float4*>(kr + k);
-          dq[k] += ds * kk.x;
-          dq[k + 1] += ds * kk.y;
-          dq[k + 2] += ds * kk.z;
-          dq[k + 3] += ds * kk.w;
-        }
-      }
-      // un-rotate and scale: q_rot = R(theta_i) (scale q)  ->  dq = scale R^T dq_rot
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float cs = RT[(i * 16 + k) * 2], sn = RT[(i * 16 + k) * 2 + 1];
-        const float a = dq[2 * k], c = dq[2 * k + 1];
-        dq[2 * k] = (a * cs + c * sn) * scale;
-        dq[2 * k + 1] = (c * cs - a * sn) * scale;
-      }
-      uint16_t* orow = dqkv + rowi * 3 * HD + h * BDH;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) bst8f(orow + k * 8, fmt, dq + k * 8);
-    }
-    __syncthreads();
-    // ---- phase 2: key ti (frame key, and cond key ti when conditioned)
-    if (live) {
-      const int j = ti, h = th, p = tp;
-      float dk[BDH], dv[BDH];
-#pragma unroll
-      for (int k = 0; k < BDH; ++k) dk[k] = dv[k] = 0.f;
-      const int col = cond ? NF + j : j;
-#pragma unroll 1
-      for (int i = 0; i < NF; ++i) {
-        const float ds = Ss[((p * heads + h) * NF + i) * NK2 + col];
-        const float pr = Ps[((p * heads + h) * NF + i) * NK2 + col];
-        const float* qr = Qs + (p * NF + i) * HS + h * BDHP;
-        const float* dr = Ds + (p * NF + i) * HS + h * BDHP;
-#pragma unroll
-        for (int k = 0; k < BDH; k += 4) {
-          const float4 qq = *reinterpret_cast<const float4*>(qr + k);
-          const float4 dd = *reinterpret_cast<const float4*>(dr + k);
-          dk[k] += ds * qq.x;
-          dk[k + 1] += ds * qq.y;
-          dk[k + 2] += ds * qq.z;
-          dk[k + 3] += ds * qq.w;
-          dv[k] += pr * dd.x;
-          dv[k + 1] += pr * dd.y;
-          dv[k + 2] += pr * dd.z;
-          dv[k + 3] += pr * dd.w;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float cs = RT[(j * 16 + k) * 2], sn = RT[(j * 16 + k) * 2 + 1];
-        const float a = dk[2 * k], c = dk[2 * k + 1];
-        dk[2 * k] = a * cs + c * sn;
-        dk[2 * k + 1] = c * cs - a * sn;
-      }
-      const long long rowj = (static_cast<long long>(b) * NF + j) * HW + p0 + p;
-      uint16_t* krow = dqkv + rowj * 3 * HD + HD + h * BDH;
-      uint16_t* vrow = dqkv + rowj * 3 * HD + 2 * HD + h * BDH;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        bst8f(krow + k * 8, fmt, dk + k * 8);
-        bst8f(vrow + k * 8, fmt, dv + k * 8);
-      }
-      if (cond) {
-        float gek[BDH], gev[BDH];
-#pragma unroll
-        for (int k = 0; k < BDH; ++k) gek[k] = gev[k] = 0.f;
-#pragma unroll 1
-        for (int i = 0; i < NF; ++i) {
-          const float ds = Ss[((p * heads + h) * NF + i) * NK2 + j];
-          const float pr = Ps[((p * heads + h) * NF + i) * NK2 + j];
-          const float* qr = Qs + (p * NF + i) * HS + h * BDHP;
-          const float* dr = Ds + (p * NF + i) * HS + h * BDHP;
-#pragma unroll
-          for (int k = 0; k < BDH; k += 4) {
-            const float4 qq = *reinterpret_cast<const float4*>(qr + k);
-            const float4 dd = *reinterpret_cast<const float4*>(dr + k);
-            gek[k] += ds * qq.x;
-            gek[k + 1] += ds * qq.y;
-            gek[k + 2] += ds * qq.z;
-            gek[k + 3] += ds * qq.w;
-            gev[k] += pr * dd.x;
-            gev[k + 1] += pr * dd.y;
-            gev[k + 2] += pr * dd.z;
-            gev[k + 3] += pr * dd.w;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < BDH; ++k) {
-          GA[k * nth + tid] += gek[k];
-          GA[(BDH + k) * nth + tid] += gev[k];
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (tlive) {
-    if (cond && dekv) {
-      float* ge = dekv + (static_cast<long long>(b) * NF + ti) * 2 * HD + th * BDH;
-      for (int k = 0; k < BDH; ++k) {
-        atomicAdd(ge + k, GA[k * nth + tid]);
-        atomicAdd(ge + HD + k, GA[(BDH + k) * nth + tid]);
-      }
-    }
-    if (dbias) {
-      for (int k = 0; k < NF; ++k) atomicAdd(dbias + (th * NF + ti) * NF + k, GB[k * nth + tid]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // linear attention backward
 //  kernel 1: dctx[bf][h][d][e] = sum_n qs[n,d] dout[n,e]   (qs = softmax_d(q) * scale)        one CTA per (h, bf)
 //  kernel 2: per (head, pixel): dq, dk, dv; block 0 also handles the T cond tokens (atomics into dekv)
@@ -648,37 +377,6 @@ __global__ void __launch_bounds__(256) sattn_bwd_kernel(const uint16_t* __restri
 }  // namespace vmm
 
 using namespace vmm;
-
-extern "C" int vmm_tattn_bwd(const void* qkv, const float* ekv, const float* bias, const float* rot, const void* dout, void* dqkv,
-                             float* dekv, float* dbias, int fmt, int B, int frames, int HW, int heads, float scale, void* stream_) {
-  if (!qkv || !bias || !rot || !dout || !dqkv) return set_error(VMM_ERR_ARG, "vmm_tattn_bwd: null pointer");
-  if (frames != 11) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: only 11 frames");
-  if (heads < 1 || heads > 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: heads must be <= 8");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int NF = 11;
-  int PX = 192 / (heads * NF);
-  if (PX < 1) PX = 1;
-  if (PX > 2) PX = 2;
-  const int HS = heads * BDHP;
-  const int nthreads = PX * heads * NF;
-  const size_t smem = (static_cast<size_t>(4) * PX * NF * HS + static_cast<size_t>(2) * PX * heads * NF * 2 * NF + 2 * NF * HS + NF * 32 +
-                       heads * NF * NF + static_cast<size_t>(64 + NF) * nthreads) * sizeof(float);
-  if (smem > 227 * 1024) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: shared memory");
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tattn_bwd_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return set_cuda_error(e, "vmm_tattn_bwd: attr");
-    attr = true;
-  }
-  const int groups = (HW + PX - 1) / PX;
-  int cps = (2 * num_sms() + B - 1) / B;   // CTAs per sample
-  if (cps > groups) cps = groups;
-  tattn_bwd_kernel<11><<<dim3(cps, B), PX * heads * NF, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot,
-                                                                         static_cast<const uint16_t*>(dout), static_cast<uint16_t*>(dqkv),
-                                                                         dekv, dbias, fmt, HW, heads, scale, PX);
-  count_launch();
-  return check_launch("vmm_tattn_bwd");
-}
 
 extern "C" int vmm_lattn_bwd(const void* qkv, const float* ekv, int T, const void* dout, const float* ctx, const float* kstat, float* dctx,
                              void* dqkv, float* dekv, int fmt, int BF, int frames, int HW, int heads, float scale, float vscale,

@@ -1,5 +1,5 @@
-// Attention cores (forward): temporal attention over frames, O(n) linear attention over pixels, and the
-// quadratic spatial attention of the bottleneck.  Projections (to_qkv / to_out) run on vmm_cgemm; these
+// Attention cores (forward): O(n) linear attention over pixels and the quadratic spatial attention of the
+// bottleneck (the temporal attention lives in tattn_mma.cu).  Projections (to_qkv / to_out) run on vmm_cgemm; these
 // kernels take the packed qkv rows [position, 3*heads*32] (q | k | v, each split (head, 32)) and write the
 // attention output rows [position, heads*32].  dim_head is fixed at 32 (model.yaml: unet_attn_dim_head).
 #include "common.cuh"
@@ -27,137 +27,6 @@ __device__ __forceinline__ void st8f(uint16_t* p, int fmt, const float* v) {
   q.z = pack2_h16(v[4], v[5], fmt);
   q.w = pack2_h16(v[6], v[7], fmt);
   *reinterpret_cast<uint4*>(p) = q;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Temporal attention, VDDP:425-535 through EinopsToAndFrom('b c f h w','b (h w) f c') VDDP:615.
-//   sequence = one pixel, tokens = NF frames; keys = [NF rotated cond keys ; NF rotated frame keys]
-//   sim[i, j] = <rot(q_i * scale), key_j> + bias[h, i, j mod NF];   out_i = softmax_j(sim) . values
-// thread = (pixel, head, query frame).  K / V of the CTA's pixels are staged in shared memory as fp32
-// (K already rotated); the cond keys/values of the sample are shared by every pixel.
-// rot: [NF][16][2] (cos, sin of frame * freqs).  ekv: [B][NF][2*HD] fp32 (rotated cond keys | cond values) or NULL.
-// ------------------------------------------------------------------------------------------------
-template <int NF>
-__global__ void __launch_bounds__(384) tattn_fwd_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv,
-                                                        const float* __restrict__ bias, const float* __restrict__ rot,
-                                                        uint16_t* __restrict__ out, int fmt, int HW, int heads, float scale, int PX) {
-  extern __shared__ float sm[];
-  const int HD = heads * DH;
-  const int HS = heads * DHP;                 // padded row of all heads
-  float* Ks = sm;                             // [PX][NF][HS]
-  float* Vs = Ks + PX * NF * HS;              // [PX][NF][HS]
-  float* EK = Vs + PX * NF * HS;              // [NF][HS]
-  float* EV = EK + NF * HS;                   // [NF][HS]
-  float* RT = EV + NF * HS;                   // [NF][16][2]
-  float* BS = RT + NF * 32;                   // [heads][NF][NF]
-  const int b = blockIdx.y;
-  const int p0 = blockIdx.x * PX;
-  const int tid = threadIdx.x, nth = blockDim.x;
-
-  for (int i = tid; i < NF * 32; i += nth) RT[i] = rot[i];
-  for (int i = tid; i < heads * NF * NF; i += nth) BS[i] = bias[i];
-  if (ekv) {
-    for (int i = tid; i < NF * HD; i += nth) {
-      const int j = i / HD, c = i % HD;
-      EK[j * HS + (c / DH) * DHP + (c % DH)] = ekv[(static_cast<long long>(b) * NF + j) * 2 * HD + c];
-      EV[j * HS + (c / DH) * DHP + (c % DH)] = ekv[(static_cast<long long>(b) * NF + j) * 2 * HD + HD + c];
-    }
-  }
-  __syncthreads();   // RT needed for the K rotation below
-  const int vec_per_row = HD / 8;
-  for (int i = tid; i < PX * NF * vec_per_row; i += nth) {
-    const int c8 = i % vec_per_row;
-    const int f = (i / vec_per_row) % NF;
-    const int p = i / (vec_per_row * NF);
-    float kv[8], vv[8];
-    if (p0 + p < HW) {
-      const uint16_t* row = qkv + ((static_cast<long long>(b) * NF + f) * HW + p0 + p) * 3 * HD;
-      ld8f(row + HD + c8 * 8, fmt, kv);
-      ld8f(row + 2 * HD + c8 * 8, fmt, vv);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) kv[j] = vv[j] = 0.f;
-    }
-    const int c = c8 * 8;
-    const int h = c / DH, d0 = c % DH;
-    float* kd = Ks + (p * NF + f) * HS + h * DHP + d0;
-    float* vd = Vs + (p * NF + f) * HS + h * DHP + d0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float cs = RT[(f * 16 + d0 / 2 + j) * 2], sn = RT[(f * 16 + d0 / 2 + j) * 2 + 1];
-      kd[2 * j] = kv[2 * j] * cs - kv[2 * j + 1] * sn;
-      kd[2 * j + 1] = kv[2 * j + 1] * cs + kv[2 * j] * sn;
-      vd[2 * j] = vv[2 * j];
-      vd[2 * j + 1] = vv[2 * j + 1];
-    }
-  }
-  __syncthreads();
-
-  const int i = tid % NF;
-  const int h = (tid / NF) % heads;
-  const int p = tid / (NF * heads);
-  if (p >= PX || p0 + p >= HW) return;
-  float q[DH];
-  {
-    const uint16_t* row = qkv + ((static_cast<long long>(b) * NF + i) * HW + p0 + p) * 3 * HD + h * DH;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ld8f(row + k * 8, fmt, q + k * 8);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float cs = RT[(i * 16 + k) * 2], sn = RT[(i * 16 + k) * 2 + 1];
-      const float a = q[2 * k] * scale, c = q[2 * k + 1] * scale;
-      q[2 * k] = a * cs - c * sn;
-      q[2 * k + 1] = c * cs + a * sn;
-    }
-  }
-  const int NK = ekv ? 2 * NF : NF;
-  float s[2 * NF];
-  float mx = -1e30f;
-#pragma unroll
-  for (int j = 0; j < 2 * NF; ++j) {
-    if (j < NK) {
-      const float* kr = (ekv && j < NF) ? (EK + j * HS + h * DHP) : (Ks + (p * NF + (ekv ? j - NF : j)) * HS + h * DHP);
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < DH; k += 4) {
-        const float4 kk = *reinterpret_cast<const float4*>(kr + k);
-        acc += q[k] * kk.x + q[k + 1] * kk.y + q[k + 2] * kk.z + q[k + 3] * kk.w;
-      }
-      const int jb = (j < NF) ? j : j - NF;
-      acc += BS[(h * NF + i) * NF + jb];
-      s[j] = acc;
-      mx = fmaxf(mx, acc);
-    }
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < 2 * NF; ++j)
-    if (j < NK) {
-      s[j] = __expf(s[j] - mx);
-      sum += s[j];
-    }
-  const float inv = 1.f / sum;
-  float o[DH];
-#pragma unroll
-  for (int k = 0; k < DH; ++k) o[k] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 2 * NF; ++j) {
-    if (j < NK) {
-      const float* vr = (ekv && j < NF) ? (EV + j * HS + h * DHP) : (Vs + (p * NF + (ekv ? j - NF : j)) * HS + h * DHP);
-      const float pj = s[j] * inv;
-#pragma unroll
-      for (int k = 0; k < DH; k += 4) {
-        const float4 vv = *reinterpret_cast<const float4*>(vr + k);
-        o[k] += pj * vv.x;
-        o[k + 1] += pj * vv.y;
-        o[k + 2] += pj * vv.z;
-        o[k + 3] += pj * vv.w;
-      }
-    }
-  }
-  uint16_t* orow = out + ((static_cast<long long>(b) * NF + i) * HW + p0 + p) * HD + h * DH;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) st8f(orow + k * 8, fmt, o + k * 8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -389,30 +258,6 @@ __global__ void __launch_bounds__(256) sattn_fwd_kernel(const uint16_t* __restri
 }  // namespace vmm
 
 using namespace vmm;
-
-extern "C" int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bias, const float* rot, void* out, int fmt, int B,
-                             int frames, int HW, int heads, float scale, void* stream_) {
-  if (!qkv || !bias || !rot || !out) return set_error(VMM_ERR_ARG, "vmm_tattn_fwd: null pointer");
-  if (frames != 11) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: only 11 frames (the reference hard-codes 11 cond tokens, VDDP:603)");
-  if (heads < 1 || heads > 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: heads must be <= 8");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int NF = 11;
-  int PX = 384 / (heads * NF);
-  if (PX > 4) PX = 4;
-  const int HS = heads * DHP;
-  const size_t smem = (static_cast<size_t>(2) * PX * NF * HS + 2 * NF * HS + NF * 32 + heads * NF * NF) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tattn_fwd_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return set_cuda_error(e, "vmm_tattn_fwd: attr");
-    attr = true;
-  }
-  dim3 grid((HW + PX - 1) / PX, B);
-  tattn_fwd_kernel<11><<<grid, PX * heads * NF, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot,
-                                                                static_cast<uint16_t*>(out), fmt, HW, heads, scale, PX);
-  count_launch();
-  return check_launch("vmm_tattn_fwd");
-}
 
 extern "C" int vmm_lattn_fwd(const void* qkv, const float* ekv, int T, void* out, float* ctx, float* kstat, int fmt, int BF,
                              int frames, int HW, int heads, float scale, void* stream_) {

@@ -1,0 +1,630 @@
+// Temporal attention on warp-level tensor cores (mma.sync m16n8k16).  VDDP:425-535 via VDDP:615.
+//
+// One CTA = 8 warps = the 8 heads of one sample for a group of PXB pixels.  The CTA stages the qkv rows of its
+// pixels (11 frames x 768 channels, fully coalesced) in shared memory; warp h then rotates the q / k slices of
+// head h in place (rotary, q also scaled) and runs, per pixel,
+//     S = Q K^T   (16 x 32 keys: [cond 0..10 | pad][frame 0..10 | pad])      8 MMAs
+//     O = P V                                                               8 MMAs
+// with the softmax on the accumulator fragments.  The conditioning keys / values of (sample, head) and the
+// relative position bias are the same for every pixel and live in registers as ready-made B fragments.
+#include "common.cuh"
+#include "mma_sync.cuh"
+
+namespace vmm {
+
+constexpr int TNF = 11;          // frames == cond tokens (VDDP:603)
+constexpr int TPITCH = 776;      // smem row pitch in elements: 768 + 8 keeps ldmatrix rows on distinct banks
+constexpr int TPXB = 4;          // pixels per CTA iteration
+
+template <int FMT>
+__global__ void __launch_bounds__(256) tattn_fwd_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv,
+                                                            const float* __restrict__ bias, const float* __restrict__ rot,
+                                                            uint16_t* __restrict__ out, int HW, int heads, float scale) {
+  extern __shared__ __align__(16) uint16_t tsm[];
+  uint16_t* tile = tsm;                                   // [TPXB][TNF][TPITCH]
+  uint16_t* zrow = tile + TPXB * TNF * TPITCH;            // one row of zeros (frames >= 11)
+  float* RT = reinterpret_cast<float*>(zrow + TPITCH);    // [TNF][16][2]
+  const int HD = heads * 32;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = warp;
+  const bool cond = ekv != nullptr;
+
+  for (int i = tid; i < TPITCH; i += 256) zrow[i] = 0;
+  for (int i = tid; i < TNF * 32; i += 256) RT[i] = rot[i];
+
+  // ---- per-warp constants: cond key / value fragments, bias (+ key mask)
+  uint32_t kc[2][2][2];   // [key tile][k-step][b0b1, b2b3]   B[k = d][n = cond key]
+  uint32_t vc[4][2];      // [d tile][b0b1, b2b3]             B[k = cond key][n = d]
+  float bs[2][2][2];      // [row half (g, g+8)][key tile][col 2t, 2t+1]  (-inf on padded keys)
+  if (h < heads) {
+    if (cond) {
+      const float* eb = ekv + static_cast<long long>(b) * TNF * 2 * HD;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int key = 8 * nt + g;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int d = 16 * ks + 8 * hf + 2 * t;
+            float a0 = 0.f, a1 = 0.f;
+            if (key < TNF) {
+              a0 = eb[key * 2 * HD + h * 32 + d];
+              a1 = eb[key * 2 * HD + h * 32 + d + 1];
+            }
+            kc[nt][ks][hf] = pack2<FMT>(a0, a1);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int d = 8 * nt + g;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int k0 = 2 * t + 8 * hf;
+          const float a0 = (k0 < TNF) ? eb[k0 * 2 * HD + HD + h * 32 + d] : 0.f;
+          const float a1 = (k0 + 1 < TNF) ? eb[(k0 + 1) * 2 * HD + HD + h * 32 + d] : 0.f;
+          vc[nt][hf] = pack2<FMT>(a0, a1);
+        }
+      }
+    }
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const int i = g + 8 * rh;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = 8 * nt + 2 * t + c;
+          bs[rh][nt][c] = (j < TNF) ? ((i < TNF) ? bias[(h * TNF + i) * TNF + j] : 0.f) : -1e30f;
+        }
+    }
+  }
+  __syncthreads();
+
+  const uint32_t tile_s = smem_u32(tile), zrow_s = smem_u32(zrow);
+  const int groups = (HW + TPXB - 1) / TPXB;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int p0 = grp * TPXB;
+    // ---- stage qkv rows: TPXB x 11 rows of 1536 bytes, 16-byte chunks
+    for (int i = tid; i < TPXB * TNF * 96; i += 256) {
+      const int c = i % 96;
+      const int f = (i / 96) % TNF;
+      const int p = i / (96 * TNF);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (p0 + p < HW) v = __ldg(reinterpret_cast<const uint4*>(qkv + ((static_cast<long long>(b) * TNF + f) * HW + p0 + p) * 3 * HD) + c);
+      *reinterpret_cast<uint4*>(tile + (p * TNF + f) * TPITCH + c * 8) = v;
+    }
+    __syncthreads();
+    if (h < heads) {
+      // ---- rotary in place on this head's q (scaled) and k slices
+      for (int i = lane; i < TPXB * TNF * 16; i += 32) {
+        const int k = i & 15;
+        const int f = (i >> 4) % TNF;
+        const int p = i / (16 * TNF);
+        const float cs = RT[(f * 16 + k) * 2], sn = RT[(f * 16 + k) * 2 + 1];
+        uint32_t* qp = reinterpret_cast<uint32_t*>(tile + (p * TNF + f) * TPITCH + h * 32 + 2 * k);
+        uint32_t* kp = reinterpret_cast<uint32_t*>(tile + (p * TNF + f) * TPITCH + HD + h * 32 + 2 * k);
+        float2 q = unpack2<FMT>(*qp), kk = unpack2<FMT>(*kp);
+        q.x *= scale;
+        q.y *= scale;
+        *qp = pack2<FMT>(q.x * cs - q.y * sn, q.y * cs + q.x * sn);
+        *kp = pack2<FMT>(kk.x * cs - kk.y * sn, kk.y * cs + kk.x * sn);
+      }
+      __syncwarp();
+      for (int p = 0; p < TPXB; ++p) {
+        if (p0 + p >= HW) break;
+        const uint32_t pbase = tile_s + static_cast<uint32_t>(p * TNF * TPITCH) * 2;
+        // lane -> row address helpers
+        const int lm = lane >> 3, lr = lane & 7;
+        float S[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) S[nt][c] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t qa[4];
+          {   // A tile: rows = frames 0..15, cols = d 16ks..16ks+15
+            const int row = lr + 8 * (lm & 1);
+            const int col = h * 32 + 16 * ks + 8 * (lm >> 1);
+            const uint32_t addr = (row < TNF) ? pbase + static_cast<uint32_t>(row * TPITCH + col) * 2 : zrow_s + static_cast<uint32_t>(col) * 2;
+            ldsm_x4(qa, addr);
+          }
+          if (cond) {
+            mma16816<FMT>(S[0], qa, kc[0][ks]);
+            mma16816<FMT>(S[1], qa, kc[1][ks]);
+          }
+          uint32_t kb[4];
+          {   // B tiles: keys 0-7 / 8-15, d halves
+            const int row = lr + 8 * (lm >> 1);
+            const int col = HD + h * 32 + 16 * ks + 8 * (lm & 1);
+            const uint32_t addr = (row < TNF) ? pbase + static_cast<uint32_t>(row * TPITCH + col) * 2 : zrow_s + static_cast<uint32_t>(col) * 2;
+            ldsm_x4(kb, addr);
+          }
+          mma16816<FMT>(S[2], qa, kb);
+          mma16816<FMT>(S[3], qa, kb + 2);
+        }
+        // ---- bias, mask, softmax over the 32 key slots (rows g and g+8)
+        float mx[2] = {-1e30f, -1e30f}, sum[2] = {0.f, 0.f};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          if (!cond && nt < 2) continue;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            S[nt][c] += bs[c >> 1][nt & 1][c & 1];
+            mx[c >> 1] = fmaxf(mx[c >> 1], S[nt][c]);
+          }
+        }
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          mx[rh] = fmaxf(mx[rh], __shfl_xor_sync(0xffffffffu, mx[rh], 1));
+          mx[rh] = fmaxf(mx[rh], __shfl_xor_sync(0xffffffffu, mx[rh], 2));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float e = (!cond && nt < 2) ? 0.f : __expf(S[nt][c] - mx[c >> 1]);
+            S[nt][c] = e;
+            sum[c >> 1] += e;
+          }
+        }
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          sum[rh] += __shfl_xor_sync(0xffffffffu, sum[rh], 1);
+          sum[rh] += __shfl_xor_sync(0xffffffffu, sum[rh], 2);
+        }
+        // ---- O = P V
+        float O[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) O[nt][c] = 0.f;
+        if (cond) {
+          uint32_t pa[4] = {pack2<FMT>(S[0][0], S[0][1]), pack2<FMT>(S[0][2], S[0][3]), pack2<FMT>(S[1][0], S[1][1]), pack2<FMT>(S[1][2], S[1][3])};
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma16816<FMT>(O[nt], pa, vc[nt]);
+        }
+        {
+          uint32_t pa[4] = {pack2<FMT>(S[2][0], S[2][1]), pack2<FMT>(S[2][2], S[2][3]), pack2<FMT>(S[3][0], S[3][1]), pack2<FMT>(S[3][2], S[3][3])};
+#pragma unroll
+          for (int dh = 0; dh < 2; ++dh) {
+            uint32_t vb[4];
+            const int row = lr + 8 * (lm & 1);
+            const int col = 2 * HD + h * 32 + 16 * dh + 8 * (lm >> 1);
+            const uint32_t addr = (row < TNF) ? pbase + static_cast<uint32_t>(row * TPITCH + col) * 2 : zrow_s + static_cast<uint32_t>(col) * 2;
+            ldsm_x4_trans(vb, addr);
+            mma16816<FMT>(O[2 * dh], pa, vb);
+            mma16816<FMT>(O[2 * dh + 1], pa, vb + 2);
+          }
+        }
+        // ---- normalise and store rows g (< 8 <= 11) and g + 8 (< 11)
+        const float inv0 = 1.f / sum[0], inv1 = 1.f / sum[1];
+        uint16_t* o0 = out + ((static_cast<long long>(b) * TNF + g) * HW + p0 + p) * HD + h * 32 + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<uint32_t*>(o0 + 8 * nt) = pack2<FMT>(O[nt][0] * inv0, O[nt][1] * inv0);
+        if (g + 8 < TNF) {
+          uint16_t* o1 = out + ((static_cast<long long>(b) * TNF + g + 8) * HW + p0 + p) * HD + h * 32 + 2 * t;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<uint32_t*>(o1 + 8 * nt) = pack2<FMT>(O[nt][2] * inv1, O[nt][3] * inv1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace vmm
+
+using namespace vmm;
+
+extern "C" int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bias, const float* rot, void* out, int fmt, int B,
+                             int frames, int HW, int heads, float scale, void* stream_) {
+  if (!qkv || !bias || !rot || !out) return set_error(VMM_ERR_ARG, "vmm_tattn_fwd: null pointer");
+  if (frames != TNF) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: only 11 frames (the reference hard-codes 11 cond tokens, VDDP:603)");
+  if (heads != 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: heads must be 8 (one warp per head, rows of 3*8*32 channels)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t smem = (static_cast<size_t>(TPXB) * TNF * TPITCH + TPITCH) * sizeof(uint16_t) + TNF * 32 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tattn_fwd_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tattn_fwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, "vmm_tattn_fwd: attr");
+    attr = true;
+  }
+  const int groups = (HW + TPXB - 1) / TPXB;
+  int gx = (3 * num_sms() + B - 1) / B;     // ~3 resident CTAs per SM, each walking several pixel groups
+  if (gx > groups) gx = groups;
+  dim3 grid(gx, B);
+  if (fmt == VMM_FMT_F16)
+    tattn_fwd_mma_kernel<0><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<uint16_t*>(out), HW, heads, scale);
+  else
+    tattn_fwd_mma_kernel<1><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<uint16_t*>(out), HW, heads, scale);
+  count_launch();
+  return check_launch("vmm_tattn_fwd");
+}
+
+// ================================================================================================
+// Backward.  Same CTA shape (8 warps = 8 heads, TPXB pixels per iteration).  Per pixel and head:
+//   pass A (rows = queries): S, P, dP = dO V^T, D = rowsum(P dP), dS = P (dP - D), dQ = dS K      -> dq, log-sum-exp / D
+//   pass B (rows = keys, once for the 16 cond slots, once for the 16 frame slots):
+//            S^T = K Q^T, P^T = exp(S^T + bias^T - lse), dP^T = V dO^T, dS^T = P^T (dP^T - D),
+//            dK = dS^T Q, dV = P^T dO                                                            -> dk, dv | cond grads
+// Gradients of the cond keys / values and of the position bias are summed over the CTA's pixels in accumulator
+// fragments and added atomically once per CTA.  The cond keys / values sit in shared memory as a 16-bit tile so that
+// every operand fragment comes from ldmatrix.
+// ================================================================================================
+namespace vmm {
+
+constexpr int DPITCH = 264;      // dO rows: 256 + 8
+constexpr int CPITCH = 520;      // cond rows: ek(256) | ev(256) + 8
+constexpr int BPXB = 4;
+
+struct FragAddr {
+  uint32_t zrow;
+  int lm, lr;
+  // A operand (16 x 16, rows = tile rows): matrices (r0-7,c0-7) (r8-15,c0-7) (r0-7,c8-15) (r8-15,c8-15)
+  __device__ __forceinline__ uint32_t a(uint32_t base, int pitch, int col) const {
+    const int row = lr + 8 * (lm & 1), c = col + 8 * (lm >> 1);
+    return (row < TNF) ? base + static_cast<uint32_t>(row * pitch + c) * 2 : zrow + static_cast<uint32_t>(c) * 2;
+  }
+  // B operand, k contiguous in memory (rows = n index): two n-tiles x (k lo, k hi)
+  __device__ __forceinline__ uint32_t b(uint32_t base, int pitch, int col) const {
+    const int row = lr + 8 * (lm >> 1), c = col + 8 * (lm & 1);
+    return (row < TNF) ? base + static_cast<uint32_t>(row * pitch + c) * 2 : zrow + static_cast<uint32_t>(c) * 2;
+  }
+  // B operand, n contiguous in memory (rows = k index), loaded with .trans: two n-tiles (cols) x (k lo, k hi)
+  __device__ __forceinline__ uint32_t bt(uint32_t base, int pitch, int col) const { return a(base, pitch, col); }
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(256, 1) tattn_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv,
+                                                               const float* __restrict__ bias, const float* __restrict__ rot,
+                                                               const uint16_t* __restrict__ dout, uint16_t* __restrict__ dqkv,
+                                                               float* __restrict__ dekv, float* __restrict__ dbias, int HW, int heads,
+                                                               float scale) {
+  extern __shared__ __align__(16) uint16_t tsm[];
+  uint16_t* tile = tsm;                                     // [BPXB][TNF][TPITCH]   q | k | v   (q, k rotated in place)
+  uint16_t* dtile = tile + BPXB * TNF * TPITCH;             // [BPXB][TNF][DPITCH]   dO
+  uint16_t* ctile = dtile + BPXB * TNF * DPITCH;            // [TNF][CPITCH]         cond ek | ev
+  uint16_t* zrow = ctile + TNF * CPITCH;                    // [TPITCH] zeros
+  float* RT = reinterpret_cast<float*>(zrow + TPITCH);      // [TNF][16][2]
+  float* ST = RT + TNF * 32;                                // [8 warps][2][16]  lse, D per query
+  const int HD = heads * 32;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = warp;
+  const bool cond = ekv != nullptr;
+
+  for (int i = tid; i < TPITCH; i += 256) zrow[i] = 0;
+  for (int i = tid; i < TNF * 32; i += 256) RT[i] = rot[i];
+  if (cond) {
+    for (int i = tid; i < TNF * 2 * HD; i += 256) {
+      const int j = i / (2 * HD), c = i % (2 * HD);
+      const float v = ekv[(static_cast<long long>(b) * TNF + j) * 2 * HD + c];
+      ctile[j * CPITCH + c] = FMT ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+    }
+  }
+  float bs[2][2][2], bsT[2][2][2];
+#pragma unroll
+  for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int i = g + 8 * rh, j = 8 * nt + 2 * t + c;                    // pass A: row = query i, col = key j
+        bs[rh][nt][c] = (j < TNF) ? ((i < TNF) ? bias[(h * TNF + i) * TNF + j] : 0.f) : -1e30f;
+        const int jj = g + 8 * rh, ii = 8 * nt + 2 * t + c;                  // pass B: row = key jj, col = query ii
+        bsT[rh][nt][c] = (jj < TNF && ii < TNF) ? bias[(h * TNF + ii) * TNF + jj] : -1e30f;
+      }
+  float gb[2][2][2];
+  float gEK[4][4], gEV[4][4];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) (&gb[0][0][0])[x] = 0.f;
+#pragma unroll
+  for (int x = 0; x < 16; ++x) (&gEK[0][0])[x] = (&gEV[0][0])[x] = 0.f;
+  __syncthreads();
+
+  FragAddr fa;
+  fa.zrow = smem_u32(zrow);
+  fa.lm = lane >> 3;
+  fa.lr = lane & 7;
+  const uint32_t tile_s = smem_u32(tile), dtile_s = smem_u32(dtile), ctile_s = smem_u32(ctile);
+  float* lse_s = ST + warp * 32;
+  float* dd_s = lse_s + 16;
+  const int groups = (HW + BPXB - 1) / BPXB;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int p0 = grp * BPXB;
+    for (int i = tid; i < BPXB * TNF * 96; i += 256) {
+      const int c = i % 96, f = (i / 96) % TNF, p = i / (96 * TNF);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (p0 + p < HW) v = __ldg(reinterpret_cast<const uint4*>(qkv + ((static_cast<long long>(b) * TNF + f) * HW + p0 + p) * 3 * HD) + c);
+      *reinterpret_cast<uint4*>(tile + (p * TNF + f) * TPITCH + c * 8) = v;
+    }
+    for (int i = tid; i < BPXB * TNF * 32; i += 256) {
+      const int c = i % 32, f = (i / 32) % TNF, p = i / (32 * TNF);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (p0 + p < HW) v = __ldg(reinterpret_cast<const uint4*>(dout + ((static_cast<long long>(b) * TNF + f) * HW + p0 + p) * HD) + c);
+      *reinterpret_cast<uint4*>(dtile + (p * TNF + f) * DPITCH + c * 8) = v;
+    }
+    __syncthreads();
+    // rotary in place (q scaled)
+    for (int i = lane; i < BPXB * TNF * 16; i += 32) {
+      const int k = i & 15, f = (i >> 4) % TNF, p = i / (16 * TNF);
+      const float cs = RT[(f * 16 + k) * 2], sn = RT[(f * 16 + k) * 2 + 1];
+      uint32_t* qp = reinterpret_cast<uint32_t*>(tile + (p * TNF + f) * TPITCH + h * 32 + 2 * k);
+      uint32_t* kp = reinterpret_cast<uint32_t*>(tile + (p * TNF + f) * TPITCH + HD + h * 32 + 2 * k);
+      float2 q = unpack2<FMT>(*qp), kk = unpack2<FMT>(*kp);
+      q.x *= scale;
+      q.y *= scale;
+      *qp = pack2<FMT>(q.x * cs - q.y * sn, q.y * cs + q.x * sn);
+      *kp = pack2<FMT>(kk.x * cs - kk.y * sn, kk.y * cs + kk.x * sn);
+    }
+    __syncwarp();
+    for (int p = 0; p < BPXB; ++p) {
+      if (p0 + p >= HW) break;
+      const uint32_t tp = tile_s + static_cast<uint32_t>(p * TNF * TPITCH) * 2;
+      const uint32_t dp_s = dtile_s + static_cast<uint32_t>(p * TNF * DPITCH) * 2;
+      // =========================== pass A: rows = queries
+      float S[4][4], dP[4][4];
+#pragma unroll
+      for (int x = 0; x < 16; ++x) (&S[0][0])[x] = (&dP[0][0])[x] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t qa[4], da[4], kb[4], vb[4];
+        ldsm_x4(qa, fa.a(tp, TPITCH, h * 32 + 16 * ks));
+        ldsm_x4(da, fa.a(dp_s, DPITCH, h * 32 + 16 * ks));
+        if (cond) {
+          ldsm_x4(kb, fa.b(ctile_s, CPITCH, h * 32 + 16 * ks));
+          ldsm_x4(vb, fa.b(ctile_s, CPITCH, HD + h * 32 + 16 * ks));
+          mma16816<FMT>(S[0], qa, kb);
+          mma16816<FMT>(S[1], qa, kb + 2);
+          mma16816<FMT>(dP[0], da, vb);
+          mma16816<FMT>(dP[1], da, vb + 2);
+        }
+        ldsm_x4(kb, fa.b(tp, TPITCH, HD + h * 32 + 16 * ks));
+        ldsm_x4(vb, fa.b(tp, TPITCH, 2 * HD + h * 32 + 16 * ks));
+        mma16816<FMT>(S[2], qa, kb);
+        mma16816<FMT>(S[3], qa, kb + 2);
+        mma16816<FMT>(dP[2], da, vb);
+        mma16816<FMT>(dP[3], da, vb + 2);
+      }
+      float mx[2] = {-1e30f, -1e30f}, sum[2] = {0.f, 0.f}, Dr[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (!cond && nt < 2) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          S[nt][c] += bs[c >> 1][nt & 1][c & 1];
+          mx[c >> 1] = fmaxf(mx[c >> 1], S[nt][c]);
+        }
+      }
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        mx[rh] = fmaxf(mx[rh], __shfl_xor_sync(0xffffffffu, mx[rh], 1));
+        mx[rh] = fmaxf(mx[rh], __shfl_xor_sync(0xffffffffu, mx[rh], 2));
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float e = (!cond && nt < 2) ? 0.f : __expf(S[nt][c] - mx[c >> 1]);
+          S[nt][c] = e;
+          sum[c >> 1] += e;
+        }
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        sum[rh] += __shfl_xor_sync(0xffffffffu, sum[rh], 1);
+        sum[rh] += __shfl_xor_sync(0xffffffffu, sum[rh], 2);
+      }
+      const float inv[2] = {1.f / sum[0], 1.f / sum[1]};
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          S[nt][c] *= inv[c >> 1];                 // P
+          Dr[c >> 1] += S[nt][c] * dP[nt][c];
+        }
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        Dr[rh] += __shfl_xor_sync(0xffffffffu, Dr[rh], 1);
+        Dr[rh] += __shfl_xor_sync(0xffffffffu, Dr[rh], 2);
+      }
+      if (t == 0) {
+        lse_s[g] = mx[0] + __logf(sum[0]);
+        lse_s[g + 8] = mx[1] + __logf(sum[1]);
+        dd_s[g] = Dr[0];
+        dd_s[g + 8] = Dr[1];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float ds = S[nt][c] * (dP[nt][c] - Dr[c >> 1]);
+          dP[nt][c] = ds;                          // dS
+          gb[c >> 1][nt & 1][c & 1] += ds;
+        }
+      {   // dQ_rot = dS K  (k-step 0: cond keys, k-step 1: frame keys)
+        float dQ[4][4];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) (&dQ[0][0])[x] = 0.f;
+        uint32_t sa[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          sa[ks][0] = pack2<FMT>(dP[2 * ks][0], dP[2 * ks][1]);
+          sa[ks][1] = pack2<FMT>(dP[2 * ks][2], dP[2 * ks][3]);
+          sa[ks][2] = pack2<FMT>(dP[2 * ks + 1][0], dP[2 * ks + 1][1]);
+          sa[ks][3] = pack2<FMT>(dP[2 * ks + 1][2], dP[2 * ks + 1][3]);
+        }
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh) {
+          uint32_t kb[4];
+          if (cond) {
+            ldsm_x4_trans(kb, fa.bt(ctile_s, CPITCH, h * 32 + 16 * dh));
+            mma16816<FMT>(dQ[2 * dh], sa[0], kb);
+            mma16816<FMT>(dQ[2 * dh + 1], sa[0], kb + 2);
+          }
+          ldsm_x4_trans(kb, fa.bt(tp, TPITCH, HD + h * 32 + 16 * dh));
+          mma16816<FMT>(dQ[2 * dh], sa[1], kb);
+          mma16816<FMT>(dQ[2 * dh + 1], sa[1], kb + 2);
+        }
+        // dq = scale R^T dQ_rot
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          const int i = g + 8 * rh;
+          if (i < TNF) {
+            uint16_t* orow = dqkv + ((static_cast<long long>(b) * TNF + i) * HW + p0 + p) * 3 * HD + h * 32 + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const int k = 4 * nt + t;
+              const float cs = RT[(i * 16 + k) * 2], sn = RT[(i * 16 + k) * 2 + 1];
+              const float a = dQ[nt][2 * rh], c = dQ[nt][2 * rh + 1];
+              *reinterpret_cast<uint32_t*>(orow + 8 * nt) = pack2<FMT>((a * cs + c * sn) * scale, (c * cs - a * sn) * scale);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      // =========================== pass B: rows = keys (mt 0: cond slots, mt 1: frame slots)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt == 0 && !cond) continue;
+        const uint32_t kbase = mt == 0 ? ctile_s : tp;
+        const int kpitch = mt == 0 ? CPITCH : TPITCH;
+        const int kcol = (mt == 0 ? 0 : HD) + h * 32;
+        const int vcol = (mt == 0 ? HD : 2 * HD) + h * 32;
+        float STt[2][4], dPT[2][4];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) (&STt[0][0])[x] = (&dPT[0][0])[x] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t ka[4], va[4], qb[4], db[4];
+          ldsm_x4(ka, fa.a(kbase, kpitch, kcol + 16 * ks));
+          ldsm_x4(va, fa.a(kbase, kpitch, vcol + 16 * ks));
+          ldsm_x4(qb, fa.b(tp, TPITCH, h * 32 + 16 * ks));
+          ldsm_x4(db, fa.b(dp_s, DPITCH, h * 32 + 16 * ks));
+          mma16816<FMT>(STt[0], ka, qb);
+          mma16816<FMT>(STt[1], ka, qb + 2);
+          mma16816<FMT>(dPT[0], va, db);
+          mma16816<FMT>(dPT[1], va, db + 2);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int qi = 8 * nt + 2 * t + (c & 1);
+            const float pt = __expf(STt[nt][c] + bsT[c >> 1][nt][c & 1] - lse_s[qi]);     // 0 on padded keys / queries
+            STt[nt][c] = pt;                                   // P^T
+            dPT[nt][c] = pt * (dPT[nt][c] - dd_s[qi]);         // dS^T
+          }
+        uint32_t pa[4] = {pack2<FMT>(STt[0][0], STt[0][1]), pack2<FMT>(STt[0][2], STt[0][3]), pack2<FMT>(STt[1][0], STt[1][1]),
+                          pack2<FMT>(STt[1][2], STt[1][3])};
+        uint32_t sa[4] = {pack2<FMT>(dPT[0][0], dPT[0][1]), pack2<FMT>(dPT[0][2], dPT[0][3]), pack2<FMT>(dPT[1][0], dPT[1][1]),
+                          pack2<FMT>(dPT[1][2], dPT[1][3])};
+        float dK[4][4], dV[4][4];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) (&dK[0][0])[x] = (&dV[0][0])[x] = 0.f;
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh) {
+          uint32_t qb[4], db[4];
+          ldsm_x4_trans(qb, fa.bt(tp, TPITCH, h * 32 + 16 * dh));
+          ldsm_x4_trans(db, fa.bt(dp_s, DPITCH, h * 32 + 16 * dh));
+          mma16816<FMT>(dK[2 * dh], sa, qb);
+          mma16816<FMT>(dK[2 * dh + 1], sa, qb + 2);
+          mma16816<FMT>(dV[2 * dh], pa, db);
+          mma16816<FMT>(dV[2 * dh + 1], pa, db + 2);
+        }
+        if (mt == 0) {
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            (&gEK[0][0])[x] += (&dK[0][0])[x];
+            (&gEV[0][0])[x] += (&dV[0][0])[x];
+          }
+        } else {
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const int j = g + 8 * rh;
+            if (j < TNF) {
+              uint16_t* krow = dqkv + ((static_cast<long long>(b) * TNF + j) * HW + p0 + p) * 3 * HD + HD + h * 32 + 2 * t;
+              uint16_t* vrow = krow + HD;
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) {
+                const int k = 4 * nt + t;
+                const float cs = RT[(j * 16 + k) * 2], sn = RT[(j * 16 + k) * 2 + 1];
+                const float a = dK[nt][2 * rh], c = dK[nt][2 * rh + 1];
+                *reinterpret_cast<uint32_t*>(krow + 8 * nt) = pack2<FMT>(a * cs + c * sn, c * cs - a * sn);
+                *reinterpret_cast<uint32_t*>(vrow + 8 * nt) = pack2<FMT>(dV[nt][2 * rh], dV[nt][2 * rh + 1]);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+  // ---- flush the per-CTA sums
+  if (cond && dekv) {
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const int j = g + 8 * rh;
+      if (j < TNF) {
+        float* ge = dekv + (static_cast<long long>(b) * TNF + j) * 2 * HD + h * 32 + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          atomicAdd(ge + 8 * nt, gEK[nt][2 * rh]);
+          atomicAdd(ge + 8 * nt + 1, gEK[nt][2 * rh + 1]);
+          atomicAdd(ge + HD + 8 * nt, gEV[nt][2 * rh]);
+          atomicAdd(ge + HD + 8 * nt + 1, gEV[nt][2 * rh + 1]);
+        }
+      }
+    }
+  }
+  if (dbias) {
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int i = g + 8 * rh, j = 8 * nt + 2 * t + c;
+          if (i < TNF && j < TNF) atomicAdd(dbias + (h * TNF + i) * TNF + j, gb[rh][nt][c]);
+        }
+  }
+}
+
+}  // namespace vmm
+
+extern "C" int vmm_tattn_bwd(const void* qkv, const float* ekv, const float* bias, const float* rot, const void* dout, void* dqkv,
+                             float* dekv, float* dbias, int fmt, int B, int frames, int HW, int heads, float scale, void* stream_) {
+  using namespace vmm;
+  if (!qkv || !bias || !rot || !dout || !dqkv) return set_error(VMM_ERR_ARG, "vmm_tattn_bwd: null pointer");
+  if (frames != TNF) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: only 11 frames");
+  if (heads != 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: heads must be 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t smem = (static_cast<size_t>(BPXB) * TNF * (TPITCH + DPITCH) + TNF * CPITCH + TPITCH) * sizeof(uint16_t) +
+                      (TNF * 32 + 8 * 32) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tattn_bwd_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tattn_bwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, "vmm_tattn_bwd: attr");
+    attr = true;
+  }
+  const int groups = (HW + BPXB - 1) / BPXB;
+  int gx = (2 * num_sms() + B - 1) / B;
+  if (gx > groups) gx = groups;
+  dim3 grid(gx, B);
+  if (fmt == VMM_FMT_F16)
+    tattn_bwd_mma_kernel<0><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<const uint16_t*>(dout),
+                                                         static_cast<uint16_t*>(dqkv), dekv, dbias, HW, heads, scale);
+  else
+    tattn_bwd_mma_kernel<1><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<const uint16_t*>(dout),
+                                                         static_cast<uint16_t*>(dqkv), dekv, dbias, HW, heads, scale);
+  count_launch();
+  return check_launch("vmm_tattn_bwd");
+}
