@@ -79,39 +79,41 @@ __device__ __forceinline__ void decode_tile(const CgemmDev& p, int t, int& phase
 
 constexpr int kBiasSmem = 1024;
 
-// Add the shared-memory GroupNorm partial sums of (first sample smp0, n-tile n0) to the global fp64 statistics
-// and clear them.  Called by all 128 epilogue threads between two named-barrier syncs.
-__device__ __forceinline__ void gn_flush(const CgemmDev& p, float (*gacc)[16][2], int ethread, int smp0, int n0) {
-  if (ethread < 2 * 16 * 2) {
-    const int sl = ethread >> 5, gl = (ethread >> 1) & 15, w = ethread & 1;
+constexpr int kGnGroups = 8;   // GroupNorm groups per n-tile (BN is capped accordingly on the host)
+
+// GroupNorm partial sums live in per-thread shared-memory slots s_racc[slot][group][thread][sum|sumsq]: the epilogue
+// adds to its own slot with plain loads/stores (no shuffles, no atomics per tile).  gn_flush reduces the 128 slots of
+// each (slot, group) and adds them to the global fp64 statistics of (first sample smp0, n-tile n0); it is called by
+// all 128 epilogue threads between two named-barrier syncs, only when the CTA moves to another sample / n-tile.
+__device__ __forceinline__ void gn_flush(const CgemmDev& p, float (*racc)[kGnGroups][128][2], int ethread, int smp0, int n0) {
+  if (ethread < 2 * kGnGroups * 2) {
+    const int sl = ethread / (kGnGroups * 2), gl = (ethread >> 1) % kGnGroups, w = ethread & 1;
+    float val = 0.f;
+    for (int i = 0; i < 128; ++i) val += racc[sl][gl][(i + ethread) & 127][w];     // skewed start: fewer bank conflicts
     const int g = n0 / p.gn_gs + gl;
-    const float val = gacc[sl][gl][w];
     const int nsamp = (p.BF + p.fps - 1) / p.fps;
     if (g < p.gn_groups && smp0 + sl < nsamp && val != 0.f)
       atomicAdd(p.gn_stats + (static_cast<long long>(smp0 + sl) * p.gn_groups + g) * 2 + w, static_cast<double>(val));
-    gacc[sl][gl][w] = 0.f;
   }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int sl = 0; sl < 2; ++sl)
+    for (int gl = 0; gl < kGnGroups; ++gl) {
+      racc[sl][gl][ethread][0] = 0.f;
+      racc[sl][gl][ethread][1] = 0.f;
+    }
 }
 
-// warp-reduce one group's (sum, sumsq) and add it to the CTA accumulators (shared-memory atomics)
-__device__ __forceinline__ void gn_warp_add(float (*gacc)[16][2], int gl, int slot, bool two_samples, float a1, float a2, int lane) {
-  for (int sl = 0; sl < (two_samples ? 2 : 1); ++sl) {
-    float a = (slot == sl) ? a1 : 0.f, b = (slot == sl) ? a2 : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    if (lane == 0) {
-      atomicAdd(&gacc[sl][gl][0], a);
-      atomicAdd(&gacc[sl][gl][1], b);
-    }
-  }
+__device__ __forceinline__ void gn_thread_add(float (*racc)[kGnGroups][128][2], int gl, int slot, int ethread, float a1, float a2) {
+  float2* q = reinterpret_cast<float2*>(&racc[slot][gl][ethread][0]);
+  float2 v = *q;
+  v.x += a1;
+  v.y += a2;
+  *q = v;
 }
 
 __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ CgemmDev p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ float s_gn[2][16][2];        // [sample slot][group in n-tile][sum, sumsq], kept across tiles of one (sample, n-tile)
+  __shared__ __align__(8) float s_gn[2][kGnGroups][128][2];   // per-thread GroupNorm partial sums, see gn_flush
   __shared__ __align__(16) float s_bias[kBiasSmem];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   CgemmSmemCtl* ctl = reinterpret_cast<CgemmSmemCtl*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
@@ -139,8 +141,8 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
     tmem_relinquish();
   }
   if (warp == 3) {
-    float* g = &s_gn[0][0][0];
-    for (int i = lane; i < 2 * 16 * 2; i += 32) g[i] = 0.f;
+    float* g = &s_gn[0][0][0][0];
+    for (int i = lane; i < 2 * kGnGroups * 128 * 2; i += 32) g[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
                 gs2 += b2[b];
                 const int cend = ncol + 8 * (b + 1);
                 if ((cend % gs) == 0 && cend - gs < p.N) {   // group complete (uniform across the warp)
-                  gn_warp_add(s_gn, (cend - gs - n0) / gs, slot, two_samples, gs1, gs2, lane);
+                  gn_thread_add(s_gn, (cend - gs - n0) / gs, slot, ethread, gs1, gs2);
                   gs1 = gs2 = 0.f;
                 }
               }
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
                 if (((cj + 1) % gs) == 0) {
                   const int c0g = ncol + cj + 1 - gs;
                   const int gl = (c0g - n0) / gs;
-                  if (c0g < p.N && gl < 16) gn_warp_add(s_gn, gl, slot, two_samples, gs1, gs2, lane);
+                  if (c0g < p.N && gl < kGnGroups) gn_thread_add(s_gn, gl, slot, ethread, gs1, gs2);
                   gs1 = gs2 = 0.f;
                 }
               }
@@ -510,7 +512,8 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     BN = (BN / h.gn_group) * h.gn_group;
     if (BN == 0) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: gn_group larger than an n-tile");
   }
-  if (h.gn_stats && h.gn_group < 16 && BN / h.gn_group > 16) BN = 16 * h.gn_group;
+  if (h.gn_stats && BN / h.gn_group > kGnGroups) BN = kGnGroups * h.gn_group;
+  if (h.gn_stats && (BN % 16) != 0) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: gn_group too small for a 16-wide n-tile");
   d.N = h.n;
   d.BN = BN;
   d.n_ntiles = (n_pad + BN - 1) / BN;
@@ -529,7 +532,7 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   d.total_tiles = static_cast<int>(total);
   d.stage_bytes = kABytes + BN * 128;
   d.tx_bytes = d.stage_bytes;
-  const int smem_budget = 196 * 1024;
+  const int smem_budget = 176 * 1024;   // + ~20 KB static (bias, GroupNorm slots)
   int stages = smem_budget / static_cast<int>(d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile too large for shared memory");
@@ -600,7 +603,7 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + sizeof(CgemmSmemCtl) + 1024;   // + ~4.4 KB static
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "vmm_cgemm: cudaFuncSetAttribute");
     attr_set = true;
   }

@@ -14,15 +14,15 @@ namespace vmm {
 
 constexpr int TNF = 11;          // frames == cond tokens (VDDP:603)
 constexpr int TPITCH = 776;      // smem row pitch in elements: 768 + 8 keeps ldmatrix rows on distinct banks
-constexpr int TPXB = 4;          // pixels per CTA iteration
+constexpr int TPXB = 2;          // pixels per pipeline stage (two stages in flight)
 
 template <int FMT>
 __global__ void __launch_bounds__(256) tattn_fwd_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv,
                                                             const float* __restrict__ bias, const float* __restrict__ rot,
                                                             uint16_t* __restrict__ out, int HW, int heads, float scale) {
   extern __shared__ __align__(16) uint16_t tsm[];
-  uint16_t* tile = tsm;                                   // [TPXB][TNF][TPITCH]
-  uint16_t* zrow = tile + TPXB * TNF * TPITCH;            // one row of zeros (frames >= 11)
+  uint16_t* tile0 = tsm;                                  // [2 stages][TPXB][TNF][TPITCH]
+  uint16_t* zrow = tile0 + 2 * TPXB * TNF * TPITCH;       // one row of zeros (frames >= 11)
   float* RT = reinterpret_cast<float*>(zrow + TPITCH);    // [TNF][16][2]
   const int HD = heads * 32;
   const int b = blockIdx.y;
@@ -84,20 +84,33 @@ __global__ void __launch_bounds__(256) tattn_fwd_mma_kernel(const uint16_t* __re
   }
   __syncthreads();
 
-  const uint32_t tile_s = smem_u32(tile), zrow_s = smem_u32(zrow);
+  const uint32_t zrow_s = smem_u32(zrow);
   const int groups = (HW + TPXB - 1) / TPXB;
-  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+  // stage = TPXB x 11 rows of 1536 bytes, copied with cp.async (zero fill past the last pixel); the copy of group
+  // i+1 overlaps the MMAs of group i
+  auto stage_load = [&](int st, int grp) {
     const int p0 = grp * TPXB;
-    // ---- stage qkv rows: TPXB x 11 rows of 1536 bytes, 16-byte chunks
+    const uint32_t dst0 = smem_u32(tile0 + st * TPXB * TNF * TPITCH);
     for (int i = tid; i < TPXB * TNF * 96; i += 256) {
       const int c = i % 96;
       const int f = (i / 96) % TNF;
       const int p = i / (96 * TNF);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (p0 + p < HW) v = __ldg(reinterpret_cast<const uint4*>(qkv + ((static_cast<long long>(b) * TNF + f) * HW + p0 + p) * 3 * HD) + c);
-      *reinterpret_cast<uint4*>(tile + (p * TNF + f) * TPITCH + c * 8) = v;
+      const bool ok = p0 + p < HW;
+      const uint16_t* src = qkv + ((static_cast<long long>(b) * TNF + f) * HW + (ok ? p0 + p : 0)) * 3 * HD + c * 8;
+      cp_async16(dst0 + static_cast<uint32_t>((p * TNF + f) * TPITCH + c * 8) * 2, src, ok ? 16 : 0);
     }
+  };
+  if (static_cast<int>(blockIdx.x) < groups) stage_load(0, blockIdx.x);
+  cp_async_commit();
+  int it = 0;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x, ++it) {
+    const int p0 = grp * TPXB;
+    if (grp + static_cast<int>(gridDim.x) < groups) stage_load((it + 1) & 1, grp + gridDim.x);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    uint16_t* tile = tile0 + (it & 1) * TPXB * TNF * TPITCH;
+    const uint32_t tile_s = smem_u32(tile);
     if (h < heads) {
       // ---- rotary in place on this head's q (scaled) and k slices
       for (int i = lane; i < TPXB * TNF * 16; i += 32) {
@@ -227,7 +240,7 @@ extern "C" int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bia
   if (frames != TNF) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: only 11 frames (the reference hard-codes 11 cond tokens, VDDP:603)");
   if (heads != 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: heads must be 8 (one warp per head, rows of 3*8*32 channels)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t smem = (static_cast<size_t>(TPXB) * TNF * TPITCH + TPITCH) * sizeof(uint16_t) + TNF * 32 * sizeof(float);
+  const size_t smem = (static_cast<size_t>(2) * TPXB * TNF * TPITCH + TPITCH) * sizeof(uint16_t) + TNF * 32 * sizeof(float);
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tattn_fwd_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -261,7 +274,7 @@ namespace vmm {
 
 constexpr int DPITCH = 264;      // dO rows: 256 + 8
 constexpr int CPITCH = 520;      // cond rows: ek(256) | ev(256) + 8
-constexpr int BPXB = 4;
+constexpr int BPXB = 2;          // pixels per pipeline stage
 
 struct FragAddr {
   uint32_t zrow;
@@ -287,9 +300,9 @@ __global__ void __launch_bounds__(256, 1) tattn_bwd_mma_kernel(const uint16_t* _
                                                                float* __restrict__ dekv, float* __restrict__ dbias, int HW, int heads,
                                                                float scale) {
   extern __shared__ __align__(16) uint16_t tsm[];
-  uint16_t* tile = tsm;                                     // [BPXB][TNF][TPITCH]   q | k | v   (q, k rotated in place)
-  uint16_t* dtile = tile + BPXB * TNF * TPITCH;             // [BPXB][TNF][DPITCH]   dO
-  uint16_t* ctile = dtile + BPXB * TNF * DPITCH;            // [TNF][CPITCH]         cond ek | ev
+  uint16_t* tile0 = tsm;                                    // [2][BPXB][TNF][TPITCH]   q | k | v   (q, k rotated in place)
+  uint16_t* dtile0 = tile0 + 2 * BPXB * TNF * TPITCH;       // [2][BPXB][TNF][DPITCH]   dO
+  uint16_t* ctile = dtile0 + 2 * BPXB * TNF * DPITCH;       // [TNF][CPITCH]            cond ek | ev
   uint16_t* zrow = ctile + TNF * CPITCH;                    // [TPITCH] zeros
   float* RT = reinterpret_cast<float*>(zrow + TPITCH);      // [TNF][16][2]
   float* ST = RT + TNF * 32;                                // [8 warps][2][16]  lse, D per query
@@ -333,25 +346,32 @@ __global__ void __launch_bounds__(256, 1) tattn_bwd_mma_kernel(const uint16_t* _
   fa.zrow = smem_u32(zrow);
   fa.lm = lane >> 3;
   fa.lr = lane & 7;
-  const uint32_t tile_s = smem_u32(tile), dtile_s = smem_u32(dtile), ctile_s = smem_u32(ctile);
+  const uint32_t ctile_s = smem_u32(ctile);
   float* lse_s = ST + warp * 32;
   float* dd_s = lse_s + 16;
   const int groups = (HW + BPXB - 1) / BPXB;
-  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+  auto stage_load = [&](int st, int grp) {
     const int p0 = grp * BPXB;
-    for (int i = tid; i < BPXB * TNF * 96; i += 256) {
-      const int c = i % 96, f = (i / 96) % TNF, p = i / (96 * TNF);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (p0 + p < HW) v = __ldg(reinterpret_cast<const uint4*>(qkv + ((static_cast<long long>(b) * TNF + f) * HW + p0 + p) * 3 * HD) + c);
-      *reinterpret_cast<uint4*>(tile + (p * TNF + f) * TPITCH + c * 8) = v;
+    const uint32_t t0 = smem_u32(tile0 + st * BPXB * TNF * TPITCH), d0 = smem_u32(dtile0 + st * BPXB * TNF * DPITCH);
+    for (int i = tid; i < BPXB * TNF * 128; i += 256) {
+      const int c = i & 127, f = (i >> 7) % TNF, p = i / (128 * TNF);
+      const bool ok = p0 + p < HW;
+      const long long row = (static_cast<long long>(b) * TNF + f) * HW + (ok ? p0 + p : 0);
+      if (c < 96) cp_async16(t0 + static_cast<uint32_t>((p * TNF + f) * TPITCH + c * 8) * 2, qkv + row * 3 * HD + c * 8, ok ? 16 : 0);
+      else cp_async16(d0 + static_cast<uint32_t>((p * TNF + f) * DPITCH + (c - 96) * 8) * 2, dout + row * HD + (c - 96) * 8, ok ? 16 : 0);
     }
-    for (int i = tid; i < BPXB * TNF * 32; i += 256) {
-      const int c = i % 32, f = (i / 32) % TNF, p = i / (32 * TNF);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (p0 + p < HW) v = __ldg(reinterpret_cast<const uint4*>(dout + ((static_cast<long long>(b) * TNF + f) * HW + p0 + p) * HD) + c);
-      *reinterpret_cast<uint4*>(dtile + (p * TNF + f) * DPITCH + c * 8) = v;
-    }
+  };
+  if (static_cast<int>(blockIdx.x) < groups) stage_load(0, blockIdx.x);
+  cp_async_commit();
+  int it = 0;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x, ++it) {
+    const int p0 = grp * BPXB;
+    if (grp + static_cast<int>(gridDim.x) < groups) stage_load((it + 1) & 1, grp + gridDim.x);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    uint16_t* tile = tile0 + (it & 1) * BPXB * TNF * TPITCH;
+    const uint32_t tile_s = smem_u32(tile), dtile_s = smem_u32(dtile0 + (it & 1) * BPXB * TNF * DPITCH);
     // rotary in place (q scaled)
     for (int i = lane; i < BPXB * TNF * 16; i += 32) {
       const int k = i & 15, f = (i >> 4) % TNF, p = i / (16 * TNF);
@@ -606,7 +626,7 @@ extern "C" int vmm_tattn_bwd(const void* qkv, const float* ekv, const float* bia
   if (frames != TNF) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: only 11 frames");
   if (heads != 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: heads must be 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t smem = (static_cast<size_t>(BPXB) * TNF * (TPITCH + DPITCH) + TNF * CPITCH + TPITCH) * sizeof(uint16_t) +
+  const size_t smem = (static_cast<size_t>(2) * BPXB * TNF * (TPITCH + DPITCH) + TNF * CPITCH + TPITCH) * sizeof(uint16_t) +
                       (TNF * 32 + 8 * 32) * sizeof(float);
   static bool attr = false;
   if (!attr) {
