@@ -222,15 +222,16 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
-    if rank != 0:
-        return
-    pk = peaks()
-    # roofline of the dominant kernel (vmm_cgemm): profile two more steps with per-launch events
+    # roofline of the dominant kernel (vmm_cgemm): profile two more steps with per-launch events.  Every rank runs
+    # them (the steps contain the gradient all-reduce); only rank 0 reports.
     ops.PROFILE = []
     for _ in range(2):
         step_resident()
-    torch.cuda.synchronize()
+    barrier()
     prof, ops.PROFILE = ops.PROFILE, None
+    if rank != 0:
+        return
+    pk = peaks()
     by = {}
     for name, flops, a, b in prof:
         d = by.setdefault(name, [0.0, 0.0, 0])

@@ -20,9 +20,12 @@ struct WgTapDev {
   long long wofs;     // element offset of this tap inside dW
 };
 
-struct WgColDev {
-  int16_t tap;
-  int16_t c0;         // first B channel of this column block
+constexpr int kWgMaxChunks = 3;
+struct WgColDev {     // one column block of the accumulator = up to 3 chunks of 64 B-operand channels, possibly of different taps
+  int16_t n_chunks;
+  int16_t a_src;      // all chunks of a block share the A view
+  int16_t tap[kWgMaxChunks];
+  int16_t c0[kWgMaxChunks];
 };
 
 struct WgradDev {
@@ -32,12 +35,12 @@ struct WgradDev {
   WgColDev cols[kWgMaxCols];
   int n_cols, m_tiles, ksplit, total_items;
   int N;                 // rows of dW covered (channels of dY)
-  int BNc;               // column block (64 or 128)
+  int BNc;               // widest column block: 64 * chunks
   int a_chunks;          // 64-channel chunks of A loaded per stage (1 or 2)
   int tf_log, th_log, tw_log;
   int tiles_f, tiles_y, tiles_x, pix_tiles;
   int stages;
-  uint32_t stage_bytes, tx_bytes, idesc;
+  uint32_t stage_bytes, idesc_by_chunks[kWgMaxChunks + 1];
   float* dw;
   long long sM, sC, sC2;
   int cmod, c_valid, k_valid;
@@ -76,7 +79,6 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   WgSmemCtl* ctl = reinterpret_cast<WgSmemCtl*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b_chunks = p.BNc >> 6;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < VMM_MAX_VIEWS; ++i) {
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(&ctl->tmem_base, 256);
+    tmem_alloc(&ctl->tmem_base, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -112,17 +114,18 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         int col, mt, kt0, kt1;
         wg_decode(p, item, col, mt, kt0, kt1);
         const WgColDev cd = p.cols[col];
-        const WgTapDev T = p.taps[cd.tap];
         for (int kt = kt0; kt < kt1; ++kt) {
           int bf0, y0, x0;
           wg_pix(p, kt, bf0, y0, x0);
           mbar_wait(&ctl->empty[s], ph ^ 1);
           uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
-          mbar_expect_tx(&ctl->full[s], p.tx_bytes);
+          mbar_expect_tx(&ctl->full[s], (p.a_chunks + cd.n_chunks) * kChunkBytes);
           for (int a = 0; a < p.a_chunks; ++a)
-            tma_load_4d(st + a * kChunkBytes, &p.amap[T.a_src], &ctl->full[s], mt * 128 + a * 64, x0, y0, bf0);
-          for (int b = 0; b < b_chunks; ++b)
-            tma_load_4d(st + (2 + b) * kChunkBytes, &p.bmap[T.b_src], &ctl->full[s], cd.c0 + b * 64, x0 + T.dx, y0 + T.dy, bf0);
+            tma_load_4d(st + a * kChunkBytes, &p.amap[cd.a_src], &ctl->full[s], mt * 128 + a * 64, x0, y0, bf0);
+          for (int b = 0; b < cd.n_chunks; ++b) {
+            const WgTapDev T = p.taps[cd.tap[b]];
+            tma_load_4d(st + (p.a_chunks + b) * kChunkBytes, &p.bmap[T.b_src], &ctl->full[s], cd.c0[b], x0 + T.dx, y0 + T.dy, bf0);
+          }
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
@@ -141,19 +144,20 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&ctl->tempty[acc], acc_ph ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 128;
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      const uint32_t idesc = p.idesc_by_chunks[p.cols[col].n_chunks];
       uint32_t accumulate = 0;
       for (int kt = kt0; kt < kt1; ++kt) {
         mbar_wait(&ctl->full[s], ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
-          const uint32_t b_addr = a_addr + 2 * kChunkBytes;
+          const uint32_t b_addr = a_addr + p.a_chunks * kChunkBytes;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {   // 8 x 16 pixels
             const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, kChunkBytes, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, kChunkBytes, 1024);
-            umma_f16(d_tmem, adesc, bdesc, p.idesc, accumulate);
+            umma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
             accumulate = 1;
           }
           umma_commit(&ctl->empty[s]);
@@ -175,26 +179,28 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       int col, mt, kt0, kt1;
       wg_decode(p, item, col, mt, kt0, kt1);
       const WgColDev cd = p.cols[col];
-      const WgTapDev T = p.taps[cd.tap];
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&ctl->tfull[acc], acc_ph);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
       const int m = mt * 128 + row;
       const bool mvalid = (m < p.N) && (kt1 > kt0);
-      float* dst = p.dw + T.wofs + static_cast<long long>(m) * p.sM;
-      for (int c = 0; c < (p.BNc >> 4); ++c) {
-        uint32_t r[16];
-        tmem_ld16(t_addr + c * 16, r);
-        tmem_ld_wait();
-        if (!mvalid) continue;
+      for (int ch = 0; ch < cd.n_chunks; ++ch) {
+        const WgTapDev T = p.taps[cd.tap[ch]];
+        float* dst = p.dw + T.wofs + static_cast<long long>(m) * p.sM;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[16];
+          tmem_ld16(t_addr + ch * 64 + c * 16, r);
+          tmem_ld_wait();
+          if (!mvalid) continue;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int cj = cd.c0 + c * 16 + j;
-          if (cj < T.c) {
-            const int lo = cj % p.cmod, hi = cj / p.cmod;
-            if (lo < p.c_valid && hi < p.k_valid) atomicAdd(dst + lo * p.sC + hi * p.sC2, __uint_as_float(r[j]));
+          for (int j = 0; j < 16; ++j) {
+            const int cj = cd.c0[ch] + c * 16 + j;
+            if (cj < T.c) {
+              const int lo = cj % p.cmod, hi = cj / p.cmod;
+              if (lo < p.c_valid && hi < p.k_valid) atomicAdd(dst + lo * p.sC + hi * p.sC2, __uint_as_float(r[j]));
+            }
           }
         }
       }
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -269,10 +275,11 @@ extern "C" int vmm_wgrad(const vmm_wgrad_params* hp, void* stream_) {
   d.N = h.n;
   d.m_tiles = (h.n + 127) / 128;
   d.a_chunks = h.n > 64 ? 2 : 1;
-  int cmax = 0;
-  for (int t = 0; t < h.n_taps; ++t) cmax = h.taps[t].c > cmax ? h.taps[t].c : cmax;
-  d.BNc = cmax > 64 ? 128 : 64;
+  // blocks of up to 3 chunks (2 when the A operand already needs two 64-channel chunks): more accumulator columns per
+  // loaded A tile = fewer re-reads of dY
+  const int max_chunks = d.a_chunks == 1 ? 3 : 2;
   int ncols = 0;
+  d.BNc = 64;
   for (int t = 0; t < h.n_taps; ++t) {
     const vmm_wgrad_tap& T = h.taps[t];
     if (T.a_src < 0 || T.a_src >= h.n_a_views || T.b_src < 0 || T.b_src >= h.n_b_views || T.c < 1)
@@ -283,11 +290,18 @@ extern "C" int vmm_wgrad(const vmm_wgrad_params* hp, void* stream_) {
     d.taps[t].dx = static_cast<int16_t>(T.dx);
     d.taps[t].c = T.c;
     d.taps[t].wofs = T.wofs;
-    for (int c0 = 0; c0 < T.c; c0 += d.BNc) {
-      if (ncols >= kWgMaxCols) return set_error(VMM_ERR_UNSUPPORTED, "vmm_wgrad: too many column blocks");
-      d.cols[ncols].tap = static_cast<int16_t>(t);
-      d.cols[ncols].c0 = static_cast<int16_t>(c0);
-      ++ncols;
+    for (int c0 = 0; c0 < T.c; c0 += 64) {
+      WgColDev* blk = ncols > 0 ? &d.cols[ncols - 1] : nullptr;
+      if (!blk || blk->n_chunks >= max_chunks || blk->a_src != T.a_src) {
+        if (ncols >= kWgMaxCols) return set_error(VMM_ERR_UNSUPPORTED, "vmm_wgrad: too many column blocks");
+        blk = &d.cols[ncols++];
+        blk->n_chunks = 0;
+        blk->a_src = static_cast<int16_t>(T.a_src);
+      }
+      blk->tap[blk->n_chunks] = static_cast<int16_t>(t);
+      blk->c0[blk->n_chunks] = static_cast<int16_t>(c0);
+      ++blk->n_chunks;
+      if (64 * blk->n_chunks > d.BNc) d.BNc = 64 * blk->n_chunks;
     }
   }
   d.n_cols = ncols;
@@ -306,11 +320,10 @@ extern "C" int vmm_wgrad(const vmm_wgrad_params* hp, void* stream_) {
   if (d.pix_tiles / ksplit < 4 && d.pix_tiles >= 4) ksplit = d.pix_tiles / 4;
   d.ksplit = ksplit;
   d.total_items = base_items * ksplit;
-  d.stage_bytes = (2 + (d.BNc >> 6)) * kChunkBytes;
-  d.tx_bytes = (d.a_chunks + (d.BNc >> 6)) * kChunkBytes;
+  d.stage_bytes = (d.a_chunks + (d.BNc >> 6)) * kChunkBytes;
   d.stages = (200 * 1024) / static_cast<int>(d.stage_bytes);
   if (d.stages > 8) d.stages = 8;
-  d.idesc = make_idesc_f16(128, d.BNc, h.fmt, 1, 1);
+  for (int nc = 1; nc <= kWgMaxChunks; ++nc) d.idesc_by_chunks[nc] = make_idesc_f16(128, 64 * nc, h.fmt, 1, 1);
   d.dw = h.dw;
   d.sM = h.s_m;
   d.sC = h.s_c;
