@@ -8,6 +8,7 @@
 // Two TMEM accumulators (double buffer) let the epilogue of tile i overlap the main loop of tile i+1.
 // The ring of smem stages is shared across tiles (the producer runs ahead of the MMA warp).
 #include "common.cuh"
+#include "mma_sync.cuh"
 #include "sm100_ptx.cuh"
 
 namespace vmm {
@@ -111,6 +112,7 @@ __device__ __forceinline__ void gn_thread_add(float (*racc)[kGnGroups][128][2], 
   *q = v;
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ CgemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) float s_gn[2][kGnGroups][128][2];   // per-thread GroupNorm partial sums, see gn_flush
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
               const uint32_t w4[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const float2 f = unpack2_h16(w4[k], p.fmt);
+                const float2 f = unpack2<FMT>(w4[k]);
                 v[j * 8 + 2 * k] += f.x;
                 v[j * 8 + 2 * k + 1] += f.y;
               }
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (ncol + j < p.N) v[j] += h16_to_f(*res_ptr(ncol + j), p.fmt);
+              if (ncol + j < p.N) v[j] += h16_to_f(*res_ptr(ncol + j), FMT);
           }
           // prefetch the next 32 columns
           if (res_al && st + 1 < nsteps && ncol + 64 <= p.N && !straddles(ncol + 32)) {
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
         } else {
           uint32_t w[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = pack2_h16(v[2 * j], v[2 * j + 1], p.fmt);
+          for (int j = 0; j < 16; ++j) w[j] = pack2<FMT>(v[2 * j], v[2 * j + 1]);
           if (valid) {
             uint16_t* op = reinterpret_cast<uint16_t*>(obase) + pix * ld + ocol;
             if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
@@ -392,23 +394,19 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
             }
           }
           if (p.gn_stats) {
-            // statistics of the values as stored (rounded to 16 bit), like GroupNorm on the fp16 conv output:
+            // statistics from the fp32 values before the 16-bit rounding (the rounding error is unbiased and ~2^-9
+            // relative per element, far below what mean / variance over >= 10^4 elements can resolve);
             // per 8-column block sums first (static indexing), then group them
             float b1[4], b2[4];
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
               float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 f = unpack2_h16(w[b * 4 + k], p.fmt);
-                const bool in0 = full || (ncol + b * 8 + 2 * k < p.N), in1 = full || (ncol + b * 8 + 2 * k + 1 < p.N);
-                if (in0) {
-                  a1 += f.x;
-                  a2 += f.x * f.x;
-                }
-                if (in1) {
-                  a1 += f.y;
-                  a2 += f.y * f.y;
+              for (int k = 0; k < 8; ++k) {
+                const float x = v[b * 8 + k];
+                if (full || (ncol + b * 8 + k < p.N)) {
+                  a1 += x;
+                  a2 = fmaf(x, x, a2);
                 }
               }
               b1[b] = valid ? a1 : 0.f;
@@ -431,9 +429,8 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
 #pragma unroll
               for (int cj = 0; cj < 32; ++cj) {
                 if (ncol + cj < p.N && valid) {
-                  const float f = h16_to_f(static_cast<uint16_t>((w[cj >> 1] >> ((cj & 1) * 16)) & 0xFFFF), p.fmt);
-                  gs1 += f;
-                  gs2 += f * f;
+                  gs1 += v[cj];
+                  gs2 = fmaf(v[cj], v[cj], gs2);
                 }
                 if (((cj + 1) % gs) == 0) {
                   const int c0g = ncol + cj + 1 - gs;
@@ -532,7 +529,7 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   d.total_tiles = static_cast<int>(total);
   d.stage_bytes = kABytes + BN * 128;
   d.tx_bytes = d.stage_bytes;
-  const int smem_budget = 176 * 1024;   // + ~20 KB static (bias, GroupNorm slots)
+  const int smem_budget = 200 * 1024;   // + ~20 KB static (bias, GroupNorm slots) + control block: 4 stages at BN = 256
   int stages = smem_budget / static_cast<int>(d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile too large for shared memory");
@@ -603,12 +600,14 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + sizeof(CgemmSmemCtl) + 1024;   // + ~4.4 KB static
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "vmm_cgemm: cudaFuncSetAttribute");
     attr_set = true;
   }
   const int grid = d.total_tiles < num_sms() ? d.total_tiles : num_sms();
-  cgemm_kernel<<<grid, 256, smem, stream>>>(d);
+  if (h.fmt == VMM_FMT_F16) cgemm_kernel<0><<<grid, 256, smem, stream>>>(d);
+  else cgemm_kernel<1><<<grid, 256, smem, stream>>>(d);
   count_launch();
   return check_launch("vmm_cgemm");
 }

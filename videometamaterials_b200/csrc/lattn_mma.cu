@@ -122,37 +122,57 @@ __global__ void __launch_bounds__(256) lattn_ctx_mma_kernel(const uint16_t* __re
   const int first = (blockIdx.x == 0) ? -T : 0;
   for (int s0 = r_begin + first; s0 < r_end; s0 += LROWS) {
     const int cnt = min(LROWS, r_end - s0);
-    // stage + exponentiate: thread -> (row, 8 channels) of k ; plain copy of v
-    for (int i = tid; i < LROWS * 64; i += 256) {
-      const int r = i >> 6, c8 = i & 63;
-      const int m = s0 + r;
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (r < cnt) {
-        float v[8];
-        if (m < 0) {
-          const float* src = ekv + (static_cast<long long>(b) * T + (m + T)) * 2 * HD + c8 * 8;
+    // stage + exponentiate: thread -> (row, 8 channels) of k ; plain copy of v.  Loads are issued in batches of 8
+    // before any use: one dependent global load per iteration made this loop latency-bound.
+    for (int base = 0; base < LROWS * 64; base += 256 * 8) {
+      uint4 raw[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = src[j];
-        } else {
-          const uint4 q = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + m) * 3 * HD + HD) + c8);
-          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid;
+        const int r = i >> 6, c8 = i & 63;
+        const int m = s0 + r;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (r < cnt && m >= 0) raw[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + m) * 3 * HD + HD) + c8);
+      }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack2<FMT>(w[j]);
-            v[2 * j] = f.x;
-            v[2 * j + 1] = f.y;
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid;
+        const int r = i >> 6, c8 = i & 63;
+        const int m = s0 + r;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (r < cnt) {
+          float v[8];
+          if (m < 0) {
+            const float* src = ekv + (static_cast<long long>(b) * T + (m + T)) * 2 * HD + c8 * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = src[j];
+          } else {
+            const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack2<FMT>(w[j]);
+              v[2 * j] = f.x;
+              v[2 * j + 1] = f.y;
+            }
+          }
+          if (c8 < 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __expf(v[j] - Ms[c8 * 8 + j]);
+            o.x = pack2<FMT>(v[0], v[1]);
+            o.y = pack2<FMT>(v[2], v[3]);
+            o.z = pack2<FMT>(v[4], v[5]);
+            o.w = pack2<FMT>(v[6], v[7]);
+          } else if (m < 0) {
+            o.x = pack2<FMT>(v[0], v[1]);
+            o.y = pack2<FMT>(v[2], v[3]);
+            o.z = pack2<FMT>(v[4], v[5]);
+            o.w = pack2<FMT>(v[6], v[7]);
+          } else {
+            o = raw[u];
           }
         }
-        if (c8 < 32) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __expf(v[j] - Ms[c8 * 8 + j]);
-        }
-        o.x = pack2<FMT>(v[0], v[1]);
-        o.y = pack2<FMT>(v[2], v[3]);
-        o.z = pack2<FMT>(v[4], v[5]);
-        o.w = pack2<FMT>(v[6], v[7]);
+        *reinterpret_cast<uint4*>(tile + r * LP2 + c8 * 8) = o;
       }
-      *reinterpret_cast<uint4*>(tile + r * LP2 + c8 * 8) = o;
     }
     __syncthreads();
     for (int r0 = 0; r0 < cnt; r0 += 16) {
@@ -260,11 +280,20 @@ __global__ void __launch_bounds__(256) lattn_out_mma_kernel(const uint16_t* __re
   __syncthreads();
   for (int s0 = r_begin; s0 < r_end; s0 += LROWS) {
     const int cnt = min(LROWS, r_end - s0);
-    for (int i = tid; i < LROWS * 32; i += 256) {
-      const int r = i >> 5, c8 = i & 31;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (r < cnt) v = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD) + c8);
-      *reinterpret_cast<uint4*>(tile + r * LP1 + c8 * 8) = v;
+    {
+      uint4 raw[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = u * 256 + tid;
+        const int r = i >> 5, c8 = i & 31;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (r < cnt) raw[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD) + c8);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = u * 256 + tid;
+        *reinterpret_cast<uint4*>(tile + (i >> 5) * LP1 + (i & 31) * 8) = raw[u];
+      }
     }
     __syncthreads();
     softmax_rows_inplace<FMT>(tile, LP1, 0, cnt, scale, tid);
@@ -319,14 +348,24 @@ __global__ void __launch_bounds__(256) lattn_dctx_mma_kernel(const uint16_t* __r
   __syncthreads();
   for (int s0 = r_begin; s0 < r_end; s0 += LROWS) {
     const int cnt = min(LROWS, r_end - s0);
-    for (int i = tid; i < LROWS * 64; i += 256) {
-      const int r = i >> 6, c8 = i & 63;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (r < cnt) {
-        if (c8 < 32) v = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD) + c8);
-        else v = __ldg(reinterpret_cast<const uint4*>(dout + (static_cast<long long>(bf) * HW + s0 + r) * HD) + (c8 - 32));
+    for (int base = 0; base < LROWS * 64; base += 256 * 8) {
+      uint4 raw[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid;
+        const int r = i >> 6, c8 = i & 63;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (r < cnt) {
+          if (c8 < 32) raw[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD) + c8);
+          else raw[u] = __ldg(reinterpret_cast<const uint4*>(dout + (static_cast<long long>(bf) * HW + s0 + r) * HD) + (c8 - 32));
+        }
       }
-      *reinterpret_cast<uint4*>((c8 < 32 ? qt : dt) + r * LP1 + (c8 & 31) * 8) = v;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid;
+        const int r = i >> 6, c8 = i & 63;
+        *reinterpret_cast<uint4*>((c8 < 32 ? qt : dt) + r * LP1 + (c8 & 31) * 8) = raw[u];
+      }
     }
     __syncthreads();
     softmax_rows_inplace<FMT>(qt, LP1, 0, cnt, scale, tid);
@@ -422,28 +461,39 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
   __syncthreads();
   for (int s0 = r_begin; s0 < r_end; s0 += R) {
     const int cnt = min(R, r_end - s0);
-    for (int i = tid; i < R * 128; i += 256) {
-      const int r = i >> 7, c8 = i & 127;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (r < cnt) {
-        if (c8 < 96) v = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD) + c8);
-        else v = __ldg(reinterpret_cast<const uint4*>(dout + (static_cast<long long>(bf) * HW + s0 + r) * HD) + (c8 - 96));
-      }
-      if (c8 < 96) {
-        if (c8 >= 32 && c8 < 64 && r < cnt) {      // k -> wn = exp(k - M) / Z
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-          uint32_t o[4];
+    for (int base = 0; base < R * 128; base += 256 * 8) {
+      uint4 raw[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack2<FMT>(w[j]);
-            const int c = (c8 - 32) * 8 + 2 * j;
-            o[j] = pack2<FMT>(__expf(f.x - Ms[c]) * Zi[c], __expf(f.y - Ms[c + 1]) * Zi[c + 1]);
-          }
-          v = make_uint4(o[0], o[1], o[2], o[3]);
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid;
+        const int r = i >> 7, c8 = i & 127;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (r < cnt) {
+          if (c8 < 96) raw[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD) + c8);
+          else raw[u] = __ldg(reinterpret_cast<const uint4*>(dout + (static_cast<long long>(bf) * HW + s0 + r) * HD) + (c8 - 96));
         }
-        *reinterpret_cast<uint4*>(tile + r * LP3 + c8 * 8) = v;
-      } else {
-        *reinterpret_cast<uint4*>(dt + r * LP1 + (c8 - 96) * 8) = v;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid;
+        const int r = i >> 7, c8 = i & 127;
+        uint4 v = raw[u];
+        if (c8 < 96) {
+          if (c8 >= 32 && c8 < 64 && r < cnt) {      // k -> wn = exp(k - M) / Z
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack2<FMT>(w[j]);
+              const int c = (c8 - 32) * 8 + 2 * j;
+              o[j] = pack2<FMT>(__expf(f.x - Ms[c]) * Zi[c], __expf(f.y - Ms[c + 1]) * Zi[c + 1]);
+            }
+            v = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          *reinterpret_cast<uint4*>(tile + r * LP3 + c8 * 8) = v;
+        } else {
+          *reinterpret_cast<uint4*>(dt + r * LP1 + (c8 - 96) * 8) = v;
+        }
       }
     }
     __syncthreads();

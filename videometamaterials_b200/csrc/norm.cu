@@ -468,7 +468,7 @@ extern "C" int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt,
   if (threads < vpr) threads = vpr;
   if (threads > 1024) return set_error(VMM_ERR_UNSUPPORTED, "vmm_gn_silu_bwd: C too large");
   const int rows = threads / vpr;
-  int ctas = (2 * num_sms() + B - 1) / B;
+  int ctas = (6 * num_sms() + B - 1) / B;
   int ppc = static_cast<int>((pix + ctas - 1) / ctas);
   if (ppc < rows * 4) ppc = rows * 4;
   ctas = static_cast<int>((pix + ppc - 1) / ppc);

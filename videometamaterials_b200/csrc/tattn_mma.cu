@@ -113,11 +113,12 @@ __global__ void __launch_bounds__(256) tattn_fwd_mma_kernel(const uint16_t* __re
     const uint32_t tile_s = smem_u32(tile);
     if (h < heads) {
       // ---- rotary in place on this head's q (scaled) and k slices
-      for (int i = lane; i < TPXB * TNF * 16; i += 32) {
-        const int k = i & 15;
-        const int f = (i >> 4) % TNF;
-        const int p = i / (16 * TNF);
-        const float cs = RT[(f * 16 + k) * 2], sn = RT[(f * 16 + k) * 2 + 1];
+      static_assert(TPXB == 2, "lane -> (pixel, pair) mapping below assumes two pixels per stage");
+#pragma unroll
+      for (int f = 0; f < TNF; ++f) {
+        const int k = lane & 15, p = lane >> 4;
+        const float2 cssn = *reinterpret_cast<const float2*>(&RT[(f * 16 + k) * 2]);
+        const float cs = cssn.x, sn = cssn.y;
         uint32_t* qp = reinterpret_cast<uint32_t*>(tile + (p * TNF + f) * TPITCH + h * 32 + 2 * k);
         uint32_t* kp = reinterpret_cast<uint32_t*>(tile + (p * TNF + f) * TPITCH + HD + h * 32 + 2 * k);
         float2 q = unpack2<FMT>(*qp), kk = unpack2<FMT>(*kp);
@@ -373,9 +374,12 @@ __global__ void __launch_bounds__(256, 1) tattn_bwd_mma_kernel(const uint16_t* _
     uint16_t* tile = tile0 + (it & 1) * BPXB * TNF * TPITCH;
     const uint32_t tile_s = smem_u32(tile), dtile_s = smem_u32(dtile0 + (it & 1) * BPXB * TNF * DPITCH);
     // rotary in place (q scaled)
-    for (int i = lane; i < BPXB * TNF * 16; i += 32) {
-      const int k = i & 15, f = (i >> 4) % TNF, p = i / (16 * TNF);
-      const float cs = RT[(f * 16 + k) * 2], sn = RT[(f * 16 + k) * 2 + 1];
+    static_assert(BPXB == 2, "lane -> (pixel, pair) mapping below assumes two pixels per stage");
+#pragma unroll
+    for (int f = 0; f < TNF; ++f) {
+      const int k = lane & 15, p = lane >> 4;
+      const float2 cssn = *reinterpret_cast<const float2*>(&RT[(f * 16 + k) * 2]);
+      const float cs = cssn.x, sn = cssn.y;
       uint32_t* qp = reinterpret_cast<uint32_t*>(tile + (p * TNF + f) * TPITCH + h * 32 + 2 * k);
       uint32_t* kp = reinterpret_cast<uint32_t*>(tile + (p * TNF + f) * TPITCH + HD + h * 32 + 2 * k);
       float2 q = unpack2<FMT>(*qp), kk = unpack2<FMT>(*kp);
