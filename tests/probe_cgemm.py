@@ -92,6 +92,26 @@ def run_case(name):
         "conv_smallc": lambda: conv(22, 16, 16, [16], 16, bf16, gn=True),
         "conv_smallc_cat": lambda: conv(11, 8, 8, [32, 16], 16, f16, res=True, gn=True),
     }
+    if name.startswith("perfrows"):
+        # perfrows:M:K:N  -- thin-K row GEMMs (QKV projection and friends)
+        _, M, K, N = name.split(":")
+        M, K, N = int(M), int(K), int(N)
+        a = torch.randn(M, K, device=dev).to(bf16)
+        wp = ops.pack_linear(torch.randn(N, K, device=dev) / K ** 0.5, bf16)
+        out = torch.empty(M, N, device=dev, dtype=bf16)
+        run = lambda: ops.cgemm([a.view(1, 1, M, K)], [[(0, 0, 0, 0, K)]], wp, N, out, (1, 1, M))
+        for _ in range(3):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        byts = 2.0 * M * (K + N)
+        print(f"  perf rows M={M} K={K} N={N}: {ms * 1e3:.1f} us  {2.0 * M * K * N / ms / 1e9:.1f} TFLOP/s  {byts / ms / 1e6:.0f} GB/s")
+        return True
     if name in ("perf", "perf1"):
         shapes = [(88, 96, 64, 64), (88, 48, 128, 128), (88, 24, 256, 256), (88, 12, 512, 512), (88, 96, 128, 64)]
         for (bf, h, cin, n) in (shapes[:1] if name == "perf1" else shapes):

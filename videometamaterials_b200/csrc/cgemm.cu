@@ -3,7 +3,9 @@
 //   warp 0      TMA producer   (one lane): per K block, one 4-D box of A (shifted by the tap) + one 2-D box of W
 //   warp 1      MMA issuer     (one lane): tcgen05.mma kind::f16, M=128, N=BN, K=16 x4 per 64-wide block
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue: tcgen05.ld -> bias / residual / GroupNorm partial sums -> global stores
+//   warps 4..11 epilogue (two warps per TMEM lane quarter, each takes half of the tile's columns): tcgen05.ld -> bias / residual / GroupNorm partial sums -> 16-bit rows staged in shared
+//               memory (64-byte swizzle) -> one bulk tensor store per warp and 32 columns (TMA clips the tile
+//               overhang); fp32 outputs and odd column splits keep per-thread global stores
 //
 // Two TMEM accumulators (double buffer) let the epilogue of tile i overlap the main loop of tile i+1.
 // The ring of smem stages is shared across tiles (the producer runs ahead of the MMA warp).
@@ -21,6 +23,9 @@ struct TapDev {
 struct CgemmDev {
   CUtensorMap amap[VMM_MAX_VIEWS];
   CUtensorMap bmap;
+  CUtensorMap omap[VMM_MAX_PHASES];   // output view of each phase (box = the 32 pixels of one epilogue warp x 32 columns)
+  CUtensorMap omap2;                  // columns >= nsplit (single-phase launches only)
+  int tstore;                         // epilogue uses bulk tensor stores
   TapDev taps[VMM_MAX_PHASES][VMM_MAX_TAPS];
   int n_taps[VMM_MAX_PHASES];
   int phase_oy[VMM_MAX_PHASES], phase_ox[VMM_MAX_PHASES];
@@ -82,30 +87,40 @@ constexpr int kBiasSmem = 1024;
 
 constexpr int kGnGroups = 8;   // GroupNorm groups per n-tile (BN is capped accordingly on the host)
 
-// GroupNorm partial sums live in per-thread shared-memory slots s_racc[slot][group][thread][sum|sumsq]: the epilogue
-// adds to its own slot with plain loads/stores (no shuffles, no atomics per tile).  gn_flush reduces the 128 slots of
-// each (slot, group) and adds them to the global fp64 statistics of (first sample smp0, n-tile n0); it is called by
-// all 128 epilogue threads between two named-barrier syncs, only when the CTA moves to another sample / n-tile.
-__device__ __forceinline__ void gn_flush(const CgemmDev& p, float (*racc)[kGnGroups][128][2], int ethread, int smp0, int n0) {
-  if (ethread < 2 * kGnGroups * 2) {
-    const int sl = ethread / (kGnGroups * 2), gl = (ethread >> 1) % kGnGroups, w = ethread & 1;
+// GroupNorm partial sums live in per-row shared-memory slots s_racc[group][row][sum|sumsq]: the epilogue thread that
+// owns (row, column half) adds to them with plain loads/stores (no shuffles, no atomics per tile).  gn_flush reduces the
+// 128 rows of each group, separately for the (at most two) samples the rows of the current key belong to, and adds the
+// result to the global fp64 statistics.  It is called by all 256 epilogue threads after a named-barrier sync, only when
+// the CTA moves to another (first sample, n-tile, frame tile if the tile straddles two samples) key.
+constexpr int kEpiThreads = 256;
+
+__device__ __forceinline__ void gn_flush(const CgemmDev& p, float (*racc)[128][2], int ethread, int smp0, int n0, int key_bf0) {
+  {
+    const int o = ethread >> 3, part = ethread & 7;            // 32 outputs x 8 partial sums
+    const int sl = o >> 4, gl = (o >> 1) & (kGnGroups - 1), w = o & 1;
     float val = 0.f;
-    for (int i = 0; i < 128; ++i) val += racc[sl][gl][(i + ethread) & 127][w];     // skewed start: fewer bank conflicts
+    if (sl == 0 || key_bf0 >= 0) {
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int row = part * 16 + ((i + part) & 15);           // skewed: the 8 parts hit different banks
+        int rs = 0;
+        if (key_bf0 >= 0) rs = (key_bf0 + (row >> (p.tw_log + p.th_log))) / p.fps - smp0;
+        if (rs == sl) val += racc[gl][row][w];
+      }
+    }
+    val += __shfl_xor_sync(0xffffffffu, val, 1);
+    val += __shfl_xor_sync(0xffffffffu, val, 2);
+    val += __shfl_xor_sync(0xffffffffu, val, 4);
     const int g = n0 / p.gn_gs + gl;
     const int nsamp = (p.BF + p.fps - 1) / p.fps;
-    if (g < p.gn_groups && smp0 + sl < nsamp && val != 0.f)
+    if (part == 0 && g < p.gn_groups && smp0 + sl < nsamp && val != 0.f)
       atomicAdd(p.gn_stats + (static_cast<long long>(smp0 + sl) * p.gn_groups + g) * 2 + w, static_cast<double>(val));
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  for (int sl = 0; sl < 2; ++sl)
-    for (int gl = 0; gl < kGnGroups; ++gl) {
-      racc[sl][gl][ethread][0] = 0.f;
-      racc[sl][gl][ethread][1] = 0.f;
-    }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-__device__ __forceinline__ void gn_thread_add(float (*racc)[kGnGroups][128][2], int gl, int slot, int ethread, float a1, float a2) {
-  float2* q = reinterpret_cast<float2*>(&racc[slot][gl][ethread][0]);
+__device__ __forceinline__ void gn_thread_add(float (*racc)[128][2], int gl, int row, float a1, float a2) {
+  float2* q = reinterpret_cast<float2*>(&racc[gl][row][0]);
   float2 v = *q;
   v.x += a1;
   v.y += a2;
@@ -113,10 +128,11 @@ __device__ __forceinline__ void gn_thread_add(float (*racc)[kGnGroups][128][2], 
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ CgemmDev p) {
+__global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ CgemmDev p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) float s_gn[2][kGnGroups][128][2];   // per-thread GroupNorm partial sums, see gn_flush
+  __shared__ __align__(8) float s_gn[kGnGroups][128][2];      // per-row GroupNorm partial sums, see gn_flush
   __shared__ __align__(16) float s_bias[kBiasSmem];
+  __shared__ __align__(1024) uint8_t s_stage[8][32 * 64];     // per epilogue warp: 32 rows x 32 columns (16-bit), swizzle 64B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   CgemmSmemCtl* ctl = reinterpret_cast<CgemmSmemCtl*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
 
@@ -126,6 +142,10 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < VMM_MAX_VIEWS; ++i) tma_prefetch_desc(&p.amap[i]);
     tma_prefetch_desc(&p.bmap);
+    if (p.tstore) {
+      for (int i = 0; i < p.n_phases; ++i) tma_prefetch_desc(&p.omap[i]);
+      if (p.out2) tma_prefetch_desc(&p.omap2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -134,7 +154,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&ctl->tfull[a], 1);
-      mbar_init(&ctl->tempty[a], 128);
+      mbar_init(&ctl->tempty[a], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -143,8 +163,8 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
     tmem_relinquish();
   }
   if (warp == 3) {
-    float* g = &s_gn[0][0][0][0];
-    for (int i = lane; i < 2 * kGnGroups * 128 * 2; i += 32) g[i] = 0.f;
+    float* g = &s_gn[0][0][0];
+    for (int i = lane; i < kGnGroups * 128 * 2; i += 32) g[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -221,17 +241,25 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;    // which half of the tile's columns this warp drains
+    const int ew = warp - 4;             // staging buffer
     const int row = q * 32 + lane;       // row of the 128-row tile == TMEM lane
     const int ethread = threadIdx.x - 128;
     // bias lives in shared memory for the whole kernel (global loads in the column loop were the bottleneck)
     const bool bias_smem = p.bias != nullptr && p.N <= kBiasSmem;
     if (bias_smem) {
-      for (int i = ethread; i < p.N; i += 128) s_bias[i] = __ldg(p.bias + i);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = ethread; i < p.N; i += kEpiThreads) s_bias[i] = __ldg(p.bias + i);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    // 32-column steps; the two warps of a lane quarter split them in two contiguous halves when the boundary does not
+    // cut a GroupNorm group (else the first warp takes all of them)
     const int nsteps = (p.BN + 31) >> 5;
+    int hs = (nsteps + 1) >> 1;
+    if (p.gn_stats && p.gn_gs > 32 && ((hs * 32) % p.gn_gs) != 0) hs = nsteps;
+    const int st_lo = half ? hs : 0;
+    const int st_hi = half ? nsteps : hs;
     int it = 0;
-    int gn_key_smp = -1, gn_key_n0 = -1;
+    int gn_key_smp = -1, gn_key_n0 = -1, gn_key_bf0 = -1;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int phase, bf0, y0, x0, n0;
       decode_tile(p, t, phase, bf0, y0, x0, n0);
@@ -243,27 +271,36 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
       const int fl = row >> (p.tw_log + p.th_log);
       const int bf = bf0 + fl, y = y0 + yl, x = x0 + xl;
       const bool valid = (bf < p.BF) && (y < p.OH) && (x < p.OW);
+      // first pixel of this warp's 32 rows (origin of its store box)
+      const int wx = x0 + ((q * 32) & ((1 << p.tw_log) - 1));
+      const int wy = y0 + (((q * 32) >> p.tw_log) & ((1 << p.th_log) - 1));
+      const int wf = bf0 + ((q * 32) >> (p.tw_log + p.th_log));
       const long long pix =
           (static_cast<long long>(bf) * p.OHs + (y * p.sy + p.phase_oy[phase])) * p.OWs + (x * p.sx + p.phase_ox[phase]);
 
       // GroupNorm bookkeeping.  Partial sums stay in shared memory while consecutive tiles of this CTA belong
       // to the same (first sample, n-tile); they go to global memory (fp64 atomics) only when that key changes,
       // which keeps the number of same-address atomics per launch at O(CTAs x samples) instead of O(tiles).
-      int slot = 0;
-      bool two_samples = false;
       if (p.gn_stats) {
         const int smp0 = bf0 / p.fps;
         const int last_bf = min(bf0 + (1 << p.tf_log), p.BF) - 1;
-        two_samples = (last_bf / p.fps) != smp0;
-        slot = valid ? (bf / p.fps - smp0) : 0;
-        if (smp0 != gn_key_smp || n0 != gn_key_n0) {
+        const int kbf0 = ((last_bf / p.fps) != smp0) ? bf0 : -1;     // tile straddles two samples
+        if (smp0 != gn_key_smp || n0 != gn_key_n0 || kbf0 != gn_key_bf0) {
           if (gn_key_smp >= 0) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
+            // each thread clears the slots it adds to: its row, the groups of its column half
+            for (int gl = 0; gl < kGnGroups; ++gl) {
+              const int st_g = (gl * p.gn_gs) >> 5;
+              if (st_g >= st_lo && st_g < st_hi) {
+                s_gn[gl][row][0] = 0.f;
+                s_gn[gl][row][1] = 0.f;
+              }
+            }
           }
           gn_key_smp = smp0;
           gn_key_n0 = n0;
+          gn_key_bf0 = kbf0;
         }
       }
 
@@ -277,8 +314,9 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
       uint4 rq[4];
       auto res_ptr = [&](int col) -> const uint16_t* { return (split && col >= p.nsplit) ? rrow2 + col : rrow1 + col; };
       auto straddles = [&](int col) -> bool { return split && col < p.nsplit && col + 32 > p.nsplit; };
-      if (rrow1 && res_al && n0 + 32 <= p.N && !straddles(n0)) {
-        const uint4* rp = reinterpret_cast<const uint4*>(res_ptr(n0));
+      const int ncol_lo = n0 + st_lo * 32;
+      if (rrow1 && res_al && st_lo < st_hi && ncol_lo + 32 <= p.N && !straddles(ncol_lo)) {
+        const uint4* rp = reinterpret_cast<const uint4*>(res_ptr(ncol_lo));
 #pragma unroll
         for (int j = 0; j < 4; ++j) rq[j] = __ldg(rp + j);
       }
@@ -288,7 +326,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.acc_stride;
 
       float gs1 = 0.f, gs2 = 0.f;   // running sums of the current GroupNorm group
-      for (int st = 0; st < nsteps; ++st) {
+      for (int st = st_lo; st < st_hi; ++st) {
         const int ncol = n0 + st * 32;
         uint32_t r[32];
         tmem_ld16(t_addr + st * 32, r);
@@ -338,7 +376,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
               if (ncol + j < p.N) v[j] += h16_to_f(*res_ptr(ncol + j), FMT);
           }
           // prefetch the next 32 columns
-          if (res_al && st + 1 < nsteps && ncol + 64 <= p.N && !straddles(ncol + 32)) {
+          if (res_al && st + 1 < st_hi && ncol + 64 <= p.N && !straddles(ncol + 32)) {
             const uint4* rp = reinterpret_cast<const uint4*>(res_ptr(ncol + 32));
 #pragma unroll
             for (int j = 0; j < 4; ++j) rq[j] = __ldg(rp + j);
@@ -376,7 +414,22 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
           uint32_t w[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) w[j] = pack2<FMT>(v[2 * j], v[2 * j + 1]);
-          if (valid) {
+          if (p.tstore) {
+            // the previous bulk store of this warp must have read the staging rows before they are overwritten
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            uint8_t* srow = &s_stage[ew][lane * 64];
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d((split && ncol >= p.nsplit) ? &p.omap2 : &p.omap[phase], &s_stage[ew][0], ocol, wx, wy, wf);
+              bulk_commit();
+            }
+          } else if (valid) {
             uint16_t* op = reinterpret_cast<uint16_t*>(obase) + pix * ld + ocol;
             if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
@@ -420,7 +473,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
                 gs2 += b2[b];
                 const int cend = ncol + 8 * (b + 1);
                 if ((cend % gs) == 0 && cend - gs < p.N) {   // group complete (uniform across the warp)
-                  gn_thread_add(s_gn, (cend - gs - n0) / gs, slot, ethread, gs1, gs2);
+                  gn_thread_add(s_gn, (cend - gs - n0) / gs, row, gs1, gs2);
                   gs1 = gs2 = 0.f;
                 }
               }
@@ -435,7 +488,7 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
                 if (((cj + 1) % gs) == 0) {
                   const int c0g = ncol + cj + 1 - gs;
                   const int gl = (c0g - n0) / gs;
-                  if (c0g < p.N && gl < kGnGroups) gn_thread_add(s_gn, gl, slot, ethread, gs1, gs2);
+                  if (c0g < p.N && gl < kGnGroups) gn_thread_add(s_gn, gl, row, gs1, gs2);
                   gs1 = gs2 = 0.f;
                 }
               }
@@ -448,9 +501,10 @@ __global__ void __launch_bounds__(256, 1) cgemm_kernel(const __grid_constant__ C
       mbar_arrive(&ctl->tempty[acc]);
     }
     if (p.gn_stats && gn_key_smp >= 0) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
     }
+    if (p.tstore && lane == 0) bulk_wait0();   // shared memory must outlive the last bulk store
   }
 
   tc_fence_before();
@@ -529,7 +583,7 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   d.total_tiles = static_cast<int>(total);
   d.stage_bytes = kABytes + BN * 128;
   d.tx_bytes = d.stage_bytes;
-  const int smem_budget = 200 * 1024;   // + ~20 KB static (bias, GroupNorm slots) + control block: 4 stages at BN = 256
+  const int smem_budget = 194 * 1024;   // + 28 KB static (bias, GroupNorm slots, store staging) + control block: 4 stages at BN = 256
   int stages = smem_budget / static_cast<int>(d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile too large for shared memory");
@@ -597,17 +651,47 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     if (rc) return rc;
   }
 
+  // Output tensor maps for the bulk-store epilogue: pixel (bf, y, x) of phase ph lives at
+  // out + ((bf*OHs + y*sy + oy)*OWs + x*sx + ox) * ldo, i.e. a strided 4-D view (columns, x, y, bf).
+  {
+    const bool al = (h.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(h.out) & 15) == 0;
+    const bool al2 = !h.out2 || ((h.ldo2 % 8) == 0 && (reinterpret_cast<uintptr_t>(h.out2) & 15) == 0 && (h.nsplit % 32) == 0 &&
+                                 h.n_phases == 1 && h.nsplit > 0 && h.nsplit < h.n);
+    d.tstore = !h.out_fp32 && al && al2 && ((BN % 32) == 0 || d.n_ntiles == 1);
+  }
+  if (d.tstore) {
+    // the 32 rows of one epilogue warp form a sub-box of the (tf, th, tw) pixel tile
+    const uint32_t bw = h.tw < 32 ? h.tw : 32;
+    const uint32_t bh = (32 / bw) < (uint32_t)h.th ? (32 / bw) : (uint32_t)h.th;
+    const uint32_t bfr = 32 / (bw * bh);
+    const uint32_t box[4] = {32, bw, bh, bfr};
+    for (int ph = 0; ph < h.n_phases; ++ph) {
+      const long long ncols = h.out2 ? h.nsplit : h.n;
+      uint64_t gdim[4] = {(uint64_t)ncols, (uint64_t)h.ow, (uint64_t)h.oh, (uint64_t)h.bf};
+      uint64_t gstr[3] = {(uint64_t)h.sx * h.ldo * 2, (uint64_t)h.sy * h.ows * h.ldo * 2, (uint64_t)h.ohs * h.ows * h.ldo * 2};
+      uint8_t* base = static_cast<uint8_t*>(h.out) + (1LL * h.phase_oy[ph] * h.ows + h.phase_ox[ph]) * h.ldo * 2;
+      int rc = encode_tensor_map(&d.omap[ph], dt, 4, base, gdim, gstr, box, false, 64);
+      if (rc) return rc;
+    }
+    if (h.out2) {
+      uint64_t gdim[4] = {(uint64_t)(h.n - h.nsplit), (uint64_t)h.ow, (uint64_t)h.oh, (uint64_t)h.bf};
+      uint64_t gstr[3] = {(uint64_t)h.sx * h.ldo2 * 2, (uint64_t)h.sy * h.ows * h.ldo2 * 2, (uint64_t)h.ohs * h.ows * h.ldo2 * 2};
+      int rc = encode_tensor_map(&d.omap2, dt, 4, h.out2, gdim, gstr, box, false, 64);
+      if (rc) return rc;
+    }
+  }
+
   const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + sizeof(CgemmSmemCtl) + 1024;   // + ~4.4 KB static
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(cgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "vmm_cgemm: cudaFuncSetAttribute");
     attr_set = true;
   }
   const int grid = d.total_tiles < num_sms() ? d.total_tiles : num_sms();
-  if (h.fmt == VMM_FMT_F16) cgemm_kernel<0><<<grid, 256, smem, stream>>>(d);
-  else cgemm_kernel<1><<<grid, 256, smem, stream>>>(d);
+  if (h.fmt == VMM_FMT_F16) cgemm_kernel<0><<<grid, 384, smem, stream>>>(d);
+  else cgemm_kernel<1><<<grid, 384, smem, stream>>>(d);
   count_launch();
   return check_launch("vmm_cgemm");
 }

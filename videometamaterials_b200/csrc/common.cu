@@ -55,7 +55,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* gdim,
-                      const uint64_t* gstride_bytes, const uint32_t* box, bool l2_256) {
+                      const uint64_t* gstride_bytes, const uint32_t* box, bool l2_256, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(VMM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(VMM_ERR_ARG, "tensor map: base not 16-byte aligned");
@@ -73,7 +73,7 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const 
     if (gs[i] == 0 || (gs[i] & 15) != 0) return set_error(VMM_ERR_ARG, "tensor map: stride must be a non-zero multiple of 16 bytes");
   }
   CUresult r = fn(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, l2_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, l2_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(error_buffer(), 512, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,

@@ -19,9 +19,9 @@ void count_launch();
 int num_sms();
 
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency, so the
-// library also loads on a machine without a driver).  128-byte swizzle, zero fill out of bounds.
+// library also loads on a machine without a driver).  128-byte swizzle (or 64), zero fill out of bounds.
 int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* gdim,
-                      const uint64_t* gstride_bytes, const uint32_t* box, bool l2_256);
+                      const uint64_t* gstride_bytes, const uint32_t* box, bool l2_256, int swizzle_bytes = 128);
 
 static inline unsigned int ceil_div(long long a, long long b) { return static_cast<unsigned int>((a + b - 1) / b); }
 static inline long long min64(long long a, long long b) { return a < b ? a : b; }

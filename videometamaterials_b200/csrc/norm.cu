@@ -68,23 +68,47 @@ __global__ void __launch_bounds__(256) gn_silu_fwd_kernel(const uint16_t* __rest
   const uint16_t* xb = x + static_cast<long long>(b) * pix * C;
   const uint16_t* rb = res ? res + static_cast<long long>(b) * pix * C : nullptr;
   uint16_t* yb = y + static_cast<long long>(b) * pix * C;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>((i * 8) % C);
-    float v[8];
-    load8(xb + i * 8, fmt, v);
+  // 4 independent 16-byte vectors per thread and iteration: all loads are issued before the first use
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
+    uint4 xr[4], rr[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float u = v[j] * coef[c0 + j] + coef[C + c0 + j];
-      v[j] = act ? silu_f(u) : u;
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        xr[u] = __ldg(reinterpret_cast<const uint4*>(xb) + i);
+        if (rb) rr[u] = __ldg(reinterpret_cast<const uint4*>(rb) + i);
+      }
     }
-    if (rb) {   // identity skip of a ResnetBlock whose dim == dim_out (VDDP:297,311)
-      float r8[8];
-      load8(rb + i * 8, fmt, r8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r8[j];
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) continue;
+      const int c0 = static_cast<int>((i * 8) % C);
+      const uint32_t xw[4] = {xr[u].x, xr[u].y, xr[u].z, xr[u].w};
+      const uint32_t rw[4] = {rr[u].x, rr[u].y, rr[u].z, rr[u].w};
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack2_h16(xw[j], fmt);
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float uu = v[j] * coef[c0 + j] + coef[C + c0 + j];
+        v[j] = act ? silu_f(uu) : uu;
+      }
+      if (rb) {   // identity skip of a ResnetBlock whose dim == dim_out (VDDP:297,311)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack2_h16(rw[j], fmt);
+          v[2 * j] += f.x;
+          v[2 * j + 1] += f.y;
+        }
+      }
+      store8(yb + i * 8, fmt, v);
     }
-    store8(yb + i * 8, fmt, v);
   }
 }
 
@@ -139,17 +163,36 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_reduce_kernel(const uint16_t*
   const uint16_t* xb = x + static_cast<long long>(b) * pix * C;
   const uint16_t* db = dy + static_cast<long long>(b) * pix * C;
   if (vr < rows) {
-    for (long long pp = p0 + vr; pp < p1; pp += rows) {
-      float xv[8], dv[8];
-      load8(xb + pp * C + c0, fmt, xv);
-      load8(db + pp * C + c0, fmt, dv);
+    for (long long pb = p0 + vr; pb < p1; pb += 4 * rows) {
+      uint4 xr[4], dr[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float u = xv[j] * ca[c0 + j] + cd[c0 + j];
-        const float du = act ? dv[j] * dsilu_f(u) : dv[j];
-        const float xh = (xv[j] - cm[c0 + j]) * cr[c0 + j];
-        s1[j] += du;
-        s2[j] += du * xh;
+      for (int u = 0; u < 4; ++u) {
+        const long long pp = pb + static_cast<long long>(u) * rows;
+        if (pp < p1) {
+          xr[u] = __ldg(reinterpret_cast<const uint4*>(xb + pp * C + c0));
+          dr[u] = __ldg(reinterpret_cast<const uint4*>(db + pp * C + c0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pp = pb + static_cast<long long>(u) * rows;
+        if (pp >= p1) continue;
+        const uint32_t xw[4] = {xr[u].x, xr[u].y, xr[u].z, xr[u].w};
+        const uint32_t dw[4] = {dr[u].x, dr[u].y, dr[u].z, dr[u].w};
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          const float2 xf = unpack2_h16(xw[j2], fmt), df = unpack2_h16(dw[j2], fmt);
+          const float xv2[2] = {xf.x, xf.y}, dv2[2] = {df.x, df.y};
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int j = 2 * j2 + k;
+            const float uu = xv2[k] * ca[c0 + j] + cd[c0 + j];
+            const float du = act ? dv2[k] * dsilu_f(uu) : dv2[k];
+            const float xh = (xv2[k] - cm[c0 + j]) * cr[c0 + j];
+            s1[j] += du;
+            s2[j] += du * xh;
+          }
+        }
       }
     }
   }
@@ -256,21 +299,40 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* 
   const uint16_t* xb = x + static_cast<long long>(b) * pix * C;
   const uint16_t* db = dy + static_cast<long long>(b) * pix * C;
   uint16_t* ob = dx + static_cast<long long>(b) * pix * C;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>((i * 8) % C);
-    float xv[8], dv[8], o[8];
-    load8(xb + i * 8, fmt, xv);
-    load8(db + i * 8, fmt, dv);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
+    uint4 xr[4], dr[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float u = xv[j] * ca[c] + cd[c];
-      const float du = act ? dv[j] * dsilu_f(u) : dv[j];
-      const float xh = (xv[j] - cm[c]) * cr[c];
-      o[j] = cr[c] * (ck[c] * du - c1[c] - xh * c2[c]);
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        xr[u] = __ldg(reinterpret_cast<const uint4*>(xb) + i);
+        dr[u] = __ldg(reinterpret_cast<const uint4*>(db) + i);
+      }
     }
-    store8(ob + i * 8, fmt, o);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) continue;
+      const int c0 = static_cast<int>((i * 8) % C);
+      const uint32_t xw[4] = {xr[u].x, xr[u].y, xr[u].z, xr[u].w};
+      const uint32_t dw[4] = {dr[u].x, dr[u].y, dr[u].z, dr[u].w};
+      float o[8];
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        const float2 xf = unpack2_h16(xw[j2], fmt), df = unpack2_h16(dw[j2], fmt);
+        const float xv2[2] = {xf.x, xf.y}, dv2[2] = {df.x, df.y};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c = c0 + 2 * j2 + k;
+          const float uu = xv2[k] * ca[c] + cd[c];
+          const float du = act ? dv2[k] * dsilu_f(uu) : dv2[k];
+          const float xh = (xv2[k] - cm[c]) * cr[c];
+          o[2 * j2 + k] = cr[c] * (ck[c] * du - c1[c] - xh * c2[c]);
+        }
+      }
+      store8(ob + i * 8, fmt, o);
+    }
   }
 }
 

@@ -17,6 +17,7 @@ from ._lib import CgemmParams, FMT_BF16, FMT_F16, WgradParams, check, lib
 
 # bench.py sets PROFILE = [] to collect (kernel, algorithmic flops, start event, end event) per GEMM launch
 PROFILE = None
+PROFILE_TAGS = False        # probes: append the GEMM shape to the kernel name
 
 
 def _prof_begin():
@@ -167,7 +168,9 @@ def cgemm(views: Sequence[torch.Tensor], taps: Sequence[Sequence[Tuple[int, int,
     e0 = _prof_begin()
     check(lib.vmm_cgemm(C.byref(p), stream_ptr()), "vmm_cgemm")
     if e0 is not None:
-        _prof_end("cgemm", 2.0 * bf * oh * ow * n * sum(c for tl in taps for (_, _, _, _, c) in tl), e0)
+        ksum = sum(c for tl in taps for (_, _, _, _, c) in tl)
+        tag = f"|M={bf * oh * ow} N={n} K={ksum} taps={len(taps[0])}x{len(taps)} tile={p.tf}x{p.th}x{p.tw}" if PROFILE_TAGS else ""
+        _prof_end("cgemm" + tag, 2.0 * bf * oh * ow * n * ksum, e0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -425,7 +428,8 @@ def wgrad(a_views: Sequence[torch.Tensor], b_views: Sequence[torch.Tensor], taps
     e0 = _prof_begin()
     check(lib.vmm_wgrad(C.byref(p), stream_ptr()), "vmm_wgrad")
     if e0 is not None:
-        _prof_end("wgrad", 2.0 * bf * oh * ow * n * sum(tp[4] for tp in taps), e0)
+        tag = f"|px={bf * oh * ow} M={n} C={sum(tp[4] for tp in taps)} taps={len(taps)}" if PROFILE_TAGS else ""
+        _prof_end("wgrad" + tag, 2.0 * bf * oh * ow * n * sum(tp[4] for tp in taps), e0)
 
 
 def colsum(x2d: torch.Tensor, out: torch.Tensor) -> None:
@@ -451,11 +455,16 @@ def wgrad_linear(dy2d: torch.Tensor, xs2d: Sequence[torch.Tensor], dw: torch.Ten
     """dw: (N, K_total) fp32 (any trailing singleton dims);  dy2d [M, N]; xs2d concat sources [M, K_i]."""
     n = dw.shape[0]
     ktot = dw.numel() // n
+    m = dy2d.shape[0]
+    if len(xs2d) == 1 and n > ktot:
+        # dW^T = X^T dY: put the narrower operand on the 128-row M side and pack the wide one into accumulator columns
+        # (3 chunks of 64 per block), which cuts the re-reads of the narrow operand (the kernel is L2-fill bound)
+        wgrad([rows_view(xs2d[0])], [rows_view(dy2d)], [(0, 0, 0, 0, n, 0)], ktot, dw, 1, ktot, (1, 1, m))
+        return
     taps, coff = [], 0
     for s, x in enumerate(xs2d):
         taps.append((0, s, 0, 0, x.shape[1], coff))
         coff += x.shape[1]
-    m = dy2d.shape[0]
     wgrad([rows_view(dy2d)], [rows_view(x) for x in xs2d], taps, n, dw, ktot, 1, (1, 1, m))
 
 
