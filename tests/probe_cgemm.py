@@ -56,8 +56,7 @@ def run_case(name):
         nsamp = -(-bf // fps)
         groups = 8
         stats = torch.zeros(nsamp, groups, 2, device=dev, dtype=torch.float64) if gn else None
-        ops.cgemm(xs, [taps], wp, n, out, (bf, h, w_), bias=b, res=r, gn_stats=stats, gn_group=n // groups,
-                  frames_per_sample=fps)
+        ops.conv3x3(xs, wp, n, out, bias=b, res=r, gn_stats=stats, gn_group=n // groups, frames_per_sample=fps)
         torch.cuda.synchronize()
         want = ref_conv(torch.cat(xs, dim=-1), wt, b, 1)
         if res:
@@ -91,6 +90,9 @@ def run_case(name):
         "conv_12_512": lambda: conv(22, 12, 12, [512], 512, bf16, gn=True),
         "conv_smallc": lambda: conv(22, 16, 16, [16], 16, bf16, gn=True),
         "conv_smallc_cat": lambda: conv(11, 8, 8, [32, 16], 16, f16, res=True, gn=True),
+        "conv_halo_cat": lambda: conv(13, 32, 24, [64, 64], 64, bf16, res=True, gn=True),
+        "conv_halo_96_128": lambda: conv(5, 96, 96, [64], 128, f16, gn=True),
+        "conv_halo_smallc": lambda: conv(11, 16, 16, [16, 8], 16, f16, res=True, gn=True),
     }
     if name.startswith("perfrows"):
         # perfrows:M:K:N  -- thin-K row GEMMs (QKV projection and friends)
@@ -113,21 +115,21 @@ def run_case(name):
         print(f"  perf rows M={M} K={K} N={N}: {ms * 1e3:.1f} us  {2.0 * M * K * N / ms / 1e9:.1f} TFLOP/s  {byts / ms / 1e6:.0f} GB/s")
         return True
     if name in ("perf", "perf1"):
-        shapes = [(88, 96, 64, 64), (88, 48, 128, 128), (88, 24, 256, 256), (88, 12, 512, 512), (88, 96, 128, 64)]
+        shapes = [(88, 96, 64, 64), (88, 48, 128, 128), (88, 24, 256, 256), (88, 12, 512, 512), (88, 96, 128, 64), (88, 96, 64, 128),
+                  (88, 48, 64, 128), (88, 48, 128, 64), (88, 48, 256, 128)]
         for (bf, h, cin, n) in (shapes[:1] if name == "perf1" else shapes):
             x = torch.randn(bf, h, h, cin, device=dev).to(bf16)
             wt = (torch.randn(n, cin, 3, 3, device=dev) / (9 * cin) ** 0.5).to(bf16)
             wp = ops.pack_conv_taps(wt.float(), [cin], bf16)
-            taps, _ = ops.taps_conv(3, 3, [cin], 1)
             out = torch.empty(bf, h, h, n, device=dev, dtype=bf16)
             stats = torch.zeros(8, 8, 2, device=dev, dtype=torch.float64)
             bias = torch.zeros(n, device=dev)
             for _ in range(3):
-                ops.cgemm([x], [taps], wp, n, out, (bf, h, h), bias=bias, gn_stats=stats, gn_group=n // 8, frames_per_sample=11)
+                ops.conv3x3([x], wp, n, out, bias=bias, gn_stats=stats, gn_group=n // 8, frames_per_sample=11)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(10):
-                ops.cgemm([x], [taps], wp, n, out, (bf, h, h), bias=bias, gn_stats=stats, gn_group=n // 8, frames_per_sample=11)
+                ops.conv3x3([x], wp, n, out, bias=bias, gn_stats=stats, gn_group=n // 8, frames_per_sample=11)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
@@ -138,7 +140,7 @@ def run_case(name):
 
 
 ALL = ["gemm_small", "gemm_k256", "gemm_n512", "gemm_n768_f16", "gemm_fp32out_n3", "gemm_k16", "conv_16", "conv_96_gn",
-       "conv_cat_res_gn", "conv_24_f16", "conv_12_512", "conv_smallc", "conv_smallc_cat", "perf"]
+       "conv_cat_res_gn", "conv_24_f16", "conv_12_512", "conv_smallc", "conv_smallc_cat", "conv_halo_cat", "conv_halo_96_128", "conv_halo_smallc", "perf"]
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:

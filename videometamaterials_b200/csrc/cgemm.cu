@@ -13,12 +13,16 @@
 #include "mma_sync.cuh"
 #include "sm100_ptx.cuh"
 
+#include <algorithm>
+
 namespace vmm {
 
 struct TapDev {
   int16_t src, dy, dx, nk;
   int32_t kofs;
 };
+
+constexpr int kHaloMaxChunks = 8;
 
 struct CgemmDev {
   CUtensorMap amap[VMM_MAX_VIEWS];
@@ -54,6 +58,15 @@ struct CgemmDev {
   double* gn_stats;
   int gn_gs, gn_groups, fps;
   int fmt;
+  // halo mode (3x3 stride-1 taps, tile 1 x th x 8): per (64-channel chunk, kx) one A slab of th+2 pixel rows serves the three ky taps
+  uint64_t mg_nt, mg_tx, mg_ty, mg_tf, mg_fps;   // ceil(2^32 / d) + exact-floor multipliers (fdiv below)
+  int gs_log;                         // log2(gn_gs) when it is a power of two >= 8, else -1
+  int halo;                           // 0 = generic taps
+  int h_chunks;                       // 64-channel chunks over all sources
+  int b_resident;                     // all weight tiles stay in shared memory for the whole kernel (single n-tile)
+  uint32_t slab_bytes, btile_bytes;
+  int16_t h_src[kHaloMaxChunks], h_kb[kHaloMaxChunks];
+  int32_t h_kofs[9][kHaloMaxChunks];  // K offset of (tap ky*3+kx, chunk) in the packed weights
 };
 
 constexpr int kMaxStages = 8;
@@ -64,19 +77,23 @@ struct __align__(8) CgemmSmemCtl {
   uint64_t empty[kMaxStages];
   uint64_t tfull[2];
   uint64_t tempty[2];
+  uint64_t bfull;
   uint32_t tmem_base;
   uint32_t pad;
 };
 
+// floor(t / d) for 0 <= t < 2^32 / d with m = floor(2^32 / d) + 1 (host: magic_of); d == 1 gives m = 2^32 + 1 -> t
+__device__ __forceinline__ int fdiv(int t, uint64_t m) { return static_cast<int>((static_cast<uint64_t>(static_cast<uint32_t>(t)) * m) >> 32); }
+
 __device__ __forceinline__ void decode_tile(const CgemmDev& p, int t, int& phase, int& bf0, int& y0, int& x0, int& n0) {
-  int nt = t % p.n_ntiles;
-  int r = t / p.n_ntiles;
-  int xt = r % p.tiles_x;
-  r /= p.tiles_x;
-  int yt = r % p.tiles_y;
-  r /= p.tiles_y;
-  int ft = r % p.tiles_f;
-  phase = r / p.tiles_f;
+  int r = fdiv(t, p.mg_nt);
+  const int nt = t - r * p.n_ntiles;
+  int r2 = fdiv(r, p.mg_tx);
+  const int xt = r - r2 * p.tiles_x;
+  r = fdiv(r2, p.mg_ty);
+  const int yt = r2 - r * p.tiles_y;
+  phase = fdiv(r, p.mg_tf);
+  const int ft = r - phase * p.tiles_f;
   bf0 = ft << p.tf_log;
   y0 = yt << p.th_log;
   x0 = xt << p.tw_log;
@@ -104,15 +121,15 @@ __device__ __forceinline__ void gn_flush(const CgemmDev& p, float (*racc)[128][2
       for (int i = 0; i < 16; ++i) {
         const int row = part * 16 + ((i + part) & 15);           // skewed: the 8 parts hit different banks
         int rs = 0;
-        if (key_bf0 >= 0) rs = (key_bf0 + (row >> (p.tw_log + p.th_log))) / p.fps - smp0;
+        if (key_bf0 >= 0) rs = fdiv(key_bf0 + (row >> (p.tw_log + p.th_log)), p.mg_fps) - smp0;
         if (rs == sl) val += racc[gl][row][w];
       }
     }
     val += __shfl_xor_sync(0xffffffffu, val, 1);
     val += __shfl_xor_sync(0xffffffffu, val, 2);
     val += __shfl_xor_sync(0xffffffffu, val, 4);
-    const int g = n0 / p.gn_gs + gl;
-    const int nsamp = (p.BF + p.fps - 1) / p.fps;
+    const int g = (p.gs_log >= 0 ? (n0 >> p.gs_log) : n0 / p.gn_gs) + gl;
+    const int nsamp = fdiv(p.BF + p.fps - 1, p.mg_fps);
     if (part == 0 && g < p.gn_groups && smp0 + sl < nsamp && val != 0.f)
       atomicAdd(p.gn_stats + (static_cast<long long>(smp0 + sl) * p.gn_groups + g) * 2 + w, static_cast<double>(val));
   }
@@ -134,7 +151,9 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
   __shared__ __align__(16) float s_bias[kBiasSmem];
   __shared__ __align__(1024) uint8_t s_stage[8][32 * 64];     // per epilogue warp: 32 rows x 32 columns (16-bit), swizzle 64B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  CgemmSmemCtl* ctl = reinterpret_cast<CgemmSmemCtl*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
+  uint8_t* bres = smem + static_cast<size_t>(p.stages) * p.stage_bytes;      // resident weight tiles (halo mode)
+  const size_t bres_bytes = p.b_resident ? static_cast<size_t>(9) * p.h_chunks * p.btile_bytes : 0;
+  CgemmSmemCtl* ctl = reinterpret_cast<CgemmSmemCtl*>(bres + bres_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,6 +175,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
       mbar_init(&ctl->tfull[a], 1);
       mbar_init(&ctl->tempty[a], kEpiThreads);
     }
+    mbar_init(&ctl->bfull, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -173,7 +193,36 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (lane == 0 && p.halo) {
+      if (p.b_resident) {
+        mbar_expect_tx(&ctl->bfull, static_cast<uint32_t>(bres_bytes));
+        for (int tap = 0; tap < 9; ++tap)
+          for (int c = 0; c < p.h_chunks; ++c)
+            tma_load_2d(bres + static_cast<size_t>(tap * p.h_chunks + c) * p.btile_bytes, &p.bmap, &ctl->bfull, p.h_kofs[tap][c], 0);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int phase, bf0, y0, x0, n0;
+        decode_tile(p, t, phase, bf0, y0, x0, n0);
+        for (int c = 0; c < p.h_chunks; ++c) {
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(&ctl->empty[s], ph ^ 1);
+            uint8_t* a_s = smem + static_cast<size_t>(s) * p.stage_bytes;
+            mbar_expect_tx(&ctl->full[s], p.tx_bytes);
+            tma_load_4d(a_s, &p.amap[p.h_src[c]], &ctl->full[s], p.h_kb[c] * 64, x0 + kx - 1, y0 - 1, bf0);
+            if (!p.b_resident) {
+              for (int ky = 0; ky < 3; ++ky)
+                tma_load_2d(a_s + p.slab_bytes + ky * p.btile_bytes, &p.bmap, &ctl->full[s], p.h_kofs[ky * 3 + kx][c], n0);
+            }
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -209,8 +258,42 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
       mbar_wait(&ctl->tempty[acc], acc_ph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-      const int nt = p.n_taps[phase];
+      const int nt = p.halo ? 0 : p.n_taps[phase];
       uint32_t accumulate = 0;
+      if (p.halo) {
+        if (p.b_resident && it == 0) {
+          mbar_wait(&ctl->bfull, 0);
+          tc_fence_after();
+        }
+        for (int c = 0; c < p.h_chunks; ++c) {
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(&ctl->full[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+                // rows of tap ky = slab rows shifted by ky pixel rows (8 pixels x 128 bytes = one swizzle atom each)
+                const uint64_t adesc = make_smem_desc_sw128(a_addr + ky * 1024, 16, 1024);
+                const uint32_t b_addr = p.b_resident ? smem_u32(bres + static_cast<size_t>((ky * 3 + kx) * p.h_chunks + c) * p.btile_bytes)
+                                                     : a_addr + p.slab_bytes + ky * p.btile_bytes;
+                const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), p.idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit(&ctl->empty[s]);
+            }
+            __syncwarp();
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
       for (int tap = 0; tap < nt; ++tap) {
         const int nk = p.taps[phase][tap].nk;
         for (int kb = 0; kb < nk; ++kb) {
@@ -282,9 +365,9 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
       // to the same (first sample, n-tile); they go to global memory (fp64 atomics) only when that key changes,
       // which keeps the number of same-address atomics per launch at O(CTAs x samples) instead of O(tiles).
       if (p.gn_stats) {
-        const int smp0 = bf0 / p.fps;
+        const int smp0 = fdiv(bf0, p.mg_fps);
         const int last_bf = min(bf0 + (1 << p.tf_log), p.BF) - 1;
-        const int kbf0 = ((last_bf / p.fps) != smp0) ? bf0 : -1;     // tile straddles two samples
+        const int kbf0 = (p.tf_log > 0 && fdiv(last_bf, p.mg_fps) != smp0) ? bf0 : -1;     // tile straddles two samples
         if (smp0 != gn_key_smp || n0 != gn_key_n0 || kbf0 != gn_key_bf0) {
           if (gn_key_smp >= 0) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -451,22 +534,49 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
             // relative per element, far below what mean / variance over >= 10^4 elements can resolve);
             // per 8-column block sums first (static indexing), then group them
             float b1[4], b2[4];
+            if (full) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              float a1 = 0.f, a2 = 0.f;
+              for (int b = 0; b < 4; ++b) {
+                float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float x = v[b * 8 + k];
-                if (full || (ncol + b * 8 + k < p.N)) {
+                for (int k = 0; k < 8; ++k) {
+                  const float x = v[b * 8 + k];
                   a1 += x;
                   a2 = fmaf(x, x, a2);
                 }
+                b1[b] = valid ? a1 : 0.f;
+                b2[b] = valid ? a2 : 0.f;
               }
-              b1[b] = valid ? a1 : 0.f;
-              b2[b] = valid ? a2 : 0.f;
+            } else {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float x = v[b * 8 + k];
+                  if (ncol + b * 8 + k < p.N) {
+                    a1 += x;
+                    a2 = fmaf(x, x, a2);
+                  }
+                }
+                b1[b] = valid ? a1 : 0.f;
+                b2[b] = valid ? a2 : 0.f;
+              }
             }
             const int gs = p.gn_gs;
-            if (gs >= 8) {
+            if (p.gs_log >= 3) {
+              // power-of-two groups of >= 8 columns: no divisions in the column loop
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                gs1 += b1[b];
+                gs2 += b2[b];
+                const int cend = ncol + 8 * (b + 1);
+                if ((cend & (gs - 1)) == 0 && cend - gs < p.N) {   // group complete (uniform across the warp)
+                  gn_thread_add(s_gn, (cend - gs - n0) >> p.gs_log, row, gs1, gs2);
+                  gs1 = gs2 = 0.f;
+                }
+              }
+            } else if (gs >= 8) {
 #pragma unroll
               for (int b = 0; b < 4; ++b) {
                 gs1 += b1[b];
@@ -518,6 +628,8 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
+static uint64_t magic_of(int d) { return (uint64_t(1) << 32) / static_cast<uint64_t>(d) + 1; }
+
 static int ilog2_exact(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -581,10 +693,56 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   const long long total = 1LL * d.n_phases * d.tiles_f * d.tiles_y * d.tiles_x * d.n_ntiles;
   if (total <= 0 || total > 0x7fffffffLL) return set_error(VMM_ERR_ARG, "vmm_cgemm: tile count");
   d.total_tiles = static_cast<int>(total);
-  d.stage_bytes = kABytes + BN * 128;
-  d.tx_bytes = d.stage_bytes;
+  d.mg_nt = magic_of(d.n_ntiles);
+  d.mg_tx = magic_of(d.tiles_x);
+  d.mg_ty = magic_of(d.tiles_y);
+  d.mg_tf = magic_of(d.tiles_f);
+  {
+    // fdiv is exact for t * d < 2^32
+    const long long dmax = std::max(std::max(d.n_ntiles, d.tiles_x), std::max(d.tiles_y, d.tiles_f));
+    if (total * dmax >= (1LL << 32)) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile grid too large for the fast tile decode");
+  }
   const int smem_budget = 194 * 1024;   // + 28 KB static (bias, GroupNorm slots, store staging) + control block: 4 stages at BN = 256
-  int stages = smem_budget / static_cast<int>(d.stage_bytes);
+  // Halo mode: 3x3 stride-1 taps in (ky, kx, source) order on a 1 x th x 8 tile.  Each (64-channel chunk, kx) stage loads ONE
+  // slab of th + 2 pixel rows; the three ky taps read it at +0 / +1 / +2 swizzle atoms.  A traffic drops from 9 to 3.4 tiles
+  // per chunk, and the weights stay resident when all of them fit beside the ring.
+  size_t bres_bytes = 0;
+  {
+    static const bool no_halo = getenv("VMM_NO_HALO") != nullptr;
+    bool halo = !no_halo && h.n_phases == 1 && h.tf == 1 && h.tw == 8 && h.th == 16 && h.n_taps[0] >= 9 && h.n_taps[0] <= VMM_MAX_TAPS && (h.n_taps[0] % 9) == 0;
+    const int nsrc = halo ? h.n_taps[0] / 9 : 0;
+    int chunks = 0;
+    for (int s = 0; halo && s < nsrc; ++s) {
+      const vmm_tap& T0 = h.taps[0][s];
+      for (int t9 = 0; t9 < 9 && halo; ++t9) {
+        const vmm_tap& T = h.taps[0][t9 * nsrc + s];
+        if (T.src != T0.src || T.c != T0.c || T.dy != t9 / 3 - 1 || T.dx != t9 % 3 - 1) halo = false;
+      }
+      for (int kb = 0; halo && kb < (T0.c + 63) / 64; ++kb) {
+        if (chunks >= kHaloMaxChunks) {
+          halo = false;
+          break;
+        }
+        d.h_src[chunks] = static_cast<int16_t>(T0.src);
+        d.h_kb[chunks] = static_cast<int16_t>(kb);
+        for (int t9 = 0; t9 < 9; ++t9) d.h_kofs[t9][chunks] = h.taps[0][t9 * nsrc + s].kofs + kb * 64;
+        ++chunks;
+      }
+    }
+    if (halo) {
+      d.halo = 1;
+      d.h_chunks = chunks;
+      d.slab_bytes = static_cast<uint32_t>((h.th + 2) * h.tw * 128);
+      d.btile_bytes = static_cast<uint32_t>(BN * 128);
+      const size_t all_b = static_cast<size_t>(9) * chunks * d.btile_bytes;
+      d.b_resident = (d.n_ntiles == 1 && all_b <= 80 * 1024) ? 1 : 0;
+      bres_bytes = d.b_resident ? all_b : 0;
+      d.stage_bytes = d.slab_bytes + (d.b_resident ? 0 : 3 * d.btile_bytes);
+    }
+  }
+  if (!d.halo) d.stage_bytes = kABytes + BN * 128;
+  d.tx_bytes = d.stage_bytes;
+  int stages = (smem_budget - static_cast<int>(bres_bytes)) / static_cast<int>(d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile too large for shared memory");
   d.stages = stages;
@@ -614,6 +772,8 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   d.gn_gs = h.gn_group > 0 ? h.gn_group : 1;
   d.gn_groups = h.gn_stats ? h.n / h.gn_group : 1;
   d.fps = h.frames_per_sample > 0 ? h.frames_per_sample : 1;
+  d.mg_fps = magic_of(d.fps);
+  d.gs_log = (d.gn_gs >= 8 && ilog2_exact(d.gn_gs) >= 0) ? ilog2_exact(d.gn_gs) : -1;
   d.fmt = h.fmt;
 
   for (int ph = 0; ph < h.n_phases; ++ph) {
@@ -639,7 +799,7 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     if (!v.ptr) return set_error(VMM_ERR_ARG, "vmm_cgemm: null view");
     uint64_t gdim[4] = {(uint64_t)v.dims[0], (uint64_t)v.dims[1], (uint64_t)v.dims[2], (uint64_t)v.dims[3]};
     uint64_t gstr[3] = {(uint64_t)v.strides[0] * 2, (uint64_t)v.strides[1] * 2, (uint64_t)v.strides[2] * 2};
-    uint32_t box[4] = {64, (uint32_t)h.tw, (uint32_t)h.th, (uint32_t)h.tf};
+    uint32_t box[4] = {64, (uint32_t)h.tw, (uint32_t)(d.halo ? h.th + 2 : h.th), (uint32_t)h.tf};
     int rc = encode_tensor_map(&d.amap[i], dt, 4, v.ptr, gdim, gstr, box, /*l2_256=*/false);
     if (rc) return rc;
   }
@@ -681,7 +841,7 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     }
   }
 
-  const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + sizeof(CgemmSmemCtl) + 1024;   // + ~4.4 KB static
+  const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + bres_bytes + sizeof(CgemmSmemCtl) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(cgemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);

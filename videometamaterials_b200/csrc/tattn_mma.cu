@@ -295,7 +295,7 @@ struct FragAddr {
 };
 
 template <int FMT>
-__global__ void __launch_bounds__(256, 1) tattn_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv,
+__global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv,
                                                                const float* __restrict__ bias, const float* __restrict__ rot,
                                                                const uint16_t* __restrict__ dout, uint16_t* __restrict__ dqkv,
                                                                float* __restrict__ dekv, float* __restrict__ dbias, int HW, int heads,

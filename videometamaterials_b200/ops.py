@@ -7,6 +7,7 @@ channels-last `(b, f, h, w, c)` 16-bit.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -18,6 +19,7 @@ from ._lib import CgemmParams, FMT_BF16, FMT_F16, WgradParams, check, lib
 # bench.py sets PROFILE = [] to collect (kernel, algorithmic flops, start event, end event) per GEMM launch
 PROFILE = None
 PROFILE_TAGS = False        # probes: append the GEMM shape to the kernel name
+HALO_MAX_N = int(os.environ.get("VMM_HALO_MAX_N", "128"))   # widest output of a 3x3 conv that takes the halo tile
 
 
 def _prof_begin():
@@ -242,6 +244,8 @@ def conv3x3(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch.Ten
     """xs: list of (bf, h, w, c_i) sources (implicit channel concat); 'zeros' padding 1."""
     taps, _ = taps_conv(3, 3, [x.shape[3] for x in xs], 1)
     bf, h, w, _ = xs[0].shape
+    if kw.get("tile") is None and h % 16 == 0 and w % 8 == 0 and n <= HALO_MAX_N:
+        kw["tile"] = (1, 16, 8)      # vmm_cgemm switches to its halo mode on this tile (one A slab per kx instead of one tile per tap)
     cgemm(list(xs), [taps], wp, n, out, (bf, h, w), **kw)
 
 
