@@ -190,10 +190,13 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  // one elected lane per warp issues the TMA / MMA / bulk-store instructions: behind elect.sync the compiler knows that a
+  // single thread is active and keeps descriptors and addresses in uniform registers (no per-instruction waterfall loop)
+  const bool leader = elect_one();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0 && p.halo) {
+    if (leader && p.halo) {
       if (p.b_resident) {
         mbar_expect_tx(&ctl->bfull, static_cast<uint32_t>(bres_bytes));
         for (int tap = 0; tap < 9; ++tap)
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
           }
         }
       }
-    } else if (lane == 0) {
+    } else if (leader) {
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
           for (int kx = 0; kx < 3; ++kx) {
             mbar_wait(&ctl->full[s], ph);
             tc_fence_after();
-            if (lane == 0) {
+            if (leader) {
               const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky) {
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&ctl->full[s], ph);
           tc_fence_after();
-          if (lane == 0) {
+          if (leader) {
             const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
             const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
           }
         }
       }
-      if (lane == 0) umma_commit(&ctl->tfull[acc]);
+      if (leader) umma_commit(&ctl->tfull[acc]);
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
           for (int j = 0; j < 16; ++j) w[j] = pack2<FMT>(v[2 * j], v[2 * j + 1]);
           if (p.tstore) {
             // the previous bulk store of this warp must have read the staging rows before they are overwritten
-            if (lane == 0) bulk_wait_read0();
+            if (leader) bulk_wait_read0();
             __syncwarp();
             uint8_t* srow = &s_stage[ew][lane * 64];
             const int sw = (lane >> 1) & 3;
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
               *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (leader) {
               tma_store_4d((split && ncol >= p.nsplit) ? &p.omap2 : &p.omap[phase], &s_stage[ew][0], ocol, wx, wy, wf);
               bulk_commit();
             }
@@ -614,7 +617,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
       asm volatile("bar.sync 1, 256;" ::: "memory");
       gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
     }
-    if (p.tstore && lane == 0) bulk_wait0();   // shared memory must outlive the last bulk store
+    if (p.tstore && leader) bulk_wait0();   // shared memory must outlive the last bulk store
   }
 
   tc_fence_before();

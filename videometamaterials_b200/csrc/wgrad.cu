@@ -105,9 +105,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  const bool leader = elect_one();   // see cgemm.cu: keeps the issue loops in uniform registers
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (leader) {
       int s = 0;
       uint32_t ph = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       for (int kt = kt0; kt < kt1; ++kt) {
         mbar_wait(&ctl->full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (leader) {
           const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
           const uint32_t b_addr = a_addr + p.a_chunks * kChunkBytes;
 #pragma unroll
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           ph ^= 1;
         }
       }
-      if (lane == 0) umma_commit(&ctl->tfull[acc]);
+      if (leader) umma_commit(&ctl->tfull[acc]);
       __syncwarp();
     }
   } else if (warp >= 4) {
