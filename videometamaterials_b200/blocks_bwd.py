@@ -120,8 +120,7 @@ class ResnetFn(torch.autograd.Function):
         ops.colsum(_flat(dh2), sd[pre + "block2.proj.bias"].grad)
         ops.wgrad_conv3x3(ops.as_bfhwc(dh2), [ops.as_bfhwc(a1)], sd[pre + "block2.proj.weight"].grad)
         da1 = torch.empty_like(a1)
-        taps, _ = ops.taps_conv(3, 3, [cout], 1)
-        ops.cgemm([ops.as_bfhwc(dh2)], [taps], P[pre + "block2.wd"], cout, da1, (B * Fr, H, W))
+        ops.conv3x3([ops.as_bfhwc(dh2)], P[pre + "block2.wd"], cout, da1)
         # block1
         dh1 = dh2   # reuse the buffer
         dss = torch.zeros_like(ss) if ss is not None else None
@@ -133,8 +132,8 @@ class ResnetFn(torch.autograd.Function):
             res, res2 = dxs[0], (dxs[1] if len(xs) > 1 else None)     # in-place accumulate on the res_conv gradient
         else:
             res, res2 = dout, None                                      # identity skip
-        ops.cgemm([ops.as_bfhwc(dh1)], [taps], P[pre + "block1.wd"], cin, dxs[0], (B * Fr, H, W),
-                  out2=dxs[1] if len(xs) > 1 else None, nsplit=cins[0], res=res, res2=res2)
+        ops.conv3x3([ops.as_bfhwc(dh1)], P[pre + "block1.wd"], cin, dxs[0],
+                    out2=dxs[1] if len(xs) > 1 else None, nsplit=cins[0], res=res, res2=res2)
         return (None, None, dss, *dxs)
 
 

@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
       const int m = mt * 128 + row;
       const bool mvalid = (m < p.N) && (kt1 > kt0);
+      const bool plain = p.cmod >= (1 << 30);   // no (column -> (lo, hi)) remapping: column cj lives at dst + cj * sC
       for (int ch = 0; ch < cd.n_chunks; ++ch) {
         const WgTapDev T = p.taps[cd.tap[ch]];
         float* dst = p.dw + T.wofs + static_cast<long long>(m) * p.sM;
@@ -194,13 +195,34 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           uint32_t r[16];
           tmem_ld16(t_addr + ch * 64 + c * 16, r);
           tmem_ld_wait();
-          if (!mvalid) continue;
+          const int cj0 = cd.c0[ch] + c * 16;
+          if (!mvalid || cj0 >= T.c) continue;
+          if (plain) {
+            float* d0 = dst + static_cast<long long>(cj0) * p.sC;
+            if (cj0 + 16 <= T.c) {
+              if (p.sC == 1 && ((reinterpret_cast<uintptr_t>(d0) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int cj = cd.c0[ch] + c * 16 + j;
-            if (cj < T.c) {
-              const int lo = cj % p.cmod, hi = cj / p.cmod;
-              if (lo < p.c_valid && hi < p.k_valid) atomicAdd(dst + lo * p.sC + hi * p.sC2, __uint_as_float(r[j]));
+                for (int j = 0; j < 16; j += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d0 + j), "f"(__uint_as_float(r[j])),
+                               "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(d0 + j * p.sC, __uint_as_float(r[j]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cj0 + j < T.c) atomicAdd(d0 + j * p.sC, __uint_as_float(r[j]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int cj = cj0 + j;
+              if (cj < T.c) {
+                const int lo = cj % p.cmod, hi = cj / p.cmod;
+                if (lo < p.c_valid && hi < p.k_valid) atomicAdd(dst + lo * p.sC + hi * p.sC2, __uint_as_float(r[j]));
+              }
             }
           }
         }
