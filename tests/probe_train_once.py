@@ -12,6 +12,7 @@ model = Unet3D(dim=64, dim_mults=(1, 2, 4, 8), channels=3, attn_heads=8, attn_di
 gd = GaussianDiffusion(model, image_size=96, channels=3, num_frames=11, timesteps=256, use_dynamic_thres=True, sampling_timesteps=256)
 tr = Trainer(gd, None, None, [0, 1, 3], train_batch_size=B, results_folder="gpurun_out/probe_run", log=False, null_cond_prob=0.1,
              per_frame_cond=True, reference_frame='lagrangian', accelerator=Accelerator("bf16"))
+tr.use_cuda_graph = False          # eager launches: one ncu row per kernel
 x = torch.rand(B, 3, 11, 96, 96, device="cuda"); c = torch.rand(B, 11, device="cuda") * 2 - 1
 for _ in range(steps):
     tr.step += 1

@@ -121,5 +121,13 @@ def check(rc: int, what: str = "vmm call") -> None:
         raise VmmError(f"{what} failed ({rc}): {lib.vmm_last_error().decode()}")
 
 
+_replayed_launches = 0      # kernel launches executed by CUDA-graph replays (the library only counts host-side launch calls)
+
+
+def add_replayed_launches(n: int) -> None:
+    global _replayed_launches
+    _replayed_launches += int(n)
+
+
 def launch_count() -> int:
-    return int(lib.vmm_launch_count())
+    return int(lib.vmm_launch_count()) + _replayed_launches

@@ -535,8 +535,10 @@ extern "C" int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt,
   if (ppc < rows * 4) ppc = rows * 4;
   ctas = static_cast<int>((pix + ppc - 1) / ppc);
   const size_t sm1 = (4 * C + static_cast<size_t>(rows) * C * 2) * sizeof(float);
-  if (sm1 > 48 * 1024) {
+  static bool attr_set = false;
+  if (!attr_set) {
     cudaFuncSetAttribute(gn_silu_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
   }
   gn_silu_bwd_reduce_kernel<<<dim3(ctas, B), threads, sm1, stream>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(dy),
                                                                       fmt, pix, C, groups, stats, gamma, beta, scale_shift, eps, act,

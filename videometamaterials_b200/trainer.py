@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 from torch.utils import data
 
-from . import ops
+from . import _lib, ops
 from .accel import Accelerator, broadcast_object_list
 from .blocks_bwd import get_arena
 from .dataset import Dataset, SyntheticLagrangianDataset, clean_pred, video_tensor_to_gif
@@ -216,11 +216,51 @@ class Trainer(object):
         return obj
 
     # ------------------------------------------------------------------ training (VDDP:1594-1672)
-    def train_step(self, x, cond):
-        """One optimisation step on a device batch: forward, backward, gradient all-reduce, fused Adam (+EMA)."""
+    # Forward + backward of one batch shape is ~1300 kernel launches: issued from Python they cost more host time than the
+    # GPU needs to run them, so after `graph_warmup` eager steps the whole forward/backward is captured once into a CUDA
+    # graph (static input buffers, torch's graph-safe Philox state for t / noise / null-cond mask) and replayed.  The
+    # gradient all-reduce and the fused optimiser stay outside the graph (step count, EMA schedule, NCCL).
+    use_cuda_graph = True
+    graph_warmup = 2
+
+    def _fwd_bwd_eager(self, x, cond):
         self.opt.zero_grad()
         loss = self.model(x=x, cond=cond, null_cond_prob=self.null_cond_prob)
-        self.accelerator.backward(loss)
+        loss.backward()
+        return loss
+
+    def _fwd_bwd(self, x, cond):
+        from . import ops as _ops
+        if not (self.use_cuda_graph and x.is_cuda) or _ops.PROFILE is not None:
+            return self._fwd_bwd_eager(x, cond)
+        key = (tuple(x.shape), tuple(cond.shape), x.dtype, cond.dtype, float(self.null_cond_prob))
+        st = getattr(self, "_graph_state", None)
+        if st is None or st["key"] != key:
+            st = self._graph_state = dict(key=key, seen=0, graph=None)
+        if st["graph"] is None:
+            st["seen"] += 1
+            if st["seen"] <= self.graph_warmup:
+                return self._fwd_bwd_eager(x, cond)
+            # capture (nothing executes during capture; the replay below is this step's work)
+            st["x"], st["cond"] = x.clone(), cond.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                st["loss"] = self._fwd_bwd_eager(st["x"], st["cond"])
+            st["launches"] = _lib.launch_count() - n0
+            _lib.add_replayed_launches(-st["launches"])      # the capture pass issued no work
+            st["graph"] = g
+        st["x"].copy_(x, non_blocking=True)
+        st["cond"].copy_(cond, non_blocking=True)
+        st["graph"].replay()
+        _lib.add_replayed_launches(st["launches"])
+        return st["loss"].clone()
+
+    def train_step(self, x, cond):
+        """One optimisation step on a device batch: forward, backward, gradient all-reduce, fused Adam (+EMA)."""
+        loss = self._fwd_bwd(x, cond)
+        self.accelerator.all_reduce_gradients()
         if self.max_grad_norm is not None:
             self.accelerator.clip_grad_norm_(get_arena(self.model.denoise_fn).params, self.max_grad_norm)
         ema_mode = 0
