@@ -184,10 +184,113 @@ def rotate_pairs(x: Tensor, freqs: Tensor) -> Tensor:
     return torch.stack((xe * c - xo * s, xo * c + xe * s), dim=-1).flatten(-2)
 
 
+class _GatherParams(torch.autograd.Function):
+    """Rows of many parameters as one matrix, read from / differentiated into the flat parameter arena with ONE gather /
+    index_add each (instead of a torch.cat of ~20 tensors and as many AccumulateGrad kernels per step)."""
+
+    @staticmethod
+    def forward(ctx, anchor: Tensor, flat_param: Tensor, flat_grad: Tensor, idx: Tensor, rows: int):
+        ctx.flat_grad, ctx.idx = flat_grad, idx
+        return flat_param.index_select(0, idx).view(rows, -1)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        ctx.flat_grad.index_add_(0, ctx.idx, g.reshape(-1).float())
+        return None, None, None, None, None
+
+
+class _SplitBlocks(torch.autograd.Function):
+    """y (rows, N) -> one contiguous (rows, n_j) tensor per block j (views of a single permuted buffer); the backward
+    concatenates the block gradients and undoes the permutation: two kernels each way for any number of blocks."""
+
+    @staticmethod
+    def forward(ctx, y: Tensor, perm: Tensor, inv: Tensor, sizes: Tuple[int, ...]):
+        rows = y.shape[0]
+        flat = y.reshape(-1).index_select(0, perm)
+        ctx.inv, ctx.shape, ctx.sizes, ctx.rows = inv, y.shape, sizes, rows
+        outs, o = [], 0
+        for n in sizes:
+            outs.append(flat[o:o + rows * n].view(rows, n))
+            o += rows * n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        parts = []
+        for g, n in zip(grads, ctx.sizes):
+            parts.append(g.reshape(-1).float() if g is not None else ctx.inv.new_zeros(ctx.rows * n, dtype=torch.float32))
+        gflat = torch.cat(parts)
+        return gflat.index_select(0, ctx.inv).view(ctx.shape), None, None, None
+
+
+def _split_plan(rows: int, sizes: Sequence[int], device) -> Tuple[Tensor, Tensor]:
+    """perm[out position] = flat index into the row-major (rows, sum(sizes)) matrix; inv = its inverse."""
+    N = sum(sizes)
+    r = torch.arange(rows)[:, None] * N
+    chunks, o = [], 0
+    for n in sizes:
+        chunks.append((r + o + torch.arange(n)[None, :]).reshape(-1))
+        o += n
+    perm = torch.cat(chunks)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(perm.numel())
+    return perm.to(device), inv.to(device)
+
+
+def _cond_plan(model, sd, b: int, frames_tok: int, device):
+    """Per (model, batch) constants of the conditioning path: gather indices into the parameter arena, split permutations,
+    the rotary table of the stacked cond keys.  Cached on the model."""
+    arena = getattr(model, "_vmm_arena", None)
+    if arena is not None and (arena.flat_param.device != device or device.type != "cuda"):
+        arena = None
+    key = (b, frames_tok, str(device), id(arena))
+    cache = model.__dict__.setdefault("_vmm_cond_plans", {})
+    plan = cache.get(key)
+    if plan is not None:
+        return plan
+    rn, an = resnet_names(model), attn_names(model)
+    heads = model.heads
+    hd = heads * 32
+    plan = dict(arena=arena, rn=rn, an=an)
+    if arena is not None:
+        off, o = {}, 0
+        for q in arena.params:
+            off[id(q)] = o
+            o += q.numel()
+
+        def rows_of(names):
+            return torch.cat([off[id(sd[n])] + torch.arange(sd[n].numel()) for n in names]).to(device)
+        plan["idx_wm"] = rows_of([q + "mlp.1.weight" for q in rn])
+        plan["idx_bm"] = rows_of([q + "mlp.1.bias" for q in rn])
+        plan["idx_wkv"] = rows_of([q + w for q, _ in an for w in ("to_k.weight", "to_v.weight")])
+    plan["ss_sizes"] = tuple(int(sd[q + "mlp.1.bias"].shape[0]) for q in rn)
+    plan["ss_perm"], plan["ss_inv"] = _split_plan(b, plan["ss_sizes"], device)
+    plan["kv_sizes"] = tuple(2 * hd for _ in an)
+    plan["kv_perm"], plan["kv_inv"] = _split_plan(b * frames_tok, plan["kv_sizes"], device)
+    # rotary of the cond keys (VDDP:470-471), for every temporal block at once: cos = 1 / sin = 0 elsewhere
+    freqs = sd["init_temporal_attn.fn.fn.fn.rotary_emb.freqs"].detach().float()
+    ang = torch.arange(frames_tok, device=device, dtype=torch.float32)[:, None] * freqs[None, :].to(device)       # (T, 16)
+    is_t = torch.tensor([1.0 if kind == "temporal" else 0.0 for _, kind in an], device=device)
+    sel = torch.zeros(len(an), 2, device=device)
+    sel[:, 0] = is_t                                                                                              # keys only
+    c = 1.0 + sel[None, :, :, None, None] * (ang.cos()[:, None, None, None, :] - 1.0)                           # (T, A, 2, 1, 16)
+    sn = sel[None, :, :, None, None] * ang.sin()[:, None, None, None, :]
+    plan["rot_c"], plan["rot_s"] = c.contiguous(), sn.contiguous()
+    cache[key] = plan
+    return plan
+
+
 def conditioning(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: int):
-    """Returns (scale_shift per resnet block, ekv per attention block, bias (h,f,f), rot (f,16,2))."""
+    """Returns (scale_shift per resnet block, ekv per attention block, bias (h,f,f), rot (f,16,2)).
+    The per-block fan-out (18 ResnetBlock MLPs, 17 to_k / to_v pairs) is batched: parameters are gathered from the arena,
+    results are split by one permutation, so the path is ~40 kernels forward instead of several hundred."""
     sd = dict(model.named_parameters())
     heads = model.heads
+    hd = heads * 32
+    dev = time.device
+    b, T = cond.shape[0], cond.shape[1]
+    plan = _cond_plan(model, sd, b, T, dev)
+    rn, an, arena = plan["rn"], plan["an"], plan["arena"]
     e = sinusoidal(time, model.dim)
     e = F.gelu(F.linear(e, sd["time_mlp.1.weight"], sd["time_mlp.1.bias"]))
     t = F.linear(e, sd["time_mlp.3.weight"], sd["time_mlp.3.bias"])
@@ -199,32 +302,28 @@ def conditioning(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: i
     tok = torch.where(null_mask[:, None, None], sd["null_text_token"], tok)
     hid = torch.where(null_mask[:, None], sd["null_text_hidden"], hid)
     t = t + hid
-    # every ResnetBlock.mlp in one GEMM
-    rn = resnet_names(model)
-    wm = torch.cat([sd[p + "mlp.1.weight"] for p in rn], dim=0)
-    bm = torch.cat([sd[p + "mlp.1.bias"] for p in rn], dim=0)
+    if arena is not None:
+        anchor = torch.zeros(1, device=dev, requires_grad=torch.is_grad_enabled())
+        wm = _GatherParams.apply(anchor, arena.flat_param, arena.flat_grad, plan["idx_wm"], sum(plan["ss_sizes"]))
+        bm = _GatherParams.apply(anchor, arena.flat_param, arena.flat_grad, plan["idx_bm"], 1).reshape(-1)
+        wkv = _GatherParams.apply(anchor, arena.flat_param, arena.flat_grad, plan["idx_wkv"], len(an) * 2 * hd)
+    else:
+        wm = torch.cat([sd[q + "mlp.1.weight"] for q in rn], dim=0)
+        bm = torch.cat([sd[q + "mlp.1.bias"] for q in rn], dim=0)
+        wkv = torch.cat([torch.cat((sd[q + "to_k.weight"], sd[q + "to_v.weight"]), dim=0) for q, _ in an], dim=0)
+    # every ResnetBlock.mlp in one GEMM, split into per-block (b, 2 dim_out) tensors
     ss_all = F.linear(F.silu(t), wm, bm)
-    ss, o = {}, 0
-    for p in rn:
-        n = sd[p + "mlp.1.bias"].shape[0]
-        ss[p] = ss_all[:, o:o + n].contiguous()
-        o += n
-    # every to_k / to_v on the tokens in one GEMM
-    an = attn_names(model)
-    wkv = torch.cat([torch.cat((sd[p + "to_k.weight"], sd[p + "to_v.weight"]), dim=0) for p, _ in an], dim=0)
-    kv_all = F.linear(tok, wkv)                                   # (b, T, n_attn * 2 * hd)
-    hd = heads * 32
-    freqs = sd["init_temporal_attn.fn.fn.fn.rotary_emb.freqs"]
-    ekv = {}
-    for j, (p, kind) in enumerate(an):
-        ek = kv_all[..., j * 2 * hd: j * 2 * hd + hd]
-        ev = kv_all[..., j * 2 * hd + hd: (j + 1) * 2 * hd]
-        if kind == "temporal":                                   # VDDP:470-471: cond keys are rotated by token index
-            b, T, _ = ek.shape
-            ek = rotate_pairs(ek.reshape(b, T, heads, 32).transpose(1, 2), freqs).transpose(1, 2).reshape(b, T, hd)
-        ekv[p] = torch.cat((ek, ev), dim=-1).contiguous()
+    ss = dict(zip(rn, _SplitBlocks.apply(ss_all, plan["ss_perm"], plan["ss_inv"], plan["ss_sizes"])))
+    # every to_k / to_v on the tokens in one GEMM; cond keys of the temporal blocks rotated by token index
+    kv = F.linear(tok, wkv).view(b, T, len(an), 2, heads, 16, 2)
+    xe, xo = kv[..., 0], kv[..., 1]
+    c, sn = plan["rot_c"], plan["rot_s"]
+    kv = torch.stack((xe * c - xo * sn, xo * c + xe * sn), dim=-1).reshape(b * T, len(an) * 2 * hd)
+    parts = _SplitBlocks.apply(kv, plan["kv_perm"], plan["kv_inv"], plan["kv_sizes"])
+    ekv = {q: part.view(b, T, 2 * hd) for (q, _), part in zip(an, parts)}
     table = sd["time_rel_pos_bias.relative_attention_bias.weight"]
     bias = table[rel_pos_buckets(frames, table.device)].permute(2, 0, 1).contiguous()      # (h, f, f)
+    freqs = sd["init_temporal_attn.fn.fn.fn.rotary_emb.freqs"]
     ang = torch.arange(frames, device=freqs.device, dtype=freqs.dtype)[:, None] * freqs[None, :]
     rot = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous()                          # (f, 16, 2)
     return ss, ekv, bias, rot
