@@ -61,6 +61,7 @@ struct CgemmDev {
   // halo mode (3x3 stride-1 taps, tile 1 x th x 8): per (64-channel chunk, kx) one A slab of th+2 pixel rows serves the three ky taps
   uint64_t mg_nt, mg_tx, mg_ty, mg_tf, mg_fps;   // ceil(2^32 / d) + exact-floor multipliers (fdiv below)
   int gs_log;                         // log2(gn_gs) when it is a power of two >= 8, else -1
+  int fast_epi;                       // the launch qualifies for epilogue_fast (see there)
   int halo;                           // 0 = generic taps
   int h_chunks;                       // 64-channel chunks over all sources
   int b_resident;                     // all weight tiles stay in shared memory for the whole kernel (single n-tile)
@@ -142,6 +143,165 @@ __device__ __forceinline__ void gn_thread_add(float (*racc)[128][2], int gl, int
   v.x += a1;
   v.y += a2;
   *q = v;
+}
+
+// Lean epilogue for the common launch shape: 16-bit output through bulk tensor stores, every 32-column step full
+// (N % 32 == 0), bias in shared memory, GroupNorm groups of 8 / 16 / 32 / 64 columns, 16-byte aligned residual rows.
+// Same arithmetic and the same shared-memory / barrier protocol as the generic column loop in cgemm_kernel, with every
+// launch-invariant decision hoisted out of the tile and column loops.
+template <int FMT>
+__device__ __forceinline__ void epilogue_fast(const CgemmDev& p, CgemmSmemCtl* ctl, const uint32_t tmem_base, float (*s_gn)[128][2],
+                                              const float* s_bias, uint8_t* stage, const int warp, const int lane, const bool leader) {
+  const int q = warp & 3;
+  const int half = (warp - 4) >> 2;
+  const int row = q * 32 + lane;
+  const int ethread = threadIdx.x - 128;
+  const bool has_bias = p.bias != nullptr, has_gn = p.gn_stats != nullptr, has_res = p.res != nullptr, split = p.out2 != nullptr;
+  const bool scaled = p.alpha != 1.f;
+  const float alpha = p.alpha;
+  const int nsteps = (p.BN + 31) >> 5;
+  int hs = (nsteps + 1) >> 1;
+  if (has_gn && p.gn_gs > 32 && ((hs * 32) % p.gn_gs) != 0) hs = nsteps;
+  const int st_lo = half ? hs : 0;
+  const int st_hi = half ? nsteps : hs;
+  const int tw_m = (1 << p.tw_log) - 1, th_m = (1 << p.th_log) - 1, tyx_log = p.tw_log + p.th_log;
+  const int xl = row & tw_m, yl = (row >> p.tw_log) & th_m, fl = row >> tyx_log;
+  const int wxo = (q * 32) & tw_m, wyo = ((q * 32) >> p.tw_log) & th_m, wfo = (q * 32) >> tyx_log;
+  const int gs = p.gn_gs, gs_log = p.gs_log, gs_m = p.gn_gs - 1;
+  uint8_t* srow = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  int it = 0;
+  int gn_key_smp = -1, gn_key_n0 = -1, gn_key_bf0 = -1;
+  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    int phase, bf0, y0, x0, n0;
+    decode_tile(p, t, phase, bf0, y0, x0, n0);
+    const int acc = it & 1;
+    const uint32_t acc_ph = (it >> 1) & 1;
+    const int bf = bf0 + fl, y = y0 + yl, x = x0 + xl;
+    const bool valid = (bf < p.BF) && (y < p.OH) && (x < p.OW);
+    const int wx = x0 + wxo, wy = y0 + wyo, wf = bf0 + wfo;
+    if (has_gn) {
+      const int smp0 = fdiv(bf0, p.mg_fps);
+      const int last_bf = min(bf0 + (1 << p.tf_log), p.BF) - 1;
+      const int kbf0 = (p.tf_log > 0 && fdiv(last_bf, p.mg_fps) != smp0) ? bf0 : -1;
+      if (smp0 != gn_key_smp || n0 != gn_key_n0 || kbf0 != gn_key_bf0) {
+        if (gn_key_smp >= 0) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
+          for (int gl = 0; gl < kGnGroups; ++gl) {
+            const int st_g = (gl * gs) >> 5;
+            if (st_g >= st_lo && st_g < st_hi) {
+              s_gn[gl][row][0] = 0.f;
+              s_gn[gl][row][1] = 0.f;
+            }
+          }
+        }
+        gn_key_smp = smp0;
+        gn_key_n0 = n0;
+        gn_key_bf0 = kbf0;
+      }
+    }
+    const uint16_t* rrow1 = nullptr;
+    const uint16_t* rrow2 = nullptr;
+    uint4 rq[4];
+    const int ncol_lo = n0 + st_lo * 32;
+    if (has_res && valid) {
+      const long long pix =
+          (static_cast<long long>(bf) * p.OHs + (y * p.sy + p.phase_oy[phase])) * p.OWs + (x * p.sx + p.phase_ox[phase]);
+      rrow1 = reinterpret_cast<const uint16_t*>(p.res) + pix * p.ldr;
+      rrow2 = split ? reinterpret_cast<const uint16_t*>(p.res2) + pix * p.ldr2 - p.nsplit : rrow1;
+      if (st_lo < st_hi && ncol_lo < p.N) {
+        const uint4* rp = reinterpret_cast<const uint4*>(((split && ncol_lo >= p.nsplit) ? rrow2 : rrow1) + ncol_lo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rq[j] = __ldg(rp + j);
+      }
+    }
+    mbar_wait(&ctl->tfull[acc], acc_ph);
+    tc_fence_after();
+    const uint32_t t_addr = lane_taddr + acc * p.acc_stride;
+    float gs1 = 0.f, gs2 = 0.f;
+    for (int st = st_lo; st < st_hi; ++st) {
+      const int ncol = n0 + st * 32;
+      if (ncol >= p.N) break;          // padded columns of the last n-tile (uniform)
+      float v[32];
+      tmem_ld32f(t_addr + st * 32, v);
+      tmem_ld_wait();
+      if (has_bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[ncol + j]);
+          v[j] += b4.x;
+          v[j + 1] += b4.y;
+          v[j + 2] += b4.z;
+          v[j + 3] += b4.w;
+        }
+      }
+      if (scaled) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= alpha;
+      }
+      if (rrow1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w4[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = unpack2<FMT>(w4[k]);
+            v[j * 8 + 2 * k] += f.x;
+            v[j * 8 + 2 * k + 1] += f.y;
+          }
+        }
+        if (st + 1 < st_hi && ncol + 32 < p.N) {
+          const uint4* rp = reinterpret_cast<const uint4*>(((split && ncol + 32 >= p.nsplit) ? rrow2 : rrow1) + ncol + 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rq[j] = __ldg(rp + j);
+        }
+      }
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = pack2<FMT>(v[2 * j], v[2 * j + 1]);
+      if (leader) bulk_wait_read0();     // the previous bulk store of this warp has read the staging rows
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (leader) {
+        const bool second = split && ncol >= p.nsplit;
+        tma_store_4d(second ? &p.omap2 : &p.omap[phase], stage, second ? ncol - p.nsplit : ncol, wx, wy, wf);
+        bulk_commit();
+      }
+      if (has_gn) {
+        // statistics from the fp32 values before the 16-bit rounding, 8-column blocks first
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float xv = v[b * 8 + k];
+            a1 += xv;
+            a2 = fmaf(xv, xv, a2);
+          }
+          gs1 += valid ? a1 : 0.f;
+          gs2 += valid ? a2 : 0.f;
+          const int cend = ncol + 8 * (b + 1);
+          if ((cend & gs_m) == 0) {          // group complete (uniform across the warp)
+            gn_thread_add(s_gn, (cend - gs - n0) >> gs_log, row, gs1, gs2);
+            gs1 = gs2 = 0.f;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(&ctl->tempty[acc]);
+  }
+  if (has_gn && gn_key_smp >= 0) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
+  }
+  if (leader) bulk_wait0();   // shared memory must outlive the last bulk store
 }
 
 template <int FMT>
@@ -337,6 +497,9 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
       for (int i = ethread; i < p.N; i += kEpiThreads) s_bias[i] = __ldg(p.bias + i);
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    if (p.fast_epi) {
+      epilogue_fast<FMT>(p, ctl, tmem_base, s_gn, s_bias, &s_stage[ew][0], warp, lane, leader);
+    } else {
     // 32-column steps; the two warps of a lane quarter split them in two contiguous halves when the boundary does not
     // cut a GroupNorm group (else the first warp takes all of them)
     const int nsteps = (p.BN + 31) >> 5;
@@ -618,6 +781,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
       gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
     }
     if (p.tstore && leader) bulk_wait0();   // shared memory must outlive the last bulk store
+    }
   }
 
   tc_fence_before();
@@ -821,6 +985,13 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     const bool al2 = !h.out2 || ((h.ldo2 % 8) == 0 && (reinterpret_cast<uintptr_t>(h.out2) & 15) == 0 && (h.nsplit % 32) == 0 &&
                                  h.n_phases == 1 && h.nsplit > 0 && h.nsplit < h.n);
     d.tstore = !h.out_fp32 && al && al2 && ((BN % 32) == 0 || d.n_ntiles == 1);
+  }
+  {
+    static const bool no_fast = getenv("VMM_NO_FAST_EPI") != nullptr;
+    const bool res_al = !h.res || (((h.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(h.res) & 15) == 0) &&
+                                   (!h.out2 || (((h.ldr2 & 7) == 0) && ((reinterpret_cast<uintptr_t>(h.res2) & 15) == 0))));
+    d.fast_epi = (!no_fast && d.tstore && (h.n % 32) == 0 && (BN % 32) == 0 && (!h.bias || h.n <= kBiasSmem) &&
+                  (!h.gn_stats || d.gs_log >= 3) && res_al) ? 1 : 0;
   }
   if (d.tstore) {
     // the 32 rows of one epilogue warp form a sub-box of the (tf, th, tw) pixel tile

@@ -148,6 +148,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
+// 32 lanes x 32 consecutive fp32 columns as floats.
+__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+        "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+        "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+        "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr));
+}
+
 // Shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bit set.
 //   K-major operand  (rows of 64 16-bit elements = 128 B, 8-row groups 1024 B apart): sbo = 1024, lbo unused (1).
 //   MN-major operand (128 B of 64 contiguous M/N elements per k, 8 k per 1024 B atom): sbo = stride between
