@@ -62,6 +62,7 @@ struct CgemmDev {
   uint64_t mg_nt, mg_tx, mg_ty, mg_tf, mg_fps;   // ceil(2^32 / d) + exact-floor multipliers (fdiv below)
   int gs_log;                         // log2(gn_gs) when it is a power of two >= 8, else -1
   int fast_epi;                       // the launch qualifies for epilogue_fast (see there)
+  int acc_mask, acc_log;              // TMEM accumulator ring: 2 buffers, or 4 when they fit in the 512 columns
   int halo;                           // 0 = generic taps
   int h_chunks;                       // 64-channel chunks over all sources
   int b_resident;                     // all weight tiles stay in shared memory for the whole kernel (single n-tile)
@@ -76,8 +77,8 @@ constexpr int kABytes = 128 * 128;   // 128 rows x 64 16-bit elements
 struct __align__(8) CgemmSmemCtl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t tfull[2];
-  uint64_t tempty[2];
+  uint64_t tfull[4];
+  uint64_t tempty[4];
   uint64_t bfull;
   uint32_t tmem_base;
   uint32_t pad;
@@ -112,7 +113,7 @@ constexpr int kGnGroups = 8;   // GroupNorm groups per n-tile (BN is capped acco
 // the CTA moves to another (first sample, n-tile, frame tile if the tile straddles two samples) key.
 constexpr int kEpiThreads = 256;
 
-__device__ __forceinline__ void gn_flush(const CgemmDev& p, float (*racc)[128][2], int ethread, int smp0, int n0, int key_bf0) {
+__device__ __forceinline__ void gn_flush(const CgemmDev& p, float (*racc)[128][2], int ethread, int smp0, int n0, int key_bf0, int bar_id = 1) {
   {
     const int o = ethread >> 3, part = ethread & 7;            // 32 outputs x 8 partial sums
     const int sl = o >> 4, gl = (o >> 1) & (kGnGroups - 1), w = o & 1;
@@ -134,7 +135,7 @@ __device__ __forceinline__ void gn_flush(const CgemmDev& p, float (*racc)[128][2
     if (part == 0 && g < p.gn_groups && smp0 + sl < nsamp && val != 0.f)
       atomicAdd(p.gn_stats + (static_cast<long long>(smp0 + sl) * p.gn_groups + g) * 2 + w, static_cast<double>(val));
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
 }
 
 __device__ __forceinline__ void gn_thread_add(float (*racc)[128][2], int gl, int row, float a1, float a2) {
@@ -149,13 +150,17 @@ __device__ __forceinline__ void gn_thread_add(float (*racc)[128][2], int gl, int
 // (N % 32 == 0), bias in shared memory, GroupNorm groups of 8 / 16 / 32 / 64 columns, 16-byte aligned residual rows.
 // Same arithmetic and the same shared-memory / barrier protocol as the generic column loop in cgemm_kernel, with every
 // launch-invariant decision hoisted out of the tile and column loops.
-template <int FMT>
+// G = 2: two groups of eight epilogue warps take alternate tiles of the CTA (own GroupNorm slots, own named barrier), which
+// doubles the drain rate when the per-tile epilogue latency, not the MMA, bounds a narrow tile.
+template <int FMT, int G>
 __device__ __forceinline__ void epilogue_fast(const CgemmDev& p, CgemmSmemCtl* ctl, const uint32_t tmem_base, float (*s_gn)[128][2],
-                                              const float* s_bias, uint8_t* stage, const int warp, const int lane, const bool leader) {
+                                              const float* s_bias, uint8_t* stage, const int warp, const int lane, const bool leader,
+                                              const int eg) {
   const int q = warp & 3;
-  const int half = (warp - 4) >> 2;
+  const int half = ((warp - 4) >> 2) & 1;
   const int row = q * 32 + lane;
-  const int ethread = threadIdx.x - 128;
+  const int ethread = (threadIdx.x - 128) & 255;
+  const int bar_id = 1 + eg;
   const bool has_bias = p.bias != nullptr, has_gn = p.gn_stats != nullptr, has_res = p.res != nullptr, split = p.out2 != nullptr;
   const bool scaled = p.alpha != 1.f;
   const float alpha = p.alpha;
@@ -174,10 +179,11 @@ __device__ __forceinline__ void epilogue_fast(const CgemmDev& p, CgemmSmemCtl* c
   int it = 0;
   int gn_key_smp = -1, gn_key_n0 = -1, gn_key_bf0 = -1;
   for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    if (G == 2 && (it & 1) != eg) continue;
     int phase, bf0, y0, x0, n0;
     decode_tile(p, t, phase, bf0, y0, x0, n0);
-    const int acc = it & 1;
-    const uint32_t acc_ph = (it >> 1) & 1;
+    const int acc = it & p.acc_mask;
+    const uint32_t acc_ph = (it >> p.acc_log) & 1;
     const int bf = bf0 + fl, y = y0 + yl, x = x0 + xl;
     const bool valid = (bf < p.BF) && (y < p.OH) && (x < p.OW);
     const int wx = x0 + wxo, wy = y0 + wyo, wf = bf0 + wfo;
@@ -187,8 +193,8 @@ __device__ __forceinline__ void epilogue_fast(const CgemmDev& p, CgemmSmemCtl* c
       const int kbf0 = (p.tf_log > 0 && fdiv(last_bf, p.mg_fps) != smp0) ? bf0 : -1;
       if (smp0 != gn_key_smp || n0 != gn_key_n0 || kbf0 != gn_key_bf0) {
         if (gn_key_smp >= 0) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
+          asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+          gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0, bar_id);
           for (int gl = 0; gl < kGnGroups; ++gl) {
             const int st_g = (gl * gs) >> 5;
             if (st_g >= st_lo && st_g < st_hi) {
@@ -298,22 +304,24 @@ __device__ __forceinline__ void epilogue_fast(const CgemmDev& p, CgemmSmemCtl* c
     mbar_arrive(&ctl->tempty[acc]);
   }
   if (has_gn && gn_key_smp >= 0) {
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0, bar_id);
   }
   if (leader) bulk_wait0();   // shared memory must outlive the last bulk store
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ CgemmDev p) {
+template <int FMT, int G>
+__global__ void __launch_bounds__(128 + 256 * G, 1) cgemm_kernel(const __grid_constant__ CgemmDev p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) float s_gn[kGnGroups][128][2];      // per-row GroupNorm partial sums, see gn_flush
+  __shared__ __align__(8) float s_gn[G][kGnGroups][128][2];   // per-row GroupNorm partial sums (per epilogue group), see gn_flush
   __shared__ __align__(16) float s_bias[kBiasSmem];
-  __shared__ __align__(1024) uint8_t s_stage[8][32 * 64];     // per epilogue warp: 32 rows x 32 columns (16-bit), swizzle 64B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bres = smem + static_cast<size_t>(p.stages) * p.stage_bytes;      // resident weight tiles (halo mode)
   const size_t bres_bytes = p.b_resident ? static_cast<size_t>(9) * p.h_chunks * p.btile_bytes : 0;
   CgemmSmemCtl* ctl = reinterpret_cast<CgemmSmemCtl*>(bres + bres_bytes);
+  // per epilogue warp: 32 rows x 32 columns (16-bit) staged for the bulk tensor store, 64-byte swizzle
+  uint8_t (*s_stage)[32 * 64] = reinterpret_cast<uint8_t (*)[32 * 64]>(
+      (reinterpret_cast<uintptr_t>(ctl) + sizeof(CgemmSmemCtl) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
       mbar_init(&ctl->full[s], 1);
       mbar_init(&ctl->empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       mbar_init(&ctl->tfull[a], 1);
       mbar_init(&ctl->tempty[a], kEpiThreads);
     }
@@ -343,8 +351,8 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
     tmem_relinquish();
   }
   if (warp == 3) {
-    float* g = &s_gn[0][0][0];
-    for (int i = lane; i < kGnGroups * 128 * 2; i += 32) g[i] = 0.f;
+    float* g = &s_gn[0][0][0][0];
+    for (int i = lane; i < G * kGnGroups * 128 * 2; i += 32) g[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -416,8 +424,8 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int phase, bf0, y0, x0, n0;
       decode_tile(p, t, phase, bf0, y0, x0, n0);
-      const int acc = it & 1;
-      const uint32_t acc_ph = (it >> 1) & 1;
+      const int acc = it & p.acc_mask;
+      const uint32_t acc_ph = (it >> p.acc_log) & 1;
       mbar_wait(&ctl->tempty[acc], acc_ph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
@@ -494,12 +502,16 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
     // bias lives in shared memory for the whole kernel (global loads in the column loop were the bottleneck)
     const bool bias_smem = p.bias != nullptr && p.N <= kBiasSmem;
     if (bias_smem) {
-      for (int i = ethread; i < p.N; i += kEpiThreads) s_bias[i] = __ldg(p.bias + i);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = ethread; i < p.N; i += kEpiThreads * G) s_bias[i] = __ldg(p.bias + i);
+      if (G == 1) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 3, 512;" ::: "memory");
     }
-    if (p.fast_epi) {
-      epilogue_fast<FMT>(p, ctl, tmem_base, s_gn, s_bias, &s_stage[ew][0], warp, lane, leader);
-    } else {
+    if (G == 2) {
+      // launched only for fast_epi shapes (host): the generic column loop is not instantiated here
+      epilogue_fast<FMT, G>(p, ctl, tmem_base, s_gn[(warp - 4) >> 3], s_bias, &s_stage[ew][0], warp, lane, leader, (warp - 4) >> 3);
+    } else if (p.fast_epi) {
+      epilogue_fast<FMT, 1>(p, ctl, tmem_base, s_gn[0], s_bias, &s_stage[ew][0], warp, lane, leader, 0);
+    } else if (G == 1) {
     // 32-column steps; the two warps of a lane quarter split them in two contiguous halves when the boundary does not
     // cut a GroupNorm group (else the first warp takes all of them)
     const int nsteps = (p.BN + 31) >> 5;
@@ -512,8 +524,8 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int phase, bf0, y0, x0, n0;
       decode_tile(p, t, phase, bf0, y0, x0, n0);
-      const int acc = it & 1;
-      const uint32_t acc_ph = (it >> 1) & 1;
+      const int acc = it & p.acc_mask;
+      const uint32_t acc_ph = (it >> p.acc_log) & 1;
 
       const int xl = row & ((1 << p.tw_log) - 1);
       const int yl = (row >> p.tw_log) & ((1 << p.th_log) - 1);
@@ -537,13 +549,13 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
         if (smp0 != gn_key_smp || n0 != gn_key_n0 || kbf0 != gn_key_bf0) {
           if (gn_key_smp >= 0) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
+            gn_flush(p, s_gn[0], ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
             // each thread clears the slots it adds to: its row, the groups of its column half
             for (int gl = 0; gl < kGnGroups; ++gl) {
               const int st_g = (gl * p.gn_gs) >> 5;
               if (st_g >= st_lo && st_g < st_hi) {
-                s_gn[gl][row][0] = 0.f;
-                s_gn[gl][row][1] = 0.f;
+                s_gn[0][gl][row][0] = 0.f;
+                s_gn[0][gl][row][1] = 0.f;
               }
             }
           }
@@ -738,7 +750,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
                 gs2 += b2[b];
                 const int cend = ncol + 8 * (b + 1);
                 if ((cend & (gs - 1)) == 0 && cend - gs < p.N) {   // group complete (uniform across the warp)
-                  gn_thread_add(s_gn, (cend - gs - n0) >> p.gs_log, row, gs1, gs2);
+                  gn_thread_add(s_gn[0], (cend - gs - n0) >> p.gs_log, row, gs1, gs2);
                   gs1 = gs2 = 0.f;
                 }
               }
@@ -749,7 +761,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
                 gs2 += b2[b];
                 const int cend = ncol + 8 * (b + 1);
                 if ((cend % gs) == 0 && cend - gs < p.N) {   // group complete (uniform across the warp)
-                  gn_thread_add(s_gn, (cend - gs - n0) / gs, row, gs1, gs2);
+                  gn_thread_add(s_gn[0], (cend - gs - n0) / gs, row, gs1, gs2);
                   gs1 = gs2 = 0.f;
                 }
               }
@@ -764,7 +776,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
                 if (((cj + 1) % gs) == 0) {
                   const int c0g = ncol + cj + 1 - gs;
                   const int gl = (c0g - n0) / gs;
-                  if (c0g < p.N && gl < kGnGroups) gn_thread_add(s_gn, gl, row, gs1, gs2);
+                  if (c0g < p.N && gl < kGnGroups) gn_thread_add(s_gn[0], gl, row, gs1, gs2);
                   gs1 = gs2 = 0.f;
                 }
               }
@@ -778,7 +790,7 @@ __global__ void __launch_bounds__(384, 1) cgemm_kernel(const __grid_constant__ C
     }
     if (p.gn_stats && gn_key_smp >= 0) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      gn_flush(p, s_gn, ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
+      gn_flush(p, s_gn[0], ethread, gn_key_smp, gn_key_n0, gn_key_bf0);
     }
     if (p.tstore && leader) bulk_wait0();   // shared memory must outlive the last bulk store
     }
@@ -869,7 +881,24 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     const long long dmax = std::max(std::max(d.n_ntiles, d.tiles_x), std::max(d.tiles_y, d.tiles_f));
     if (total * dmax >= (1LL << 32)) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile grid too large for the fast tile decode");
   }
-  const int smem_budget = 194 * 1024;   // + 28 KB static (bias, GroupNorm slots, store staging) + control block: 4 stages at BN = 256
+  // Epilogue flavour, decided before the shared-memory budget because the two-group kernel carries more static memory.
+  {
+    const bool al = (h.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(h.out) & 15) == 0;
+    const bool al2 = !h.out2 || ((h.ldo2 % 8) == 0 && (reinterpret_cast<uintptr_t>(h.out2) & 15) == 0 && (h.nsplit % 32) == 0 &&
+                                 h.n_phases == 1 && h.nsplit > 0 && h.nsplit < h.n);
+    d.tstore = !h.out_fp32 && al && al2 && ((BN % 32) == 0 || d.n_ntiles == 1);
+    static const bool no_fast = getenv("VMM_NO_FAST_EPI") != nullptr;
+    const bool res_al = !h.res || (((h.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(h.res) & 15) == 0) &&
+                                   (!h.out2 || (((h.ldr2 & 7) == 0) && ((reinterpret_cast<uintptr_t>(h.res2) & 15) == 0))));
+    const int gsz = h.gn_stats ? h.gn_group : 0;
+    const bool gs_ok = !h.gn_stats || (gsz >= 8 && ilog2_exact(gsz) >= 0);
+    d.fast_epi = (!no_fast && d.tstore && (h.n % 32) == 0 && (BN % 32) == 0 && (!h.bias || h.n <= kBiasSmem) && gs_ok && res_al) ? 1 : 0;
+  }
+  // Narrow tiles (BN <= 128) are bound by the latency of the per-tile epilogue, not by the MMAs: two groups of eight
+  // epilogue warps then drain alternate tiles (4 TMEM accumulators).  Costs 24 KB more static shared memory.
+  static const bool one_group = getenv("VMM_ONE_EPI_GROUP") != nullptr;
+  const bool two_groups = !one_group && d.fast_epi && BN > 64 && BN <= 128;   // BN = 64 is bound by the operand reads of the MMAs (48 clk each)
+  const int smem_budget = (two_groups ? 170 : 194) * 1024;   // + 12 / 20 KB static (bias, GroupNorm slots) + 16 / 32 KB store staging + control block
   // Halo mode: 3x3 stride-1 taps in (ky, kx, source) order on a 1 x th x 8 tile.  Each (64-channel chunk, kx) stage loads ONE
   // slab of th + 2 pixel rows; the three ky taps read it at +0 / +1 / +2 swizzle atoms.  A traffic drops from 9 to 3.4 tiles
   // per chunk, and the weights stay resident when all of them fit beside the ring.
@@ -914,9 +943,15 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   if (stages < 2) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile too large for shared memory");
   d.stages = stages;
   d.acc_stride = (BN + 31) / 32 * 32;
-  uint32_t cols = 32;
-  while (cols < 2 * d.acc_stride) cols <<= 1;
-  d.tmem_cols = cols;
+  {
+    static const bool two_acc = getenv("VMM_TWO_ACC") != nullptr;
+    const int nacc = (!two_acc && 4 * d.acc_stride <= 512) ? 4 : 2;     // a deeper ring decouples the MMA warp from the epilogue latency
+    d.acc_log = nacc == 4 ? 2 : 1;
+    d.acc_mask = nacc - 1;
+    uint32_t cols = 32;
+    while (cols < nacc * d.acc_stride) cols <<= 1;
+    d.tmem_cols = cols;
+  }
   d.idesc = make_idesc_f16(128, BN, h.fmt, 0, 0);
   d.out = h.out;
   d.ldo = h.ldo;
@@ -980,19 +1015,6 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
 
   // Output tensor maps for the bulk-store epilogue: pixel (bf, y, x) of phase ph lives at
   // out + ((bf*OHs + y*sy + oy)*OWs + x*sx + ox) * ldo, i.e. a strided 4-D view (columns, x, y, bf).
-  {
-    const bool al = (h.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(h.out) & 15) == 0;
-    const bool al2 = !h.out2 || ((h.ldo2 % 8) == 0 && (reinterpret_cast<uintptr_t>(h.out2) & 15) == 0 && (h.nsplit % 32) == 0 &&
-                                 h.n_phases == 1 && h.nsplit > 0 && h.nsplit < h.n);
-    d.tstore = !h.out_fp32 && al && al2 && ((BN % 32) == 0 || d.n_ntiles == 1);
-  }
-  {
-    static const bool no_fast = getenv("VMM_NO_FAST_EPI") != nullptr;
-    const bool res_al = !h.res || (((h.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(h.res) & 15) == 0) &&
-                                   (!h.out2 || (((h.ldr2 & 7) == 0) && ((reinterpret_cast<uintptr_t>(h.res2) & 15) == 0))));
-    d.fast_epi = (!no_fast && d.tstore && (h.n % 32) == 0 && (BN % 32) == 0 && (!h.bias || h.n <= kBiasSmem) &&
-                  (!h.gn_stats || d.gs_log >= 3) && res_al) ? 1 : 0;
-  }
   if (d.tstore) {
     // the 32 rows of one epilogue warp form a sub-box of the (tf, th, tw) pixel tile
     const uint32_t bw = h.tw < 32 ? h.tw : 32;
@@ -1015,17 +1037,25 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     }
   }
 
-  const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + bres_bytes + sizeof(CgemmSmemCtl) + 1024;
+  const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + bres_bytes + sizeof(CgemmSmemCtl) + 2048 +
+                      static_cast<size_t>(two_groups ? 16 : 8) * 2048;   // ring + resident weights + control + store staging
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(cgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(cgemm_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 214 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cgemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 214 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cgemm_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cgemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "vmm_cgemm: cudaFuncSetAttribute");
     attr_set = true;
   }
   const int grid = d.total_tiles < num_sms() ? d.total_tiles : num_sms();
-  if (h.fmt == VMM_FMT_F16) cgemm_kernel<0><<<grid, 384, smem, stream>>>(d);
-  else cgemm_kernel<1><<<grid, 384, smem, stream>>>(d);
+  if (two_groups) {
+    if (h.fmt == VMM_FMT_F16) cgemm_kernel<0, 2><<<grid, 640, smem, stream>>>(d);
+    else cgemm_kernel<1, 2><<<grid, 640, smem, stream>>>(d);
+  } else {
+    if (h.fmt == VMM_FMT_F16) cgemm_kernel<0, 1><<<grid, 384, smem, stream>>>(d);
+    else cgemm_kernel<1, 1><<<grid, 384, smem, stream>>>(d);
+  }
   count_launch();
   return check_launch("vmm_cgemm");
 }
