@@ -115,13 +115,16 @@ int vmm_cgemm(const vmm_cgemm_params* p, void* stream);
  * VDDP:304-306) or NULL.  act: 1 = SiLU, 0 = identity.  res (may be NULL) is added after the
  * activation: the identity skip of ResnetBlock (VDDP:311) when dim == dim_out.
  * The backward also accumulates dgamma/dbeta (+=) and writes d(scale_shift) [B][2C] (may be NULL).
+ * dx_colsum (may be NULL): [C] fp32, += sum over samples and pixels of dx: the bias gradient of the convolution that
+ * produced x (Block.proj, VDDP:277), folded into the apply pass instead of a separate column-sum launch.
  * ------------------------------------------------------------------------------------------ */
 int vmm_gn_silu_fwd(const void* x, const void* res, void* y, int fmt, int B, long long pix, int C, int groups, const double* stats,
                     const float* gamma, const float* beta, const float* scale_shift, float eps, int act, void* stream);
 size_t vmm_gn_silu_bwd_workspace(int B, int C, int groups);
 int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt, int B, long long pix, int C, int groups,
                     const double* stats, const float* gamma, const float* beta, const float* scale_shift, float eps, int act,
-                    float* dgamma, float* dbeta, float* dscale_shift, void* workspace, size_t workspace_bytes, void* stream);
+                    float* dgamma, float* dbeta, float* dscale_shift, float* dx_colsum, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* channel LayerNorm with gain only (VDDP:245-254) over rows of C 16-bit values.
  * backward: dx = LN'(dy) (+ dres if non-NULL, the Residual skip VDDP:137); dgamma accumulated (+=). */

@@ -349,8 +349,14 @@ def test_gn_silu_bwd(ops, dt, shape):
     dx = torch.empty_like(x)
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     dss = torch.zeros(B, 2 * C, device="cuda") if with_ss else None
-    ops.gn_silu_bwd(x, dy, dx, stats, gamma.detach(), beta.detach(), ss.detach() if with_ss else None, B, pix, C, 8, dg, db, dss)
+    dcs = torch.full((C,), 0.25, device="cuda")      # accumulated into (+=): the conv bias gradient = column sums of dx
+    ops.gn_silu_bwd(x, dy, dx, stats, gamma.detach(), beta.detach(), ss.detach() if with_ss else None, B, pix, C, 8, dg, db, dss,
+                    dx_colsum=dcs)
     assert rel(dx, xf.grad) < TOL[dt]
+    # per channel the column sum of dx nearly cancels (GroupNorm removes the group mean): compare against the sum of the
+    # kernel's own 16-bit dx plus an absolute tolerance from its rounding
+    want = dx.float().sum(dim=(0, 1)) + 0.25
+    assert float((dcs - want).abs().max()) < 2e-2 * float(dx.float().abs().sum(dim=(0, 1)).max()) * TOL[dt] + 1e-3
     assert rel(dg, gamma.grad) < 2e-3 and rel(db, beta.grad) < 2e-3
     if with_ss:
         assert rel(dss, ss.grad) < 2e-3

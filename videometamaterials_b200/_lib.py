@@ -88,7 +88,7 @@ _SIGNATURES = {
     "vmm_colsum": [_P, _L, _I, _L, _I, _P, _P],
     "vmm_gn_silu_fwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P],
     "vmm_gn_silu_bwd_workspace": [_I, _I, _I],
-    "vmm_gn_silu_bwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _Z, _P],
+    "vmm_gn_silu_bwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _Z, _P],
     "vmm_ln_fwd": [_P, _P, _I, _L, _I, _P, _F, _P, _P],
     "vmm_ln_bwd": [_P, _P, _P, _P, _I, _L, _I, _P, _F, _P, _P],
     "vmm_tattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],

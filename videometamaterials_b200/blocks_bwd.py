@@ -116,8 +116,8 @@ class ResnetFn(torch.autograd.Function):
         # block2: GroupNorm + SiLU backward, then conv gradients
         dh2 = torch.empty_like(h2)
         ops.gn_silu_bwd(h2, dout, dh2, st2, sd[pre + "block2.norm.weight"], sd[pre + "block2.norm.bias"], None, B, pix, cout, g,
-                        sd[pre + "block2.norm.weight"].grad, sd[pre + "block2.norm.bias"].grad, None)
-        ops.colsum(_flat(dh2), sd[pre + "block2.proj.bias"].grad)
+                        sd[pre + "block2.norm.weight"].grad, sd[pre + "block2.norm.bias"].grad, None,
+                        dx_colsum=sd[pre + "block2.proj.bias"].grad)       # conv bias gradient = column sums of dh2
         ops.wgrad_conv3x3(ops.as_bfhwc(dh2), [ops.as_bfhwc(a1)], sd[pre + "block2.proj.weight"].grad)
         da1 = torch.empty_like(a1)
         ops.conv3x3([ops.as_bfhwc(dh2)], P[pre + "block2.wd"], cout, da1)
@@ -125,8 +125,8 @@ class ResnetFn(torch.autograd.Function):
         dh1 = dh2   # reuse the buffer
         dss = torch.zeros_like(ss) if ss is not None else None
         ops.gn_silu_bwd(h1, da1, dh1, st1, sd[pre + "block1.norm.weight"], sd[pre + "block1.norm.bias"], ss, B, pix, cout, g,
-                        sd[pre + "block1.norm.weight"].grad, sd[pre + "block1.norm.bias"].grad, dss)
-        ops.colsum(_flat(dh1), sd[pre + "block1.proj.bias"].grad)
+                        sd[pre + "block1.norm.weight"].grad, sd[pre + "block1.norm.bias"].grad, dss,
+                        dx_colsum=sd[pre + "block1.proj.bias"].grad)
         ops.wgrad_conv3x3(ops.as_bfhwc(dh1), [ops.as_bfhwc(x) for x in xs], sd[pre + "block1.proj.weight"].grad)
         if has_res:
             res, res2 = dxs[0], (dxs[1] if len(xs) > 1 else None)     # in-place accumulate on the res_conv gradient

@@ -257,8 +257,9 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* 
                                                                 uint16_t* __restrict__ dx, int fmt, long long pix, int C, int groups,
                                                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, const float* __restrict__ scale_shift,
-                                                                float eps, int act, const float* __restrict__ gm) {
-  extern __shared__ float sm[];   // a[C], d[C], mean[C], rstd[C], k[C], m1[C], m2[C]
+                                                                float eps, int act, const float* __restrict__ gm,
+                                                                float* __restrict__ dx_colsum) {
+  extern __shared__ float sm[];   // a[C], d[C], mean[C], rstd[C], k[C], m1[C], m2[C], colsum[C]
   float* ca = sm;
   float* cd = sm + C;
   float* cm = sm + 2 * C;
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* 
   float* ck = sm + 4 * C;
   float* c1 = sm + 5 * C;
   float* c2 = sm + 6 * C;
+  float* cs = sm + 7 * C;         // block partial of the column sums of dx
   const int b = blockIdx.y;
   const int gs = C / groups;
   const double n = static_cast<double>(pix) * gs;
@@ -293,6 +295,7 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* 
     ck[c] = gamma[c] * sc;
     c1[c] = gm[(static_cast<long long>(b) * groups + g) * 2];
     c2[c] = gm[(static_cast<long long>(b) * groups + g) * 2 + 1];
+    cs[c] = 0.f;
   }
   __syncthreads();
   const long long nvec = pix * C / 8;
@@ -300,6 +303,8 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* 
   const uint16_t* db = dy + static_cast<long long>(b) * pix * C;
   uint16_t* ob = dx + static_cast<long long>(b) * pix * C;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  // the host picks gridDim.x so that (stride * 8) % C == 0: every vector of this thread covers the same 8 channels
+  float colacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
     uint4 xr[4], dr[4];
 #pragma unroll
@@ -332,7 +337,31 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* 
         }
       }
       store8(ob + i * 8, fmt, o);
+      if (dx_colsum) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) colacc[j] += o[j];
+      }
     }
+  }
+  if (dx_colsum) {
+    const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int c0 = static_cast<int>((i0 * 8) % C);
+    // lanes (l, l + vpr, l + 2 vpr, ...) of a warp hold the same 8 channels: fold them with shuffles first
+    const int vpr = C >> 3;
+    bool owner = true;
+    if (vpr < 32 && (vpr & (vpr - 1)) == 0) {
+      for (int o = 16; o >= vpr; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) colacc[j] += __shfl_xor_sync(0xffffffffu, colacc[j], o);
+      }
+      owner = (threadIdx.x & 31) < vpr;
+    }
+    if (owner) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&cs[c0 + j], colacc[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dx_colsum + c, cs[c]);
   }
 }
 
@@ -513,8 +542,8 @@ extern "C" size_t vmm_gn_silu_bwd_workspace(int B, int C, int groups) {
 
 extern "C" int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt, int B, long long pix, int C, int groups,
                                const double* stats, const float* gamma, const float* beta, const float* scale_shift, float eps,
-                               int act, float* dgamma, float* dbeta, float* dscale_shift, void* workspace, size_t workspace_bytes,
-                               void* stream_) {
+                               int act, float* dgamma, float* dbeta, float* dscale_shift, float* dx_colsum, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
   if (!x || !dy || !dx || !stats || !gamma || !beta || !dgamma || !dbeta || !workspace)
     return set_error(VMM_ERR_ARG, "vmm_gn_silu_bwd: null pointer");
   if (C % 8 || C % groups || C > 2048) return set_error(VMM_ERR_ARG, "vmm_gn_silu_bwd: bad C");
@@ -549,9 +578,19 @@ extern "C" int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt,
   const long long nvec = pix * C / 8;
   int gx = static_cast<int>(min64((nvec + 255) / 256, (4LL * num_sms() + B - 1) / B * 2));
   if (gx < 1) gx = 1;
-  gn_silu_bwd_apply_kernel<<<dim3(gx, B), 256, 7 * C * sizeof(float), stream>>>(
+  if (dx_colsum) {
+    // column sums need a fixed thread -> channel mapping: (gridDim.x * 256 * 8) % C == 0
+    const int unit = (C + 2047) / 2048 * 1;                 // C <= 2048: any gx works when 2048 % C == 0
+    if ((2048 % C) != 0) {
+      int m = 1;
+      while ((static_cast<long long>(m) * 2048) % C) ++m;   // smallest multiplier making the stride a multiple of C
+      gx = (gx + m - 1) / m * m;
+    }
+    (void)unit;
+  }
+  gn_silu_bwd_apply_kernel<<<dim3(gx, B), 256, 8 * C * sizeof(float), stream>>>(
       static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(dy), static_cast<uint16_t*>(dx), fmt, pix, C, groups, stats, gamma,
-      beta, scale_shift, eps, act, gm);
+      beta, scale_shift, eps, act, gm, dx_colsum);
   count_launch();
   return check_launch("vmm_gn_silu_bwd");
 }

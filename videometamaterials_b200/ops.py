@@ -322,11 +322,11 @@ def gn_silu_fwd(x, y, stats, gamma, beta, scale_shift, B, pix, C_, groups, act=T
                               eps, 1 if act else 0, stream_ptr()), "vmm_gn_silu_fwd")
 
 
-def gn_silu_bwd(x, dy, dx, stats, gamma, beta, scale_shift, B, pix, C_, groups, dgamma, dbeta, dss, act=True, eps=1e-5):
+def gn_silu_bwd(x, dy, dx, stats, gamma, beta, scale_shift, B, pix, C_, groups, dgamma, dbeta, dss, act=True, eps=1e-5, dx_colsum=None):
     nbytes = int(lib.vmm_gn_silu_bwd_workspace(B, C_, groups))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     check(lib.vmm_gn_silu_bwd(_p(x), _p(dy), _p(dx), fmt_of(x), B, pix, C_, groups, _p(stats), _p(gamma), _p(beta),
-                              _p(scale_shift), eps, 1 if act else 0, _p(dgamma), _p(dbeta), _p(dss), _p(ws), nbytes,
+                              _p(scale_shift), eps, 1 if act else 0, _p(dgamma), _p(dbeta), _p(dss), _p(dx_colsum), _p(ws), nbytes,
                               stream_ptr()), "vmm_gn_silu_bwd")
 
 
