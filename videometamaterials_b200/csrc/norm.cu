@@ -2,6 +2,7 @@
 // All tensors are channels-last [sample, pixel, C] 16-bit; statistics / parameters are fp32 or fp64.
 // These kernels are HBM-bound: 16-byte vector accesses, one read (+ one write) of the activation.
 #include "common.cuh"
+#include "mma_sync.cuh"
 #include "sm100_ptx.cuh"
 
 namespace vmm {
@@ -34,181 +35,200 @@ __device__ __forceinline__ void store8(uint16_t* p, int fmt, const float* v) {
 // ------------------------------------------------------------------------------------------------
 // GroupNorm apply:  y = silu( ((x - mean) * rstd * gamma + beta) * (scale + 1) + shift )     VDDP:279-285
 // statistics come from the conv epilogue as fp64 (sum, sum of squares) per (sample, group).
+//
+// These kernels were ALU / MUFU bound, not HBM bound (per element: runtime-format conversions, 4-7 shared-memory
+// coefficient loads, exp + reciprocal).  Now: the 16-bit format is a template parameter, every thread keeps the
+// coefficients of its 8 channels in registers (the grid stride is a multiple of C, so they never change), and the sigmoid
+// is one MUFU.TANH (sigmoid(u) = 0.5 tanh(0.5 u) + 0.5; relative error 2^-11, below the 2^-9 rounding of the bf16 output;
+// the fp16 forward used for sampling keeps exp + division).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_silu_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ res,
-                                                          uint16_t* __restrict__ y, int fmt,
-                                                          long long pix, int C, int groups, const double* __restrict__ stats,
-                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          const float* __restrict__ scale_shift, float eps, int act) {
-  extern __shared__ float coef[];   // [2][C]
-  const int b = blockIdx.y;
-  const int gs = C / groups;
-  const double n = static_cast<double>(pix) * gs;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / gs;
-    const double s1 = stats[(static_cast<long long>(b) * groups + g) * 2];
-    const double s2 = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
-    const double mean = s1 / n;
-    double var = s2 / n - mean * mean;
-    if (var < 0) var = 0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    float a = rstd * gamma[c];
-    float d = beta[c] - static_cast<float>(mean) * a;
-    if (scale_shift) {
-      const float sc = scale_shift[static_cast<long long>(b) * 2 * C + c] + 1.f;
-      const float sh = scale_shift[static_cast<long long>(b) * 2 * C + C + c];
-      a *= sc;
-      d = d * sc + sh;
-    }
-    coef[c] = a;
-    coef[C + c] = d;
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int FMT>
+__device__ __forceinline__ float sigmoid_fast(float u) {
+  if (FMT == 1) return fmaf(0.5f, tanh_approx(0.5f * u), 0.5f);
+  return 1.f / (1.f + __expf(-u));
+}
+// d silu(u) / du = s (1 + u (1 - s)),  s = sigmoid(u)
+__device__ __forceinline__ float dsilu_fast(float u) {
+  const float s = fmaf(0.5f, tanh_approx(0.5f * u), 0.5f);
+  const float q = fmaf(-u, s, u);      // u (1 - s)
+  return fmaf(s, q, s);
+}
+
+template <int FMT>
+__device__ __forceinline__ void unpack8(const uint4& q, float* v) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack2<FMT>(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
   }
-  __syncthreads();
+}
+template <int FMT>
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack2<FMT>(v[0], v[1]), pack2<FMT>(v[2], v[3]), pack2<FMT>(v[4], v[5]), pack2<FMT>(v[6], v[7]));
+}
+
+// per-channel affine of the forward: u = x * a + d   (mean / rstd / gamma / beta / scale / shift folded)
+__device__ __forceinline__ void gn_channel_affine(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, const float* __restrict__ scale_shift, int b, int c,
+                                                  int C, int groups, long long pix, float eps, float& a, float& d, float& mean,
+                                                  float& rstd, float& sc) {
+  const int gs = C / groups;
+  const int g = c / gs;
+  const double n = static_cast<double>(pix) * gs;
+  const double s1 = stats[(static_cast<long long>(b) * groups + g) * 2];
+  const double s2 = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
+  const double m = s1 / n;
+  double var = s2 / n - m * m;
+  if (var < 0) var = 0;
+  mean = static_cast<float>(m);
+  rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  a = rstd * gamma[c];
+  d = beta[c] - mean * a;
+  sc = 1.f;
+  if (scale_shift) {
+    sc = scale_shift[static_cast<long long>(b) * 2 * C + c] + 1.f;
+    const float sh = scale_shift[static_cast<long long>(b) * 2 * C + C + c];
+    a *= sc;
+    d = d * sc + sh;
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) gn_silu_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ res,
+                                                          uint16_t* __restrict__ y, long long pix, int C, int groups,
+                                                          const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ scale_shift,
+                                                          float eps, int act) {
+  const int b = blockIdx.y;
+  const long long i00 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c0 = static_cast<int>((i00 * 8) % C);          // fixed for this thread: the host keeps (grid stride * 8) % C == 0
+  float ca[8], cd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float mean, rstd, sc;
+    gn_channel_affine(stats, gamma, beta, scale_shift, b, c0 + j, C, groups, pix, eps, ca[j], cd[j], mean, rstd, sc);
+  }
   const long long nvec = pix * C / 8;
-  const uint16_t* xb = x + static_cast<long long>(b) * pix * C;
-  const uint16_t* rb = res ? res + static_cast<long long>(b) * pix * C : nullptr;
-  uint16_t* yb = y + static_cast<long long>(b) * pix * C;
-  // 4 independent 16-byte vectors per thread and iteration: all loads are issued before the first use
+  const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * pix * C);
+  const uint4* rb = res ? reinterpret_cast<const uint4*>(res + static_cast<long long>(b) * pix * C) : nullptr;
+  uint4* yb = reinterpret_cast<uint4*>(y + static_cast<long long>(b) * pix * C);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
+  for (long long i0 = i00; i0 < nvec; i0 += 4 * stride) {
     uint4 xr[4], rr[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long i = i0 + u * stride;
       if (i < nvec) {
-        xr[u] = __ldg(reinterpret_cast<const uint4*>(xb) + i);
-        if (rb) rr[u] = __ldg(reinterpret_cast<const uint4*>(rb) + i);
+        xr[u] = __ldg(xb + i);
+        if (rb) rr[u] = __ldg(rb + i);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long i = i0 + u * stride;
       if (i >= nvec) continue;
-      const int c0 = static_cast<int>((i * 8) % C);
-      const uint32_t xw[4] = {xr[u].x, xr[u].y, xr[u].z, xr[u].w};
-      const uint32_t rw[4] = {rr[u].x, rr[u].y, rr[u].z, rr[u].w};
       float v[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack2_h16(xw[j], fmt);
-        v[2 * j] = f.x;
-        v[2 * j + 1] = f.y;
-      }
+      unpack8<FMT>(xr[u], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float uu = v[j] * coef[c0 + j] + coef[C + c0 + j];
-        v[j] = act ? silu_f(uu) : uu;
+        const float uu = fmaf(v[j], ca[j], cd[j]);
+        v[j] = act ? uu * sigmoid_fast<FMT>(uu) : uu;
       }
       if (rb) {   // identity skip of a ResnetBlock whose dim == dim_out (VDDP:297,311)
+        float r[8];
+        unpack8<FMT>(rr[u], r);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack2_h16(rw[j], fmt);
-          v[2 * j] += f.x;
-          v[2 * j + 1] += f.y;
-        }
+        for (int j = 0; j < 8; ++j) v[j] += r[j];
       }
-      store8(yb + i * 8, fmt, v);
+      yb[i] = pack8<FMT>(v);
     }
   }
 }
 
 // Backward pass 1: per (sample, channel)  S1 = sum_pix du,  S2 = sum_pix du * xhat   with du = dy * silu'(u).
+// The loop accumulates S1 and T = sum du * x; S2 = rstd * (T - mean * S1) per channel at the end.
 // part: [B][C][2] fp32, accumulated atomically (zeroed by the caller).
+template <int FMT>
 __global__ void __launch_bounds__(256) gn_silu_bwd_reduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dy,
-                                                                 int fmt, long long pix, int C, int groups,
-                                                                 const double* __restrict__ stats, const float* __restrict__ gamma,
-                                                                 const float* __restrict__ beta, const float* __restrict__ scale_shift,
-                                                                 float eps, int act, float* __restrict__ part, int pix_per_cta) {
-  extern __shared__ float sm[];   // coef a[C], d[C], mean_rstd: m[C], r[C]; then reduction scratch [rows][C][2]
-  float* ca = sm;
-  float* cd = sm + C;
-  float* cm = sm + 2 * C;
-  float* cr = sm + 3 * C;
-  float* red = sm + 4 * C;
+                                                                 long long pix, int C, int groups, const double* __restrict__ stats,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const float* __restrict__ scale_shift, float eps, int act,
+                                                                 float* __restrict__ part) {
+  extern __shared__ float red[];   // [2][C] block partials
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) red[c] = 0.f;
   const int b = blockIdx.y;
-  const int gs = C / groups;
-  const double n = static_cast<double>(pix) * gs;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / gs;
-    const double s1 = stats[(static_cast<long long>(b) * groups + g) * 2];
-    const double s2 = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
-    const double mean = s1 / n;
-    double var = s2 / n - mean * mean;
-    if (var < 0) var = 0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    float a = rstd * gamma[c];
-    float d = beta[c] - static_cast<float>(mean) * a;
-    if (scale_shift) {
-      const float sc = scale_shift[static_cast<long long>(b) * 2 * C + c] + 1.f;
-      const float sh = scale_shift[static_cast<long long>(b) * 2 * C + C + c];
-      a *= sc;
-      d = d * sc + sh;
-    }
-    ca[c] = a;
-    cd[c] = d;
-    cm[c] = static_cast<float>(mean);
-    cr[c] = rstd;
+  const long long i00 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c0 = static_cast<int>((i00 * 8) % C);
+  float ca[8], cd[8], cm[8], cr[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float sc;
+    gn_channel_affine(stats, gamma, beta, scale_shift, b, c0 + j, C, groups, pix, eps, ca[j], cd[j], cm[j], cr[j], sc);
   }
   __syncthreads();
-  const int vpr = C / 8;                 // 16-byte vectors per pixel row
-  const int rows = blockDim.x / vpr;     // pixel rows processed per step (blockDim is a multiple of vpr)
-  const int vc = threadIdx.x % vpr;
-  const int vr = threadIdx.x / vpr;
-  const int c0 = vc * 8;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_cta;
-  const long long p1 = min(p0 + pix_per_cta, pix);
-  const uint16_t* xb = x + static_cast<long long>(b) * pix * C;
-  const uint16_t* db = dy + static_cast<long long>(b) * pix * C;
-  if (vr < rows) {
-    for (long long pb = p0 + vr; pb < p1; pb += 4 * rows) {
-      uint4 xr[4], dr[4];
+  const long long nvec = pix * C / 8;
+  const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * pix * C);
+  const uint4* db = reinterpret_cast<const uint4*>(dy + static_cast<long long>(b) * pix * C);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = i00; i0 < nvec; i0 += 4 * stride) {
+    uint4 xr[4], dr[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long pp = pb + static_cast<long long>(u) * rows;
-        if (pp < p1) {
-          xr[u] = __ldg(reinterpret_cast<const uint4*>(xb + pp * C + c0));
-          dr[u] = __ldg(reinterpret_cast<const uint4*>(db + pp * C + c0));
-        }
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        xr[u] = __ldg(xb + i);
+        dr[u] = __ldg(db + i);
       }
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long pp = pb + static_cast<long long>(u) * rows;
-        if (pp >= p1) continue;
-        const uint32_t xw[4] = {xr[u].x, xr[u].y, xr[u].z, xr[u].w};
-        const uint32_t dw[4] = {dr[u].x, dr[u].y, dr[u].z, dr[u].w};
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) continue;
+      float xv[8], dv[8];
+      unpack8<FMT>(xr[u], xv);
+      unpack8<FMT>(dr[u], dv);
 #pragma unroll
-        for (int j2 = 0; j2 < 4; ++j2) {
-          const float2 xf = unpack2_h16(xw[j2], fmt), df = unpack2_h16(dw[j2], fmt);
-          const float xv2[2] = {xf.x, xf.y}, dv2[2] = {df.x, df.y};
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int j = 2 * j2 + k;
-            const float uu = xv2[k] * ca[c0 + j] + cd[c0 + j];
-            const float du = act ? dv2[k] * dsilu_f(uu) : dv2[k];
-            const float xh = (xv2[k] - cm[c0 + j]) * cr[c0 + j];
-            s1[j] += du;
-            s2[j] += du * xh;
-          }
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float du = act ? dv[j] * dsilu_fast(fmaf(xv[j], ca[j], cd[j])) : dv[j];
+        s1[j] += du;
+        s2[j] = fmaf(du, xv[j], s2[j]);
       }
     }
   }
-  // reduce over the `rows` thread rows through shared memory
-  if (vr < rows) {
+  // lanes (l, l + vpr, ...) of a warp hold the same 8 channels: fold them with shuffles, then block partials, then global
+  const int vpr = C >> 3;
+  bool owner = true;
+  if (vpr < 32 && (vpr & (vpr - 1)) == 0) {
+    for (int o = 16; o >= vpr; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+      }
+    }
+    owner = (threadIdx.x & 31) < vpr;
+  }
+  if (owner) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      red[(vr * C + c0 + j) * 2] = s1[j];
-      red[(vr * C + c0 + j) * 2 + 1] = s2[j];
+      atomicAdd(&red[c0 + j], s1[j]);
+      atomicAdd(&red[C + c0 + j], cr[j] * (s2[j] - cm[j] * s1[j]));      // sum du * xhat
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float a = 0.f;
-    for (int r = 0; r < rows; ++r) a += red[r * 2 * C + i];
-    atomicAdd(part + static_cast<long long>(b) * 2 * C + i, a);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(part + (static_cast<long long>(b) * C + c) * 2, red[c]);
+    atomicAdd(part + (static_cast<long long>(b) * C + c) * 2 + 1, red[C + c]);
   }
 }
 
@@ -252,101 +272,67 @@ __global__ void gn_silu_bwd_finalize_kernel(const float* __restrict__ part, int 
   }
 }
 
-// Backward pass 2: dx = rstd * ( gamma*(1+sc)*du - m1_g - xhat * m2_g )
+// Backward pass 2: dx = rstd * ( gamma*(1+sc)*du - m1_g - xhat * m2_g ) = K du - (x P + Q)  with per-channel
+//   K = rstd gamma (1+sc),  P = rstd^2 m2_g,  Q = rstd (m1_g - mean rstd m2_g)
+template <int FMT>
 __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dy,
-                                                                uint16_t* __restrict__ dx, int fmt, long long pix, int C, int groups,
+                                                                uint16_t* __restrict__ dx, long long pix, int C, int groups,
                                                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, const float* __restrict__ scale_shift,
                                                                 float eps, int act, const float* __restrict__ gm,
                                                                 float* __restrict__ dx_colsum) {
-  extern __shared__ float sm[];   // a[C], d[C], mean[C], rstd[C], k[C], m1[C], m2[C], colsum[C]
-  float* ca = sm;
-  float* cd = sm + C;
-  float* cm = sm + 2 * C;
-  float* cr = sm + 3 * C;
-  float* ck = sm + 4 * C;
-  float* c1 = sm + 5 * C;
-  float* c2 = sm + 6 * C;
-  float* cs = sm + 7 * C;         // block partial of the column sums of dx
+  extern __shared__ float cs[];    // [C] block partial of the column sums of dx
+  for (int c = threadIdx.x; c < C; c += blockDim.x) cs[c] = 0.f;
   const int b = blockIdx.y;
   const int gs = C / groups;
-  const double n = static_cast<double>(pix) * gs;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / gs;
-    const double s1 = stats[(static_cast<long long>(b) * groups + g) * 2];
-    const double s2 = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
-    const double mean = s1 / n;
-    double var = s2 / n - mean * mean;
-    if (var < 0) var = 0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    float a = rstd * gamma[c];
-    float d = beta[c] - static_cast<float>(mean) * a;
-    float sc = 1.f;
-    if (scale_shift) {
-      sc = scale_shift[static_cast<long long>(b) * 2 * C + c] + 1.f;
-      const float sh = scale_shift[static_cast<long long>(b) * 2 * C + C + c];
-      a *= sc;
-      d = d * sc + sh;
-    }
-    ca[c] = a;
-    cd[c] = d;
-    cm[c] = static_cast<float>(mean);
-    cr[c] = rstd;
-    ck[c] = gamma[c] * sc;
-    c1[c] = gm[(static_cast<long long>(b) * groups + g) * 2];
-    c2[c] = gm[(static_cast<long long>(b) * groups + g) * 2 + 1];
-    cs[c] = 0.f;
+  const long long i00 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c0 = static_cast<int>((i00 * 8) % C);
+  float ca[8], cd[8], cK[8], cP[8], cQ[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float mean, rstd, sc;
+    gn_channel_affine(stats, gamma, beta, scale_shift, b, c0 + j, C, groups, pix, eps, ca[j], cd[j], mean, rstd, sc);
+    const int g = (c0 + j) / gs;
+    const float m1 = gm[(static_cast<long long>(b) * groups + g) * 2];
+    const float m2 = gm[(static_cast<long long>(b) * groups + g) * 2 + 1];
+    cK[j] = rstd * gamma[c0 + j] * sc;
+    cP[j] = rstd * rstd * m2;
+    cQ[j] = rstd * (m1 - mean * rstd * m2);
   }
   __syncthreads();
   const long long nvec = pix * C / 8;
-  const uint16_t* xb = x + static_cast<long long>(b) * pix * C;
-  const uint16_t* db = dy + static_cast<long long>(b) * pix * C;
-  uint16_t* ob = dx + static_cast<long long>(b) * pix * C;
+  const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * pix * C);
+  const uint4* db = reinterpret_cast<const uint4*>(dy + static_cast<long long>(b) * pix * C);
+  uint4* ob = reinterpret_cast<uint4*>(dx + static_cast<long long>(b) * pix * C);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  // the host picks gridDim.x so that (stride * 8) % C == 0: every vector of this thread covers the same 8 channels
   float colacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
+  for (long long i0 = i00; i0 < nvec; i0 += 4 * stride) {
     uint4 xr[4], dr[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long i = i0 + u * stride;
       if (i < nvec) {
-        xr[u] = __ldg(reinterpret_cast<const uint4*>(xb) + i);
-        dr[u] = __ldg(reinterpret_cast<const uint4*>(db) + i);
+        xr[u] = __ldg(xb + i);
+        dr[u] = __ldg(db + i);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long i = i0 + u * stride;
       if (i >= nvec) continue;
-      const int c0 = static_cast<int>((i * 8) % C);
-      const uint32_t xw[4] = {xr[u].x, xr[u].y, xr[u].z, xr[u].w};
-      const uint32_t dw[4] = {dr[u].x, dr[u].y, dr[u].z, dr[u].w};
-      float o[8];
+      float xv[8], dv[8], o[8];
+      unpack8<FMT>(xr[u], xv);
+      unpack8<FMT>(dr[u], dv);
 #pragma unroll
-      for (int j2 = 0; j2 < 4; ++j2) {
-        const float2 xf = unpack2_h16(xw[j2], fmt), df = unpack2_h16(dw[j2], fmt);
-        const float xv2[2] = {xf.x, xf.y}, dv2[2] = {df.x, df.y};
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int c = c0 + 2 * j2 + k;
-          const float uu = xv2[k] * ca[c] + cd[c];
-          const float du = act ? dv2[k] * dsilu_f(uu) : dv2[k];
-          const float xh = (xv2[k] - cm[c]) * cr[c];
-          o[2 * j2 + k] = cr[c] * (ck[c] * du - c1[c] - xh * c2[c]);
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float du = act ? dv[j] * dsilu_fast(fmaf(xv[j], ca[j], cd[j])) : dv[j];
+        o[j] = fmaf(cK[j], du, -fmaf(xv[j], cP[j], cQ[j]));
+        colacc[j] += o[j];
       }
-      store8(ob + i * 8, fmt, o);
-      if (dx_colsum) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) colacc[j] += o[j];
-      }
+      ob[i] = pack8<FMT>(o);
     }
   }
   if (dx_colsum) {
-    const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int c0 = static_cast<int>((i0 * 8) % C);
-    // lanes (l, l + vpr, l + 2 vpr, ...) of a warp hold the same 8 channels: fold them with shuffles first
     const int vpr = C >> 3;
     bool owner = true;
     if (vpr < 32 && (vpr & (vpr - 1)) == 0) {
@@ -522,16 +508,30 @@ static int ln_shape(int C, int& tpr, int& vpt) {
 
 using namespace vmm;
 
+// grid.x for the streaming GroupNorm kernels: enough CTAs to fill the machine, and (gridDim.x * 256 * 8) % C == 0 so that
+// every thread keeps the same 8 channels over its whole grid-stride loop
+static int gn_grid_x(long long nvec, int B, int C) {
+  int gx = static_cast<int>(min64((nvec + 255) / 256, (4LL * num_sms() + B - 1) / B * 2));
+  if (gx < 1) gx = 1;
+  int m = 1;
+  while ((static_cast<long long>(m) * 2048) % C) ++m;
+  return (gx + m - 1) / m * m;
+}
+
 extern "C" int vmm_gn_silu_fwd(const void* x, const void* res, void* y, int fmt, int B, long long pix, int C, int groups, const double* stats,
                                const float* gamma, const float* beta, const float* scale_shift, float eps, int act, void* stream) {
   if (!x || !y || !stats || !gamma || !beta) return set_error(VMM_ERR_ARG, "vmm_gn_silu_fwd: null pointer");
   if (C % 8 || C % groups || C > 4096) return set_error(VMM_ERR_ARG, "vmm_gn_silu_fwd: C must be a multiple of 8 and of groups");
+  if (fmt != VMM_FMT_F16 && fmt != VMM_FMT_BF16) return set_error(VMM_ERR_ARG, "vmm_gn_silu_fwd: bad fmt");
   const long long nvec = pix * C / 8;
-  int gx = static_cast<int>(min64((nvec + 255) / 256, (4LL * num_sms() + B - 1) / B * 2));
-  if (gx < 1) gx = 1;
-  gn_silu_fwd_kernel<<<dim3(gx, B), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(res), static_cast<uint16_t*>(y), fmt, pix, C, groups, stats, gamma,
-      beta, scale_shift, eps, act);
+  const dim3 grid(gn_grid_x(nvec, B, C), B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (fmt == VMM_FMT_F16)
+    gn_silu_fwd_kernel<0><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(res), static_cast<uint16_t*>(y), pix,
+                                                C, groups, stats, gamma, beta, scale_shift, eps, act);
+  else
+    gn_silu_fwd_kernel<1><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(res), static_cast<uint16_t*>(y), pix,
+                                                C, groups, stats, gamma, beta, scale_shift, eps, act);
   count_launch();
   return check_launch("vmm_gn_silu_fwd");
 }
@@ -547,50 +547,30 @@ extern "C" int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt,
   if (!x || !dy || !dx || !stats || !gamma || !beta || !dgamma || !dbeta || !workspace)
     return set_error(VMM_ERR_ARG, "vmm_gn_silu_bwd: null pointer");
   if (C % 8 || C % groups || C > 2048) return set_error(VMM_ERR_ARG, "vmm_gn_silu_bwd: bad C");
+  if (fmt != VMM_FMT_F16 && fmt != VMM_FMT_BF16) return set_error(VMM_ERR_ARG, "vmm_gn_silu_bwd: bad fmt");
   if (workspace_bytes < vmm_gn_silu_bwd_workspace(B, C, groups)) return set_error(VMM_ERR_ARG, "vmm_gn_silu_bwd: workspace too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   float* part = static_cast<float*>(workspace);
   float* gm = part + static_cast<size_t>(B) * C * 2;
   cudaError_t e = cudaMemsetAsync(part, 0, static_cast<size_t>(B) * C * 2 * sizeof(float), stream);
   if (e != cudaSuccess) return set_cuda_error(e, "vmm_gn_silu_bwd: memset");
-  const int vpr = C / 8;
-  int threads = 256;
-  if (threads % vpr) threads = (256 / vpr) * vpr;
-  if (threads < vpr) threads = vpr;
-  if (threads > 1024) return set_error(VMM_ERR_UNSUPPORTED, "vmm_gn_silu_bwd: C too large");
-  const int rows = threads / vpr;
-  int ctas = (6 * num_sms() + B - 1) / B;
-  int ppc = static_cast<int>((pix + ctas - 1) / ctas);
-  if (ppc < rows * 4) ppc = rows * 4;
-  ctas = static_cast<int>((pix + ppc - 1) / ppc);
-  const size_t sm1 = (4 * C + static_cast<size_t>(rows) * C * 2) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gn_silu_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
-  }
-  gn_silu_bwd_reduce_kernel<<<dim3(ctas, B), threads, sm1, stream>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(dy),
-                                                                      fmt, pix, C, groups, stats, gamma, beta, scale_shift, eps, act,
-                                                                      part, ppc);
+  const long long nvec = pix * C / 8;
+  const dim3 grid(gn_grid_x(nvec, B, C), B);
+  const uint16_t* xp = static_cast<const uint16_t*>(x);
+  const uint16_t* dp = static_cast<const uint16_t*>(dy);
+  if (fmt == VMM_FMT_F16)
+    gn_silu_bwd_reduce_kernel<0><<<grid, 256, 2 * C * sizeof(float), stream>>>(xp, dp, pix, C, groups, stats, gamma, beta, scale_shift, eps, act, part);
+  else
+    gn_silu_bwd_reduce_kernel<1><<<grid, 256, 2 * C * sizeof(float), stream>>>(xp, dp, pix, C, groups, stats, gamma, beta, scale_shift, eps, act, part);
   count_launch();
   gn_silu_bwd_finalize_kernel<<<4, 256, 0, stream>>>(part, B, pix, C, groups, gamma, beta, scale_shift, gm, dgamma, dbeta, dscale_shift);
   count_launch();
-  const long long nvec = pix * C / 8;
-  int gx = static_cast<int>(min64((nvec + 255) / 256, (4LL * num_sms() + B - 1) / B * 2));
-  if (gx < 1) gx = 1;
-  if (dx_colsum) {
-    // column sums need a fixed thread -> channel mapping: (gridDim.x * 256 * 8) % C == 0
-    const int unit = (C + 2047) / 2048 * 1;                 // C <= 2048: any gx works when 2048 % C == 0
-    if ((2048 % C) != 0) {
-      int m = 1;
-      while ((static_cast<long long>(m) * 2048) % C) ++m;   // smallest multiplier making the stride a multiple of C
-      gx = (gx + m - 1) / m * m;
-    }
-    (void)unit;
-  }
-  gn_silu_bwd_apply_kernel<<<dim3(gx, B), 256, 8 * C * sizeof(float), stream>>>(
-      static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(dy), static_cast<uint16_t*>(dx), fmt, pix, C, groups, stats, gamma,
-      beta, scale_shift, eps, act, gm, dx_colsum);
+  if (fmt == VMM_FMT_F16)
+    gn_silu_bwd_apply_kernel<0><<<grid, 256, C * sizeof(float), stream>>>(xp, dp, static_cast<uint16_t*>(dx), pix, C, groups, stats, gamma, beta,
+                                                                         scale_shift, eps, act, gm, dx_colsum);
+  else
+    gn_silu_bwd_apply_kernel<1><<<grid, 256, C * sizeof(float), stream>>>(xp, dp, static_cast<uint16_t*>(dx), pix, C, groups, stats, gamma, beta,
+                                                                         scale_shift, eps, act, gm, dx_colsum);
   count_launch();
   return check_launch("vmm_gn_silu_bwd");
 }
