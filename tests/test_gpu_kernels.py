@@ -481,3 +481,62 @@ def test_spatial_attention_bwd(ops, dt):
     # the kernel uses the 16-bit forward output for rowsum(dO * O): allow the matching rounding
     assert rel(dqkv, qf.grad) < 2 * TOL[dt]
     assert rel(dekv, ef.grad) < 2 * TOL[dt]
+
+
+# ------------------------------------------------------------------------------------------------
+# 3x3 convolutions through ops.conv3x3: on H % 16 == 0, W % 8 == 0 grids vmm_cgemm runs its halo mode (one A slab per kx,
+# weights resident in shared memory when they fit, two epilogue groups for 64 < N <= 128); other grids take the generic taps.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("case", [
+    (5, 32, 24, [64], 64, True, True),        # halo, weights resident (72 KB), GroupNorm statistics + residual
+    (3, 16, 16, [64, 64], 64, True, False),   # halo, two sources (144 KB of weights: streamed)
+    (3, 48, 48, [128], 128, False, True),     # halo, N = 128: two epilogue groups, 4 TMEM accumulators
+    (11, 16, 8, [16, 8], 16, True, True),     # halo with partial 64-channel chunks, tiny GroupNorm groups (generic epilogue)
+    (4, 24, 24, [64], 64, True, True),        # H % 16 != 0: generic taps
+    (2, 96, 96, [64], 128, False, True),      # full-resolution rows
+])
+def test_conv3x3_forward_modes(ops, dt, case):
+    bf, H, W, cins, n, with_res, with_gn = case
+    torch.manual_seed(31)
+    cin = sum(cins)
+    xs = [torch.randn(bf, H, W, c, device="cuda").to(dt) for c in cins]
+    w = (torch.randn(n, cin, 3, 3, device="cuda") / (9 * cin) ** 0.5).to(dt)
+    b = torch.randn(n, device="cuda")
+    r = torch.randn(bf, H, W, n, device="cuda").to(dt) if with_res else None
+    fps, groups = 2, 8
+    nsamp = -(-bf // fps)
+    stats = torch.zeros(nsamp, groups, 2, device="cuda", dtype=torch.float64) if with_gn else None
+    out = torch.empty(bf, H, W, n, device="cuda", dtype=dt)
+    ops.conv3x3(xs, ops.pack_conv_taps(w.float(), cins, dt), n, out, bias=b, res=r, gn_stats=stats, gn_group=n // groups,
+                frames_per_sample=fps)
+    want = F.conv2d(torch.cat(xs, -1).float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
+    if with_res:
+        want = want + r.float()
+    assert rel(out, want) < TOL[dt]
+    if with_gn:
+        o = want.double()
+        if nsamp * fps != bf:
+            o = torch.cat((o, o.new_zeros(nsamp * fps - bf, H, W, n)), 0)
+        o = o.view(nsamp, fps, H, W, groups, n // groups)
+        ws = torch.stack((o.sum(dim=(1, 2, 3, 5)), (o * o).sum(dim=(1, 2, 3, 5))), -1)
+        assert float((stats[..., 1] - ws[..., 1]).abs().max() / ws[..., 1].abs().max()) < 1e-4      # sum of squares
+        assert float((stats[..., 0] - ws[..., 0]).abs().max()) < 1e-4 * float(o.abs().sum(dim=(1, 2, 3, 5)).max())
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_conv3x3_dgrad_halo_split(ops, dt):
+    """Data gradient of a 3x3 conv over two concatenated sources on a halo-mode grid: flipped / transposed weights, output
+    columns split over the two sources (out2 / nsplit), accumulated onto a residual (res / res2)."""
+    bf, H, W, cins, cout = 3, 32, 16, [64, 64], 64
+    torch.manual_seed(32)
+    cin = sum(cins)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") / (9 * cin) ** 0.5).to(dt)
+    dy = torch.randn(bf, H, W, cout, device="cuda").to(dt)
+    x0 = torch.randn(bf, H, W, cin, device="cuda").to(dt)
+    dx_want, _ = _conv_grads(x0, w, dy, padding=1)
+    acc = [torch.randn(bf, H, W, c, device="cuda").to(dt) for c in cins]
+    wd = ops.pack_conv_taps(w.float().flip(2, 3).permute(1, 0, 2, 3), [cout], dt)
+    dxs = [a.clone() for a in acc]
+    ops.conv3x3([dy], wd, cin, dxs[0], out2=dxs[1], nsplit=cins[0], res=dxs[0], res2=dxs[1])
+    assert rel(torch.cat(dxs, -1), dx_want + torch.cat(acc, -1).float()) < TOL[dt]
