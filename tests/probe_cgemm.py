@@ -114,10 +114,10 @@ def run_case(name):
         byts = 2.0 * M * (K + N)
         print(f"  perf rows M={M} K={K} N={N}: {ms * 1e3:.1f} us  {2.0 * M * K * N / ms / 1e9:.1f} TFLOP/s  {byts / ms / 1e6:.0f} GB/s")
         return True
-    if name in ("perf", "perf1"):
+    if name in ("perf", "perf1", "perf256"):
         shapes = [(88, 96, 64, 64), (88, 48, 128, 128), (88, 24, 256, 256), (88, 12, 512, 512), (88, 96, 128, 64), (88, 96, 64, 128),
                   (88, 48, 64, 128), (88, 48, 128, 64), (88, 48, 256, 128)]
-        for (bf, h, cin, n) in (shapes[:1] if name == "perf1" else shapes):
+        for (bf, h, cin, n) in (shapes[:1] if name == "perf1" else shapes[2:3] if name == "perf256" else shapes):
             x = torch.randn(bf, h, h, cin, device=dev).to(bf16)
             wt = (torch.randn(n, cin, 3, 3, device=dev) / (9 * cin) ** 0.5).to(bf16)
             wp = ops.pack_conv_taps(wt.float(), [cin], bf16)

@@ -56,10 +56,12 @@ struct __align__(8) WgSmemCtl {
 };
 
 __device__ __forceinline__ void wg_decode(const WgradDev& p, int item, int& col, int& mt, int& kt0, int& kt1) {
-  const int ks = item % p.ksplit;
-  const int r = item / p.ksplit;
+  // column block fastest: the CTAs that run concurrently work on the same pixel range (same dY tile, neighbouring taps of the
+  // same X pixels), so all but the first read of a pixel tile hit L2 instead of HBM
+  col = item % p.n_cols;
+  const int r = item / p.n_cols;
   mt = r % p.m_tiles;
-  col = r / p.m_tiles;
+  const int ks = r / p.m_tiles;
   kt0 = static_cast<int>(static_cast<long long>(ks) * p.pix_tiles / p.ksplit);
   kt1 = static_cast<int>(static_cast<long long>(ks + 1) * p.pix_tiles / p.ksplit);
 }
