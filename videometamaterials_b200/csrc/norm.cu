@@ -354,8 +354,8 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* 
 // ------------------------------------------------------------------------------------------------
 // channel LayerNorm (gain only, biased variance)  VDDP:245-254, rows = every (b, f, h, w) position
 // ------------------------------------------------------------------------------------------------
-template <int VPT>   // 16-byte vectors per thread (C = 8 * VPT * tpr)
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int fmt,
+template <int VPT, int FMT>   // 16-byte vectors per thread (C = 8 * VPT * tpr); 16-bit format
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
                                                      long long rows, int C, int tpr, const float* __restrict__ gamma, float eps,
                                                      float* __restrict__ mean_rstd) {
   const int rpb = blockDim.x / tpr;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const uint16_t* __restrict_
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       if (live) {
-        load8(x + r * C + (k * tpr + lc) * 8, fmt, v[k]);
+        unpack8<FMT>(__ldg(reinterpret_cast<const uint4*>(x + r * C + (k * tpr + lc) * 8)), v[k]);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
@@ -400,15 +400,15 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const uint16_t* __restrict_
       const int c0 = (k * tpr + lc) * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[k][j] = (v[k][j] - mean) * rstd * __ldg(gamma + c0 + j);
-      store8(y + r * C + c0, fmt, v[k]);
+      *reinterpret_cast<uint4*>(y + r * C + c0) = pack8<FMT>(v[k]);
     }
   }
 }
 
 // backward: dx = rstd * (g*dy - mean_c(g*dy) - xhat * mean_c(g*dy*xhat)) (+ dres),  dgamma[c] += sum_rows dy*xhat
-template <int VPT>
+template <int VPT, int FMT>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ dy,
-                                                     const uint16_t* __restrict__ dres, uint16_t* __restrict__ dx, int fmt,
+                                                     const uint16_t* __restrict__ dres, uint16_t* __restrict__ dx,
                                                      long long rows, int C, int tpr, const float* __restrict__ gamma, float eps,
                                                      float* __restrict__ dgamma) {
   extern __shared__ float sdg[];   // [C] block partial of dgamma
@@ -430,8 +430,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       if (live) {
-        load8(x + r * C + (k * tpr + lc) * 8, fmt, v[k]);
-        load8(dy + r * C + (k * tpr + lc) * 8, fmt, d[k]);
+        unpack8<FMT>(__ldg(reinterpret_cast<const uint4*>(x + r * C + (k * tpr + lc) * 8)), v[k]);
+        unpack8<FMT>(__ldg(reinterpret_cast<const uint4*>(dy + r * C + (k * tpr + lc) * 8)), d[k]);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[k][j] = d[k][j] = 0.f;
@@ -477,13 +477,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
     for (int k = 0; k < VPT; ++k) {
       const int c0 = (k * tpr + lc) * 8;
       float o8[8];
-      if (dres) load8(dres + r * C + c0, fmt, o8);
+      if (dres) unpack8<FMT>(__ldg(reinterpret_cast<const uint4*>(dres + r * C + c0)), o8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float g = rstd * (d[k][j] - a1 - v[k][j] * a2);
         o8[j] = dres ? o8[j] + g : g;
       }
-      store8(dx + r * C + c0, fmt, o8);
+      *reinterpret_cast<uint4*>(dx + r * C + c0) = pack8<FMT>(o8);
     }
   }
 #pragma unroll
@@ -576,10 +576,13 @@ extern "C" int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt,
 }
 
 #define LN_DISPATCH(KERNEL, ...)                                  \
-  switch (vpt) {                                                  \
-    case 1: KERNEL<1> __VA_ARGS__; break;                         \
-    case 2: KERNEL<2> __VA_ARGS__; break;                         \
-    case 4: KERNEL<4> __VA_ARGS__; break;                         \
+  switch (vpt * 2 + (fmt == VMM_FMT_BF16 ? 1 : 0)) {              \
+    case 2: KERNEL<1, 0> __VA_ARGS__; break;                      \
+    case 3: KERNEL<1, 1> __VA_ARGS__; break;                      \
+    case 4: KERNEL<2, 0> __VA_ARGS__; break;                      \
+    case 5: KERNEL<2, 1> __VA_ARGS__; break;                      \
+    case 8: KERNEL<4, 0> __VA_ARGS__; break;                      \
+    case 9: KERNEL<4, 1> __VA_ARGS__; break;                      \
     default: return set_error(VMM_ERR_UNSUPPORTED, "layernorm: unsupported channel count"); \
   }
 
@@ -591,7 +594,7 @@ extern "C" int vmm_ln_fwd(const void* x, void* y, int fmt, long long rows, int C
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int rpb = 256 / tpr;
   const int grid = static_cast<int>(min64((rows + rpb - 1) / rpb, 8LL * num_sms()));
-  LN_DISPATCH(ln_fwd_kernel, <<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), fmt, rows, C, tpr,
+  LN_DISPATCH(ln_fwd_kernel, <<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), rows, C, tpr,
                                                         gamma, eps, mean_rstd));
   count_launch();
   return check_launch("vmm_ln_fwd");
@@ -606,7 +609,7 @@ extern "C" int vmm_ln_bwd(const void* x, const void* dy, const void* dres, void*
   const int rpb = 256 / tpr;
   const int grid = static_cast<int>(min64((rows + rpb - 1) / rpb, 4LL * num_sms()));
   LN_DISPATCH(ln_bwd_kernel, <<<grid, 256, C * sizeof(float), stream>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(dy),
-                                                                        static_cast<const uint16_t*>(dres), static_cast<uint16_t*>(dx), fmt,
+                                                                        static_cast<const uint16_t*>(dres), static_cast<uint16_t*>(dx),
                                                                         rows, C, tpr, gamma, eps, dgamma));
   count_launch();
   return check_launch("vmm_ln_bwd");

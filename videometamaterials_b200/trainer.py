@@ -243,6 +243,11 @@ class Trainer(object):
                 return self._fwd_bwd_eager(x, cond)
             # capture (nothing executes during capture; the replay below is this step's work)
             st["x"], st["cond"] = x.clone(), cond.clone()
+            # the AccumulateGrad nodes of the (few) torch-autograd parameters were created on the eager stream; the capture
+            # stream differs by design and the engine orders the two with events inside the capture
+            _warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if _warn is not None:
+                _warn(False)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
