@@ -20,6 +20,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -268,25 +269,49 @@ def run_own(args):
 
     # roofline of the dominant kernel (vmm_cgemm): profile two more steps with per-launch events.  Every rank runs
     # them (the steps contain the gradient all-reduce); only rank 0 reports.
-    ops.PROFILE = []
+    ops.PROFILE, ops.PROFILE_TAGS = [], True
     for _ in range(2):
-        step_resident()
+        step_resident()                      # Trainer falls back to eager launches while ops.PROFILE is set
     barrier()
-    prof, ops.PROFILE = ops.PROFILE, None
+    prof, ops.PROFILE, ops.PROFILE_TAGS = ops.PROFILE, None, False
     if rank != 0:
         return
     pk = peaks()
     by = {}
-    for name, flops, a, b in prof:
-        d = by.setdefault(name, [0.0, 0.0, 0])
-        d[0] += flops
-        d[1] += a.elapsed_time(b) * 1e-3
-        d[2] += 1
-    cg = by.get("cgemm", [0.0, 1.0, 1])
+    for name, flops, a, b, nbytes in prof:
+        kern, _, shape = name.partition("|")
+        cls = kern
+        if kern == "cgemm":
+            cls = "cgemm/conv3x3" if re.search(r"taps=(9|18)x1", shape) else "cgemm/other"
+        for key in {kern, cls, name}:
+            d = by.setdefault(key, [0.0, 0.0, 0, 0.0])
+            d[0] += flops
+            d[1] += a.elapsed_time(b) * 1e-3
+            d[2] += 1
+            d[3] += nbytes
+    cg = by.get("cgemm", [0.0, 1.0, 1, 0.0])
     achieved = cg[0] / cg[1] / 1e12
-    roof = {"bound": "tensor", "kernel": "vmm::cgemm_kernel", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (bf16_tflops_sustained)",
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram.json")       # ncu dram__bytes_{read,write}.sum of every cgemm launch of one step
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("cgemm", {}).get("dram_bytes_per_launch")
+
+    def sub(key):
+        d = by.get(key)
+        if not d:
+            return None
+        t = d[0] / d[1] / 1e12
+        return {"achieved": t, "frac": t / pk["tflops_sustained"], "launches_per_step": d[2] // 2, "share_of_step": (d[1] / 2) / (ms * 1e-3)}
+    top = sorted(((k, v) for k, v in by.items() if "|" in k and k.startswith("cgemm")), key=lambda kv: -kv[1][1])[:6]
+    roof = {"bound": "tensor", "kernel": "vmm::cgemm_kernel (all launches of a step)", "achieved": achieved, "peak": pk["tflops_sustained"],
+            "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+            "traffic_note": "average DRAM bytes per launch, ncu (profiles/r1_gemm_dram.json); algorithmic_bytes_per_launch = operands read once + output written once",
+            "algorithmic_bytes_per_launch": cg[3] / max(1, cg[2]), "algorithmic_flops_per_launch": cg[0] / max(1, cg[2]),
+            "avg_launch_us": cg[1] / max(1, cg[2]) * 1e6,
+            "peak_source": pk["source"] + " (bf16_tflops_sustained)",
             "launches_per_step": cg[2] // 2, "share_of_step": (cg[1] / 2) / (ms * 1e-3),
+            "conv3x3": sub("cgemm/conv3x3"), "other_gemm": sub("cgemm/other"),
+            "top_shapes": [{"shape": k.partition("|")[2], "tflops": v[0] / v[1] / 1e12, "ms_per_step": v[1] / 2 * 1e3} for k, v in top],
             "wgrad": {"achieved": by["wgrad"][0] / by["wgrad"][1] / 1e12 if "wgrad" in by else None,
                       "share_of_step": (by["wgrad"][1] / 2) / (ms * 1e-3) if "wgrad" in by else None}}
     # sampling metric (second half of BASELINE.json's metric): ancestral p_sample with guidance, b=4, CUDA graph
@@ -317,6 +342,7 @@ def run_own(args):
         "config": {"workload": "Unet3D fwd+bwd bf16, batch=8 per GPU, 96x96x11 (BASELINE configs[1]); step = forward + backward + "
                                "gradient all-reduce + fused Adam/EMA + weight repack", "global_batch": world * B,
                    "l2": "activation working set per step (>20 GB) is far larger than the 126 MB L2; no explicit flush",
+                   "launch": "forward + backward replayed from one CUDA graph per step; all-reduce, Adam/EMA and repack launched eagerly",
                    "parallelism": f"dp{world}", "model_tflops_per_gpu": B * FWD_BWD_GFLOP_PER_CLIP / ms},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + c_host.numel() * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},

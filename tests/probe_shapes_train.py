@@ -22,7 +22,7 @@ for _ in range(N):
 torch.cuda.synchronize()
 prof, ops.PROFILE = ops.PROFILE, None
 agg = collections.OrderedDict()
-for name, flops, a, b in prof:
+for name, flops, a, b, _ in prof:
     d = agg.setdefault(name, [0, 0.0, 0.0])
     d[0] += 1; d[1] += flops; d[2] += a.elapsed_time(b) * 1e-3
 tot = sum(d[2] for d in agg.values()) / N

@@ -21,3 +21,6 @@ full gn_silu_bwd_apply_L0 gn_silu_bwd_apply 0 python tests/probe_train_once.py 8
 full gn_silu_bwd_reduce_L0 gn_silu_bwd_reduce 0 python tests/probe_train_once.py 8 1
 full gn_silu_fwd_L0 gn_silu_fwd 0 python tests/probe_train_once.py 8 1
 ls gpurun_out | grep ${tag}_ | head -50
+# DRAM traffic of every GEMM launch of one eager step (two metrics only: cheap), for roofline.traffic
+timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'cgemm|wgrad_kernel' --csv \
+    --log-file gpurun_out/${tag}_gemm_dram.csv python tests/probe_train_once.py 8 1 > gpurun_out/${tag}_gemm_dram.log 2>&1

@@ -30,12 +30,13 @@ def _prof_begin():
     return e
 
 
-def _prof_end(name: str, flops: float, e0) -> None:
+def _prof_end(name: str, flops: float, e0, nbytes: float = 0.0) -> None:
+    """(kernel, algorithmic FLOPs, start, end, algorithmic bytes = every operand read once + the output written once)."""
     if e0 is None:
         return
     e1 = torch.cuda.Event(enable_timing=True)
     e1.record()
-    PROFILE.append((name, flops, e0, e1))
+    PROFILE.append((name, flops, e0, e1, nbytes))
 
 
 def fmt_of(t: torch.Tensor) -> int:
@@ -172,7 +173,11 @@ def cgemm(views: Sequence[torch.Tensor], taps: Sequence[Sequence[Tuple[int, int,
     if e0 is not None:
         ksum = sum(c for tl in taps for (_, _, _, _, c) in tl)
         tag = f"|M={bf * oh * ow} N={n} K={ksum} taps={len(taps[0])}x{len(taps)} tile={p.tf}x{p.th}x{p.tw}" if PROFILE_TAGS else ""
-        _prof_end("cgemm" + tag, 2.0 * bf * oh * ow * n * ksum, e0)
+        m = bf * oh * ow
+        nbytes = sum(t.shape[0] * t.shape[1] * t.shape[2] * t.shape[3] * 2 for t in views) + w.numel() * 2 + m * n * out.element_size() * len(taps)
+        if res is not None:
+            nbytes += m * n * 2 * len(taps)
+        _prof_end("cgemm" + tag, 2.0 * m * n * ksum, e0, nbytes)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -433,7 +438,8 @@ def wgrad(a_views: Sequence[torch.Tensor], b_views: Sequence[torch.Tensor], taps
     check(lib.vmm_wgrad(C.byref(p), stream_ptr()), "vmm_wgrad")
     if e0 is not None:
         tag = f"|px={bf * oh * ow} M={n} C={sum(tp[4] for tp in taps)} taps={len(taps)}" if PROFILE_TAGS else ""
-        _prof_end("wgrad" + tag, 2.0 * bf * oh * ow * n * sum(tp[4] for tp in taps), e0)
+        nbytes = sum(t.shape[0] * t.shape[1] * t.shape[2] * t.shape[3] * 2 for t in list(a_views) + list(b_views)) + n * sum(tp[4] for tp in taps) * 4
+        _prof_end("wgrad" + tag, 2.0 * bf * oh * ow * n * sum(tp[4] for tp in taps), e0, nbytes)
 
 
 def colsum(x2d: torch.Tensor, out: torch.Tensor) -> None:
