@@ -585,33 +585,29 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
 // cond-token gradients (tiny): thread = (bf, h, token j); summed over frames with atomics
 __global__ void lattn_bwd_tokens_kernel(const float* __restrict__ ekv, int T, const float* __restrict__ ctx, const float* __restrict__ dctx,
                                         const float* __restrict__ kstat, float* __restrict__ dekv, int BF, int frames, float vscale) {
+  // one WARP per (frame-image, head, token): a thread per unit walked the 32 x 32 matrices serially (1024 dependent steps,
+  // 60 us per launch whatever the batch); now lane = d for the key gradient and lane = e for the value gradient, 64 steps
   const int HD = 256;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= BF * 8 * T) return;
-  const int j = idx % T, h = (idx / T) % 8, bf = idx / (T * 8);
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= BF * 8 * T) return;
+  const int j = wid % T, h = (wid / T) % 8, bf = wid / (T * 8);
   const int b = bf / frames;
   const float* src = ekv + (static_cast<long long>(b) * T + j) * 2 * HD + h * 32;
   const float* ch = ctx + (static_cast<long long>(bf) * 8 + h) * 1024;
   const float* gh = dctx + (static_cast<long long>(bf) * 8 + h) * 1024;
   const float* ks = kstat + (static_cast<long long>(bf) * HD + h * 32) * 2;
-  float dv[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) dv[e] = 0.f;
   float* dst = dekv + (static_cast<long long>(b) * T + j) * 2 * HD + h * 32;
-  for (int d = 0; d < 32; ++d) {
-    const float w = __expf(src[d] - ks[d * 2]) / ks[d * 2 + 1];
-    float dw = 0.f, c = 0.f;
-#pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const float G = gh[d * 32 + e] * vscale;
-      dv[e] += w * G;
-      dw += G * src[HD + e];
-      c += gh[d * 32 + e] * ch[d * 32 + e];
-    }
-    atomicAdd(dst + d, w * (dw - c));
-  }
-#pragma unroll
-  for (int e = 0; e < 32; ++e) atomicAdd(dst + HD + e, dv[e]);
+  // lane = d:  dk[d] = w[d] * sum_e dctx[d][e] (vscale v[e] - ctx[d][e])
+  const float w = __expf(src[lane] - ks[lane * 2]) / ks[lane * 2 + 1];
+  float r = 0.f;
+#pragma unroll 8
+  for (int e = 0; e < 32; ++e) r = fmaf(gh[lane * 32 + e], fmaf(vscale, src[HD + e], -ch[lane * 32 + e]), r);
+  atomicAdd(dst + lane, w * r);
+  // lane = e:  dv[e] = vscale * sum_d w[d] dctx[d][e]
+  float dv = 0.f;
+#pragma unroll 8
+  for (int d = 0; d < 32; ++d) dv = fmaf(__shfl_sync(0xffffffffu, w, d), gh[d * 32 + lane], dv);
+  atomicAdd(dst + HD + lane, dv * vscale);
 }
 
 static int lat_rows_per_cta(int HW, int BF) {
@@ -703,7 +699,7 @@ extern "C" int vmm_lattn_bwd(const void* qkv, const float* ekv, int T, const voi
   }
   count_launch();
   const int ntok = BF * 8 * T;
-  lattn_bwd_tokens_kernel<<<(ntok + 127) / 128, 128, 0, stream>>>(ekv, T, ctx, dctx, kstat, dekv, BF, frames, vscale);
+  lattn_bwd_tokens_kernel<<<(ntok + 3) / 4, 128, 0, stream>>>(ekv, T, ctx, dctx, kstat, dekv, BF, frames, vscale);
   count_launch();
   return check_launch("vmm_lattn_bwd");
 }

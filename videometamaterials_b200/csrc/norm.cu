@@ -106,14 +106,20 @@ __global__ void __launch_bounds__(256) gn_silu_fwd_kernel(const uint16_t* __rest
                                                           const double* __restrict__ stats, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, const float* __restrict__ scale_shift,
                                                           float eps, int act) {
+  extern __shared__ float coef[];   // [2][C]: the fp64 statistics -> affine step runs once per channel and block, not per thread
   const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd, sc;
+    gn_channel_affine(stats, gamma, beta, scale_shift, b, c, C, groups, pix, eps, coef[c], coef[C + c], mean, rstd, sc);
+  }
+  __syncthreads();
   const long long i00 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c0 = static_cast<int>((i00 * 8) % C);          // fixed for this thread: the host keeps (grid stride * 8) % C == 0
   float ca[8], cd[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float mean, rstd, sc;
-    gn_channel_affine(stats, gamma, beta, scale_shift, b, c0 + j, C, groups, pix, eps, ca[j], cd[j], mean, rstd, sc);
+    ca[j] = coef[c0 + j];
+    cd[j] = coef[C + c0 + j];
   }
   const long long nvec = pix * C / 8;
   const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * pix * C);
@@ -161,18 +167,25 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_reduce_kernel(const uint16_t*
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  const float* __restrict__ scale_shift, float eps, int act,
                                                                  float* __restrict__ part) {
-  extern __shared__ float red[];   // [2][C] block partials
-  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) red[c] = 0.f;
+  extern __shared__ float red[];   // [2][C] block partials, then [4][C] per-channel coefficients (a, d, mean, rstd)
+  float* coef = red + 2 * C;
   const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sc;
+    red[c] = red[C + c] = 0.f;
+    gn_channel_affine(stats, gamma, beta, scale_shift, b, c, C, groups, pix, eps, coef[c], coef[C + c], coef[2 * C + c], coef[3 * C + c], sc);
+  }
+  __syncthreads();
   const long long i00 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c0 = static_cast<int>((i00 * 8) % C);
   float ca[8], cd[8], cm[8], cr[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float sc;
-    gn_channel_affine(stats, gamma, beta, scale_shift, b, c0 + j, C, groups, pix, eps, ca[j], cd[j], cm[j], cr[j], sc);
+    ca[j] = coef[c0 + j];
+    cd[j] = coef[C + c0 + j];
+    cm[j] = coef[2 * C + c0 + j];
+    cr[j] = coef[3 * C + c0 + j];
   }
-  __syncthreads();
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
@@ -281,25 +294,33 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* 
                                                                 const float* __restrict__ beta, const float* __restrict__ scale_shift,
                                                                 float eps, int act, const float* __restrict__ gm,
                                                                 float* __restrict__ dx_colsum) {
-  extern __shared__ float cs[];    // [C] block partial of the column sums of dx
-  for (int c = threadIdx.x; c < C; c += blockDim.x) cs[c] = 0.f;
+  extern __shared__ float cs[];    // [C] block partial of the column sums of dx, then [5][C] coefficients (a, d, K, P, Q)
+  float* coef = cs + C;
   const int b = blockIdx.y;
   const int gs = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd, sc;
+    cs[c] = 0.f;
+    gn_channel_affine(stats, gamma, beta, scale_shift, b, c, C, groups, pix, eps, coef[c], coef[C + c], mean, rstd, sc);
+    const int g = c / gs;
+    const float m1 = gm[(static_cast<long long>(b) * groups + g) * 2];
+    const float m2 = gm[(static_cast<long long>(b) * groups + g) * 2 + 1];
+    coef[2 * C + c] = rstd * gamma[c] * sc;
+    coef[3 * C + c] = rstd * rstd * m2;
+    coef[4 * C + c] = rstd * (m1 - mean * rstd * m2);
+  }
+  __syncthreads();
   const long long i00 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c0 = static_cast<int>((i00 * 8) % C);
   float ca[8], cd[8], cK[8], cP[8], cQ[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float mean, rstd, sc;
-    gn_channel_affine(stats, gamma, beta, scale_shift, b, c0 + j, C, groups, pix, eps, ca[j], cd[j], mean, rstd, sc);
-    const int g = (c0 + j) / gs;
-    const float m1 = gm[(static_cast<long long>(b) * groups + g) * 2];
-    const float m2 = gm[(static_cast<long long>(b) * groups + g) * 2 + 1];
-    cK[j] = rstd * gamma[c0 + j] * sc;
-    cP[j] = rstd * rstd * m2;
-    cQ[j] = rstd * (m1 - mean * rstd * m2);
+    ca[j] = coef[c0 + j];
+    cd[j] = coef[C + c0 + j];
+    cK[j] = coef[2 * C + c0 + j];
+    cP[j] = coef[3 * C + c0 + j];
+    cQ[j] = coef[4 * C + c0 + j];
   }
-  __syncthreads();
   const long long nvec = pix * C / 8;
   const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * pix * C);
   const uint4* db = reinterpret_cast<const uint4*>(dy + static_cast<long long>(b) * pix * C);
@@ -527,10 +548,10 @@ extern "C" int vmm_gn_silu_fwd(const void* x, const void* res, void* y, int fmt,
   const dim3 grid(gn_grid_x(nvec, B, C), B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (fmt == VMM_FMT_F16)
-    gn_silu_fwd_kernel<0><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(res), static_cast<uint16_t*>(y), pix,
+    gn_silu_fwd_kernel<0><<<grid, 256, 2 * C * sizeof(float), st>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(res), static_cast<uint16_t*>(y), pix,
                                                 C, groups, stats, gamma, beta, scale_shift, eps, act);
   else
-    gn_silu_fwd_kernel<1><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(res), static_cast<uint16_t*>(y), pix,
+    gn_silu_fwd_kernel<1><<<grid, 256, 2 * C * sizeof(float), st>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(res), static_cast<uint16_t*>(y), pix,
                                                 C, groups, stats, gamma, beta, scale_shift, eps, act);
   count_launch();
   return check_launch("vmm_gn_silu_fwd");
@@ -559,17 +580,17 @@ extern "C" int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt,
   const uint16_t* xp = static_cast<const uint16_t*>(x);
   const uint16_t* dp = static_cast<const uint16_t*>(dy);
   if (fmt == VMM_FMT_F16)
-    gn_silu_bwd_reduce_kernel<0><<<grid, 256, 2 * C * sizeof(float), stream>>>(xp, dp, pix, C, groups, stats, gamma, beta, scale_shift, eps, act, part);
+    gn_silu_bwd_reduce_kernel<0><<<grid, 256, 6 * C * sizeof(float), stream>>>(xp, dp, pix, C, groups, stats, gamma, beta, scale_shift, eps, act, part);
   else
-    gn_silu_bwd_reduce_kernel<1><<<grid, 256, 2 * C * sizeof(float), stream>>>(xp, dp, pix, C, groups, stats, gamma, beta, scale_shift, eps, act, part);
+    gn_silu_bwd_reduce_kernel<1><<<grid, 256, 6 * C * sizeof(float), stream>>>(xp, dp, pix, C, groups, stats, gamma, beta, scale_shift, eps, act, part);
   count_launch();
   gn_silu_bwd_finalize_kernel<<<4, 256, 0, stream>>>(part, B, pix, C, groups, gamma, beta, scale_shift, gm, dgamma, dbeta, dscale_shift);
   count_launch();
   if (fmt == VMM_FMT_F16)
-    gn_silu_bwd_apply_kernel<0><<<grid, 256, C * sizeof(float), stream>>>(xp, dp, static_cast<uint16_t*>(dx), pix, C, groups, stats, gamma, beta,
+    gn_silu_bwd_apply_kernel<0><<<grid, 256, 6 * C * sizeof(float), stream>>>(xp, dp, static_cast<uint16_t*>(dx), pix, C, groups, stats, gamma, beta,
                                                                          scale_shift, eps, act, gm, dx_colsum);
   else
-    gn_silu_bwd_apply_kernel<1><<<grid, 256, C * sizeof(float), stream>>>(xp, dp, static_cast<uint16_t*>(dx), pix, C, groups, stats, gamma, beta,
+    gn_silu_bwd_apply_kernel<1><<<grid, 256, 6 * C * sizeof(float), stream>>>(xp, dp, static_cast<uint16_t*>(dx), pix, C, groups, stats, gamma, beta,
                                                                          scale_shift, eps, act, gm, dx_colsum);
   count_launch();
   return check_launch("vmm_gn_silu_bwd");

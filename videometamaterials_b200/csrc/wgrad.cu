@@ -6,6 +6,8 @@
 // the shared-memory descriptors are built with the MN-major flag.  One work item = (tap, 128-wide slice of n,
 // <=128-wide slice of c, K range of pixel tiles); partial sums are added atomically into the fp32 gradient in
 // the parameter's own (master) layout, so no unpack pass is needed.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -338,11 +340,27 @@ extern "C" int vmm_wgrad(const vmm_wgrad_params* hp, void* stream_) {
   d.tiles_x = (h.ow + h.tw - 1) / h.tw;
   d.pix_tiles = d.tiles_f * d.tiles_y * d.tiles_x;
   const int base_items = ncols * d.m_tiles;
-  int ksplit = (3 * num_sms() + base_items - 1) / base_items;
-  if (ksplit > d.pix_tiles) ksplit = d.pix_tiles;
-  if (ksplit < 1) ksplit = 1;
-  // keep at least 4 pixel tiles per item so the accumulate / drain overhead stays small
-  if (d.pix_tiles / ksplit < 4 && d.pix_tiles >= 4) ksplit = d.pix_tiles / 4;
+  // split-K over pixel tiles.  Candidates: 1..4 items per SM; cost model (fitted to the b=8 step, profiles/README.md): the CTAs run
+  // `waves` items one after the other, an item costs its pixel tiles plus ~6 tile-times for draining 128 x N fp32 reductions.
+  // Few long items win for the deep levels (large dW, few pixels), three per SM for level 0 (3 column blocks x 148 splits).
+  static const int forced = getenv("VMM_WGRAD_ITEMS_PER_SM") ? atoi(getenv("VMM_WGRAD_ITEMS_PER_SM")) : 0;
+  int ksplit = 1;
+  double best_cost = 1e30;
+  for (int j = 1; j <= 4; ++j) {
+    if (forced && j != forced) continue;
+    int ks = (j * num_sms() + base_items - 1) / base_items;
+    if (ks > d.pix_tiles) ks = d.pix_tiles;
+    if (ks < 1) ks = 1;
+    // keep at least 4 pixel tiles per item so the accumulate / drain overhead stays small
+    if (d.pix_tiles / ks < 4 && d.pix_tiles >= 4) ks = d.pix_tiles / 4;
+    const long long items = 1LL * base_items * ks;
+    const long long waves = (items + num_sms() - 1) / num_sms();
+    const double cost = static_cast<double>(waves) * ((d.pix_tiles + ks - 1) / ks + 6.0);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      ksplit = ks;
+    }
+  }
   d.ksplit = ksplit;
   d.total_items = base_items * ksplit;
   d.stage_bytes = (d.a_chunks + (d.BNc >> 6)) * kChunkBytes;
