@@ -208,3 +208,60 @@ def test_graph_replay_matches_eager_step():
     torch.cuda.manual_seed(123)
     loss_2 = float(tr._fwd_bwd(x.flip(0) * 0.5, cond))
     assert abs(loss_2 - loss_e) > 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_full_size_batch_properties(dtype):
+    """BASELINE configs[1] size (b=8, 96x96x11): properties that need no oracle.  Tolerance = FWD_TOL, the bound of one
+    forward against the fp32 reference: two runs of the same clip differ by the order of the fp32 / fp64 atomics (linear
+    attention context, GroupNorm statistics), which flips 16-bit roundings that then propagate through ~60 layers.
+    (1) batch invariance: every normalisation is per sample, so sample 5 of the batch equals the same clip run alone;
+    (2) the conditioning drop: null_cond_prob = 1 output is independent of cond;
+    (3) the fused guidance step at w = 1 short-circuits to the conditional forward (VDDP:719-721)."""
+    model, gd, _ = build(64, (1, 2, 4, 8), 256, 96, 256, dtype, 0)
+    tol = FWD_TOL[dtype]
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(8, 3, 11, 96, 96, generator=gen).cuda()
+    cond = (torch.rand(8, 11, generator=gen) * 2 - 1).cuda()
+    t = torch.randint(0, 256, (8,), generator=gen).cuda()
+    with torch.no_grad():
+        y8 = model(x, t, cond=cond, null_cond_prob=0.0)
+        y1 = model(x[5:6], t[5:6], cond=cond[5:6], null_cond_prob=0.0)
+        assert torch.isfinite(y8).all()
+        assert rel(y8[5:6], y1) < tol
+        yn_a = model(x[:2], t[:2], cond=cond[:2], null_cond_prob=1.0)
+        yn_b = model(x[:2], t[:2], cond=-cond[:2], null_cond_prob=1.0)
+        assert rel(yn_a, yn_b) < tol
+        yg = model.forward_with_guidance_scale(x[:2], t[:2], cond=cond[:2], guidance_scale=1.0)
+        assert rel(yg, y8[:2]) < tol
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_full_size_conv_linearity(dt):
+    """Level-0 3x3 conv at the full b=8 size (88 frame-images of 96x96, 64 -> 64, halo mode with resident weights):
+    conv(x1 + x2) = conv(x1) + conv(x2) and conv(2 x) = 2 conv(x) without bias, to 16-bit rounding; a one-hot input
+    reproduces the (flipped) kernel taps exactly."""
+    from videometamaterials_b200 import ops
+    torch.manual_seed(5)
+    bf, H, W, C = 88, 96, 96, 64
+    w = (torch.randn(C, C, 3, 3, device="cuda") / (9 * C) ** 0.5).to(dt)
+    wp = ops.pack_conv_taps(w.float(), [C], dt)
+    x1 = torch.randn(bf, H, W, C, device="cuda").to(dt)
+    x2 = torch.randn(bf, H, W, C, device="cuda").to(dt)
+    outs = []
+    for xin in (x1, x2, (x1.float() + x2.float()).to(dt), (2 * x1.float()).to(dt)):
+        o = torch.empty(bf, H, W, C, device="cuda", dtype=dt)
+        ops.conv3x3([xin], wp, C, o)
+        outs.append(o.float())
+    tol = 1.2e-2 if dt == torch.bfloat16 else 1.5e-3          # three roundings: the summed input and two outputs
+    assert rel(outs[2], outs[0] + outs[1]) < tol
+    assert rel(outs[3], 2 * outs[0]) < 1e-6                   # scaling by two is exact in binary floating point
+    # impulse response: x = delta at (frame 3, y 40, x 50, channel 7) -> out[3, 40 + dy, 50 + dx, n] = w[n, 7, 1 - dy, 1 - dx]
+    imp = torch.zeros(bf, H, W, C, device="cuda", dtype=dt)
+    imp[3, 40, 50, 7] = 1.0
+    o = torch.empty(bf, H, W, C, device="cuda", dtype=dt)
+    ops.conv3x3([imp], wp, C, o)
+    want = w[:, 7].float().flip(1, 2).permute(1, 2, 0)       # (dy, dx, n)
+    assert torch.equal(o[3, 39:42, 49:52].float(), want)
+    o[3, 39:42, 49:52] = 0
+    assert float(o.float().abs().max()) == 0.0
