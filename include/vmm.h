@@ -104,6 +104,12 @@ typedef struct {
   double* gn_stats;   /* [samples][n / gn_group][2] (sum, sum of squares), accumulated atomically; or NULL */
   int32_t gn_group;   /* channels per group */
   int32_t frames_per_sample;
+  /* Rotary epilogue (to_qkv of the temporal attention, VDDP:449,456,496): output columns [0, rot_cols) are rotated in
+   * interleaved pairs (2i, 2i+1) of every 32-wide head slice by the angle of the row's frame, f = (row / rot_hw) % rot_frames
+   * (rows GEMM: row = position index (b, f, pixel)); columns [0, rot_qcols) use table 0 (queries: cos/sin pre-multiplied by
+   * the attention scale), the others table 1 (keys).  rot: fp32 [2][rot_frames][16][2] (cos, sin) or NULL. */
+  const float* rot;
+  int32_t rot_frames, rot_hw, rot_cols, rot_qcols;
 } vmm_cgemm_params;
 
 int vmm_cgemm(const vmm_cgemm_params* p, void* stream);
@@ -146,8 +152,9 @@ int vmm_ln_bwd(const void* x, const void* dy, const void* dres, void* dx, int fm
  * vmm_sattn_*: quadratic spatial attention of the bottleneck VDDP:687-689: one cond token per frame
  *   (ekv row bf), no rotary, no bias; lse [BF][heads][HW] kept for the backward.
  * ------------------------------------------------------------------------------------------ */
+/* pre_rotated != 0: the q / k columns of qkv already carry the rotary embedding and q the scale (vmm_cgemm rotary epilogue) */
 int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bias, const float* rot, void* out, int fmt, int B, int frames,
-                  int HW, int heads, float scale, void* stream);
+                  int HW, int heads, float scale, int pre_rotated, void* stream);
 int vmm_lattn_fwd(const void* qkv, const float* ekv, int T, void* out, float* ctx, float* kstat, int fmt, int BF, int frames,
                   int HW, int heads, float scale, void* stream);
 int vmm_sattn_fwd(const void* qkv, const float* ekv, void* out, float* lse, int fmt, int BF, int frames, int HW, int heads,
@@ -157,7 +164,7 @@ int vmm_sattn_fwd(const void* qkv, const float* ekv, void* out, float* lse, int 
  * keys|values (dekv, fp32, ACCUMULATED with atomics except vmm_sattn_bwd which overwrites its rows) and, for the
  * temporal attention, the relative position bias (dbias, accumulated).  vscale = 1 / (h*w) of VDDP:371. */
 int vmm_tattn_bwd(const void* qkv, const float* ekv, const float* bias, const float* rot, const void* dout, void* dqkv, float* dekv,
-                  float* dbias, int fmt, int B, int frames, int HW, int heads, float scale, void* stream);
+                  float* dbias, int fmt, int B, int frames, int HW, int heads, float scale, int pre_rotated, void* stream);
 int vmm_lattn_bwd(const void* qkv, const float* ekv, int T, const void* dout, const float* ctx, const float* kstat, float* dctx,
                   void* dqkv, float* dekv, int fmt, int BF, int frames, int HW, int heads, float scale, float vscale, void* stream);
 int vmm_sattn_bwd(const void* qkv, const float* ekv, const void* aout, const void* dout, const float* lse, void* dqkv, float* dekv,

@@ -540,3 +540,45 @@ def test_conv3x3_dgrad_halo_split(ops, dt):
     dxs = [a.clone() for a in acc]
     ops.conv3x3([dy], wd, cin, dxs[0], out2=dxs[1], nsplit=cins[0], res=dxs[0], res2=dxs[1])
     assert rel(torch.cat(dxs, -1), dx_want + torch.cat(acc, -1).float()) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_qkv_projection_rotary_epilogue(ops, dt):
+    """vmm_cgemm rotary epilogue (to_qkv of the temporal attention): q columns scaled and rotated, k columns rotated by the
+    angle of the row's frame, v columns untouched; checked against the oracle's rotary on the plain projection, and the
+    attention core on pre-rotated rows against the core that rotates in place."""
+    from oracle import vdm_oracle as O
+    B, Fr, HW, heads, C = 2, 11, 35, 8, 64
+    hd = heads * 32
+    torch.manual_seed(41)
+    x = torch.randn(B * Fr * HW, C, device="cuda").to(dt)
+    w = (torch.randn(3 * hd, C, device="cuda") / C ** 0.5).to(dt)
+    wp = ops.pack_linear(w.float(), dt)
+    freqs, rot = _rot_tables(Fr)
+    tabs = ops.rotary_tables(rot, 32 ** -0.5)
+    plain = torch.empty(B * Fr * HW, 3 * hd, device="cuda", dtype=dt)
+    rotd = torch.empty_like(plain)
+    ops.linear_rows([x], wp, 3 * hd, plain)
+    ops.linear_rows([x], wp, 3 * hd, rotd, rot=(tabs, Fr, HW, 2 * hd, hd))
+    y = (x.float() @ w.float().t()).view(B, Fr, HW, 3, heads, 32)
+    q, k, v = y[:, :, :, 0], y[:, :, :, 1], y[:, :, :, 2]                       # (B, Fr, HW, heads, 32)
+    qr = O.rotary((q * 32 ** -0.5).permute(0, 2, 3, 1, 4), freqs).permute(0, 3, 1, 2, 4)      # rotary over the frame axis
+    kr = O.rotary(k.permute(0, 2, 3, 1, 4), freqs).permute(0, 3, 1, 2, 4)
+    want = torch.stack((qr, kr, v), dim=3).reshape(B * Fr * HW, 3 * hd)
+    assert rel(rotd, want) < TOL[dt]
+    assert torch.equal(rotd[:, 2 * hd:], plain[:, 2 * hd:])
+    # attention core: pre-rotated rows vs in-place rotary of the plain rows
+    ekv = torch.randn(B, 11, 2 * hd, device="cuda")
+    bias = torch.randn(heads, Fr, Fr, device="cuda")
+    o1 = torch.empty(B * Fr * HW, hd, device="cuda", dtype=dt)
+    o2 = torch.empty_like(o1)
+    ops.tattn_fwd(plain, ekv, bias, rot, o1, B, Fr, HW, heads)
+    ops.tattn_fwd(rotd, ekv, bias, rot, o2, B, Fr, HW, heads, pre_rotated=True)
+    assert rel(o2, o1) < TOL[dt]
+    dout = torch.randn(B * Fr * HW, hd, device="cuda").to(dt)
+    g1, g2 = torch.empty_like(plain), torch.empty_like(plain)
+    de1, de2 = torch.zeros_like(ekv), torch.zeros_like(ekv)
+    db1, db2 = torch.zeros_like(bias), torch.zeros_like(bias)
+    ops.tattn_bwd(plain, ekv, bias, rot, dout, g1, de1, db1, B, Fr, HW, heads)
+    ops.tattn_bwd(rotd, ekv, bias, rot, dout, g2, de2, db2, B, Fr, HW, heads, pre_rotated=True)
+    assert rel(g2, g1) < 2.5 * TOL[dt] and rel(de2, de1) < TOL[dt] and rel(db2, db1) < TOL[dt]

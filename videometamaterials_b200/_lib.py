@@ -37,6 +37,7 @@ class CgemmParams(C.Structure):
         ("bias", C.c_void_p), ("res", C.c_void_p), ("ldr", C.c_int64), ("res2", C.c_void_p), ("ldr2", C.c_int64),
         ("alpha", C.c_float),
         ("gn_stats", C.c_void_p), ("gn_group", C.c_int32), ("frames_per_sample", C.c_int32),
+        ("rot", C.c_void_p), ("rot_frames", C.c_int32), ("rot_hw", C.c_int32), ("rot_cols", C.c_int32), ("rot_qcols", C.c_int32),
     ]
 
 
@@ -91,10 +92,10 @@ _SIGNATURES = {
     "vmm_gn_silu_bwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _Z, _P],
     "vmm_ln_fwd": [_P, _P, _I, _L, _I, _P, _F, _P, _P],
     "vmm_ln_bwd": [_P, _P, _P, _P, _I, _L, _I, _P, _F, _P, _P],
-    "vmm_tattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "vmm_tattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "vmm_lattn_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vmm_sattn_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
-    "vmm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "vmm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "vmm_lattn_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P],
     "vmm_sattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "vmm_prep_input": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

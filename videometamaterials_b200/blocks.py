@@ -8,6 +8,7 @@ Each *_fwd returns `(out, saved)`; `saved` is what the matching backward needs.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -16,6 +17,7 @@ import torch.nn.functional as F
 from . import ops
 
 Tensor = torch.Tensor
+ROTARY_IN_EPILOGUE = os.environ.get("VMM_NO_ROT_EPILOGUE") is None     # debugging switch: rotate q / k inside the attention kernels
 
 
 def prob_mask_like(shape, prob, device):
@@ -281,7 +283,8 @@ def _cond_plan(model, sd, b: int, frames_tok: int, device):
 
 
 def conditioning(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: int):
-    """Returns (scale_shift per resnet block, ekv per attention block, bias (h,f,f), rot (f,16,2)).
+    """Returns (scale_shift per resnet block, ekv per attention block, bias (h,f,f), rot (2,f,16,2): cos/sin tables of the
+    rotary embedding, [0] pre-multiplied by the attention scale (queries), [1] plain (keys and the attention kernels).
     The per-block fan-out (18 ResnetBlock MLPs, 17 to_k / to_v pairs) is batched: parameters are gathered from the arena,
     results are split by one permutation, so the path is ~40 kernels forward instead of several hundred."""
     sd = dict(model.named_parameters())
@@ -325,7 +328,7 @@ def conditioning(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: i
     bias = table[rel_pos_buckets(frames, table.device)].permute(2, 0, 1).contiguous()      # (h, f, f)
     freqs = sd["init_temporal_attn.fn.fn.fn.rotary_emb.freqs"]
     ang = torch.arange(frames, device=freqs.device, dtype=freqs.dtype)[:, None] * freqs[None, :]
-    rot = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous()                          # (f, 16, 2)
+    rot = ops.rotary_tables(torch.stack((ang.cos(), ang.sin()), dim=-1), 32 ** -0.5)        # (2, f, 16, 2)
     return ss, ekv, bias, rot
 
 
@@ -376,11 +379,14 @@ def attn_block_fwd(P, sd, pre: str, kind: str, x: Tensor, ekv: Optional[Tensor],
     xn = torch.empty_like(x2)
     ops.ln_fwd(x2, xn, gamma)
     qkv = torch.empty(x2.shape[0], 3 * hd, dtype=dt, device=dev)
-    ops.linear_rows([xn], P[pre + "qkv.w"], 3 * hd, qkv)
+    # temporal attention: the rotary embedding of q / k (and the scale of q) ride in the epilogue of the projection, so the
+    # attention kernels (forward and backward) read ready-made rows
+    pre_rot = kind == "temporal" and ROTARY_IN_EPILOGUE
+    ops.linear_rows([xn], P[pre + "qkv.w"], 3 * hd, qkv, rot=(rot, Fr, H * W, 2 * hd, hd) if pre_rot else None)
     ao = torch.empty(x2.shape[0], hd, dtype=dt, device=dev)
     extra = None
     if kind == "temporal":
-        ops.tattn_fwd(qkv, ekv, bias, rot, ao, B, Fr, H * W, heads)
+        ops.tattn_fwd(qkv, ekv, bias, rot[1], ao, B, Fr, H * W, heads, pre_rotated=pre_rot)
     elif kind == "linear":
         ctx = torch.empty(B * Fr, heads, 32, 32, dtype=torch.float32, device=dev)
         kstat = torch.empty(B * Fr, heads, 32, 2, dtype=torch.float32, device=dev)

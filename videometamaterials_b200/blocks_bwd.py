@@ -186,7 +186,7 @@ class AttnBlockFn(torch.autograd.Function):
         dbias = None
         if kind == "temporal":
             dbias = torch.zeros_like(bias)
-            ops.tattn_bwd(qkv, ekv, bias, rot, dao, dqkv, dekv, dbias, B, Fr, H * W, heads)
+            ops.tattn_bwd(qkv, ekv, bias, rot[1], dao, dqkv, dekv, dbias, B, Fr, H * W, heads, pre_rotated=blocks.ROTARY_IN_EPILOGUE)
         elif kind == "linear":
             ctxm, kstat = extra
             dctx = torch.empty_like(ctxm)

@@ -63,6 +63,10 @@ struct CgemmDev {
   int gs_log;                         // log2(gn_gs) when it is a power of two >= 8, else -1
   int fast_epi;                       // the launch qualifies for epilogue_fast (see there)
   int acc_mask, acc_log;              // TMEM accumulator ring: 2 buffers, or 4 when they fit in the 512 columns
+  const float* rot;                   // rotary epilogue tables [2][rot_frames][16][2], see vmm.h
+  int rot_frames, rot_cols, rot_qcols;
+  uint64_t mg_rfr;                    // fdiv multiplier of rot_frames
+  int rot_hw;
   int halo;                           // 0 = generic taps
   int h_chunks;                       // 64-channel chunks over all sources
   int b_resident;                     // all weight tiles stay in shared memory for the whole kernel (single n-tile)
@@ -163,6 +167,7 @@ __device__ __forceinline__ void epilogue_fast(const CgemmDev& p, CgemmSmemCtl* c
   const int bar_id = 1 + eg;
   const bool has_bias = p.bias != nullptr, has_gn = p.gn_stats != nullptr, has_res = p.res != nullptr, split = p.out2 != nullptr;
   const bool scaled = p.alpha != 1.f;
+  const bool has_rot = p.rot != nullptr;
   const float alpha = p.alpha;
   const int nsteps = (p.BN + 31) >> 5;
   int hs = (nsteps + 1) >> 1;
@@ -187,6 +192,12 @@ __device__ __forceinline__ void epilogue_fast(const CgemmDev& p, CgemmSmemCtl* c
     const int bf = bf0 + fl, y = y0 + yl, x = x0 + xl;
     const bool valid = (bf < p.BF) && (y < p.OH) && (x < p.OW);
     const int wx = x0 + wxo, wy = y0 + wyo, wf = bf0 + wfo;
+    const float* rot_row = nullptr;      // rotary tables of this row's frame (rows GEMM: x = position index (b, f, pixel))
+    if (has_rot) {
+      const int q1 = x / p.rot_hw;        // exact division: position * hw exceeds the 2^32 range of fdiv at level 0
+      const int fr = q1 - fdiv(q1, p.mg_rfr) * p.rot_frames;
+      rot_row = p.rot + fr * 32;
+    }
     if (has_gn) {
       const int smp0 = fdiv(bf0, p.mg_fps);
       const int last_bf = min(bf0 + (1 << p.tf_log), p.BF) - 1;
@@ -262,6 +273,19 @@ __device__ __forceinline__ void epilogue_fast(const CgemmDev& p, CgemmSmemCtl* c
           const uint4* rp = reinterpret_cast<const uint4*>(((split && ncol + 32 >= p.nsplit) ? rrow2 : rrow1) + ncol + 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j) rq[j] = __ldg(rp + j);
+        }
+      }
+      if (has_rot && ncol < p.rot_cols) {
+        // one head slice per step: pair i of the slice turns by the angle (cos, sin) = table[frame][i]
+        const float4* tb = reinterpret_cast<const float4*>(rot_row + (ncol < p.rot_qcols ? 0 : p.rot_frames * 32));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 cs = __ldg(tb + j);          // (cos, sin) of pairs 2j and 2j + 1
+          const float a0 = v[4 * j], b0 = v[4 * j + 1], a1 = v[4 * j + 2], b1 = v[4 * j + 3];
+          v[4 * j] = a0 * cs.x - b0 * cs.y;
+          v[4 * j + 1] = b0 * cs.x + a0 * cs.y;
+          v[4 * j + 2] = a1 * cs.z - b1 * cs.w;
+          v[4 * j + 3] = b1 * cs.z + a1 * cs.w;
         }
       }
       uint32_t w[16];
@@ -893,6 +917,18 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     const int gsz = h.gn_stats ? h.gn_group : 0;
     const bool gs_ok = !h.gn_stats || (gsz >= 8 && ilog2_exact(gsz) >= 0);
     d.fast_epi = (!no_fast && d.tstore && (h.n % 32) == 0 && (BN % 32) == 0 && (!h.bias || h.n <= kBiasSmem) && gs_ok && res_al) ? 1 : 0;
+  }
+  if (h.rot) {
+    if (!d.fast_epi) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: the rotary epilogue needs the fast epilogue (16-bit bulk-store output, N % 32 == 0)");
+    if (h.rot_frames < 1 || h.rot_hw < 1 || (h.rot_cols % 32) != 0 || (h.rot_qcols % 32) != 0 || h.rot_qcols > h.rot_cols || h.rot_cols > h.n ||
+        h.tf != 1 || h.th != 1 || h.bf != 1 || h.oh != 1)
+      return set_error(VMM_ERR_ARG, "vmm_cgemm: rotary epilogue: rows GEMM only, column ranges in multiples of 32");
+    d.rot = h.rot;
+    d.rot_frames = h.rot_frames;
+    d.rot_hw = h.rot_hw;
+    d.rot_cols = h.rot_cols;
+    d.rot_qcols = h.rot_qcols;
+    d.mg_rfr = magic_of(h.rot_frames);
   }
   // Narrow tiles (BN <= 128) are bound by the latency of the per-tile epilogue, not by the MMAs: two groups of eight
   // epilogue warps then drain alternate tiles (4 TMEM accumulators).  Costs 24 KB more static shared memory.

@@ -53,8 +53,9 @@ __device__ __forceinline__ float sigmoid_fast(float u) {
   return 1.f / (1.f + __expf(-u));
 }
 // d silu(u) / du = s (1 + u (1 - s)),  s = sigmoid(u)
+template <int FMT>
 __device__ __forceinline__ float dsilu_fast(float u) {
-  const float s = fmaf(0.5f, tanh_approx(0.5f * u), 0.5f);
+  const float s = sigmoid_fast<FMT>(u);
   const float q = fmaf(-u, s, u);      // u (1 - s)
   return fmaf(s, q, s);
 }
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_reduce_kernel(const uint16_t*
       unpack8<FMT>(dr[u], dv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float du = act ? dv[j] * dsilu_fast(fmaf(xv[j], ca[j], cd[j])) : dv[j];
+        const float du = act ? dv[j] * dsilu_fast<FMT>(fmaf(xv[j], ca[j], cd[j])) : dv[j];
         s1[j] += du;
         s2[j] = fmaf(du, xv[j], s2[j]);
       }
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const uint16_t* 
       unpack8<FMT>(dr[u], dv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float du = act ? dv[j] * dsilu_fast(fmaf(xv[j], ca[j], cd[j])) : dv[j];
+        const float du = act ? dv[j] * dsilu_fast<FMT>(fmaf(xv[j], ca[j], cd[j])) : dv[j];
         o[j] = fmaf(cK[j], du, -fmaf(xv[j], cP[j], cQ[j]));
         colacc[j] += o[j];
       }

@@ -19,7 +19,7 @@ constexpr int TPXB = 2;          // pixels per pipeline stage (two stages in fli
 template <int FMT>
 __global__ void __launch_bounds__(256) tattn_fwd_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv,
                                                             const float* __restrict__ bias, const float* __restrict__ rot,
-                                                            uint16_t* __restrict__ out, int HW, int heads, float scale) {
+                                                            uint16_t* __restrict__ out, int HW, int heads, float scale, int pre_rotated) {
   extern __shared__ __align__(16) uint16_t tsm[];
   uint16_t* tile0 = tsm;                                  // [2 stages][TPXB][TNF][TPITCH]
   uint16_t* zrow = tile0 + 2 * TPXB * TNF * TPITCH;       // one row of zeros (frames >= 11)
@@ -112,10 +112,11 @@ __global__ void __launch_bounds__(256) tattn_fwd_mma_kernel(const uint16_t* __re
     uint16_t* tile = tile0 + (it & 1) * TPXB * TNF * TPITCH;
     const uint32_t tile_s = smem_u32(tile);
     if (h < heads) {
-      // ---- rotary in place on this head's q (scaled) and k slices
+      // ---- rotary in place on this head's q (scaled) and k slices (skipped when the to_qkv epilogue already did it)
       static_assert(TPXB == 2, "lane -> (pixel, pair) mapping below assumes two pixels per stage");
 #pragma unroll
       for (int f = 0; f < TNF; ++f) {
+        if (pre_rotated) break;
         const int k = lane & 15, p = lane >> 4;
         const float2 cssn = *reinterpret_cast<const float2*>(&RT[(f * 16 + k) * 2]);
         const float cs = cssn.x, sn = cssn.y;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(256) tattn_fwd_mma_kernel(const uint16_t* __re
 using namespace vmm;
 
 extern "C" int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bias, const float* rot, void* out, int fmt, int B,
-                             int frames, int HW, int heads, float scale, void* stream_) {
+                             int frames, int HW, int heads, float scale, int pre_rotated, void* stream_) {
   if (!qkv || !bias || !rot || !out) return set_error(VMM_ERR_ARG, "vmm_tattn_fwd: null pointer");
   if (frames != TNF) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: only 11 frames (the reference hard-codes 11 cond tokens, VDDP:603)");
   if (heads != 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: heads must be 8 (one warp per head, rows of 3*8*32 channels)");
@@ -254,9 +255,9 @@ extern "C" int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bia
   if (gx > groups) gx = groups;
   dim3 grid(gx, B);
   if (fmt == VMM_FMT_F16)
-    tattn_fwd_mma_kernel<0><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<uint16_t*>(out), HW, heads, scale);
+    tattn_fwd_mma_kernel<0><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<uint16_t*>(out), HW, heads, scale, pre_rotated);
   else
-    tattn_fwd_mma_kernel<1><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<uint16_t*>(out), HW, heads, scale);
+    tattn_fwd_mma_kernel<1><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<uint16_t*>(out), HW, heads, scale, pre_rotated);
   count_launch();
   return check_launch("vmm_tattn_fwd");
 }
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
                                                                const float* __restrict__ bias, const float* __restrict__ rot,
                                                                const uint16_t* __restrict__ dout, uint16_t* __restrict__ dqkv,
                                                                float* __restrict__ dekv, float* __restrict__ dbias, int HW, int heads,
-                                                               float scale) {
+                                                               float scale, int pre_rotated) {
   extern __shared__ __align__(16) uint16_t tsm[];
   uint16_t* tile0 = tsm;                                    // [2][BPXB][TNF][TPITCH]   q | k | v   (q, k rotated in place)
   uint16_t* dtile0 = tile0 + 2 * BPXB * TNF * TPITCH;       // [2][BPXB][TNF][DPITCH]   dO
@@ -373,10 +374,11 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
     __syncthreads();
     uint16_t* tile = tile0 + (it & 1) * BPXB * TNF * TPITCH;
     const uint32_t tile_s = smem_u32(tile), dtile_s = smem_u32(dtile0 + (it & 1) * BPXB * TNF * DPITCH);
-    // rotary in place (q scaled)
+    // rotary in place (q scaled); skipped when the to_qkv epilogue already did it
     static_assert(BPXB == 2, "lane -> (pixel, pair) mapping below assumes two pixels per stage");
 #pragma unroll
     for (int f = 0; f < TNF; ++f) {
+        if (pre_rotated) break;
       const int k = lane & 15, p = lane >> 4;
       const float2 cssn = *reinterpret_cast<const float2*>(&RT[(f * 16 + k) * 2]);
       const float cs = cssn.x, sn = cssn.y;
@@ -624,7 +626,8 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
 }  // namespace vmm
 
 extern "C" int vmm_tattn_bwd(const void* qkv, const float* ekv, const float* bias, const float* rot, const void* dout, void* dqkv,
-                             float* dekv, float* dbias, int fmt, int B, int frames, int HW, int heads, float scale, void* stream_) {
+                             float* dekv, float* dbias, int fmt, int B, int frames, int HW, int heads, float scale, int pre_rotated,
+                             void* stream_) {
   using namespace vmm;
   if (!qkv || !bias || !rot || !dout || !dqkv) return set_error(VMM_ERR_ARG, "vmm_tattn_bwd: null pointer");
   if (frames != TNF) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: only 11 frames");
@@ -645,10 +648,10 @@ extern "C" int vmm_tattn_bwd(const void* qkv, const float* ekv, const float* bia
   dim3 grid(gx, B);
   if (fmt == VMM_FMT_F16)
     tattn_bwd_mma_kernel<0><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<const uint16_t*>(dout),
-                                                         static_cast<uint16_t*>(dqkv), dekv, dbias, HW, heads, scale);
+                                                         static_cast<uint16_t*>(dqkv), dekv, dbias, HW, heads, scale, pre_rotated);
   else
     tattn_bwd_mma_kernel<1><<<grid, 256, smem, stream>>>(static_cast<const uint16_t*>(qkv), ekv, bias, rot, static_cast<const uint16_t*>(dout),
-                                                         static_cast<uint16_t*>(dqkv), dekv, dbias, HW, heads, scale);
+                                                         static_cast<uint16_t*>(dqkv), dekv, dbias, HW, heads, scale, pre_rotated);
   count_launch();
   return check_launch("vmm_tattn_bwd");
 }

@@ -107,7 +107,8 @@ def cgemm(views: Sequence[torch.Tensor], taps: Sequence[Sequence[Tuple[int, int,
           phase_off: Optional[Sequence[Tuple[int, int]]] = None, bias: Optional[torch.Tensor] = None,
           res: Optional[torch.Tensor] = None, gn_stats: Optional[torch.Tensor] = None, gn_group: int = 0,
           frames_per_sample: int = 1, out2: Optional[torch.Tensor] = None, nsplit: int = 0,
-          tile: Optional[Tuple[int, int, int]] = None, res2: Optional[torch.Tensor] = None, alpha: float = 1.0) -> None:
+          tile: Optional[Tuple[int, int, int]] = None, res2: Optional[torch.Tensor] = None, alpha: float = 1.0,
+          rot: Optional[Tuple[torch.Tensor, int, int, int, int]] = None) -> None:
     """Launch vmm_cgemm.
 
     views : list of (bf, h, w, c) 16-bit tensors (A operand sources)
@@ -168,6 +169,10 @@ def cgemm(views: Sequence[torch.Tensor], taps: Sequence[Sequence[Tuple[int, int,
         p.gn_stats = gn_stats.data_ptr()
         p.gn_group = gn_group
         p.frames_per_sample = frames_per_sample
+    if rot is not None:
+        tab, p.rot_frames, p.rot_hw, p.rot_cols, p.rot_qcols = rot      # tab: fp32 (2, frames, 16, 2), see rotary_tables
+        assert tab.dtype == torch.float32 and tab.is_contiguous() and tab.shape == (2, p.rot_frames, 16, 2)
+        p.rot = tab.data_ptr()
     e0 = _prof_begin()
     check(lib.vmm_cgemm(C.byref(p), stream_ptr()), "vmm_cgemm")
     if e0 is not None:
@@ -233,8 +238,13 @@ def rows_view(x2d: torch.Tensor) -> torch.Tensor:
     return x2d.as_strided((1, 1, x2d.shape[0], x2d.shape[1]), (x2d.stride(0) * x2d.shape[0], x2d.stride(0) * x2d.shape[0], x2d.stride(0), 1))
 
 
+def rotary_tables(rot: torch.Tensor, scale: float) -> torch.Tensor:
+    """(frames, 16, 2) cos/sin -> (2, frames, 16, 2): table 0 pre-multiplied by the attention scale (queries), table 1 plain (keys)."""
+    return torch.stack((rot * scale, rot), dim=0).contiguous()
+
+
 def linear_rows(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch.Tensor, *, bias=None, res=None,
-                gn_stats=None, gn_group=0, frames_per_sample=1, out2=None, nsplit=0, res2=None, alpha=1.0) -> None:
+                gn_stats=None, gn_group=0, frames_per_sample=1, out2=None, nsplit=0, res2=None, alpha=1.0, rot=None) -> None:
     """out[m, :n] = cat(xs, dim=1)[m] @ W^T  for 2-D operands [M, C_i]; wp = pack_linear / pack_conv_taps(1x1)."""
     taps, kofs = [], 0
     for s, x in enumerate(xs):
@@ -242,7 +252,7 @@ def linear_rows(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch
         kofs += ceil64(x.shape[1])
     m = xs[0].shape[0]
     cgemm([rows_view(x) for x in xs], [taps], wp, n, out, (1, 1, m), bias=bias, res=res, gn_stats=gn_stats,
-          gn_group=gn_group, frames_per_sample=frames_per_sample, out2=out2, nsplit=nsplit, res2=res2, alpha=alpha)
+          gn_group=gn_group, frames_per_sample=frames_per_sample, out2=out2, nsplit=nsplit, res2=res2, alpha=alpha, rot=rot)
 
 
 def conv3x3(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch.Tensor, **kw) -> None:
@@ -346,9 +356,9 @@ def ln_bwd(x2d, dy2d, dres2d, dx2d, gamma, dgamma, eps=1e-5):
                          stream_ptr()), "vmm_ln_bwd")
 
 
-def tattn_fwd(qkv, ekv, bias, rot, out, B, frames, HW, heads):
+def tattn_fwd(qkv, ekv, bias, rot, out, B, frames, HW, heads, pre_rotated=False):
     check(lib.vmm_tattn_fwd(_p(qkv), _p(ekv), _p(bias), _p(rot), _p(out), fmt_of(qkv), B, frames, HW, heads, 32 ** -0.5,
-                            stream_ptr()), "vmm_tattn_fwd")
+                            1 if pre_rotated else 0, stream_ptr()), "vmm_tattn_fwd")
 
 
 def lattn_fwd(qkv, ekv, T, out, ctx, kstat, BF, frames, HW, heads):
@@ -513,9 +523,9 @@ def wgrad_init_conv(dy: torch.Tensor, xin: torch.Tensor, dw: torch.Tensor, chann
     wgrad([dy], [view], taps, n, dw, channels * 49, 49, (bf, h, w), s_c2=1, cmod=8, c_valid=channels, k_valid=7)
 
 
-def tattn_bwd(qkv, ekv, bias, rot, dout, dqkv, dekv, dbias, B, frames, HW, heads):
+def tattn_bwd(qkv, ekv, bias, rot, dout, dqkv, dekv, dbias, B, frames, HW, heads, pre_rotated=False):
     check(lib.vmm_tattn_bwd(_p(qkv), _p(ekv), _p(bias), _p(rot), _p(dout), _p(dqkv), _p(dekv), _p(dbias), fmt_of(qkv), B, frames, HW,
-                            heads, 32 ** -0.5, stream_ptr()), "vmm_tattn_bwd")
+                            heads, 32 ** -0.5, 1 if pre_rotated else 0, stream_ptr()), "vmm_tattn_bwd")
 
 
 def lattn_bwd(qkv, ekv, T, dout, ctx, kstat, dctx, dqkv, dekv, BF, frames, HW, heads):
