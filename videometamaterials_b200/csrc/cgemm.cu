@@ -1,14 +1,20 @@
 // vmm_cgemm: persistent, warp-specialised implicit-GEMM convolution for sm_100a.
 //
-//   warp 0      TMA producer   (one lane): per K block, one 4-D box of A (shifted by the tap) + one 2-D box of W
-//   warp 1      MMA issuer     (one lane): tcgen05.mma kind::f16, M=128, N=BN, K=16 x4 per 64-wide block
+//   warp 0      TMA producer (one ELECTED lane, so that descriptors stay in uniform registers): per K block one 4-D box of A
+//               (shifted by the tap) + one 2-D box of W; in halo mode one slab of th + 2 pixel rows per (64-channel chunk, kx)
+//               that serves the three ky taps, with the weights resident in shared memory when all of them fit
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma kind::f16, M=128, N=BN, K=16 x4 per 64-wide block
 //   warp 2      TMEM allocator
-//   warps 4..11 epilogue (two warps per TMEM lane quarter, each takes half of the tile's columns): tcgen05.ld -> bias / residual / GroupNorm partial sums -> 16-bit rows staged in shared
-//               memory (64-byte swizzle) -> one bulk tensor store per warp and 32 columns (TMA clips the tile
-//               overhang); fp32 outputs and odd column splits keep per-thread global stores
+//   warps 4..   epilogue, two warps per TMEM lane quarter, each half of the tile's columns: tcgen05.ld -> alpha / bias /
+//               residual / rotary / GroupNorm partial sums -> 16-bit rows staged in shared memory (64-byte swizzle) -> one bulk
+//               tensor store per warp and 32 columns (TMA clips the tile overhang); fp32 outputs and odd column splits keep
+//               per-thread global stores.  8 warps (kernel<FMT, 1>), or 16 in two groups that drain alternate tiles
+//               (kernel<FMT, 2>, 64 < BN <= 128).  epilogue_fast is the lean path of the common launch shape.
 //
-// Two TMEM accumulators (double buffer) let the epilogue of tile i overlap the main loop of tile i+1.
+// Two TMEM accumulators (four when 4 x BN <= 512 columns) let the epilogue of tile i overlap the main loop of the next tiles.
 // The ring of smem stages is shared across tiles (the producer runs ahead of the MMA warp).
+//
+// Debug / experiment switches (environment, read once): VMM_NO_HALO, VMM_NO_FAST_EPI, VMM_ONE_EPI_GROUP, VMM_TWO_ACC.
 #include "common.cuh"
 #include "mma_sync.cuh"
 #include "sm100_ptx.cuh"
