@@ -103,3 +103,88 @@ def test_dataset_roundtrip_and_postprocessing(tmp_path):
 def test_cond_to_gpu_split():
     from videometamaterials_b200.trainer import num_to_groups
     assert num_to_groups(5, 2) == [2, 2, 1] and num_to_groups(4, 2) == [2, 2] and num_to_groups(0, 2) == []
+
+
+def test_batched_conditioning_matches_per_block_oracle():
+    """blocks.conditioning batches the 18 ResnetBlock MLPs and the 17 to_k / to_v projections into one GEMM each and
+    splits the results with one permutation (`_SplitBlocks`); on the CPU (no parameter arena: torch.cat path) its outputs
+    and its parameter gradients must equal the oracle's per-block restatement (VDDP:304-306, 349-353, 459-471, 637-661)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import Unet3D, blocks
+    cfg = O.UnetCfg(dim=16, dim_mults=(1, 2))
+    sd = O.synthetic_state_dict(cfg, seed=5)
+    model = Unet3D(dim=16, dim_mults=(1, 2), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
+                   cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, cond_to_time='add', per_frame_cond=True)
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(9)
+    b = 3
+    time = torch.tensor([0, 3, 7])
+    cond = torch.rand(b, 11, generator=g) * 2 - 1
+    mask = torch.tensor([False, True, False])
+    ss, ekv, bias, rot = blocks.conditioning(model, time, cond, mask, 11)
+    P = {k: v.clone().requires_grad_(v.is_floating_point() and "freqs" not in k) for k, v in sd.items()}
+    t_ref, tok_ref = O.conditioning(P, cfg, time, cond, mask)
+    heads, hd = 8, 256
+    freqs = P["init_temporal_attn.fn.fn.fn.rotary_emb.freqs"]
+    # forward: every block's scale/shift and cond keys | values
+    ref_ss, ref_ekv = {}, {}
+    for pre in blocks.resnet_names(model):
+        ref_ss[pre] = F.linear(F.silu(t_ref), P[pre + "mlp.1.weight"], P[pre + "mlp.1.bias"])
+        assert torch.allclose(ss[pre], ref_ss[pre], atol=1e-5, rtol=1e-5), pre
+        assert ss[pre].is_contiguous()
+    for pre, kind in blocks.attn_names(model):
+        ek = F.linear(tok_ref, P[pre + "to_k.weight"])
+        ev = F.linear(tok_ref, P[pre + "to_v.weight"])
+        if kind == "temporal":        # cond keys are rotated by token index before they are stacked (VDDP:470-471)
+            ek = O.rotary(ek.reshape(b, 11, heads, 32).transpose(1, 2), freqs).transpose(1, 2).reshape(b, 11, hd)
+        ref_ekv[pre] = torch.cat((ek, ev), -1)
+        assert torch.allclose(ekv[pre], ref_ekv[pre], atol=1e-5, rtol=1e-5), pre
+        assert ekv[pre].is_contiguous()
+    assert torch.allclose(bias, O.time_pos_bias(P, 11), atol=1e-6)
+    ang = torch.arange(11).float()[:, None] * freqs.detach()[None, :]
+    assert torch.allclose(rot[1], torch.stack((ang.cos(), ang.sin()), -1), atol=1e-6)
+    assert torch.allclose(rot[0], rot[1] * 32 ** -0.5, atol=1e-7)
+    # backward: random upstream gradients on every output, compared parameter by parameter
+    gen = torch.Generator().manual_seed(10)
+    ups_ss = {k: torch.randn(v.shape, generator=gen) for k, v in ss.items()}
+    ups_kv = {k: torch.randn(v.shape, generator=gen) for k, v in ekv.items()}
+    loss = sum((ss[k] * ups_ss[k]).sum() for k in ss) + sum((ekv[k] * ups_kv[k]).sum() for k in ekv)
+    loss.backward()
+    loss_ref = sum((ref_ss[k] * ups_ss[k]).sum() for k in ref_ss) + sum((ref_ekv[k] * ups_kv[k]).sum() for k in ref_ekv)
+    loss_ref.backward()
+    checked = 0
+    for k, p in model.named_parameters():
+        r = P[k].grad
+        if r is None or float(r.abs().max()) == 0.0:
+            continue
+        assert p.grad is not None, k
+        assert torch.allclose(p.grad, r, atol=1e-4 * float(r.abs().max()) + 1e-7, rtol=1e-4), k
+        checked += 1
+    assert checked >= 2 * len(ss) + 2 * len(ekv) + 10
+
+
+def test_bench_contract_on_cpu():
+    """bench.py: the reference arm (CPU oracle port) prints ONE JSON line with the driver's keys; the own arm refuses to run
+    without a CUDA device instead of falling back to anything."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
