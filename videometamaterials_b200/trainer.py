@@ -233,7 +233,11 @@ class Trainer(object):
         from . import ops as _ops
         if not (self.use_cuda_graph and x.is_cuda) or _ops.PROFILE is not None:
             return self._fwd_bwd_eager(x, cond)
-        key = (tuple(x.shape), tuple(cond.shape), x.dtype, cond.dtype, float(self.null_cond_prob))
+        net = self.model.denoise_fn
+        # everything the captured launches bake in: shapes, the drop probability, the 16-bit format of the packed weights and the
+        # identity of the parameter / gradient arena (device pointers)
+        key = (tuple(x.shape), tuple(cond.shape), x.dtype, cond.dtype, float(self.null_cond_prob), str(getattr(net, "compute_dtype", None)),
+               id(getattr(net, "_vmm_arena", None)))
         st = getattr(self, "_graph_state", None)
         if st is None or st["key"] != key:
             st = self._graph_state = dict(key=key, seen=0, graph=None)
