@@ -17,9 +17,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
-sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
-sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)                                   # the reference's `denoising_diffusion_pytorch` must shadow this repo's re-export
+sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
 os.chdir(REF)   # the reference imports `src.*` relative to its repo root
 
 from denoising_diffusion_pytorch.video_denoising_diffusion_pytorch import (  # noqa: E402

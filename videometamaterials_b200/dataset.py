@@ -45,8 +45,35 @@ def fixed_normalization(gmin: float, gmax: float) -> Normalization:
     return n
 
 
-def _gif_frames(path, image_size: int) -> torch.Tensor:
-    """(frames, h, w) float in [0, 1] from an 8-bit GIF (T.Resize + CenterCrop + ToTensor of the reference)."""
+def _resize_short_edge(fr, size: int):
+    """T.Resize(int) on a PIL image: short edge -> `size`, aspect ratio kept, bilinear."""
+    from PIL import Image
+    w, h = fr.size
+    short, long = (w, h) if w <= h else (h, w)
+    if short == size:
+        return fr
+    new_long = int(size * long / short)
+    return fr.resize((size, new_long) if w <= h else (new_long, size), Image.BILINEAR)
+
+
+def _center_crop(fr, size: int):
+    """T.CenterCrop(int) on a PIL image (zero padding when the image is smaller, torchvision's rounding of the offsets)."""
+    from PIL import Image
+    w, h = fr.size
+    if w < size or h < size:
+        pl, pt = max((size - w) // 2, 0), max((size - h) // 2, 0)
+        canvas = Image.new(fr.mode, (max(w, size), max(h, size)), 0)
+        canvas.paste(fr, (pl, pt))
+        fr, (w, h) = canvas, canvas.size
+    if (w, h) == (size, size):
+        return fr
+    top, left = int(round((h - size) / 2.0)), int(round((w - size) / 2.0))
+    return fr.crop((left, top, left + size, top + size))
+
+
+def _gif_frames(path, image_size: int, horizontal_flip: bool = False) -> torch.Tensor:
+    """(1, frames, h, w) float32 in [0, 1] from an 8-bit GIF: every frame converted to 'L', then Resize -> (flip) ->
+    CenterCrop -> /255 as the reference's transform does (VDDP:1076-1106, 1252-1257)."""
     from PIL import Image
     img = Image.open(path)
     frames, i = [], 0
@@ -55,12 +82,13 @@ def _gif_frames(path, image_size: int) -> torch.Tensor:
             img.seek(i)
         except EOFError:
             break
-        fr = img.convert('L')
-        if fr.size != (image_size, image_size):
-            fr = fr.resize((image_size, image_size), Image.BILINEAR)
-        frames.append(torch.from_numpy(np.asarray(fr, dtype=np.uint8).copy()).float() / 255.)
+        fr = _resize_short_edge(img.convert('L'), image_size)
+        if horizontal_flip and float(torch.rand(1)) < 0.5:
+            fr = fr.transpose(Image.FLIP_LEFT_RIGHT)
+        fr = _center_crop(fr, image_size)
+        frames.append(torch.from_numpy(np.asarray(fr, dtype=np.uint8).copy()).to(torch.float32).div(255))
         i += 1
-    return torch.stack(frames, dim=0)
+    return torch.stack(frames, dim=0)[None]
 
 
 def _cast_frames(t: torch.Tensor, frames: int) -> torch.Tensor:
@@ -72,75 +100,119 @@ def _cast_frames(t: torch.Tensor, frames: int) -> torch.Tensor:
     return torch.nn.functional.pad(t, (0, 0, 0, 0, 0, frames - f))
 
 
+def _interp_curves(curves: np.ndarray, num_frames: int, strain: float = 0.2) -> np.ndarray:
+    """Stress curves sampled at `num_frames` strains in [0, strain]; the first frame sits at 1 % of the final strain
+    (VDDP:1260-1269, 1789-1799)."""
+    given = np.linspace(0., strain, num=curves.shape[1])
+    ev = np.linspace(0., strain, num=num_frames)
+    ev[0] = 0.01 * strain
+    return np.array([np.interp(ev, given, curves[i, :]) for i in range(curves.shape[0])])
+
+
+# Per reference frame: the GIF sub-folders that must exist, and for every tensor channel
+#   (sub-folder, column of frame_range_data.csv holding the per-sample min or None for 0, column of the per-sample max,
+#    attribute with the global min or None for 0, attribute with the global max); a channel with no columns is the
+#    topology mask itself and is passed through.
+_LAYOUT = {
+    'eulerian': dict(
+        folders=('topo', 's_mises', 's_22', 'ener'),
+        globals_=(('max_s_mises', 0, 'max'), ('min_s_22', 1, 'min'), ('max_s_22', 2, 'max'), ('max_strain_energy', 3, 'max')),
+        channels=(('topo', None, None, None, None), ('s_mises', None, 0, None, 'max_s_mises'), ('s_22', 1, 2, 'min_s_22', 'max_s_22'),
+                  ('ener', None, 3, None, 'max_strain_energy'))),
+    'lagrangian': dict(
+        folders=('topo', 'u_1', 'u_2', 's_mises', 's_22', 'ener'),
+        globals_=(('min_u_1', 0, 'min'), ('max_u_1', 1, 'max'), ('min_u_2', 2, 'min'), ('max_u_2', 3, 'max'), ('max_s_mises', 4, 'max'),
+                  ('min_s_22', 5, 'min'), ('max_s_22', 6, 'max'), ('max_strain_energy', 7, 'max')),
+        channels=(('u_1', 0, 1, 'min_u_1', 'max_u_1'), ('u_2', 2, 3, 'min_u_2', 'max_u_2'), ('s_mises', None, 4, None, 'max_s_mises'),
+                  ('s_22', 5, 6, 'min_s_22', 'max_s_22'))),
+    # single-frame ablation of the Lagrangian data: topology + sigma_22 (VDDP:1365-1390)
+    'lagrangian_1': dict(channels=(('topo', None, None, None, None), ('s_22', 5, 6, 'min_s_22', 'max_s_22'))),
+}
+
+
 class Dataset(data.Dataset):
-    def __init__(self, folder, image_size, labels_scaling=None, selected_channels=(0, 1, 2, 3), num_frames=11, per_frame_cond=True,
-                 reference_frame='lagrangian', **unused):
+    """The reference's GIF dataset (VDDP:1126-1397), same constructor arguments and the same tensors: fields are stored per
+    sample as 8-bit GIFs scaled to that sample's own range (`frame_range_data.csv`); an item maps them back to physical
+    values, zeroes the void pixels of the topology mask and rescales with the global extrema of the folder.  The arithmetic
+    keeps the reference's types (float32 pixels, float64 0-dim range scalars) so that items are bit-identical."""
+
+    def __init__(self, folder, image_size, labels_scaling=None, selected_channels=[0, 1, 2, 3], num_frames=16, horizontal_flip=False,
+                 force_num_frames=True, exts=['gif'], per_frame_cond=False, reference_frame='eulerian'):
         super().__init__()
-        if reference_frame != 'lagrangian' or not per_frame_cond or num_frames == 1:
-            raise NotImplementedError("only the shipped configuration (lagrangian frame, per-frame labels) is implemented")
+        if reference_frame not in ('eulerian', 'lagrangian'):
+            raise ValueError(f'unknown reference_frame {reference_frame!r}')
         folder = str(folder)
-        if not folder.endswith('/'):
-            folder += '/'
-        self.image_size, self.num_frames, self.selected_channels = image_size, num_frames, list(selected_channels)
+        self.image_size, self.num_frames, self.selected_channels = image_size, num_frames, selected_channels
+        self.horizontal_flip, self.force_num_frames = horizontal_flip, force_num_frames
         self.reference_frame = reference_frame
+        lay = _LAYOUT[reference_frame]
 
         def listing(sub):
-            paths = sorted(Path(folder + 'gifs/' + sub + '/').glob('*.gif'), key=lambda p: int(p.stem))
+            paths = sorted((p for ext in exts for p in Path(folder + 'gifs/' + sub + '/').glob(f'**/*.{ext}')),
+                           key=lambda p: int(p.name.split('.')[0]))
             assert all(int(p.stem) == i for i, p in enumerate(paths)), 'file position is not equal to index'
             return paths
 
-        self.paths = {k: listing(k) for k in ('topo', 'u_1', 'u_2', 's_mises', 's_22')}
-        n = len(self.paths['topo'])
-        assert all(len(v) == n for v in self.paths.values()), 'number of files in fields and top folders are not equal.'
-        self.frame_ranges = torch.tensor(np.genfromtxt(folder + 'frame_range_data.csv', delimiter=',')).reshape(n, -1)
-        fr = self.frame_ranges
-        self.min_u_1, self.max_u_1 = fr[:, 0].min(), fr[:, 1].max()
-        self.min_u_2, self.max_u_2 = fr[:, 2].min(), fr[:, 3].max()
-        self.max_s_mises = fr[:, 4].max()
-        self.min_s_22, self.max_s_22 = fr[:, 5].min(), fr[:, 6].max()
-        self.max_strain_energy = fr[:, 7].max()
-        self.zero_u_2 = self._norm(torch.zeros(1), self.min_u_2, self.max_u_2)
+        self.paths = {}
+        for sub in lay['folders']:
+            self.paths[sub] = listing(sub)
+            assert len(self.paths[sub]) == len(self.paths['topo']), 'number of files in fields and top folders are not equal.'
+        self.frame_ranges = torch.tensor(np.genfromtxt(folder + 'frame_range_data.csv', delimiter=','))
+        rows = []
+        for name, col, kind in lay['globals_']:
+            v = torch.min(self.frame_ranges[:, col]) if kind == 'min' else torch.max(self.frame_ranges[:, col])
+            setattr(self, name, v)
+            rows.append([name, v.item()])
+        self.zero_u_2 = self.normalize(torch.zeros(1), self.min_u_2, self.max_u_2) if reference_frame == 'lagrangian' else None
         with open(folder + 'min_max_values.csv', 'w', newline='') as f:
-            csv.writer(f).writerows([['min_u_1', self.min_u_1.item()], ['max_u_1', self.max_u_1.item()], ['min_u_2', self.min_u_2.item()],
-                                     ['max_u_2', self.max_u_2.item()], ['max_s_mises', self.max_s_mises.item()],
-                                     ['min_s_22', self.min_s_22.item()], ['max_s_22', self.max_s_22.item()],
-                                     ['max_strain_energy', self.max_strain_energy.item()]])
-        labels = np.genfromtxt(folder + 'stress_strain_data.csv', delimiter=',').reshape(n, -1)
-        strain = 0.2
-        given = np.linspace(0., strain, num=labels.shape[1])
-        ev = np.linspace(0., strain, num=num_frames)
-        ev[0] = 0.01 * strain
-        labels = np.array([np.interp(ev, given, labels[i, :]) for i in range(n)])
-        self.labels = torch.tensor(labels).float()
-        self.labels_scaling = labels_scaling if labels_scaling is not None else Normalization(self.labels)
+            csv.writer(f).writerows(rows)
+        labels = np.genfromtxt(folder + 'stress_strain_data.csv', delimiter=',')
+        if per_frame_cond:
+            self.labels = torch.tensor(_interp_curves(labels, num_frames)).float()
+        else:
+            self.labels = torch.tensor(labels[:, 1:]).float()            # the first point of every curve is zero
+        self.detached_labels = self.labels.clone().detach().numpy()
+        self.labels_scaling = labels_scaling if labels_scaling is not None else \
+            Normalization(self.labels, ['continuous'] * self.labels.shape[1], 'global-min-max-2')
         self.labels = self.labels_scaling.normalize(self.labels)
 
-    @staticmethod
-    def _norm(a, lo, hi):
-        return (a - lo) / (hi - lo)
+    def interpolate(self, tensor, num_frames):
+        f = tensor.shape[1]
+        if f == num_frames:
+            return tensor
+        if f > num_frames:
+            return tensor[:, :num_frames]
+        return torch.nn.functional.interpolate(tensor.unsqueeze(0), num_frames).squeeze(0)
 
-    @staticmethod
-    def _unnorm(a, lo, hi):
-        return a * (hi - lo) + lo
+    def normalize(self, arr, min_val, max_val):
+        return (arr - min_val) / (max_val - min_val)
+
+    def unnorm(self, arr, min_val, max_val):
+        return arr * (max_val - min_val) + min_val
 
     def __len__(self):
         return len(self.paths['topo'])
 
-    def __getitem__(self, i):
-        g = lambda k: _gif_frames(self.paths[k][i], self.image_size)
-        topo = g('topo')
-        t = torch.stack((g('u_1'), g('u_2'), g('s_mises'), g('s_22')), dim=0).double()
-        r = self.frame_ranges[i]
-        t[0] = self._unnorm(t[0], r[0], r[1])
-        t[1] = self._unnorm(t[1], r[2], r[3])
-        t[2] = self._unnorm(t[2], 0., r[4])
-        t[3] = self._unnorm(t[3], r[5], r[6])
-        t[:, topo == 0.] = 0.                                            # void pixels carry the true zero of each field
-        t[0] = self._norm(t[0], self.min_u_1, self.max_u_1)
-        t[1] = self._norm(t[1], self.min_u_2, self.max_u_2)
-        t[2] = self._norm(t[2], 0., self.max_s_mises)
-        t[3] = self._norm(t[3], self.min_s_22, self.max_s_22)
-        return _cast_frames(t[self.selected_channels].float(), self.num_frames), self.labels[i, :]
+    def __getitem__(self, index):
+        key = self.reference_frame
+        if key == 'lagrangian' and self.num_frames == 1:
+            key = 'lagrangian_1'
+            self.selected_channels = [0, 1]
+        load = lambda sub: _gif_frames(self.paths[sub][index], self.image_size, self.horizontal_flip)
+        void = load('topo')[0] == 0.
+        r = self.frame_ranges[index]
+        planes = []
+        for sub, lo, hi, glo, ghi in _LAYOUT[key]['channels']:
+            t = load(sub)[0]
+            if hi is not None:
+                t = self.unnorm(t, r[lo] if lo is not None else 0., r[hi])     # physical value of this sample
+                t[void] = 0.                                                        # true zero of the field outside the material
+                t = self.normalize(t, getattr(self, glo) if glo is not None else 0., getattr(self, ghi))
+            planes.append(t)
+        tensor = torch.stack(planes, dim=0)[self.selected_channels, :, :, :]
+        if self.force_num_frames:
+            tensor = _cast_frames(tensor, self.num_frames)
+        return tensor, self.labels[index, :]
 
 
 class SyntheticLagrangianDataset(data.Dataset):
@@ -161,52 +233,94 @@ class SyntheticLagrangianDataset(data.Dataset):
         return torch.rand(self.shape, generator=g), torch.rand(self.num_frames, generator=g) * 2 - 1
 
 
-def write_synthetic_dataset(folder, n: int, image_size: int = 96, num_frames: int = 11, curve_points: int = 51, seed: int = 0) -> None:
-    """Write `n` random samples in the reference's on-disk layout (see module docstring)."""
+_FOLDERS = ('topo', 'u_1', 'u_2', 's_mises', 's_22', 'ener')
+
+
+def write_dataset(folder, fields: dict, frame_ranges: np.ndarray, curves: np.ndarray) -> None:
+    """Write samples in the reference's on-disk layout (module docstring).  `fields[sub]` is a uint8 array (n, frames, h, w)
+    for every sub-folder to create; `frame_ranges` is n x 8 (Lagrangian) or n x 4 (Eulerian), `curves` n x K."""
     from PIL import Image
     folder = str(folder)
-    rng = np.random.default_rng(seed)
-    for sub in ('topo', 'u_1', 'u_2', 's_mises', 's_22', 'ener'):
+    for sub, arr in fields.items():
         os.makedirs(os.path.join(folder, 'gifs', sub), exist_ok=True)
-    ranges, curves = [], []
-    for i in range(n):
-        for sub in ('topo', 'u_1', 'u_2', 's_mises', 's_22', 'ener'):
-            # every frame differs (identical GIF frames would be merged by the encoder); topology frames are binary masks
-            frames = [Image.fromarray(((rng.random((image_size, image_size)) > 0.3).astype(np.uint8) * 255) if sub == 'topo'
-                                      else rng.integers(0, 256, (image_size, image_size), dtype=np.uint8), 'L')
-                      for _ in range(num_frames)]
+        for i in range(arr.shape[0]):
+            frames = [Image.fromarray(np.ascontiguousarray(fr), 'L') for fr in arr[i]]
             frames[0].save(os.path.join(folder, 'gifs', sub, f'{i}.gif'), save_all=True, append_images=frames[1:], duration=200, loop=0)
-        ranges.append([-rng.random(), rng.random(), -rng.random(), rng.random(), 50 + 50 * rng.random(), -30 * rng.random(), 30 * rng.random(), rng.random()])
-        curves.append(np.cumsum(rng.random(curve_points)) * 2.0)
-    np.savetxt(os.path.join(folder, 'frame_range_data.csv'), np.array(ranges), delimiter=',')
-    np.savetxt(os.path.join(folder, 'stress_strain_data.csv'), np.array(curves), delimiter=',')
+    np.savetxt(os.path.join(folder, 'frame_range_data.csv'), np.asarray(frame_ranges), delimiter=',')
+    np.savetxt(os.path.join(folder, 'stress_strain_data.csv'), np.asarray(curves), delimiter=',')
 
 
-def video_tensor_to_gif(tensor: torch.Tensor, path: str, duration: int = 200, loop: int = 0):
-    """(channels, frames, h, w) in [0, 1] -> animated GIF (VDDP:1091-1098)."""
+def synthetic_dataset_arrays(n: int, image_size: int = 96, num_frames: int = 11, curve_points: int = 51, seed: int = 0,
+                             reference_frame: str = 'lagrangian', size_hw=None):
+    """Random content for `write_dataset`: binary topology masks, uniformly random 8-bit fields (every frame differs: the GIF
+    encoder would merge identical frames), plausible per-sample ranges and monotone stress curves."""
+    rng = np.random.default_rng(seed)
+    h, w = size_hw if size_hw is not None else (image_size, image_size)
+    fields = {}
+    for sub in (_FOLDERS if reference_frame == 'lagrangian' else ('topo', 's_mises', 's_22', 'ener')):
+        if sub == 'topo':
+            fields[sub] = (rng.random((n, num_frames, h, w)) > 0.3).astype(np.uint8) * 255
+        else:
+            fields[sub] = rng.integers(0, 256, (n, num_frames, h, w), dtype=np.uint8)
+    u = rng.random((n, 8))
+    ranges = np.stack([-u[:, 0], u[:, 1], -u[:, 2], u[:, 3], 50 + 50 * u[:, 4], -30 * u[:, 5], 30 * u[:, 6], u[:, 7]], axis=1)
+    if reference_frame != 'lagrangian':
+        ranges = ranges[:, 4:]
+    curves = np.cumsum(rng.random((n, curve_points)), axis=1) * 2.0
+    curves[:, 0] = 0.
+    return fields, ranges, curves
+
+
+def write_synthetic_dataset(folder, n: int, image_size: int = 96, num_frames: int = 11, curve_points: int = 51, seed: int = 0,
+                            reference_frame: str = 'lagrangian') -> None:
+    """Write `n` random samples in the reference's on-disk layout (the real dataset is an external download)."""
+    write_dataset(folder, *synthetic_dataset_arrays(n, image_size, num_frames, curve_points, seed, reference_frame))
+
+
+def video_tensor_to_gif(tensor: torch.Tensor, path: str, duration: int = 200, loop: int = 0, optimize: bool = False):
+    """(channels, frames, h, w) in [0, 1] -> animated GIF (VDDP:1091-1098).  Pixels are `floor(255 x)` like the reference's
+    `T.ToPILImage` (`mul(255).byte()`); values outside [0, 1] are clamped here (the reference lets them wrap modulo 256)."""
     from PIL import Image
     frames = []
     for fr in tensor.unbind(dim=1):
-        arr = (fr.clamp(0, 1) * 255).round().to(torch.uint8).cpu().numpy()
-        arr = arr[0] if arr.shape[0] == 1 else np.moveaxis(arr, 0, -1)
-        frames.append(Image.fromarray(arr).convert('L').convert('P'))
-    frames[0].save(path, save_all=True, append_images=frames[1:], duration=duration, loop=loop, optimize=False)
+        arr = fr.detach().float().clamp(0, 1).mul(255).to(torch.uint8).cpu().numpy()
+        img = Image.fromarray(arr[0]) if arr.shape[0] == 1 else Image.fromarray(np.ascontiguousarray(np.moveaxis(arr, 0, -1)))
+        frames.append(img.convert('L').convert('P') if not optimize else img)
+    frames[0].save(path, save_all=True, append_images=frames[1:], duration=duration, loop=loop, optimize=optimize)
+    return frames
 
 
 def clean_pred(geom: np.ndarray, pixels: int) -> np.ndarray:
-    """Binarise, drop pixels without any 4-neighbour, keep the largest 4-connected component (src/utils.py:32-82);
-    returns (n, pixels*pixels) ints."""
+    """Post-processing of predicted geometries (src/utils.py:32-82): binarise at 0.5, drop pixels without a 4-neighbour, keep
+    the largest 4-connected component; returns (n, pixels*pixels) ints.
+
+    The reference does this with a Python double loop and a networkx graph per sample (O(pixels^2) interpreter work, the
+    dominant cost of `eval_target` once sampling is fast); here it is one `scipy.ndimage.label` pass.  Components of equal
+    size are resolved as networkx enumerates them there: components containing an axis-0 edge first, by the raster position
+    of their first such edge, then the single-row components by their first axis-1 edge.  A geometry without any pair of
+    adjacent pixels comes back empty (the reference raises IndexError on it)."""
     from scipy import ndimage
     g = (np.asarray(geom).reshape(-1, pixels, pixels) > 0.5).astype(int)
     out = np.zeros_like(g)
+    big = 2 * pixels * pixels
+    raster = np.arange(pixels * pixels).reshape(pixels, pixels)
     for i in range(g.shape[0]):
-        cur = g[i].copy()
+        cur = g[i]
         pad = np.pad(cur, 1)
         neigh = pad[:-2, 1:-1] + pad[2:, 1:-1] + pad[1:-1, :-2] + pad[1:-1, 2:]
-        cur[(cur == 1) & (neigh == 0)] = 0
+        cur = cur * (neigh > 0)
         lab, k = ndimage.label(cur)
-        if k > 0:
-            sizes = ndimage.sum(cur, lab, index=np.arange(1, k + 1))
-            cur = (lab == (1 + int(np.argmax(sizes)))).astype(int)
-        out[i] = cur
+        if k == 0:
+            continue
+        sizes = np.bincount(lab.ravel(), minlength=k + 1)[1:]
+        cand = np.flatnonzero(sizes == sizes.max()) + 1
+        if len(cand) > 1:
+            key0, key1 = np.full(k + 1, big), np.full(k + 1, big)
+            e0 = (cur[1:] & cur[:-1]).astype(bool)
+            np.minimum.at(key0, lab[:-1][e0], raster[:-1][e0])
+            e1 = (cur[:, 1:] & cur[:, :-1]).astype(bool)
+            np.minimum.at(key1, lab[:, :-1][e1], raster[:, :-1][e1])
+            key = np.where(key0 < big, key0, pixels * pixels + key1)
+            cand = cand[np.argsort(key[cand], kind='stable')]
+        out[i] = (lab == cand[0]).astype(int)
     return out.reshape(g.shape[0], -1)
