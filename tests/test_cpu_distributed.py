@@ -71,3 +71,83 @@ def test_two_rank_gloo():
     assert o0 == o1 == {"cond": [1, 2, 3]}
     # VDDP:1506-1532: rank 0 gets rows [0, 2), the last rank the remainder [2, 5), chunked by test_batch_size
     assert c0 == [[[0, 1], [2, 3]]] and c1 == [[[4, 5], [6, 7]], [[8, 9]]]
+
+
+def _stub_sample(cond, guidance_scale=1.):
+    """Deterministic stand-in for GaussianDiffusion.sample (a smooth function of the conditioning only)."""
+    size, ch, nf = 12, 3, 11
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, size), torch.linspace(0, 1, size), indexing="ij")
+    base = torch.stack([torch.sin(3.0 * (k + 1) * xx + 2.0 * yy) for k in range(ch)])
+    return 0.5 + 0.5 * torch.tanh(base[None, :, None] * (1.0 + cond[:, None, :nf, None, None]) * guidance_scale * 0.3)
+
+
+def _eval_target_run(workdir, targets):
+    """Build a small Trainer on the CPU accelerator, replace the sampler by the stub and run eval_target + eval_network."""
+    import numpy as np
+    from videometamaterials_b200 import Accelerator, GaussianDiffusion, Trainer, Unet3D
+    from videometamaterials_b200.dataset import fixed_normalization
+    os.chdir(workdir)
+    m = Unet3D(dim=16, dim_mults=(1, 2), channels=3, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, per_frame_cond=True)
+    gd = GaussianDiffusion(m, image_size=12, channels=3, num_frames=11, timesteps=8, use_dynamic_thres=True, sampling_timesteps=8)
+    t = Trainer(gd, None, None, [0, 1, 3], train_batch_size=2, test_batch_size=4, results_folder='run', log=True, null_cond_prob=0.1,
+                per_frame_cond=True, reference_frame='lagrangian', accelerator=Accelerator(cpu=True))
+    t.step = 3
+    t.ds.labels_scaling = fixed_normalization(0., 100.)
+    t.ema_model.sample = _stub_sample
+    t.model = lambda **kw: kw["x"].mean() * 0 + 0.25 * (1 + t.accelerator.process_index)       # per-rank validation "loss"
+    np.random.seed(4)
+    gathered = t.eval_target(targets, guidance_scale=5., num_preds=1)
+    t.eval_network(0., None, num_samples=3, num_preds=1)
+    return t, gathered
+
+
+def _eval_worker(rank, world, port, workdir, targets, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    t, gathered = _eval_target_run(workdir, targets)
+    q.put((rank, tuple(gathered.shape), [l for l in t.accelerator.logs if 'validation loss' in l]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_eval_target_matches_single_process(tmp_path):
+    """Five conditionings over two ranks (2 + 3, the shorter rank padded for the gather): rank 0 must write the same
+    geometries.csv and GIFs as a single process does (VDDP:1755-1846), and the validation loss is the mean over ranks."""
+    import numpy as np
+    targets = str(tmp_path / "targets.csv")
+    rng = np.random.default_rng(0)
+    np.savetxt(targets, np.cumsum(rng.random((5, 11)), axis=1) * 15.0, delimiter=',')
+    one, two = tmp_path / "one", tmp_path / "two"
+    one.mkdir()
+    two.mkdir()
+    cwd = os.getcwd()
+    try:
+        t, g1 = _eval_target_run(str(one), targets)
+    finally:
+        os.chdir(cwd)
+    assert tuple(g1.shape) == (5, 3, 11, 12, 12)
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_eval_worker, args=(r, world, port, str(two), targets, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] == (6, 3, 11, 12, 12)                 # 2 x max(2, 3) rows, one of them padding
+    assert res[0][2] and abs(res[0][2][0]['validation loss'] - 0.375) < 1e-6 and not res[1][2]
+    sub = "eval_target_w_5.0_0/step_3"
+    a = np.genfromtxt(str(one / "run" / sub / "geometries.csv"), delimiter=',')
+    b = np.genfromtxt(str(two / "run" / sub / "geometries.csv"), delimiter=',')
+    assert a.shape == b.shape == (5, 36) and np.array_equal(a, b)
+    for ch in (0, 1, 3):
+        fa = open(str(one / "run" / sub / f"gifs/prediction_channel_{ch}.gif"), "rb").read()
+        fb = open(str(two / "run" / sub / f"gifs/prediction_channel_{ch}.gif"), "rb").read()
+        assert fa == fb, ch
+    # eval_network: the validation loader is sharded over ranks (as accelerate's prepared loader is), so the sampled conditionings
+    # differ from the single-process run; the files of the three requested samples must exist with the right shapes
+    for root in (one, two):
+        assert np.genfromtxt(str(root / "run" / "training/step_3" / "geometries.csv"), delimiter=',').shape == (3, 36)
+        assert all(os.path.getsize(str(root / "run" / "training/step_3" / f"gifs/prediction_channel_{ch}.gif")) > 0 for ch in (0, 1, 3))

@@ -332,12 +332,16 @@ class Trainer(object):
         mode = 'training'
         if self.accelerator.is_main_process:
             os.makedirs('./' + str(self.results_folder) + '/' + mode + '/step_' + str(self.step) + '/gifs', exist_ok=True)
-        losses, conds = [], []
+        losses, conds, picked = [], [], ()
+        if self.accelerator.is_main_process:
+            # conditionings for the sampled videos come from randomly chosen validation batches (numpy's global stream, VDDP:1691-1693)
+            picked = np.random.choice(len(self.dl_test), int(np.ceil(num_samples / self.test_batch_size)), replace=False)
         with torch.no_grad():
-            for x, cond in self.dl_test:
+            for idx, (x, cond) in enumerate(self.dl_test):
                 loss = self.model(x=x, cond=cond, null_cond_prob=self.null_cond_prob)
                 losses.append(self.accelerator.gather_for_metrics(loss.detach()).mean().item())
-                conds.append(cond.clone())
+                if idx in picked:
+                    conds.append(cond.clone())
         cond_full = None
         if self.accelerator.is_main_process:
             self.log_fn({'validation loss': float(np.mean(losses))}, step=self.step)
