@@ -465,6 +465,29 @@ def ddim_sample(P: Params, cfg: UnetCfg, S, x_T: Tensor, cond: Tensor, w: float,
 
 
 # ----------------------------------------------------------------------------------------------
+# optimiser + EMA (Trainer.train, VDDP:1622-1640)
+# ----------------------------------------------------------------------------------------------
+def adam_ema_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, ema: Optional[Tensor], step: int, *, lr: float = 1e-4,
+                  beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, grad_scale: float = 1.0, ema_mode: int = 0,
+                  ema_beta: float = 0.995) -> None:
+    """One `torch.optim.Adam(lr)` step (VDDP:1478, 1633: default betas / eps, no weight decay, no amsgrad) on flat fp32
+    tensors, in place, followed by the reference's model average (VDDP:116-129, 1493-1497): `ema_mode` 1 = the
+    `step < step_start_ema` phase (the average is a copy of the weights), 2 = `old * beta + (1 - beta) * new`.
+    `step` counts from 1.  `grad_scale` multiplies the gradient first (1 / loss scale; the reference's GradScaler does it)."""
+    g = g * grad_scale
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    p.addcdiv_(m, denom, value=-lr / bc1)
+    if ema is not None and ema_mode == 1:
+        ema.copy_(p)
+    elif ema is not None and ema_mode == 2:
+        ema.copy_(ema * ema_beta + (1 - ema_beta) * p)
+
+
+# ----------------------------------------------------------------------------------------------
 # deterministic synthetic weights (shared by tests, bench and golden generation)
 # ----------------------------------------------------------------------------------------------
 def unet_param_shapes(cfg: UnetCfg) -> Dict[str, Tuple[int, ...]]:

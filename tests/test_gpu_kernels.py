@@ -227,6 +227,29 @@ def test_quantile_edge_cases(ops):
         assert torch.equal(s, want), (n, s, want)
 
 
+def test_adam_ema_step_matches_oracle(ops):
+    """vmm_adam_ema_step (one launch over the flat arena) against the oracle's restatement of torch.optim.Adam + the reference's
+    EMA (VDDP:116-129, 1633-1639; the oracle is pinned to torch.optim.Adam in tests/test_cpu_oracle.py), through the copy phase
+    and the averaging phase, with a gradient scale.  fp32 in, fp32 out: 1e-6 (fused multiply-adds vs separate torch ops)."""
+    from oracle import vdm_oracle as O
+    torch.manual_seed(3)
+    n = 148 * 256 * 8 + 13                       # more elements than the capped grid covers in one pass, ragged tail
+    p0 = torch.randn(n)
+    p, m, v, ema = p0.clone(), torch.zeros(n), torch.zeros(n), p0.clone()
+    dp, dm, dv, dema = (t.clone().cuda() for t in (p, m, v, ema))
+    for step in range(1, 26):
+        g = torch.randn(n) * (1 + step % 4)
+        mode = 0 if step % 5 else (1 if step < 12 else 2)
+        scale = 1.0 if step % 2 else 0.25
+        O.adam_ema_step(p, g, m, v, ema, step, lr=1e-3, grad_scale=scale, ema_mode=mode, ema_beta=0.995)
+        ops.adam_ema_step(dp, g.cuda(), dm, dv, dema if mode else None, 1e-3, 0.9, 0.999, 1e-8, step, scale, mode, 0.995)
+    assert rel(dp.cpu(), p) < 1e-6 and rel(dema.cpu(), ema) < 1e-6
+    assert rel(dm.cpu(), m) < 1e-6 and rel(dv.cpu(), v) < 1e-6
+    assert float((dp.cpu() - p).abs().max()) < 1e-5
+    with pytest.raises(RuntimeError):
+        ops.adam_ema_step(dp, dp, dm, dv, None, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, 0, 0.995)       # step counts from 1
+
+
 # ------------------------------------------------------------------------------------------------
 # gradients of the GEMM-shaped layers: data gradient (vmm_cgemm with transformed weights) and weight
 # gradient (vmm_wgrad), against torch autograd in fp32 on the same 16-bit-rounded operands
