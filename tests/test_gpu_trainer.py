@@ -1,0 +1,95 @@
+"""main.py's sequence on the real kernels with a small network: Trainer(...) on a GIF dataset in the reference's on-disk
+format, train() with periodic evaluation (validation loss + guided sampling + the output files), the final checkpoint, a
+second Trainer resuming from it, and eval_target() on a target-curve file (ref main.py:96-117, VDDP:1594-1919)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer(data, train_num_steps, seed):
+    from videometamaterials_b200 import Accelerator, GaussianDiffusion, Trainer, Unet3D
+    torch.manual_seed(seed)
+    model = Unet3D(dim=16, dim_mults=(1, 2), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
+                   cond_bias=True, cond_attention='self-stacked', cond_attention_tokens=16, cond_att_GRU=False, use_temporal_attention_cond=True,
+                   cond_to_time='add', per_frame_cond=True, padding_mode='zeros')
+    gd = GaussianDiffusion(model, image_size=16, channels=3, num_frames=11, timesteps=8, loss_type='l1', use_dynamic_thres=True,
+                           sampling_timesteps=8)
+    return Trainer(gd, folder=data + "training/", validation_folder=data + "validation/", results_folder='run', selected_channels=[0, 1, 3],
+                   train_batch_size=2, test_batch_size=4, train_lr=1e-3, save_and_sample_every=3, train_num_steps=train_num_steps,
+                   ema_decay=0.9, step_start_ema=2, update_ema_every=2, log=True, null_cond_prob=0.1, per_frame_cond=True,
+                   reference_frame='lagrangian', run_name='test', accelerator=Accelerator(mixed_precision='bf16'), log_every=1)
+
+
+def test_train_evaluate_checkpoint_resume_eval_target(tmp_path, monkeypatch):
+    from videometamaterials_b200 import _lib
+    from videometamaterials_b200.dataset import write_synthetic_dataset
+    monkeypatch.chdir(tmp_path)
+    data = str(tmp_path / "data") + "/"
+    write_synthetic_dataset(data + "training/", 6, image_size=16, num_frames=11, seed=0)
+    write_synthetic_dataset(data + "validation/", 2, image_size=16, num_frames=11, seed=1)
+    tr = _trainer(data, 6, seed=0)
+    assert len(tr.ds) == 6 and tr.test_batch_size == 2
+    net = tr.model.denoise_fn
+    w0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    np.random.seed(0)
+    n0 = _lib.launch_count()
+    tr.train(num_samples=2, num_preds=1)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() > n0 + 1000                    # the vmm kernels did the work
+    assert tr.step == 6 and tr.opt.step_count == 7
+    logs = tr.accelerator.logs
+    train_losses = [l["training loss"] for l in logs if "training loss" in l]
+    assert len(train_losses) == 7 and all(np.isfinite(train_losses)) and all(0.0 < v < 10.0 for v in train_losses)
+    val = [l for l in logs if "validation loss" in l]
+    assert [l["step"] for l in val] == [3, 6] and all(np.isfinite(l["validation loss"]) for l in val)
+    # trained tensors moved; the 31 tensors that never get a gradient and the rotary table did not
+    sd = net.state_dict()
+    moved = [k for k in sd if not torch.equal(sd[k], w0[k])]
+    still = [k for k in sd if torch.equal(sd[k], w0[k])]
+    assert "init_conv.weight" in moved and "final_conv.1.weight" in moved and len(moved) > 150
+    inert = ("to_q.", "sign_emb_CNN", "rotary_emb", "init_temporal_attn.fn.fn.fn.to_k", "init_temporal_attn.fn.fn.fn.to_v",
+             "null_text_")        # the null tokens only move when the 10 % conditioning drop hits a sample of these 14
+    assert all(any(s in k for s in inert) for k in still), [k for k in still if not any(s in k for s in inert)][:8]
+    # the model average follows the weights (copy at step 0, averages at 2, 4, 6) without being equal to them
+    ema_sd = tr.ema_model.denoise_fn.state_dict()
+    d_ema = float((ema_sd["init_conv.weight"] - sd["init_conv.weight"]).abs().max())
+    assert 0 < d_ema < float((w0["init_conv.weight"] - sd["init_conv.weight"]).abs().max()) + 1e-3
+    # output files of the two evaluations and the final checkpoint
+    for s in (3, 6):
+        geom = np.atleast_2d(np.genfromtxt(f"run/training/step_{s}/geometries.csv", delimiter=','))
+        assert geom.shape == (2, 64) and set(np.unique(geom)) <= {0.0, 1.0}
+        assert sorted(os.listdir(f"run/training/step_{s}/gifs")) == [f"prediction_channel_{c}.gif" for c in (0, 1, 3)]
+    assert sorted(os.listdir("run/model")) == ["step_6"]
+    ck = torch.load("run/model/step_6/checkpoint.pt", map_location="cpu")
+    assert ck["steps"] == 6 and list(ck["model"].keys()) == list(tr.model.state_dict().keys())
+
+    # a second Trainer (different random init) resumes from the checkpoint: weights, average and optimiser moments come back
+    tr2 = _trainer(data, 6, seed=1)
+    assert not torch.equal(tr2.model.denoise_fn.init_conv.weight, net.init_conv.weight)
+    tr2.train(load_model_step=6, num_samples=0)               # already trained to train_num_steps: loads and returns (VDDP:1613-1614)
+    for k, v in tr.model.state_dict().items():
+        assert torch.equal(tr2.model.state_dict()[k], v), k
+    for k, v in tr.ema_model.state_dict().items():
+        assert torch.equal(tr2.ema_model.state_dict()[k], v), k
+    assert tr2.opt.step_count == 7 and torch.equal(tr2.opt.m, tr.opt.m) and torch.equal(tr2.opt.v, tr.opt.v)
+
+    # eval_target on three target curves given at 21 strain points (interpolated to the 11 frames), two predictions each
+    rng = np.random.default_rng(2)
+    np.savetxt("targets.csv", np.cumsum(rng.random((3, 21)), axis=1) * 4.0, delimiter=',')
+    torch.manual_seed(7)
+    vids = tr2.eval_target("targets.csv", guidance_scale=5., num_preds=2)
+    assert tuple(vids.shape) == (6, 3, 11, 16, 16) and bool(torch.isfinite(vids).all())
+    assert float(vids.min()) >= -1e-6 and float(vids.max()) <= 1 + 1e-6       # dynamic thresholding keeps x0 in [-1, 1]
+    out = "run/eval_target_w_5.0_0/step_6/"
+    geom = np.atleast_2d(np.genfromtxt(out + "geometries.csv", delimiter=','))
+    assert geom.shape == (6, 64) and set(np.unique(geom)) <= {0.0, 1.0}
+    from PIL import Image
+    img = Image.open(out + "gifs/prediction_channel_1.gif")
+    assert img.size == (2 * 20, 3 * 20)                       # (i h) x (j w) tiles, each 16 px + a 2-pixel border
+    # the same seed reproduces the same conditioning fan-out and sample count in the next free folder
+    tr2.eval_target("targets.csv", guidance_scale=1., num_preds=1)
+    assert np.atleast_2d(np.genfromtxt("run/eval_target_w_1.0_0/step_6/geometries.csv", delimiter=',')).shape == (3, 64)
