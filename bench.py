@@ -314,26 +314,42 @@ def run_own(args):
             "top_shapes": [{"shape": k.partition("|")[2], "tflops": v[0] / v[1] / 1e12, "ms_per_step": v[1] / 2 * 1e3} for k, v in top],
             "wgrad": {"achieved": by["wgrad"][0] / by["wgrad"][1] / 1e12 if "wgrad" in by else None,
                       "share_of_step": (by["wgrad"][1] / 2) / (ms * 1e-3) if "wgrad" in by else None}}
-    # sampling metric (second half of BASELINE.json's metric): ancestral p_sample with guidance, b=4, CUDA graph
+    # sampling metric (second half of BASELINE.json's metric): ancestral p_sample with guidance, b=4, replayed from a CUDA graph,
+    # timed on the device; plus BASELINE configs[2], one full 250-step DDIM sample() of the 4 conditionings
     ps = None
     try:
         ema = trainer.ema_model
         ema.denoise_fn.set_compute_dtype(torch.float16)
         ema.use_cuda_graph = True
         condp = torch.rand(4, 11, device=dev) * 2 - 1
+
+        def timed(fn):
+            fn()                                               # warm-up (captures the step graph)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3
+
         T = ema.num_timesteps
         ema.num_timesteps = 8
-        ema.sample(cond=condp, guidance_scale=5.0)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ema.sample(cond=condp, guidance_scale=5.0)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / 8
+        dt = timed(lambda: ema.sample(cond=condp, guidance_scale=5.0)) / 8
         ema.num_timesteps = T
         ps = {"value": 1.0 / dt, "unit": "p_sample steps/s", "batch": 4, "guidance_scale": 5.0, "dtype": "f16", "steps_timed": 8,
               "tflops": 4 * 2 * FWD_GFLOP_PER_CLIP / dt / 1e3}
+        if not args.no_ddim:
+            st, ddim = ema.sampling_timesteps, ema.is_ddim_sampling
+            ema.sampling_timesteps, ema.is_ddim_sampling = 250, True
+            try:
+                total = timed(lambda: ema.sample(cond=condp, guidance_scale=5.0))
+                ps["ddim250_sample"] = {"seconds": total, "steps_per_s": 250 / total, "samples_per_s": 4 / total, "batch": 4,
+                                        "workload": "GaussianDiffusion.sample 250-step DDIM, 4 conditionings, w=5 (BASELINE configs[2])"}
+            finally:
+                ema.sampling_timesteps, ema.is_ddim_sampling = st, ddim
     except Exception as e:  # noqa: BLE001
-        ps = {"error": str(e)[:200]}
+        ps = dict(ps or {}, error=str(e)[:200])
     cpu = cpu_baseline_bounded() if world == 1 and not args.no_cpu_baseline else None
     value = world * B / (ms * 1e-3)
     line = {
@@ -359,6 +375,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-ddim", dest="no_ddim", action="store_true", help="skip the 250-step DDIM sample() timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

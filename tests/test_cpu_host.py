@@ -55,6 +55,14 @@ def test_state_dict_matches_reference_layout(golden_dir):
     assert gd2.is_ddim_sampling
 
 
+def test_product_ddim_pairs_match_reference(golden_dir):
+    from videometamaterials_b200 import GaussianDiffusion, Unet3D
+    kat = json.load(open(os.path.join(golden_dir, "kat.json")))
+    m = Unet3D(dim=16, dim_mults=(1, 2), channels=3, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, per_frame_cond=True)
+    gd = GaussianDiffusion(m, image_size=16, channels=3, num_frames=11, timesteps=256, sampling_timesteps=250)
+    assert [list(p) for p in gd._ddim_pairs()] == kat["ddim_pairs_250_of_256"]          # VDDP:990-992
+
+
 def test_unsupported_configurations_raise():
     from videometamaterials_b200 import Unet3D
     with pytest.raises(NotImplementedError):

@@ -21,7 +21,7 @@ def _trainer(data, train_num_steps, seed):
     return Trainer(gd, folder=data + "training/", validation_folder=data + "validation/", results_folder='run', selected_channels=[0, 1, 3],
                    train_batch_size=2, test_batch_size=4, train_lr=1e-3, save_and_sample_every=3, train_num_steps=train_num_steps,
                    ema_decay=0.9, step_start_ema=2, update_ema_every=2, log=True, null_cond_prob=0.1, per_frame_cond=True,
-                   reference_frame='lagrangian', run_name='test', accelerator=Accelerator(mixed_precision='bf16'), log_every=1)
+                   reference_frame='lagrangian', run_name='test', accelerator=Accelerator(mixed_precision='fp16'), log_every=1)      # as main.py:34
 
 
 def test_train_evaluate_checkpoint_resume_eval_target(tmp_path, monkeypatch):
@@ -33,6 +33,7 @@ def test_train_evaluate_checkpoint_resume_eval_target(tmp_path, monkeypatch):
     write_synthetic_dataset(data + "validation/", 2, image_size=16, num_frames=11, seed=1)
     tr = _trainer(data, 6, seed=0)
     assert len(tr.ds) == 6 and tr.test_batch_size == 2
+    assert tr.model.denoise_fn.compute_dtype == torch.bfloat16 and tr.ema_model.denoise_fn.compute_dtype == torch.float16
     net = tr.model.denoise_fn
     w0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
     np.random.seed(0)

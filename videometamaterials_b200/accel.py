@@ -77,7 +77,10 @@ class Accelerator:
 
     @property
     def compute_dtype(self) -> torch.dtype:
-        return torch.float16 if self.mixed_precision == "fp16" else torch.bfloat16
+        """16-bit activation format of the training kernels.  The reference asks accelerate for 'fp16' (main.py:34: autocast plus
+        a GradScaler); the B200 path stores the same 16 bits as bf16, which needs no loss scale, so 'fp16' and 'bf16' both train
+        in bf16 here.  Sampling runs the EMA copy in fp16 (three more mantissa bits, no gradients involved), see Trainer."""
+        return torch.bfloat16
 
     # ------------------------------------------------------------------ logging
     def init_trackers(self, project_name=None, init_kwargs=None, **kw):

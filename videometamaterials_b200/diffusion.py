@@ -159,32 +159,80 @@ class GaussianDiffusion(nn.Module):
             img = self.p_sample(img, torch.full((b,), i, device=device, dtype=torch.long), cond=cond, guidance_scale=guidance_scale)
         return unnormalize_img(img)
 
-    def _graph_loop(self, img, cond, guidance_scale):
-        """The ancestral loop with one CUDA graph per step shape: t, x and the noise live in static buffers."""
-        key = (tuple(img.shape), float(guidance_scale), str(self.denoise_fn.compute_dtype))
+    def _step_graph(self, kind, img, cond, guidance_scale, make_state, step):
+        """One CUDA graph per (step kind, shape, guidance scale, 16-bit format, packed-weight storage): `step(st)` is warmed up
+        twice on a side stream and then captured; x, t, cond and the per-step scalars live in the static buffers of `st`."""
+        weights = next(iter(self.denoise_fn.packed().values())).data_ptr()      # a repack into new storage invalidates the graph
+        key = (kind, tuple(img.shape), float(guidance_scale), str(self.denoise_fn.compute_dtype), weights)
         g = self._graphs.get(key)
-        b = img.shape[0]
         if g is None:
+            b = img.shape[0]
             st = dict(x=img.clone(), t=torch.zeros(b, dtype=torch.long, device=img.device), cond=cond.clone().float(),
                       noise=torch.zeros_like(img))
-            self.denoise_fn.packed()
+            st["weights"] = self.denoise_fn.packed()        # keeps the captured operand storage alive (and its address unique)
+            make_state(st)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    st["out"] = self._p_sample_core(st["x"], st["t"], st["cond"], guidance_scale, st["noise"])
+                    st["out"] = step(st)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                st["out"] = self._p_sample_core(st["x"], st["t"], st["cond"], guidance_scale, st["noise"])
+                st["out"] = step(st)
             g = (graph, st)
             self._graphs[key] = g
         graph, st = g
         st["x"].copy_(img)
         st["cond"].copy_(cond)
+        return graph, st
+
+    def _graph_loop(self, img, cond, guidance_scale):
+        """The ancestral loop replayed from one CUDA graph per step shape: t, x and the noise live in static buffers."""
+        graph, st = self._step_graph("ancestral", img, cond, guidance_scale, lambda st: None,
+                                     lambda st: self._p_sample_core(st["x"], st["t"], st["cond"], guidance_scale, st["noise"]))
         for i in reversed(range(0, self.num_timesteps)):
             st["t"].fill_(i)
             st["noise"].normal_()
+            graph.replay()
+            st["x"].copy_(st["out"])
+        return st["x"].clone()
+
+    def _ddim_pairs(self):
+        """(time, time_next) pairs of VDDP:990-992."""
+        times = torch.linspace(-1, self.num_timesteps - 1, steps=self.sampling_timesteps + 1)
+        times = list(reversed(times.int().tolist()))
+        return list(zip(times[:-1], times[1:]))
+
+    def _ddim_step_core(self, st, guidance_scale):
+        """One eta = 0 DDIM update with every per-step scalar read on the device (graph-safe): the table `acp_next` holds
+        alphas_cumprod shifted by one with 1.0 in front, so time_next = -1 gives (1, 0) and the step returns x0 (VDDP:1010-1012)."""
+        x, t = st["x"], st["t"]
+        b, c, f, h, w = x.shape
+        eps_cl, has_null = self._eps_channels_last(x, t, st["cond"], guidance_scale)
+        ops.cfg_x0(x, eps_cl, has_null, guidance_scale, self.sqrt_recip_alphas_cumprod[t].contiguous(),
+                   self.sqrt_recipm1_alphas_cumprod[t].contiguous(), st["x0"], st["eps"], b, c, f, h, w)
+        an = st["acp_next"][st["tn"] + 1]
+        out = torch.empty_like(x)
+        # x0 * sqrt(an) + eps * sqrt(1 - an): the posterior kernel's c1 * x0 + c2 * x + sig * noise with sig = 0 and no clamp
+        ops.posterior_step(st["x0"], st["eps"], st["x0"], None, an.sqrt().contiguous(), (1. - an).sqrt().contiguous(), st["zeros"], out,
+                           b, c * f * h * w)
+        return out
+
+    def _graph_ddim(self, img, cond, guidance_scale):
+        def make_state(st):
+            b = img.shape[0]
+            st["tn"] = torch.zeros(b, dtype=torch.long, device=img.device)
+            st["x0"], st["eps"] = torch.empty_like(img), torch.empty_like(img)
+            st["zeros"] = torch.zeros(b, dtype=torch.float32, device=img.device)
+            st["acp_next"] = torch.cat((torch.ones(1, device=img.device), self.alphas_cumprod)).contiguous()
+
+        graph, st = self._step_graph("ddim", img, cond, guidance_scale, make_state, lambda st: self._ddim_step_core(st, guidance_scale))
+        for time, time_next in self._ddim_pairs():
+            st["t"].fill_(time)
+            st["tn"].fill_(time_next)
+            if time_next >= 0:
+                st["noise"].normal_()                    # the reference draws (and discards, sigma = 0) one noise per step
             graph.replay()
             st["x"].copy_(st["out"])
         return st["x"].clone()
@@ -199,12 +247,12 @@ class GaussianDiffusion(nn.Module):
     @torch.inference_mode()
     def ddim_sample(self, shape, cond=None, guidance_scale=1.):
         """VDDP:986-1018 (eta = 0: no clamp, no dynamic threshold, the drawn noise is multiplied by sigma = 0)."""
-        batch, device, total, steps = shape[0], self.betas.device, self.num_timesteps, self.sampling_timesteps
-        times = torch.linspace(-1, total - 1, steps=steps + 1)
-        times = list(reversed(times.int().tolist()))
-        pairs = list(zip(times[:-1], times[1:]))
+        batch, device = shape[0], self.betas.device
+        pairs = self._ddim_pairs()
         img = torch.randn(shape, device=device)
         b, c, f, h, w = shape
+        if self.use_cuda_graph:
+            return unnormalize_img(self._graph_ddim(img, cond, guidance_scale))
         for time, time_next in pairs:
             t = torch.full((batch,), time, device=device, dtype=torch.long)
             eps_cl, has_null = self._eps_channels_last(img, t, cond, guidance_scale)
