@@ -71,9 +71,9 @@ def _center_crop(fr, size: int):
     return fr.crop((left, top, left + size, top + size))
 
 
-def _gif_frames(path, image_size: int, horizontal_flip: bool = False) -> torch.Tensor:
-    """(1, frames, h, w) float32 in [0, 1] from an 8-bit GIF: every frame converted to 'L', then Resize -> (flip) ->
-    CenterCrop -> /255 as the reference's transform does (VDDP:1076-1106, 1252-1257)."""
+def _gif_frames_u8(path, image_size: int, horizontal_flip: bool = False) -> torch.Tensor:
+    """(frames, h, w) uint8 from an 8-bit GIF: every frame converted to 'L', then Resize -> (flip) -> CenterCrop as the
+    reference's transform does (VDDP:1076-1106, 1252-1257); the final ToTensor (/255) is left to the caller."""
     from PIL import Image
     img = Image.open(path)
     frames, i = [], 0
@@ -86,9 +86,14 @@ def _gif_frames(path, image_size: int, horizontal_flip: bool = False) -> torch.T
         if horizontal_flip and float(torch.rand(1)) < 0.5:
             fr = fr.transpose(Image.FLIP_LEFT_RIGHT)
         fr = _center_crop(fr, image_size)
-        frames.append(torch.from_numpy(np.asarray(fr, dtype=np.uint8).copy()).to(torch.float32).div(255))
+        frames.append(torch.from_numpy(np.asarray(fr, dtype=np.uint8).copy()))
         i += 1
-    return torch.stack(frames, dim=0)[None]
+    return torch.stack(frames, dim=0)
+
+
+def _gif_frames(path, image_size: int, horizontal_flip: bool = False) -> torch.Tensor:
+    """(1, frames, h, w) float32 in [0, 1] (what the reference's gif_to_tensor returns for one channel)."""
+    return _gif_frames_u8(path, image_size, horizontal_flip).to(torch.float32).div(255)[None]
 
 
 def _cast_frames(t: torch.Tensor, frames: int) -> torch.Tensor:
@@ -136,9 +141,15 @@ class Dataset(data.Dataset):
     values, zeroes the void pixels of the topology mask and rescales with the global extrema of the folder.  The arithmetic
     keeps the reference's types (float32 pixels, float64 0-dim range scalars) so that items are bit-identical."""
 
+    # Decoded 8-bit frames are kept in host memory up to this many bytes (0 disables).  PIL needs ~3 ms per 96x96x11 GIF and an
+    # item reads five of them: ~60 items/s per process, where one B200 trains > 200 clips/s.  From the cache an item costs the
+    # float32 normalisation only.  What is cached is the integer image before `/255`, so items stay bit-identical.
+    decode_cache_bytes = 32 << 30
+
     def __init__(self, folder, image_size, labels_scaling=None, selected_channels=[0, 1, 2, 3], num_frames=16, horizontal_flip=False,
                  force_num_frames=True, exts=['gif'], per_frame_cond=False, reference_frame='eulerian'):
         super().__init__()
+        self._cache, self._cache_used = {}, 0
         if reference_frame not in ('eulerian', 'lagrangian'):
             raise ValueError(f'unknown reference_frame {reference_frame!r}')
         folder = str(folder)
@@ -193,12 +204,37 @@ class Dataset(data.Dataset):
     def __len__(self):
         return len(self.paths['topo'])
 
+    def _frames_u8(self, sub, index) -> torch.Tensor:
+        key = (sub, int(index))
+        u8 = self._cache.get(key)
+        if u8 is None:
+            u8 = _gif_frames_u8(self.paths[sub][index], self.image_size, self.horizontal_flip)
+            if not self.horizontal_flip and self._cache_used + u8.numel() <= self.decode_cache_bytes:
+                self._cache[key] = u8
+                self._cache_used += u8.numel()
+        return u8
+
+    def _frames(self, sub, index) -> torch.Tensor:
+        """(frames, h, w) float32 in [0, 1]: ToTensor of the decoded frames."""
+        return self._frames_u8(sub, index).to(torch.float32).div(255)
+
+    def preload(self, num_threads: int = 0) -> int:
+        """Decode every GIF an item reads into the cache with a thread pool (PIL decodes outside the GIL); returns the number of
+        cached bytes.  Optional: without it the cache fills during the first epoch."""
+        from concurrent.futures import ThreadPoolExecutor
+        key = 'lagrangian_1' if (self.reference_frame == 'lagrangian' and self.num_frames == 1) else self.reference_frame
+        subs = sorted({'topo'} | {c[0] for c in _LAYOUT[key]['channels']})
+        jobs = [(sub, i) for i in range(len(self)) for sub in subs]
+        with ThreadPoolExecutor(max_workers=num_threads or min(32, os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda j: self._frames_u8(*j), jobs))
+        return self._cache_used
+
     def __getitem__(self, index):
         key = self.reference_frame
         if key == 'lagrangian' and self.num_frames == 1:
             key = 'lagrangian_1'
             self.selected_channels = [0, 1]
-        load = lambda sub: _gif_frames(self.paths[sub][index], self.image_size, self.horizontal_flip)
+        load = lambda sub: self._frames(sub, index)[None]
         void = load('topo')[0] == 0.
         r = self.frame_ranges[index]
         planes = []
