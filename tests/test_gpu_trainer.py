@@ -94,3 +94,30 @@ def test_train_evaluate_checkpoint_resume_eval_target(tmp_path, monkeypatch):
     # the same seed reproduces the same conditioning fan-out and sample count in the next free folder
     tr2.eval_target("targets.csv", guidance_scale=1., num_preds=1)
     assert np.atleast_2d(np.genfromtxt("run/eval_target_w_1.0_0/step_6/geometries.csv", delimiter=',')).shape == (3, 64)
+
+
+def test_main_py_on_the_shipped_configuration(tmp_path, monkeypatch):
+    """The launcher end to end at the shipped model.yaml size (96 x 96 x 11, dim 64, 256 ancestral steps, w = 5): two training
+    steps on synthetic clips, the final checkpoint, then eval_target on four target curves (BASELINE configs[2]'s workload)."""
+    import importlib.util
+    import shutil
+    import yaml
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("vmm_main", os.path.join(root, "main.py"))
+    main = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(main)
+    monkeypatch.chdir(tmp_path)
+    shutil.copy(os.path.join(root, "model.yaml"), tmp_path / "model.yaml")
+    rng = np.random.default_rng(0)
+    os.makedirs("data")
+    np.savetxt("data/target_responses.csv", np.cumsum(rng.random((4, 11)), axis=1) * 10.0, delimiter=',')
+    torch.manual_seed(0)
+    rc = main.main(["--run-name", "t", "--root", str(tmp_path), "--synthetic-data", "--train-steps", "2", "--guidance-scale", "5"])
+    assert rc == 0
+    assert yaml.safe_load(open("runs/t/model/model.yaml").read())["unet_dim"] == 64
+    ck = torch.load("runs/t/model/step_2/checkpoint.pt", map_location="cpu")
+    assert ck["steps"] == 2 and len(ck["model"]) == 377 + 12
+    out = "runs/t/eval_target_w_5.0_0/step_2/"
+    geom = np.atleast_2d(np.genfromtxt(out + "geometries.csv", delimiter=','))
+    assert geom.shape == (4, 48 * 48) and set(np.unique(geom)) <= {0.0, 1.0}
+    assert sorted(os.listdir(out + "gifs")) == [f"prediction_channel_{c}.gif" for c in (0, 1, 3)]

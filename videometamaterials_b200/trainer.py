@@ -98,7 +98,7 @@ class Trainer(object):
     def __init__(self, diffusion_model, folder, validation_folder, selected_channels, *, ema_decay=0.995, train_batch_size=4,
                  test_batch_size=2, train_lr=1.e-4, train_num_steps=100000, step_start_ema=2000, update_ema_every=10,
                  save_and_sample_every=1000, results_folder='./', max_grad_norm=None, log=True, null_cond_prob=0., per_frame_cond=False,
-                 reference_frame='eulerian', run_name=None, accelerator=None, wandb_username=None, log_every=50):
+                 reference_frame='eulerian', run_name=None, accelerator=None, wandb_username=None, log_every=50, preload_data=False):
         super().__init__()
         self.accelerator = accelerator if accelerator is not None else Accelerator()
         if log:
@@ -136,6 +136,8 @@ class Trainer(object):
                               per_frame_cond=per_frame_cond, reference_frame=reference_frame)
         else:
             self.ds = SyntheticLagrangianDataset(1024, image_size, len(selected_channels), num_frames)
+        if preload_data and hasattr(self.ds, 'preload'):
+            self.ds.preload()             # decode every GIF once, in threads; otherwise the cache fills during the first epoch
         self.dl = cycle(self.accelerator.prepare(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=True, pin_memory=True)))
         self.accelerator.print(f'found {len(self.ds)} videos in {folder}')
         assert len(self.ds) > 0, 'could not find any gif files in folder'
