@@ -29,10 +29,10 @@ def test_train_evaluate_checkpoint_resume_eval_target(tmp_path, monkeypatch):
     from videometamaterials_b200.dataset import write_synthetic_dataset
     monkeypatch.chdir(tmp_path)
     data = str(tmp_path / "data") + "/"
-    write_synthetic_dataset(data + "training/", 6, image_size=16, num_frames=11, seed=0)
+    write_synthetic_dataset(data + "training/", 7, image_size=16, num_frames=11, seed=0)       # 7 = 3 batches of 2 + a ragged one
     write_synthetic_dataset(data + "validation/", 2, image_size=16, num_frames=11, seed=1)
     tr = _trainer(data, 6, seed=0)
-    assert len(tr.ds) == 6 and tr.test_batch_size == 2
+    assert len(tr.ds) == 7 and tr.test_batch_size == 2
     assert tr.model.denoise_fn.compute_dtype == torch.bfloat16 and tr.ema_model.denoise_fn.compute_dtype == torch.float16
     net = tr.model.denoise_fn
     w0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
@@ -42,6 +42,10 @@ def test_train_evaluate_checkpoint_resume_eval_target(tmp_path, monkeypatch):
     torch.cuda.synchronize()
     assert _lib.launch_count() > n0 + 1000                    # the vmm kernels did the work
     assert tr.step == 6 and tr.opt.step_count == 7
+    # 7 steps = batches of 2, 2, 2, 1, 2, 2, 2 in some order: the full-batch shape was captured after two eager steps and survived
+    # the ragged batch, which ran eagerly (seen once)
+    shapes = {k[0][0]: (v["seen"], v["graph"] is not None) for k, v in tr._graph_states.items()}
+    assert shapes[2][1] and shapes[1] == (1, False), shapes
     logs = tr.accelerator.logs
     train_losses = [l["training loss"] for l in logs if "training loss" in l]
     assert len(train_losses) == 7 and all(np.isfinite(train_losses)) and all(0.0 < v < 10.0 for v in train_losses)

@@ -227,6 +227,7 @@ class Trainer(object):
     # gradient all-reduce and the fused optimiser stay outside the graph (step count, EMA schedule, NCCL).
     use_cuda_graph = True
     graph_warmup = 2
+    max_graphs = 2
     sample_with_cuda_graph = True
 
     def _fwd_bwd_eager(self, x, cond):
@@ -244,12 +245,16 @@ class Trainer(object):
         # identity of the parameter / gradient arena (device pointers)
         key = (tuple(x.shape), tuple(cond.shape), x.dtype, cond.dtype, float(self.null_cond_prob), str(getattr(net, "compute_dtype", None)),
                id(getattr(net, "_vmm_arena", None)))
-        st = getattr(self, "_graph_state", None)
-        if st is None or st["key"] != key:
-            st = self._graph_state = dict(key=key, seen=0, graph=None)
+        # one state per batch shape: the ragged last batch of an epoch must not evict the graph of the full batches.  At most
+        # `max_graphs` shapes are captured (each graph owns a private activation pool); further shapes run eagerly.
+        states = self.__dict__.setdefault("_graph_states", {})
+        st = states.get(key)
+        if st is None:
+            st = states[key] = dict(key=key, seen=0, graph=None)
+        self._graph_state = st
         if st["graph"] is None:
             st["seen"] += 1
-            if st["seen"] <= self.graph_warmup:
+            if st["seen"] <= self.graph_warmup or sum(1 for v in states.values() if v["graph"] is not None) >= self.max_graphs:
                 return self._fwd_bwd_eager(x, cond)
             # capture (nothing executes during capture; the replay below is this step's work)
             st["x"], st["cond"] = x.clone(), cond.clone()
