@@ -151,6 +151,42 @@ def test_full_unet_forward_slices(golden_dir, dtype):
     assert e["p_sample"] < 10 * FWD_TOL[dtype]
 
 
+@pytest.mark.parametrize("size,b", [(20, 3), (24, 1), (36, 2)])
+def test_ragged_sizes_against_the_oracle(size, b):
+    """Resolutions that are not multiples of the 8 x 16 conv tile (20 -> 10, 36 -> 18 after the downsample) and odd batch sizes:
+    forward, guided forward, loss and gradient norms against the CPU oracle computed here on the same seeded inputs."""
+    from oracle import vdm_oracle as O
+    cfg = O.UnetCfg(dim=16, dim_mults=(1, 2))
+    model, gd, sd = build(16, (1, 2), 8, size, 8, torch.float16, seed=11)
+    g = torch.Generator().manual_seed(size * 10 + b)
+    x = torch.randn(b, 3, 11, size, size, generator=g)
+    cond = torch.rand(b, 11, generator=g) * 2 - 1
+    t = torch.randint(0, 8, (b,), generator=g)
+    noise = torch.randn(b, 3, 11, size, size, generator=g)
+    with torch.no_grad():
+        y = model(x.cuda(), t.cuda(), cond=cond.cuda(), null_cond_prob=0.0)
+        yg = model.forward_with_guidance_scale(x.cuda(), t.cuda(), cond=cond.cuda(), guidance_scale=3.0)
+        y_ref = O.unet_forward(sd, cfg, x, t, cond, torch.zeros(b, dtype=torch.bool))
+        yg_ref = O.unet_forward_guided(sd, cfg, x, t, cond, 3.0)
+    e = (rel(y, y_ref), rel(yg, yg_ref))
+    print("ragged forward rel-L2:", size, b, e)
+    assert e[0] < FWD_TOL[torch.float16] and e[1] < 5 * FWD_TOL[torch.float16]
+    # loss + gradients (fp16 needs the loss scale)
+    x01 = torch.rand(b, 3, 11, size, size, generator=g)
+    P = {k: v.clone().requires_grad_(v.is_floating_point() and "freqs" not in k) for k, v in sd.items()}
+    loss_ref = O.p_losses(P, cfg, O.schedule(8), x01, t, cond, noise, torch.zeros(b, dtype=torch.bool))
+    loss_ref.backward()
+    loss = gd.p_losses((x01 * 2 - 1).cuda(), t.cuda(), cond=cond.cuda(), noise=noise.cuda(), null_cond_prob=0.0)
+    (loss * 4096.0).backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 2e-3
+    params = dict(model.named_parameters())
+    worst = max((abs(float(params[k].grad.norm()) / 4096.0 - float(p.grad.norm())) / max(float(p.grad.norm()), 1e-12), k)
+                for k, p in P.items() if p.requires_grad and p.grad is not None and float(p.grad.norm()) > 0)
+    print("ragged worst grad-norm deviation:", size, b, worst)
+    assert worst[0] < 0.08, worst            # same bound family as test_small_training_loss_and_gradients (sign flips of the L1 loss)
+
+
 def test_forward_needs_cuda():
     from videometamaterials_b200 import Unet3D
     m = Unet3D(dim=16, dim_mults=(1, 2), per_frame_cond=True, use_temporal_attention_cond=True, cond_attention='self-stacked')
