@@ -348,7 +348,8 @@ class Trainer(object):
         losses, conds, picked = [], [], ()
         if self.accelerator.is_main_process:
             # conditionings for the sampled videos come from randomly chosen validation batches (numpy's global stream, VDDP:1691-1693)
-            picked = np.random.choice(len(self.dl_test), int(np.ceil(num_samples / self.test_batch_size)), replace=False)
+            # (the reference raises when it needs more batches than the validation loader has; here all of them are taken)
+            picked = np.random.choice(len(self.dl_test), min(int(np.ceil(num_samples / self.test_batch_size)), len(self.dl_test)), replace=False)
         with torch.no_grad():
             for idx, (x, cond) in enumerate(self.dl_test):
                 loss = self.model(x=x, cond=cond, null_cond_prob=self.null_cond_prob)
