@@ -234,13 +234,17 @@ class Trainer(object):
         self.opt.zero_grad()
         loss = self.model(x=x, cond=cond, null_cond_prob=self.null_cond_prob)
         loss.backward()
-        return loss
+        # detached: a caller that keeps the loss (Trainer.train does, for logging) must not keep the autograd graph with it.  Its
+        # AccumulateGrad nodes are bound to the stream they were created on; alive during a later capture they would make the
+        # legacy stream wait on the capturing one (cudaErrorStreamCaptureImplicit)
+        return loss.detach()
 
     def _fwd_bwd(self, x, cond):
         from . import ops as _ops
         if not (self.use_cuda_graph and x.is_cuda) or _ops.PROFILE is not None:
             return self._fwd_bwd_eager(x, cond)
         net = self.model.denoise_fn
+        self.opt._ensure()                  # the arena exists before the key is taken (its identity is part of the key)
         # everything the captured launches bake in: shapes, the drop probability, the 16-bit format of the packed weights and the
         # identity of the parameter / gradient arena (device pointers)
         key = (tuple(x.shape), tuple(cond.shape), x.dtype, cond.dtype, float(self.null_cond_prob), str(getattr(net, "compute_dtype", None)),
