@@ -327,6 +327,11 @@ class Trainer(object):
         self.accelerator.end_training()
 
     # ------------------------------------------------------------------ evaluation (VDDP:1674-1919)
+    def _step_dir(self, mode: str) -> str:
+        """'./<results_folder>/<mode>/step_<n>/' as the reference spells it; an absolute results_folder stays absolute (the
+        reference's plain string concatenation would re-root it under the working directory)."""
+        return os.path.join('.', str(self.results_folder), mode, 'step_' + str(self.step)) + '/'
+
     def _sample_and_gather(self, cond_full, guidance_scale, num_samples, mode):
         cond_full = broadcast_object_list([cond_full])[0].to(self.device)
         chunks = self.cond_to_gpu(cond_full)
@@ -348,7 +353,7 @@ class Trainer(object):
     def eval_network(self, prob_focus_present, focus_present_mask, guidance_scale=5., num_samples=1, num_preds=1):
         mode = 'training'
         if self.accelerator.is_main_process:
-            os.makedirs('./' + str(self.results_folder) + '/' + mode + '/step_' + str(self.step) + '/gifs', exist_ok=True)
+            os.makedirs(self._step_dir(mode) + 'gifs', exist_ok=True)
         losses, conds, picked = [], [], ()
         if self.accelerator.is_main_process:
             # conditionings for the sampled videos come from randomly chosen validation batches (numpy's global stream, VDDP:1691-1693)
@@ -375,10 +380,10 @@ class Trainer(object):
         cond_full, num_samples = None, 0
         if self.accelerator.is_main_process:
             eval_idx = 0
-            while os.path.exists('./' + str(self.results_folder) + '/' + mode + '_' + str(eval_idx) + '/step_' + str(self.step)):
+            while os.path.exists(self._step_dir(mode + '_' + str(eval_idx))):
                 eval_idx += 1
             mode = mode + '_' + str(eval_idx)
-            os.makedirs('./' + str(self.results_folder) + '/' + mode + '/step_' + str(self.step) + '/gifs', exist_ok=True)
+            os.makedirs(self._step_dir(mode) + 'gifs', exist_ok=True)
             target = np.genfromtxt(target_labels_dir, delimiter=',')
             if target.ndim == 1:
                 target = target[np.newaxis, :]
@@ -409,7 +414,7 @@ class Trainer(object):
 
     def save_preds(self, gathered, original_lengths, max_length, num_samples, mode='training'):
         vids = self.remove_padding(gathered, original_lengths, max_length)
-        save_dir = './' + str(self.results_folder) + '/' + mode + '/step_' + str(self.step) + '/'
+        save_dir = self._step_dir(mode)
         os.makedirs(save_dir + 'gifs', exist_ok=True)
         padded = F.pad(vids, (2, 2, 2, 2))
         n, c, f, h, w = padded.shape
