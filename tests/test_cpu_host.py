@@ -230,3 +230,26 @@ def test_main_config_wiring(golden_dir, tmp_path):
     with pytest.raises(FileNotFoundError):
         main.main(["--run-name", "r2", "--root", str(tmp_path)])
     assert yaml.safe_load((tmp_path / "runs" / "r2" / "model" / "model.yaml").read_text()) == cfg
+
+
+def test_caches_filled_by_a_sampler_can_be_used_for_training():
+    """Sampling runs under torch.inference_mode(); the index / permutation tensors it leaves in the caches (relative-position
+    buckets, conditioning plans) must stay usable by a training step in the same process (autograd cannot save inference
+    tensors).  Found on the B200 when a sampling test ran before a training test."""
+    import torch
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import Unet3D, blocks
+    cfg = O.UnetCfg(dim=16, dim_mults=(1, 2))
+    model = Unet3D(dim=16, dim_mults=(1, 2), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
+                   cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, cond_to_time='add', per_frame_cond=True)
+    model.load_state_dict(O.synthetic_state_dict(cfg, seed=6))
+    blocks._BUCKET_CACHE.clear()
+    time, cond, mask = torch.tensor([1, 5]), torch.rand(2, 11) * 2 - 1, torch.tensor([False, True])
+    with torch.inference_mode():
+        blocks.conditioning(model, time, cond, mask, 11)
+    assert not any(v.is_inference() for v in blocks._BUCKET_CACHE.values())
+    for plan in model._vmm_cond_plans.values():
+        assert not any(torch.is_tensor(v) and v.is_inference() for v in plan.values())
+    ss, ekv, bias, rot = blocks.conditioning(model, time, cond, mask, 11)
+    (sum(v.sum() for v in ss.values()) + sum(v.sum() for v in ekv.values()) + bias.sum()).backward()
+    assert float(model.time_rel_pos_bias.relative_attention_bias.weight.grad.abs().sum()) > 0

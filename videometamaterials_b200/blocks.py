@@ -159,13 +159,16 @@ def rel_pos_buckets(n: int, device) -> Tensor:
     """T5-style bucket index of (k - q), num_buckets=32, max_distance=32.  VDDP:82-106."""
     key = (n, str(device))
     if key not in _BUCKET_CACHE:
-        q = torch.arange(n)[:, None]
-        k = torch.arange(n)[None, :]
-        neg = q - k
-        ret = (neg < 0).long() * 16
-        dist = neg.abs()
-        large = (8 + (torch.log(dist.float() / 8) / math.log(32 / 8) * 8).long()).clamp(max=15)
-        _BUCKET_CACHE[key] = (ret + torch.where(dist < 8, dist, large)).to(device)
+        # cached tensors must be ordinary tensors even when the first caller is a sampler under torch.inference_mode(): autograd
+        # refuses to save inference tensors, so a later training step in the same process would fail on the cached index
+        with torch.inference_mode(False):
+            q = torch.arange(n)[:, None]
+            k = torch.arange(n)[None, :]
+            neg = q - k
+            ret = (neg < 0).long() * 16
+            dist = neg.abs()
+            large = (8 + (torch.log(dist.float() / 8) / math.log(32 / 8) * 8).long()).clamp(max=15)
+            _BUCKET_CACHE[key] = (ret + torch.where(dist < 8, dist, large)).to(device)
     return _BUCKET_CACHE[key]
 
 
@@ -250,6 +253,12 @@ def _cond_plan(model, sd, b: int, frames_tok: int, device):
     plan = cache.get(key)
     if plan is not None:
         return plan
+    with torch.inference_mode(False):           # ordinary tensors in the cache, see rel_pos_buckets
+        plan = cache[key] = _build_cond_plan(model, sd, b, frames_tok, device, arena)
+    return plan
+
+
+def _build_cond_plan(model, sd, b: int, frames_tok: int, device, arena):
     rn, an = resnet_names(model), attn_names(model)
     heads = model.heads
     hd = heads * 32
@@ -278,7 +287,6 @@ def _cond_plan(model, sd, b: int, frames_tok: int, device):
     c = 1.0 + sel[None, :, :, None, None] * (ang.cos()[:, None, None, None, :] - 1.0)                           # (T, A, 2, 1, 16)
     sn = sel[None, :, :, None, None] * ang.sin()[:, None, None, None, :]
     plan["rot_c"], plan["rot_s"] = c.contiguous(), sn.contiguous()
-    cache[key] = plan
     return plan
 
 
