@@ -120,3 +120,47 @@ def test_checkpoint_loads_ddp_prefixed_state_dict(tmp_path, monkeypatch):
     t.load()
     assert torch.allclose(t.model.denoise_fn.init_conv.weight.detach(), before + 0.5)
     assert torch.allclose(t.ema_model.denoise_fn.init_conv.weight.detach(), before + 0.5)
+
+
+def test_optimizer_state_interchanges_with_torch_adam():
+    """The reference's checkpoint stores `torch.optim.Adam(model.parameters()).state_dict()` (VDDP:1478, 1547): indices run over
+    all parameters, the frozen rotary table included, and parameters that never had a gradient have no entry.  FusedAdam must
+    read that layout into the right arena slots and write a state that torch's Adam loads back."""
+    from videometamaterials_b200 import Unet3D
+    from videometamaterials_b200.trainer import FusedAdam
+    torch.manual_seed(0)
+    kw = dict(dim=16, dim_mults=(1, 2), channels=3, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, per_frame_cond=True)
+    ref_model, own_model = Unet3D(**kw), Unet3D(**kw)
+    own_model.load_state_dict(ref_model.state_dict())
+    names = [n for n, _ in ref_model.named_parameters()]
+    assert names[5].endswith("rotary_emb.freqs") and not dict(ref_model.named_parameters())[names[5]].requires_grad
+    opt = torch.optim.Adam(ref_model.parameters(), lr=3e-4)
+    never = lambda n: "to_q." in n or "sign_emb_CNN" in n                      # tensors without a gradient under the shipped config
+    for step in range(3):
+        for n, p in ref_model.named_parameters():
+            p.grad = None if (never(n) or not p.requires_grad) else torch.randn_like(p) * (step + 1)
+        opt.step()
+    sd = opt.state_dict()
+    assert 5 not in sd["state"] and len(sd["param_groups"][0]["params"]) == len(names)
+    fused = FusedAdam(own_model, lr=1e-4)
+    fused.load_state_dict(sd)
+    assert fused.step_count == 3 and fused.lr == 3e-4
+    o = 0
+    by_name = dict(own_model.named_parameters())
+    for p in fused.arena.params:
+        n = next(k for k, v in by_name.items() if v is p)
+        i = names.index(n)
+        k = p.numel()
+        if i in sd["state"]:
+            assert torch.equal(fused.m[o:o + k].view(p.shape), sd["state"][i]["exp_avg"]), n
+            assert torch.equal(fused.v[o:o + k].view(p.shape), sd["state"][i]["exp_avg_sq"]), n
+        else:
+            assert never(n) and float(fused.m[o:o + k].abs().sum()) == 0.0
+        o += k
+    # and back: torch's Adam accepts what FusedAdam writes, with the moments under the same indices
+    back = torch.optim.Adam(ref_model.parameters(), lr=1e-4)
+    out = fused.state_dict()
+    back.load_state_dict(out)
+    assert back.param_groups[0]["lr"] == 3e-4
+    for i, st in sd["state"].items():
+        assert torch.equal(out["state"][i]["exp_avg"], st["exp_avg"]) and float(out["state"][i]["step"]) == 3.0

@@ -69,28 +69,43 @@ class FusedAdam:
                           self.eps, self.step_count, grad_scale, ema_mode, ema_beta)
         self.model.repack()
 
+    def _torch_indices(self):
+        """Index of every arena parameter in `torch.optim.Adam(model.parameters())`'s numbering, and that optimiser's parameter
+        count.  The reference hands ALL parameters to Adam (VDDP:1478), frozen ones included: the shared rotary table sits at
+        index 5 and shifts every later index by one against the arena, which holds trainable tensors only."""
+        pos = {id(p): i for i, p in enumerate(self.model.parameters())}
+        return [pos[id(p)] for p in self.arena.params], len(pos)
+
     def state_dict(self):
+        """Same layout as the reference's `Adam.state_dict()` (parameters that never received a gradient have zero moments here
+        where torch has no entry; torch accepts the extra entries)."""
         self._ensure()
+        index, n_all = self._torch_indices()
         state, o = {}, 0
-        for i, p in enumerate(self.arena.params):
+        for i, p in zip(index, self.arena.params):
             k = p.numel()
             state[i] = dict(step=torch.tensor(float(self.step_count)), exp_avg=self.m[o:o + k].view(p.shape).clone(),
                             exp_avg_sq=self.v[o:o + k].view(p.shape).clone())
             o += k
-        group = dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=0, amsgrad=False, params=list(range(len(self.arena.params))))
+        group = dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=0, amsgrad=False, params=list(range(n_all)))
         return dict(state=state, param_groups=[group])
 
     def load_state_dict(self, sd):
         self._ensure()
-        o = 0
-        for i, p in enumerate(self.arena.params):
+        index, _ = self._torch_indices()
+        o, steps = 0, 0
+        for i, p in zip(index, self.arena.params):
             k = p.numel()
             st = sd["state"].get(i)
             if st is not None:
                 self.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
                 self.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
-                self.step_count = int(st["step"])
+                steps = max(steps, int(st["step"]))          # torch counts per parameter; all used parameters agree
+            else:                                    # torch keeps no state for a parameter that never had a gradient
+                self.m[o:o + k].zero_()
+                self.v[o:o + k].zero_()
             o += k
+        self.step_count = steps
         self.lr = sd["param_groups"][0]["lr"]
 
 
