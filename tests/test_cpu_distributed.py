@@ -110,13 +110,15 @@ def _eval_worker(rank, world, port, workdir, targets, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_eval_target_matches_single_process(tmp_path):
-    """Five conditionings over two ranks (2 + 3, the shorter rank padded for the gather): rank 0 must write the same
-    geometries.csv and GIFs as a single process does (VDDP:1755-1846), and the validation loss is the mean over ranks."""
+@pytest.mark.parametrize("rows", [5, 1])
+def test_two_rank_eval_target_matches_single_process(tmp_path, rows):
+    """Five conditionings over two ranks (2 + 3, the shorter rank padded for the gather), and a single conditioning (rank 0 gets
+    none and contributes an empty, fully padded block): rank 0 must write the same geometries.csv and GIFs as a single process
+    does (VDDP:1755-1846), and the validation loss is the mean over ranks."""
     import numpy as np
     targets = str(tmp_path / "targets.csv")
     rng = np.random.default_rng(0)
-    np.savetxt(targets, np.cumsum(rng.random((5, 11)), axis=1) * 15.0, delimiter=',')
+    np.savetxt(targets, np.cumsum(rng.random((rows, 11)), axis=1) * 15.0, delimiter=',')
     one, two = tmp_path / "one", tmp_path / "two"
     one.mkdir()
     two.mkdir()
@@ -125,7 +127,7 @@ def test_two_rank_eval_target_matches_single_process(tmp_path):
         t, g1 = _eval_target_run(str(one), targets)
     finally:
         os.chdir(cwd)
-    assert tuple(g1.shape) == (5, 3, 11, 12, 12)
+    assert tuple(g1.shape) == (rows, 3, 11, 12, 12)
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -136,12 +138,12 @@ def test_two_rank_eval_target_matches_single_process(tmp_path):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert res[0][1] == res[1][1] == (6, 3, 11, 12, 12)                 # 2 x max(2, 3) rows, one of them padding
+    assert res[0][1] == res[1][1] == (2 * (rows - rows // 2), 3, 11, 12, 12)     # 2 x the longer rank's rows; the rest is padding
     assert res[0][2] and abs(res[0][2][0]['validation loss'] - 0.375) < 1e-6 and not res[1][2]
     sub = "eval_target_w_5.0_0/step_3"
     a = np.genfromtxt(str(one / "run" / sub / "geometries.csv"), delimiter=',')
     b = np.genfromtxt(str(two / "run" / sub / "geometries.csv"), delimiter=',')
-    assert a.shape == b.shape == (5, 36) and np.array_equal(a, b)
+    assert np.atleast_2d(a).shape == np.atleast_2d(b).shape == (rows, 36) and np.array_equal(a, b)
     for ch in (0, 1, 3):
         fa = open(str(one / "run" / sub / f"gifs/prediction_channel_{ch}.gif"), "rb").read()
         fb = open(str(two / "run" / sub / f"gifs/prediction_channel_{ch}.gif"), "rb").read()
