@@ -20,7 +20,8 @@ algorithm (interleaved pairs, theta=10000) and is only checked against the stand
 Everything is written as functions over a flat `state_dict` (the reference's own key names), in
 the reference's `b c f h w` layout, covering the shipped configuration (model.yaml):
 `per_frame_cond=True`, `cond_attention='self-stacked'`, `cond_to_time='add'`,
-`use_temporal_attention_cond=True`, `padding_mode='zeros'`.
+`use_temporal_attention_cond=True`, `padding_mode='zeros'`; plus the two other values of `padding_mode` in the config
+surface ('circular', 'circular_1d'), pinned by tests/golden/padding_modes.pt, which the CUDA path does not implement yet.
 """
 from __future__ import annotations
 
@@ -50,6 +51,7 @@ class UnetCfg:
     groups: int = 8
     init_kernel: int = 7
     frames: int = 11
+    padding_mode: str = "zeros"          # 'zeros' (shipped) | 'circular' | 'circular_1d'  (model.yaml:13, VDDP:153-243)
 
     @property
     def dims(self) -> List[int]:
@@ -119,26 +121,57 @@ def channel_layernorm(x: Tensor, gamma: Tensor, eps: float = 1e-5) -> Tensor:
     return (x - mu) / (var + eps).sqrt() * gamma
 
 
-def conv_frames(x: Tensor, w: Tensor, b: Optional[Tensor], stride: int = 1, pad: int = 0) -> Tensor:
+def pad_frames(x: Tensor, pad: int, mode: str) -> Tensor:
+    """Explicit spatial padding of (..., H, W): 'circular' wraps both pixel axes (nn.Conv3d(padding_mode='circular'), VDDP:240,271),
+    'circular_1d' wraps the horizontal axis and zero-fills the vertical one (Circular_1d_Conv3d, VDDP:219-236)."""
+    if pad == 0:
+        return x
+    if mode == "circular":
+        return F.pad(x, (pad, pad, pad, pad), mode="circular")
+    if mode == "circular_1d":
+        return F.pad(F.pad(x, (pad, pad, 0, 0), mode="circular"), (0, 0, pad, pad))
+    raise ValueError(mode)
+
+
+def conv_frames(x: Tensor, w: Tensor, b: Optional[Tensor], stride: int = 1, pad: int = 0, mode: str = "zeros") -> Tensor:
     """nn.Conv3d with kernel depth 1 == the same 2-D conv on every frame (VDDP:271,241,626)."""
     B, C, Fr, H, W = x.shape
-    y = F.conv2d(x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, H, W), w[:, :, 0], b, stride=stride, padding=pad)
+    x2 = x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, H, W)
+    if mode == "zeros":
+        y = F.conv2d(x2, w[:, :, 0], b, stride=stride, padding=pad)
+    else:
+        y = F.conv2d(pad_frames(x2, pad, mode), w[:, :, 0], b, stride=stride, padding=0)
     return y.reshape(B, Fr, *y.shape[1:]).permute(0, 2, 1, 3, 4)
 
 
-def convT_frames(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
-    """nn.ConvTranspose3d(dim, dim, (1,4,4), (1,2,2), (0,1,1))  VDDP:155."""
+def convT_frames(x: Tensor, w: Tensor, b: Tensor, mode: str = "zeros") -> Tensor:
+    """nn.ConvTranspose3d(dim, dim, (1,4,4), (1,2,2), (0,1,1))  VDDP:155.  The circular variants (CircularUpsample /
+    Circular_1d_Upsample, VDDP:164-216) pad the INPUT by k - 1 - p = 2 pixels and let the transposed conv crop
+    k - 1 + s + p - 1 = 5 output pixels per side, which leaves exactly 2H x 2W."""
     B, C, Fr, H, W = x.shape
-    y = F.conv_transpose2d(x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, H, W), w[:, :, 0], b, stride=2, padding=1)
+    x2 = x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, H, W)
+    if mode == "zeros":
+        y = F.conv_transpose2d(x2, w[:, :, 0], b, stride=2, padding=1)
+    else:
+        y = F.conv_transpose2d(pad_frames(x2, 2, mode), w[:, :, 0], b, stride=2, padding=5)
     return y.reshape(B, Fr, *y.shape[1:]).permute(0, 2, 1, 3, 4)
+
+
+def conv_key(cfg_mode: str, kind: str) -> str:
+    """Infix of a convolution's state_dict key: the reference wraps the conv in a module for 'circular_1d'
+    (`.conv.`, VDDP:223) and for both circular upsamplers (`.conv_transpose.`, VDDP:181,204)."""
+    if kind == "up":
+        return "" if cfg_mode == "zeros" else "conv_transpose."
+    return "conv." if cfg_mode == "circular_1d" else ""
 
 
 # ----------------------------------------------------------------------------------------------
 # ResnetBlock  (VDDP:267-311)
 # ----------------------------------------------------------------------------------------------
-def block(P: Params, pre: str, x: Tensor, groups: int, scale_shift=None) -> Tensor:
+def block(P: Params, pre: str, x: Tensor, groups: int, scale_shift=None, mode: str = "zeros") -> Tensor:
     """conv(1,3,3) -> GroupNorm(groups) over (C/g, f, h, w) -> x*(scale+1)+shift -> SiLU.  VDDP:277-285."""
-    x = conv_frames(x, P[pre + "proj.weight"], P[pre + "proj.bias"], pad=1)
+    k = pre + "proj." + conv_key(mode, "conv")
+    x = conv_frames(x, P[k + "weight"], P[k + "bias"], pad=1, mode=mode)
     x = F.group_norm(x, groups, P[pre + "norm.weight"], P[pre + "norm.bias"], eps=1e-5)
     if scale_shift is not None:
         scale, shift = scale_shift
@@ -146,15 +179,15 @@ def block(P: Params, pre: str, x: Tensor, groups: int, scale_shift=None) -> Tens
     return F.silu(x)
 
 
-def resnet_block(P: Params, pre: str, x: Tensor, temb: Optional[Tensor], groups: int) -> Tensor:
+def resnet_block(P: Params, pre: str, x: Tensor, temb: Optional[Tensor], groups: int, mode: str = "zeros") -> Tensor:
     """VDDP:299-311."""
     ss = None
     if (pre + "mlp.1.weight") in P:
         e = F.linear(F.silu(temb), P[pre + "mlp.1.weight"], P[pre + "mlp.1.bias"])
         e = e[:, :, None, None, None]
         ss = e.chunk(2, dim=1)
-    h = block(P, pre + "block1.", x, groups, ss)
-    h = block(P, pre + "block2.", h, groups)
+    h = block(P, pre + "block1.", x, groups, ss, mode)
+    h = block(P, pre + "block2.", h, groups, None, mode)
     if (pre + "res_conv.weight") in P:
         x = conv_frames(x, P[pre + "res_conv.weight"], P[pre + "res_conv.bias"])
     return h + x
@@ -281,9 +314,10 @@ def conditioning(P: Params, cfg: UnetCfg, time: Tensor, cond: Tensor, null_mask:
 # Unet3D.forward  (VDDP:730-821)
 # ----------------------------------------------------------------------------------------------
 def unet_forward(P: Params, cfg: UnetCfg, x: Tensor, time: Tensor, cond: Tensor, null_mask: Tensor) -> Tensor:
-    g = cfg.groups
+    g, pm = cfg.groups, cfg.padding_mode
+    ck, uk = conv_key(pm, "conv"), conv_key(pm, "up")
     bias = time_pos_bias(P, x.shape[2])
-    x = conv_frames(x, P["init_conv.weight"], P["init_conv.bias"], pad=cfg.init_kernel // 2)
+    x = conv_frames(x, P["init_conv." + ck + "weight"], P["init_conv." + ck + "bias"], pad=cfg.init_kernel // 2, mode=pm)
     x = temporal_block(P, "init_temporal_attn.", x, cfg, bias, None)       # no conditioning here  VDDP:743
     r = x
     t, tok = conditioning(P, cfg, time, cond, null_mask)
@@ -291,28 +325,28 @@ def unet_forward(P: Params, cfg: UnetCfg, x: Tensor, time: Tensor, cond: Tensor,
     L = cfg.levels
     for i in range(L):
         p = f"downs.{i}."
-        x = resnet_block(P, p + "0.", x, t, g)
-        x = resnet_block(P, p + "1.", x, t, g)
+        x = resnet_block(P, p + "0.", x, t, g, pm)
+        x = resnet_block(P, p + "1.", x, t, g, pm)
         x = linear_block(P, p + "2.", x, cfg, tok)
         x = temporal_block(P, p + "3.", x, cfg, bias, tok)
         skips.append(x)
         if i < L - 1:
-            x = conv_frames(x, P[p + "4.weight"], P[p + "4.bias"], stride=2, pad=1)   # Downsample VDDP:241
-    x = resnet_block(P, "mid_block1.", x, t, g)
+            x = conv_frames(x, P[p + "4." + ck + "weight"], P[p + "4." + ck + "bias"], stride=2, pad=1, mode=pm)   # Downsample VDDP:238-243
+    x = resnet_block(P, "mid_block1.", x, t, g, pm)
     x = mid_spatial_block(P, "mid_spatial_attn.", x, cfg, tok)
     x = temporal_block(P, "mid_temporal_attn.", x, cfg, bias, tok)
-    x = resnet_block(P, "mid_block2.", x, t, g)
+    x = resnet_block(P, "mid_block2.", x, t, g, pm)
     for i in range(L):
         p = f"ups.{i}."
         x = torch.cat((x, skips.pop()), dim=1)
-        x = resnet_block(P, p + "0.", x, t, g)
-        x = resnet_block(P, p + "1.", x, t, g)
+        x = resnet_block(P, p + "0.", x, t, g, pm)
+        x = resnet_block(P, p + "1.", x, t, g, pm)
         x = linear_block(P, p + "2.", x, cfg, tok)
         x = temporal_block(P, p + "3.", x, cfg, bias, tok)
         if i < L - 1:
-            x = convT_frames(x, P[p + "4.weight"], P[p + "4.bias"])                    # Upsample VDDP:155
+            x = convT_frames(x, P[p + "4." + uk + "weight"], P[p + "4." + uk + "bias"], pm)      # Upsample VDDP:153-160
     x = torch.cat((x, r), dim=1)
-    x = resnet_block(P, "final_conv.0.", x, None, g)
+    x = resnet_block(P, "final_conv.0.", x, None, g, pm)
     return conv_frames(x, P["final_conv.1.weight"], P["final_conv.1.bias"])
 
 
@@ -498,8 +532,9 @@ def unet_param_shapes(cfg: UnetCfg) -> Dict[str, Tuple[int, ...]]:
     S["null_text_token"] = (1, cfg.frames, td)
     S["null_text_hidden"] = (1, td)
     S["time_rel_pos_bias.relative_attention_bias.weight"] = (32, cfg.heads)
-    S["init_conv.weight"] = (D, cfg.channels, 1, cfg.init_kernel, cfg.init_kernel)
-    S["init_conv.bias"] = (D,)
+    ck, uk = conv_key(cfg.padding_mode, "conv"), conv_key(cfg.padding_mode, "up")
+    S["init_conv." + ck + "weight"] = (D, cfg.channels, 1, cfg.init_kernel, cfg.init_kernel)
+    S["init_conv." + ck + "bias"] = (D,)
 
     def temporal(pre, c):
         a = pre + "fn.fn.fn."
@@ -535,8 +570,8 @@ def unet_param_shapes(cfg: UnetCfg) -> Dict[str, Tuple[int, ...]]:
             S[pre + "mlp.1.weight"] = (2 * co, td)
             S[pre + "mlp.1.bias"] = (2 * co,)
         for blk, c_in in (("block1.", ci), ("block2.", co)):
-            S[pre + blk + "proj.weight"] = (co, c_in, 1, 3, 3)
-            S[pre + blk + "proj.bias"] = (co,)
+            S[pre + blk + "proj." + ck + "weight"] = (co, c_in, 1, 3, 3)
+            S[pre + blk + "proj." + ck + "bias"] = (co,)
             S[pre + blk + "norm.weight"] = (co,)
             S[pre + blk + "norm.bias"] = (co,)
         if ci != co:
@@ -570,8 +605,8 @@ def unet_param_shapes(cfg: UnetCfg) -> Dict[str, Tuple[int, ...]]:
         linear(p + "2.", co)
         temporal(p + "3.", co)
         if i < L - 1:
-            S[p + "4.weight"] = (co, co, 1, 4, 4)
-            S[p + "4.bias"] = (co,)
+            S[p + "4." + ck + "weight"] = (co, co, 1, 4, 4)
+            S[p + "4." + ck + "bias"] = (co,)
     for i, (ci, co) in enumerate(reversed(io)):
         p = f"ups.{i}."
         resnet(p + "0.", co * 2, ci)
@@ -579,8 +614,8 @@ def unet_param_shapes(cfg: UnetCfg) -> Dict[str, Tuple[int, ...]]:
         linear(p + "2.", ci)
         temporal(p + "3.", ci)
         if i < L - 1:
-            S[p + "4.weight"] = (ci, ci, 1, 4, 4)
-            S[p + "4.bias"] = (ci,)
+            S[p + "4." + uk + "weight"] = (ci, ci, 1, 4, 4)
+            S[p + "4." + uk + "bias"] = (ci,)
     # the reference creates `downs` and `ups` (VDDP:664-665) before the mid blocks (VDDP:684-692)
     mid = dims[-1]
     resnet("mid_block1.", mid, mid)
