@@ -253,3 +253,30 @@ def test_caches_filled_by_a_sampler_can_be_used_for_training():
     ss, ekv, bias, rot = blocks.conditioning(model, time, cond, mask, 11)
     (sum(v.sum() for v in ss.values()) + sum(v.sum() for v in ekv.values()) + bias.sum()).backward()
     assert float(model.time_rel_pos_bias.relative_attention_bias.weight.grad.abs().sum()) > 0
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/vmm.h is the boundary a maintainer binds: it must compile as C99 and as C++, and a C program using it must link
+    against libvmm_sm100.so and run the housekeeping entry points (no GPU needed for those)."""
+    import shutil
+    import subprocess
+    from videometamaterials_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "vmm.h"\n'
+                   'int main(void) { vmm_cgemm_params p; p.n_views = 0; (void)p;\n'
+                   '  printf("%d %llu %s\\n", vmm_abi_version(), (unsigned long long)vmm_launch_count(), vmm_last_error() ? "err-ok" : "null");\n'
+                   '  /* a compute call without a device (or with null pointers) must be rejected, not crash */\n'
+                   '  return vmm_colsum(0, 0, 0, 0, 0, 0, 0) == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    if shutil.which("g++"):
+        subprocess.run(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH),
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out
+    assert out.stdout.split()[0] == "1" and out.stdout.split()[2] == "err-ok"
