@@ -153,3 +153,75 @@ def test_two_rank_eval_target_matches_single_process(tmp_path, rows):
     for root in (one, two):
         assert np.genfromtxt(str(root / "run" / "training/step_3" / "geometries.csv"), delimiter=',').shape == (3, 36)
         assert all(os.path.getsize(str(root / "run" / "training/step_3" / f"gifs/prediction_channel_{ch}.gif")) > 0 for ch in (0, 1, 3))
+
+
+def _rank_loss(self, x, *args, **kwargs):
+    """0.5 |w|^2 * (1 + rank): rank-dependent gradients (rank + 1) * w, whose mean over two ranks is 1.5 w."""
+    import torch.distributed as dist
+    w = self.denoise_fn.init_conv.weight
+    return 0.5 * (1 + dist.get_rank()) * (w ** 2).sum() + 0.0 * x.mean()
+
+
+def _train_worker(rank, world, port, workdir, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import Accelerator, GaussianDiffusion, Trainer, Unet3D, ops
+    os.chdir(workdir)
+    GaussianDiffusion.forward = _rank_loss
+    GaussianDiffusion.sample = lambda self, cond=None, batch_size=16, guidance_scale=1.: _stub_sample(cond, guidance_scale)
+    ops.adam_ema_step = lambda p, g, m, v, ema, lr, b1, b2, eps, step, gs, mode, beta: \
+        O.adam_ema_step(p, g, m, v, ema, step, lr=lr, beta1=b1, beta2=b2, eps=eps, grad_scale=gs, ema_mode=mode, ema_beta=beta)
+    torch.manual_seed(100 + rank)                     # different initial weights per rank: prepare() broadcasts rank 0's
+    m = Unet3D(dim=16, dim_mults=(1, 2), channels=3, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, per_frame_cond=True)
+    gd = GaussianDiffusion(m, image_size=12, channels=3, num_frames=11, timesteps=8, use_dynamic_thres=True, sampling_timesteps=8)
+    t = Trainer(gd, None, None, [0, 1, 3], train_batch_size=2, test_batch_size=4, train_lr=1e-2, train_num_steps=4, step_start_ema=2,
+                update_ema_every=2, save_and_sample_every=100, results_folder='run', log=True, null_cond_prob=0.1, per_frame_cond=True,
+                reference_frame='lagrangian', accelerator=Accelerator(cpu=True), log_every=1)
+    w0 = t.model.denoise_fn.init_conv.weight.detach().clone()
+    seen = []
+    dl = t.dl
+
+    def recording():
+        while True:
+            x, c = next(dl)
+            seen.append(c.clone())
+            yield x, c
+    t.dl = recording()
+    t.train(num_samples=0)
+    q.put((rank, w0, t.model.denoise_fn.init_conv.weight.detach().clone(), t.ema_model.denoise_fn.init_conv.weight.detach().clone(),
+           torch.cat(seen), os.path.isfile("run/model/step_4/checkpoint.pt")))
+    dist.destroy_process_group()
+
+
+def test_two_rank_training_loop(tmp_path):
+    """Trainer.train on two gloo ranks with a stub loss: both ranks start from rank 0's weights, see disjoint shards of the data,
+    apply the MEAN of their gradients (VDDP:1629 through DDP; here one all-reduce over the arena) and stay bit-identical; the
+    trajectory equals torch.optim.Adam on the averaged gradient, the EMA follows the reference's cadence, one checkpoint is written."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, w0a, wa, ea, ca, cka), (_, w0b, wb, eb, cb, ckb) = res
+    assert torch.equal(w0a, w0b) and torch.equal(wa, wb) and torch.equal(ea, eb)
+    assert cka and ckb                                          # rank 0 wrote it; both see the same folder
+    # disjoint data shards: no conditioning row was seen by both ranks within the first epoch (5 steps x 2 clips of 512 each)
+    rows_a, rows_b = {tuple(r.tolist()) for r in ca}, {tuple(r.tolist()) for r in cb}
+    assert len(rows_a) == len(rows_b) == 10 and not (rows_a & rows_b)
+    w = torch.nn.Parameter(w0a.clone())
+    opt = torch.optim.Adam([w], lr=1e-2)
+    ema = w0a.clone()
+    for step in range(5):                                       # steps 0..4 inclusive
+        w.grad = 1.5 * w.detach()
+        opt.step()
+        if step % 2 == 0:
+            ema = w.detach().clone() if step < 2 else ema * 0.995 + (1 - 0.995) * w.detach()
+    assert torch.allclose(wa, w.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ea, ema, rtol=1e-5, atol=1e-6)

@@ -209,6 +209,7 @@ class Trainer(object):
             obj = dict(model=self.model.state_dict(), optimizer=self.opt.state_dict(), steps=self.step, ema=self.ema_model.state_dict())
             with open(save_dir + '/checkpoint.pt', 'wb') as f:
                 torch.save(obj, f)
+        self.accelerator.wait_for_everyone()      # the file is complete before any rank goes on (e.g. to load it)
         self.accelerator.print(f'checkpoint saved to {save_dir}/checkpoint.pt')
 
     def load(self, strict=True):
