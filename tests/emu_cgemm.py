@@ -60,3 +60,26 @@ def cgemm(views: Sequence[torch.Tensor], taps, w: torch.Tensor, n: int, out: tor
         else:
             o[rows, :nsplit] = acc2[:, :nsplit].to(out.dtype)
             out2.reshape(-1, out2.shape[-1])[rows, :n - nsplit] = acc2[:, nsplit:].to(out2.dtype)
+
+
+def wgrad(a_views, b_views, taps, n: int, dw: torch.Tensor, s_m: int, s_c: int, grid: Tuple[int, int, int], *, s_c2: int = 0, cmod: int = 0,
+          c_valid: int = 0, k_valid: int = 0, tile=None) -> None:
+    """The `vmm_wgrad` contract: for every tap (a_src, b_src, dy, dx, c, wofs)
+        dw.flat[wofs + m * s_m + col(j)] += sum_pix A[pix, m] * B[pix + (dy, dx), j],   m < n, j < c
+    over the pixel grid of the a views, reads of B outside its view being zero; col(j) = j * s_c, or with cmod > 0
+    (j % cmod) * s_c + (j // cmod) * s_c2 restricted to j % cmod < c_valid and j // cmod < k_valid."""
+    bf, oh, ow = grid
+    flat = dw.reshape(-1)
+    for (a_src, b_src, dy, dx, c, wofs) in taps:
+        a = a_views[a_src].float().reshape(-1, a_views[a_src].shape[-1])[:, :n] if a_views[a_src].shape[:3] == (bf, oh, ow) \
+            else _window(a_views[a_src], 0, 0, oh, ow).reshape(-1, a_views[a_src].shape[-1])[:, :n]
+        b = _window(b_views[b_src], dy, dx, oh, ow)[..., :c].reshape(-1, c)
+        g = a.t() @ b                                              # (n, c)
+        j = torch.arange(c)
+        if cmod > 0:
+            col = (j % cmod) * s_c + (j // cmod) * s_c2
+            ok = ((j % cmod) < c_valid) & ((j // cmod) < k_valid)
+        else:
+            col, ok = j * s_c, torch.ones(c, dtype=torch.bool)
+        idx = wofs + torch.arange(n)[:, None] * s_m + col[None, :]
+        flat.index_put_((idx[:, ok].reshape(-1),), g[:, ok].reshape(-1), accumulate=True)

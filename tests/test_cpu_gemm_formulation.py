@@ -134,3 +134,69 @@ def test_wrap_padded_view_gives_circular_convolution(ops):
     ops.cgemm([xp], [taps], ops.pack_conv_taps(wt, [c], torch.float32), n, out, (bf, h, w), gn_stats=stats, gn_group=n, frames_per_sample=1)
     assert close(out, cl(y))
     assert torch.allclose(stats[:, 0, 0], cl(y).double().sum(dim=(1, 2, 3)), rtol=1e-6, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# weight gradients: the tap tables of ops.wgrad_* must scatter dY^T X into the master (torch) weight layout
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture
+def ops_w(monkeypatch):
+    from videometamaterials_b200 import ops
+    monkeypatch.setattr(ops, "cgemm", emu_cgemm.cgemm)
+    monkeypatch.setattr(ops, "wgrad", emu_cgemm.wgrad)
+    return ops
+
+
+def test_weight_gradient_tap_tables(ops_w):
+    ops = ops_w
+    g = torch.Generator().manual_seed(12)
+    bf, h, w = 2, 6, 10
+    # 3x3 conv over two concatenated sources (VDDP:271 after the skip concat VDDP:813)
+    cins, cout = [8, 24], 16
+    xs = [torch.randn(bf, c, h, w, generator=g) for c in cins]
+    wt = (torch.randn(cout, sum(cins), 1, 3, 3, generator=g) * 0.1).requires_grad_(True)
+    dy = torch.randn(bf, cout, h, w, generator=g)
+    F.conv2d(torch.cat(xs, 1), wt[:, :, 0], None, padding=1).backward(dy)
+    dw = torch.full_like(wt.detach(), 0.5)                        # accumulated into, not overwritten
+    ops.wgrad_conv3x3(cl(dy), [cl(t) for t in xs], dw)
+    assert close(dw - 0.5, wt.grad, 1e-4)
+    # linear layer, both operand orders of wgrad_linear (n > k puts the narrow operand on the row side)
+    for n, k in ((40, 24), (16, 72)):
+        x2, dy2 = torch.randn(90, k, generator=g), torch.randn(90, n, generator=g)
+        dwl = torch.zeros(n, k)
+        ops.wgrad_linear(dy2, [x2], dwl)
+        assert close(dwl, dy2.t() @ x2, 1e-4)
+    xa, xb, dy2 = torch.randn(90, 8, generator=g), torch.randn(90, 24, generator=g), torch.randn(90, 16, generator=g)
+    dwl = torch.zeros(16, 32, 1, 1, 1)                            # res_conv weight shape
+    ops.wgrad_linear(dy2, [xa, xb], dwl)
+    assert close(dwl.reshape(16, 32), dy2.t() @ torch.cat((xa, xb), 1), 1e-4)
+    # Downsample (strided 4x4) and Upsample (transposed 4x4)
+    c = 12
+    x = torch.randn(bf, c, h, w, generator=g)
+    wd_ = (torch.randn(c, c, 1, 4, 4, generator=g) * 0.1).requires_grad_(True)
+    yd = F.conv2d(x, wd_[:, :, 0], None, stride=2, padding=1)
+    dyd = torch.randn_like(yd)
+    yd.backward(dyd)
+    dwd = torch.zeros_like(wd_.detach())
+    ops.wgrad_down(cl(dyd), cl(x), dwd)
+    assert close(dwd, wd_.grad, 1e-4)
+    wu_ = (torch.randn(c, c, 1, 4, 4, generator=g) * 0.1).requires_grad_(True)
+    yu = F.conv_transpose2d(x, wu_[:, :, 0], None, stride=2, padding=1)
+    dyu = torch.randn_like(yu)
+    yu.backward(dyu)
+    dwu = torch.zeros_like(wu_.detach())
+    ops.wgrad_up(cl(dyu), cl(x), dwu)
+    assert close(dwu, wu_.grad, 1e-4)
+    # init_conv (1,7,7) on the prepared 8-channel layout: only (kx < 7, ch < 3) columns of the 64-wide window land in dw
+    ch, n = 3, 16
+    xi = torch.randn(bf, ch, h, w, generator=g)
+    wi = (torch.randn(n, ch, 1, 7, 7, generator=g) * 0.1).requires_grad_(True)
+    yi = F.conv2d(xi, wi[:, :, 0], None, padding=3)
+    dyi = torch.randn_like(yi)
+    yi.backward(dyi)
+    xin = torch.zeros(bf, h, w + 6, 8)
+    xin[:, :, 3:3 + w, :ch] = cl(xi)
+    xin = torch.cat((xin.reshape(-1), torch.zeros(8)))
+    dwi = torch.zeros_like(wi.detach())
+    ops.wgrad_init_conv(cl(dyi), xin, dwi, ch)
+    assert close(dwi, wi.grad, 1e-4)
