@@ -25,7 +25,6 @@ def _window(view: torch.Tensor, dy: int, dx: int, oh: int, ow: int) -> torch.Ten
 def cgemm(views: Sequence[torch.Tensor], taps, w: torch.Tensor, n: int, out: torch.Tensor, grid: Tuple[int, int, int], *,
           out_geom: Optional[Tuple[int, int, int, int]] = None, phase_off=None, bias=None, res=None, gn_stats=None, gn_group: int = 0,
           frames_per_sample: int = 1, out2=None, nsplit: int = 0, tile=None, res2=None, alpha: float = 1.0, rot=None) -> None:
-    assert rot is None, "the rotary epilogue is not part of this emulation"
     bf, oh, ow = grid
     ohs, ows, sy, sx = out_geom if out_geom is not None else (oh, ow, 1, 1)
     W = w.float()
@@ -50,6 +49,17 @@ def cgemm(views: Sequence[torch.Tensor], taps, w: torch.Tensor, n: int, out: tor
             else:
                 acc2 = torch.cat((acc2[:, :nsplit] + r[rows][:, :nsplit],
                                   acc2[:, nsplit:] + res2.reshape(-1, res2.shape[-1]).float()[rows][:, :n - nsplit]), dim=1)
+        if rot is not None:
+            # rotary epilogue (vmm_cgemm_params.rot): columns [0, rot_cols) are rotated in interleaved pairs of every 32-wide head
+            # slice by the angle of the row's frame f = (row / rot_hw) % rot_frames; columns < rot_qcols use table 0 (pre-scaled)
+            tab, rot_frames, rot_hw, rot_cols, rot_qcols = rot
+            f = (rows // rot_hw) % rot_frames
+            head = acc2[:, :rot_cols].reshape(-1, rot_cols // 32, 16, 2)
+            which = (torch.arange(rot_cols // 32) * 32 >= rot_qcols).long()                    # per head slice: table 0 or 1
+            cs = tab[which[None, :], f[:, None]]                                                # (rows, heads, 16, 2)
+            xe, xo = head[..., 0], head[..., 1]
+            turned = torch.stack((xe * cs[..., 0] - xo * cs[..., 1], xo * cs[..., 0] + xe * cs[..., 1]), dim=-1)
+            acc2 = torch.cat((turned.reshape(-1, rot_cols), acc2[:, rot_cols:]), dim=1)
         if gn_stats is not None:
             g = acc2.reshape(bf // frames_per_sample, -1, n // gn_group, gn_group).double()
             gn_stats[..., 0] += g.sum(dim=(1, 3))
