@@ -101,3 +101,137 @@ def install(monkeypatch, ops):
     monkeypatch.setattr(ops, "cgemm", emu_cgemm.cgemm)
     for name in ("gn_silu_fwd", "ln_fwd", "tattn_fwd", "lattn_fwd", "sattn_fwd", "prep_input"):
         monkeypatch.setattr(ops, name, globals()[name])
+
+
+# ------------------------------------------------------------------------------------------------
+# backward entry points: torch autograd of the forward statements above, written into the caller's buffers with the
+# accumulate / overwrite conventions of include/vmm.h
+# ------------------------------------------------------------------------------------------------
+def colsum(x2d, out):
+    out += x2d.float().sum(dim=0)[: out.numel()]
+
+
+def gn_silu_bwd(x, dy, dx, stats, gamma, beta, scale_shift, B, pix, C_, groups, dgamma, dbeta, dss, act=True, eps=1e-5, dx_colsum=None):
+    with torch.enable_grad():
+        xf = x.detach().float().reshape(B, pix, C_).requires_grad_(True)
+        g_, b_ = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+        ss_ = scale_shift.detach().clone().requires_grad_(True) if scale_shift is not None else None
+        y = F.group_norm(xf.transpose(1, 2), groups, g_, b_, eps=eps).transpose(1, 2)
+        if ss_ is not None:
+            y = y * (ss_[:, None, :C_] + 1) + ss_[:, None, C_:]
+        if act:
+            y = F.silu(y)
+        y.backward(dy.detach().float().reshape(B, pix, C_))
+    dx.copy_(xf.grad.reshape(dx.shape).to(dx.dtype))
+    dgamma += g_.grad
+    dbeta += b_.grad
+    if dss is not None:
+        dss.copy_(ss_.grad)
+    if dx_colsum is not None:
+        dx_colsum += xf.grad.sum(dim=(0, 1))
+
+
+def ln_bwd(x2d, dy2d, dres2d, dx2d, gamma, dgamma, eps=1e-5):
+    with torch.enable_grad():
+        xf = x2d.detach().float().requires_grad_(True)
+        g_ = gamma.detach().clone().requires_grad_(True)
+        y = (xf - xf.mean(1, keepdim=True)) / (xf.var(1, unbiased=False, keepdim=True) + eps).sqrt() * g_
+        y.backward(dy2d.detach().float())
+    d = xf.grad if dres2d is None else xf.grad + dres2d.float()
+    dx2d.copy_(d.to(dx2d.dtype))
+    dgamma += g_.grad
+
+
+def _unturn(x, rot):
+    """Inverse of _turn (rotation by the negative angle)."""
+    return _turn(x, torch.stack((rot[..., 0], -rot[..., 1]), dim=-1))
+
+
+def tattn_bwd(qkv, ekv, bias, rot, dout, dqkv, dekv, dbias, B, frames, HW, heads, pre_rotated=False):
+    """dqkv is the gradient with respect to the PLAIN projection rows: with pre_rotated the stored q / k rows are rotated (q also
+    scaled) and the kernel turns dq / dk back."""
+    hd = heads * 32
+    rows = qkv.detach().float().reshape(B * frames * HW, 3 * hd)
+    if pre_rotated:
+        q, k, v = (t.reshape(B, frames, HW, heads, 32) for t in rows.chunk(3, dim=-1))
+        r = rot[None, :, None, None]                                  # frames on dim 1 here
+        unq = _turn(q, torch.stack((r[..., 0], -r[..., 1]), -1)) / 32 ** -0.5
+        unk = _turn(k, torch.stack((r[..., 0], -r[..., 1]), -1))
+        rows = torch.cat((unq.reshape(-1, hd), unk.reshape(-1, hd), v.reshape(-1, hd)), dim=-1)
+    with torch.enable_grad():
+        rows = rows.requires_grad_(True)
+        e_ = ekv.detach().float().clone().requires_grad_(True) if ekv is not None else None
+        b_ = bias.detach().clone().requires_grad_(True)
+        out = torch.empty(B, frames, HW, hd)
+        o = _tattn_math(rows, e_, b_, rot, B, frames, HW, heads)
+        o.backward(dout.detach().float().reshape(o.shape))
+    dqkv.copy_(rows.grad.reshape(dqkv.shape).to(dqkv.dtype))
+    if dekv is not None:
+        dekv += e_.grad.to(dekv.dtype)
+    dbias += b_.grad
+
+
+def _tattn_math(rows, ekv, bias, rot, B, frames, HW, heads):
+    hd = heads * 32
+    q, k, v = (t.reshape(B, frames, HW, heads, 32).permute(0, 2, 3, 1, 4) for t in rows.chunk(3, dim=-1))
+    q, k = _turn(q * 32 ** -0.5, rot), _turn(k, rot)
+    b2 = bias
+    if ekv is not None:
+        T = ekv.shape[1]
+        ek = ekv[..., :hd].reshape(B, 1, T, heads, 32).transpose(2, 3).expand(B, HW, heads, T, 32)
+        ev = ekv[..., hd:].reshape(B, 1, T, heads, 32).transpose(2, 3).expand(B, HW, heads, T, 32)
+        k, v = torch.cat((ek, k), -2), torch.cat((ev, v), -2)
+        b2 = torch.cat((bias, bias), -1)
+    sim = torch.einsum("...id,...jd->...ij", q, k) + b2
+    o = torch.einsum("...ij,...jd->...id", sim.softmax(-1), v)       # (B, HW, heads, frames, 32)
+    return o.permute(0, 3, 1, 2, 4).reshape(B, frames, HW, hd)
+
+
+def lattn_bwd(qkv, ekv, T, dout, ctx, kstat, dctx, dqkv, dekv, BF, frames, HW, heads):
+    hd = heads * 32
+    B = BF // frames
+    with torch.enable_grad():
+        rows = qkv.detach().float().reshape(BF * HW, 3 * hd).requires_grad_(True)
+        e_ = ekv.detach().float().clone().requires_grad_(True)
+        q, k, v = (t.reshape(BF, HW, heads, 32).permute(0, 2, 3, 1) for t in rows.chunk(3, dim=-1))
+        ek = e_[..., :hd].reshape(B, 1, T, heads, 32).expand(B, frames, T, heads, 32).permute(0, 1, 3, 4, 2).reshape(BF, heads, 32, T)
+        ev = e_[..., hd:].reshape(B, 1, T, heads, 32).expand(B, frames, T, heads, 32).permute(0, 1, 3, 4, 2).reshape(BF, heads, 32, T)
+        c = torch.einsum("bhdn,bhen->bhde", torch.cat((ek, k), -1).softmax(-1), torch.cat((ev, v), -1) / HW)
+        o = torch.einsum("bhde,bhdn->bhen", c, q.softmax(-2) * 32 ** -0.5).permute(0, 3, 1, 2)
+        o.backward(dout.detach().float().reshape(o.shape))
+    dctx.zero_()
+    dqkv.copy_(rows.grad.reshape(dqkv.shape).to(dqkv.dtype))
+    dekv += e_.grad.to(dekv.dtype)
+
+
+def sattn_bwd(qkv, ekv, aout, dout, lse, dqkv, dekv, BF, HW, heads):
+    hd = heads * 32
+    with torch.enable_grad():
+        rows = qkv.detach().float().reshape(BF * HW, 3 * hd).requires_grad_(True)
+        e_ = ekv.detach().float().clone().requires_grad_(True)
+        q, k, v = (t.reshape(BF, HW, heads, 32).transpose(1, 2) for t in rows.chunk(3, dim=-1))
+        ek = e_[..., :hd].reshape(BF, 1, heads, 32).transpose(1, 2)
+        ev = e_[..., hd:].reshape(BF, 1, heads, 32).transpose(1, 2)
+        sim = torch.einsum("bhid,bhjd->bhij", q * 32 ** -0.5, torch.cat((ek, k), -2))
+        o = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), torch.cat((ev, v), -2)).transpose(1, 2)
+        o.backward(dout.detach().float().reshape(o.shape))
+    dqkv.copy_(rows.grad.reshape(dqkv.shape).to(dqkv.dtype))
+    dekv += e_.grad.to(dekv.dtype)
+
+
+def loss_fwd_bwd(pred, target, loss_sum, dpred, B, C_, F_, H, W, l2=False, grad_scale=1.0):
+    d = pred.float().reshape(B, F_, H, W, C_) - target.float().permute(0, 2, 3, 4, 1)
+    n = d.numel()
+    loss_sum += ((d * d).sum() if l2 else d.abs().sum()) / n
+    if dpred is not None:
+        g = (2.0 * d if l2 else torch.sign(d)) * (grad_scale / n)
+        dpred.zero_()
+        dpred[:, :C_] = g.reshape(-1, C_).to(dpred.dtype)
+
+
+def install_training(monkeypatch, ops):
+    """Forward and backward wrappers (everything blocks_bwd.training_loss launches)."""
+    install(monkeypatch, ops)
+    monkeypatch.setattr(ops, "wgrad", emu_cgemm.wgrad)
+    for name in ("colsum", "gn_silu_bwd", "ln_bwd", "tattn_bwd", "lattn_bwd", "sattn_bwd", "loss_fwd_bwd"):
+        monkeypatch.setattr(ops, name, globals()[name])
