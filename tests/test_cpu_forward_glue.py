@@ -76,7 +76,7 @@ def test_training_glue_matches_oracle_gradients(monkeypatch):
         a, s = S["sqrt_alphas_cumprod"][t].contiguous(), S["sqrt_one_minus_alphas_cumprod"][t].contiguous()
         loss = blocks_bwd.training_loss(model, (x01 * 2 - 1).as_subclass(_ClaimsCuda), noise, (a, None, s), t, cond, mask)
         loss.backward()
-        assert abs(float(loss) - float(want)) < 1e-5 * float(want)
+        assert abs(float(loss.detach()) - float(want.detach())) < 1e-5 * float(want.detach())
         worst = (0.0, None)
         for k, p in model.named_parameters():
             ref = P[k].grad
@@ -85,4 +85,4 @@ def test_training_glue_matches_oracle_gradients(monkeypatch):
                 continue
             e = float((p.grad - ref).norm() / ref.norm())
             worst = max(worst, (e, k))
-        assert worst[0] < 2e-3, (pre_rot, worst)
+        assert worst[0] < 1e-4, (pre_rot, worst)            # measured 3e-6 over 196 parameter tensors
