@@ -235,3 +235,40 @@ def install_training(monkeypatch, ops):
     monkeypatch.setattr(ops, "wgrad", emu_cgemm.wgrad)
     for name in ("colsum", "gn_silu_bwd", "ln_bwd", "tattn_bwd", "lattn_bwd", "sattn_bwd", "loss_fwd_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler entry points (fp32 tensors in the reference (B, C, F, H, W) layout; the network output arrives channels-last)
+# ------------------------------------------------------------------------------------------------
+def cfg_x0(x, eps_cl, has_null, w, sr, srm1, x0, eps_out, B, C_, F_, H, W):
+    e = eps_cl.float().reshape(-1, F_, H, W, C_).permute(0, 4, 1, 2, 3)
+    ec = e[:B]
+    if has_null:
+        en = e[B:2 * B]
+        ec = en + (ec - en) * w
+    if eps_out is not None:
+        eps_out.copy_(ec)
+    x0.copy_(sr.view(-1, 1, 1, 1, 1) * x - srm1.view(-1, 1, 1, 1, 1) * ec)
+
+
+def abs_quantile(v, B, n, k, frac, floor_val, s_out):
+    srt = v.reshape(B, n).abs().sort(dim=1).values
+    lo, hi = srt[:, k], srt[:, min(k + 1, n - 1)]
+    s_out.copy_(torch.lerp(lo, hi, torch.tensor(frac)).clamp(min=floor_val))
+
+
+def posterior_step(x0, x, noise, s, c1, c2, sig, out, B, per):
+    xc = x0.reshape(B, per)
+    if s is not None:
+        xc = torch.minimum(torch.maximum(xc, -s[:, None]), s[:, None]) / s[:, None]
+    out.copy_((c1[:, None] * xc + c2[:, None] * x.reshape(B, per) + sig[:, None] * noise.reshape(B, per)).reshape(out.shape))
+
+
+def axpby(a, b, ca, cb, cc, out):
+    out.copy_(ca * a + cb * b + cc)
+
+
+def install_sampler(monkeypatch, ops):
+    install(monkeypatch, ops)
+    for name in ("cfg_x0", "abs_quantile", "posterior_step", "axpby"):
+        monkeypatch.setattr(ops, name, globals()[name])

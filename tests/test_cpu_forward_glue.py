@@ -86,3 +86,69 @@ def test_training_glue_matches_oracle_gradients(monkeypatch):
             e = float((p.grad - ref).norm() / ref.norm())
             worst = max(worst, (e, k))
         assert worst[0] < 1e-4, (pre_rot, worst)            # measured 3e-6 over 196 parameter tensors
+
+
+class _Replay:
+    """torch.randn / randn_like return a recorded list of tensors, in call order (as the GPU sampling tests do)."""
+
+    def __init__(self, tensors):
+        self.tensors, self.i = list(tensors), 0
+
+    def __enter__(self):
+        self._a, self._b = torch.randn, torch.randn_like
+
+        def nxt(*a, **k):
+            t = self.tensors[self.i]
+            self.i += 1
+            return t.clone().as_subclass(_ClaimsCuda)
+
+        torch.randn, torch.randn_like = nxt, nxt
+        return self
+
+    def __exit__(self, *e):
+        torch.randn, torch.randn_like = self._a, self._b
+
+
+def test_sampler_glue_matches_oracle(monkeypatch, golden_dir):
+    """GaussianDiffusion.p_sample / sample (ancestral with dynamic thresholding, guided and unguided) and ddim_sample, eager form
+    and the device-coefficient DDIM step that the CUDA graph replays (`_ddim_step_core`), against the oracle on recorded noise."""
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import GaussianDiffusion, Unet3D, ops
+    emu_ops.install_sampler(monkeypatch, ops)
+    cfg = O.UnetCfg(dim=16, dim_mults=(1, 2))
+    sd = O.synthetic_state_dict(cfg, seed=15)
+    rel = lambda a, r: float((torch.Tensor(a) - r).norm() / r.norm())
+
+    def make(sampling_T):
+        model = Unet3D(dim=16, dim_mults=(1, 2), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
+                       cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, cond_to_time='add', per_frame_cond=True)
+        model.load_state_dict(sd)
+        model.compute_dtype, model._packed = torch.float32, None
+        return GaussianDiffusion(model, image_size=12, channels=3, num_frames=11, timesteps=8, loss_type='l1', use_dynamic_thres=True,
+                                 sampling_timesteps=sampling_T)
+
+    g = torch.Generator().manual_seed(4)
+    b = 2
+    cond = torch.rand(b, 11, generator=g) * 2 - 1
+    noises = [torch.randn(b, 3, 11, 12, 12, generator=g) for _ in range(9)]
+    S = O.schedule(8)
+    gd = make(8)
+    for w in (5.0, 1.0):
+        with _Replay(noises):
+            got = gd.sample(cond=cond, guidance_scale=w)
+        want = O.p_sample_loop(sd, cfg, S, noises[0], cond, w, noises[1:])
+        assert rel(got, want) < 1e-4, w
+    gd4 = make(4)
+    with _Replay(noises):
+        got = gd4.sample(cond=cond, guidance_scale=5.0)
+    want = O.ddim_sample(sd, cfg, S, noises[0], cond, 5.0, 4)
+    assert rel(got, want) < 1e-4
+    # the graph-replayed DDIM step: per-step scalars gathered from the shifted alphas_cumprod table on the device
+    img = noises[0].clone().as_subclass(_ClaimsCuda)
+    st = dict(x=img, t=torch.zeros(b, dtype=torch.long), tn=torch.zeros(b, dtype=torch.long), cond=cond, x0=torch.empty(b, 3, 11, 12, 12),
+              eps=torch.empty(b, 3, 11, 12, 12), zeros=torch.zeros(b), acp_next=torch.cat((torch.ones(1), gd4.alphas_cumprod)).contiguous())
+    for time, time_next in gd4._ddim_pairs():
+        st["t"].fill_(time)
+        st["tn"].fill_(time_next)
+        st["x"] = torch.Tensor(gd4._ddim_step_core(st, 5.0)).as_subclass(_ClaimsCuda)
+    assert rel((st["x"] + 1) * 0.5, want) < 1e-4
