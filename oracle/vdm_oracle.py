@@ -487,14 +487,21 @@ def ddim_step_from_eps(S, x: Tensor, time: int, time_next: int, eps: Tensor, eta
     return out
 
 
-def ddim_sample(P: Params, cfg: UnetCfg, S, x_T: Tensor, cond: Tensor, w: float, steps: int) -> Tensor:
-    """VDDP:986-1018 with eta = 0 (the reference default; the drawn noise is multiplied by sigma = 0)."""
+def ddim_sample(P: Params, cfg: UnetCfg, S, x_T: Tensor, cond: Tensor, w: float, steps: int, eta: float = 0.0,
+                noises: Optional[Sequence[Tensor]] = None) -> Tensor:
+    """VDDP:986-1018.  eta = 0 is the reference default (the drawn noise is multiplied by sigma = 0); with eta > 0, noises[k] is
+    the k-th randn_like draw (one per step whose time_next >= 0)."""
     T = S["betas"].shape[0]
     img = x_T
+    k = 0
     for time, time_next in ddim_time_pairs(T, steps):
         t = torch.full((img.shape[0],), time, dtype=torch.long, device=img.device)
         eps = unet_forward_guided(P, cfg, img, t, cond, w)
-        img = ddim_step_from_eps(S, img, time, time_next, eps)
+        noise = None
+        if eta != 0.0 and time_next >= 0:
+            noise = noises[k]
+            k += 1
+        img = ddim_step_from_eps(S, img, time, time_next, eps, eta, noise)
     return (img + 1) * 0.5
 
 

@@ -154,3 +154,21 @@ def test_sampler_glue_matches_oracle(monkeypatch, golden_dir):
         st["tn"].fill_(time_next)
         st["x"] = torch.Tensor(gd4._ddim_step_core(st, 5.0)).as_subclass(_ClaimsCuda)
     assert rel((st["x"] + 1) * 0.5, want) < 1e-4
+    # eta > 0 (ddim_sampling_eta, VDDP:1006-1016): the stochastic DDIM update through vmm_posterior_step, eager and graph-step form
+    gde = make(4)
+    gde.ddim_sampling_eta = 0.5
+    with _Replay(noises):
+        got = gde.sample(cond=cond, guidance_scale=5.0)
+    want = O.ddim_sample(sd, cfg, S, noises[0], cond, 5.0, 4, eta=0.5, noises=noises[1:])
+    assert rel(got, want) < 1e-4
+    st.update(x=noises[0].clone().as_subclass(_ClaimsCuda), noise=torch.zeros(b, 3, 11, 12, 12))
+    k = 1
+    for time, time_next in gde._ddim_pairs():
+        st["t"].fill_(time)
+        st["tn"].fill_(time_next)
+        if time_next >= 0:
+            st["noise"].copy_(noises[k])
+            k += 1
+        st["x"] = torch.Tensor(gde._ddim_step_core(st, 5.0)).as_subclass(_ClaimsCuda)
+    assert rel((st["x"] + 1) * 0.5, want) < 1e-4
+    assert float((torch.Tensor(got) - O.ddim_sample(sd, cfg, S, noises[0], cond, 5.0, 4)).abs().max()) > 1e-3      # eta changes the sample

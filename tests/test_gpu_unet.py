@@ -349,3 +349,35 @@ def test_full_size_conv_linearity(dt):
     assert torch.equal(o[3, 39:42, 49:52].float(), want)
     o[3, 39:42, 49:52] = 0
     assert float(o.float().abs().max()) == 0.0
+
+
+def test_ddim_eta_graph_matches_eager_and_golden(golden_dir):
+    """`ddim_sampling_eta` > 0 (VDDP:1006-1016): the stochastic DDIM update runs through vmm_posterior_step (c1 x0 + c2 eps +
+    sigma noise, no clamp).  Eager loop on the recorded noise against the reference's sample (tests/golden/ddim_eta.pt), and the
+    graph-replayed loop against the eager one from the same torch seed.  (Added after the round's GPU budget was spent: the CPU
+    glue test covers the arithmetic; this is its first run on a device, which is why it is the last test of the last file.)"""
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import GaussianDiffusion, Unet3D
+    gold = torch.load(os.path.join(golden_dir, "ddim_eta.pt"))[0.5]
+    cfg = O.UnetCfg(dim=16, dim_mults=(1, 2))
+    model = Unet3D(dim=16, dim_mults=(1, 2), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
+                   cond_bias=True, cond_attention='self-stacked', cond_attention_tokens=16, use_temporal_attention_cond=True,
+                   cond_to_time='add', per_frame_cond=True, padding_mode='zeros')
+    model.load_state_dict(O.synthetic_state_dict(cfg, seed=gold["seed"]), strict=True)
+    model.set_compute_dtype(torch.float16)
+    gd = GaussianDiffusion(model, image_size=12, channels=3, num_frames=11, timesteps=8, loss_type='l1', use_dynamic_thres=True,
+                           sampling_timesteps=4, ddim_sampling_eta=0.5).cuda()
+    g = torch.Generator().manual_seed(gold["data_seed"])
+    cond = (torch.rand(2, 11, generator=g) * 2 - 1).cuda()
+    noises = [torch.randn(2, 3, 11, 12, 12, generator=g) for _ in range(4)]
+    with Replay(noises):
+        got = gd.sample(cond=cond, guidance_scale=5.0)
+    e = rel(got, gold["sample"])
+    print("ddim eta=0.5 rel-L2 vs reference:", e)
+    assert e < 5e-2                                             # same bound as the eta = 0 loop in test_small_sampling
+    torch.manual_seed(5)
+    eager = gd.sample(cond=cond, guidance_scale=5.0)
+    gd.use_cuda_graph = True
+    torch.manual_seed(5)
+    graph = gd.sample(cond=cond, guidance_scale=5.0)
+    assert rel(graph, eager) < 1e-2

@@ -82,9 +82,7 @@ class GaussianDiffusion(nn.Module):
         self.sampling_timesteps = sampling_timesteps if sampling_timesteps is not None else timesteps
         assert self.sampling_timesteps <= timesteps
         self.is_ddim_sampling = self.sampling_timesteps < timesteps
-        self.ddim_sampling_eta = ddim_sampling_eta
-        if ddim_sampling_eta != 0.:
-            raise NotImplementedError("ddim_sampling_eta != 0 is not implemented (the reference default is 0)")
+        self.ddim_sampling_eta = float(ddim_sampling_eta)
         if loss_type not in ('l1', 'l2'):
             raise NotImplementedError()
         self.use_cuda_graph = False        # bench / Trainer turn this on; parity tests run eagerly
@@ -214,9 +212,17 @@ class GaussianDiffusion(nn.Module):
                    self.sqrt_recipm1_alphas_cumprod[t].contiguous(), st["x0"], st["eps"], b, c, f, h, w)
         an = st["acp_next"][st["tn"] + 1]
         out = torch.empty_like(x)
-        # x0 * sqrt(an) + eps * sqrt(1 - an): the posterior kernel's c1 * x0 + c2 * x + sig * noise with sig = 0 and no clamp
-        ops.posterior_step(st["x0"], st["eps"], st["x0"], None, an.sqrt().contiguous(), (1. - an).sqrt().contiguous(), st["zeros"], out,
-                           b, c * f * h * w)
+        if self.ddim_sampling_eta == 0.:
+            # x0 * sqrt(an) + eps * sqrt(1 - an): the posterior kernel's c1 * x0 + c2 * x + sig * noise with sig = 0 and no clamp
+            ops.posterior_step(st["x0"], st["eps"], st["x0"], None, an.sqrt().contiguous(), (1. - an).sqrt().contiguous(), st["zeros"],
+                               out, b, c * f * h * w)
+        else:
+            # eta > 0 (VDDP:1006-1016): sigma = eta sqrt((1 - a / an)(1 - an) / (1 - a)), and the step's noise enters through sig;
+            # at time_next = -1 the table gives an = 1, hence sigma = 0 and sqrt(1 - an - sigma^2) = 0: the step returns x0
+            a = self.alphas_cumprod[t]
+            sigma = self.ddim_sampling_eta * ((1. - a / an) * (1. - an) / (1. - a)).sqrt()
+            ops.posterior_step(st["x0"], st["eps"], st["noise"], None, an.sqrt().contiguous(),
+                               (1. - an - sigma * sigma).sqrt().contiguous(), sigma.contiguous(), out, b, c * f * h * w)
         return out
 
     def _graph_ddim(self, img, cond, guidance_scale):
@@ -227,12 +233,13 @@ class GaussianDiffusion(nn.Module):
             st["zeros"] = torch.zeros(b, dtype=torch.float32, device=img.device)
             st["acp_next"] = torch.cat((torch.ones(1, device=img.device), self.alphas_cumprod)).contiguous()
 
-        graph, st = self._step_graph("ddim", img, cond, guidance_scale, make_state, lambda st: self._ddim_step_core(st, guidance_scale))
+        graph, st = self._step_graph(f"ddim eta={self.ddim_sampling_eta}", img, cond, guidance_scale, make_state,
+                                     lambda st: self._ddim_step_core(st, guidance_scale))
         for time, time_next in self._ddim_pairs():
             st["t"].fill_(time)
             st["tn"].fill_(time_next)
             if time_next >= 0:
-                st["noise"].normal_()                    # the reference draws (and discards, sigma = 0) one noise per step
+                st["noise"].normal_()                    # one draw per step as in the reference (multiplied by sigma = 0 when eta = 0)
             graph.replay()
             st["x"].copy_(st["out"])
         return st["x"].clone()
@@ -246,7 +253,7 @@ class GaussianDiffusion(nn.Module):
 
     @torch.inference_mode()
     def ddim_sample(self, shape, cond=None, guidance_scale=1.):
-        """VDDP:986-1018 (eta = 0: no clamp, no dynamic threshold, the drawn noise is multiplied by sigma = 0)."""
+        """VDDP:986-1018: no clamp, no dynamic threshold; with the default eta = 0 the drawn noise is multiplied by sigma = 0."""
         batch, device = shape[0], self.betas.device
         pairs = self._ddim_pairs()
         img = torch.randn(shape, device=device)
@@ -263,10 +270,18 @@ class GaussianDiffusion(nn.Module):
             if time_next < 0:
                 img = x0
                 continue
-            an = float(self.alphas_cumprod[time_next])
-            torch.randn_like(img)                       # the reference draws (and discards, sigma = 0) one noise per step
             out = torch.empty_like(img)
-            ops.axpby(x0, eps, an ** 0.5, (1 - an) ** 0.5, 0.0, out)
+            if self.ddim_sampling_eta == 0.:
+                an = float(self.alphas_cumprod[time_next])
+                torch.randn_like(img)                   # the reference draws (and discards, sigma = 0) one noise per step
+                ops.axpby(x0, eps, an ** 0.5, (1 - an) ** 0.5, 0.0, out)
+            else:                                       # VDDP:1003-1016 in fp32 as the reference computes it
+                a, an = self.alphas_cumprod[time], self.alphas_cumprod[time_next]
+                sigma = self.ddim_sampling_eta * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()
+                coef = lambda v: v.reshape(1).expand(b).contiguous()
+                noise = torch.randn_like(img)
+                ops.posterior_step(x0, eps, noise, None, coef(an.sqrt()), coef((1 - an - sigma ** 2).sqrt()), coef(sigma), out, b,
+                                   c * f * h * w)
             img = out
         return unnormalize_img(img)
 
