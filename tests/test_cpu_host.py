@@ -69,6 +69,8 @@ def test_unsupported_configurations_raise():
         Unet3D(dim=16, per_frame_cond=False)
     with pytest.raises(NotImplementedError):
         Unet3D(dim=16, per_frame_cond=True, use_temporal_attention_cond=True, padding_mode='circular')
+    with pytest.raises(NotImplementedError, match="attn_heads"):          # at construction, not at the first kernel call
+        Unet3D(dim=16, per_frame_cond=True, use_temporal_attention_cond=True, attn_heads=4)
 
 
 def test_packing_and_tap_tables():

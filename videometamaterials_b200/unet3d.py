@@ -132,6 +132,8 @@ class Unet3D(nn.Module):
             unsupported.append("use_sparse_linear_attn=False")
         if attn_dim_head != 32:
             unsupported.append("attn_dim_head != 32")
+        if attn_heads != 8:
+            unsupported.append("attn_heads != 8 (the attention kernels map one warp to each of 8 heads)")
         if init_kernel_size != 7 or channels > 8:
             unsupported.append("init_kernel_size != 7 or channels > 8")
         if out_dim is not None and out_dim != channels:
