@@ -4,8 +4,8 @@
 
 `Unet3D(padding_mode='circular' | 'circular_1d')` (model.yaml:13, VDDP:153-243, 270-273, 624-628) on a small configuration:
 state_dict key order (the circular variants wrap some convolutions in a module, which renames their keys) and the forward
-outputs with and without conditioning on seeded inputs.  The oracle restates both modes; the B200 kernels do not implement
-them yet, so these fixtures pin the checker the next implementation step will be held to.
+outputs with and without conditioning on seeded inputs.  The oracle restates both modes; the
+product's wrap-mode path is held to these fixtures through the oracle (tests/test_cpu_forward_glue.py, tests/test_gpu_unet.py).
 """
 import os
 import sys

@@ -21,7 +21,7 @@ Everything is written as functions over a flat `state_dict` (the reference's own
 the reference's `b c f h w` layout, covering the shipped configuration (model.yaml):
 `per_frame_cond=True`, `cond_attention='self-stacked'`, `cond_to_time='add'`,
 `use_temporal_attention_cond=True`, `padding_mode='zeros'`; plus the two other values of `padding_mode` in the config
-surface ('circular', 'circular_1d'), pinned by tests/golden/padding_modes.pt, which the CUDA path does not implement yet.
+surface ('circular', 'circular_1d'), pinned by tests/golden/padding_modes.pt.
 """
 from __future__ import annotations
 

@@ -200,3 +200,87 @@ def test_weight_gradient_tap_tables(ops_w):
     dwi = torch.zeros_like(wi.detach())
     ops.wgrad_init_conv(cl(dyi), xin, dwi, ch)
     assert close(dwi, wi.grad, 1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# padding_mode = 'circular' / 'circular_1d' (model.yaml:13, VDDP:153-243): wrap-padded copies read with non-negative taps
+# ------------------------------------------------------------------------------------------------
+def _ref_pad(x, p, mode):          # (n, c, h, w), the reference's padding
+    if mode == "circular":
+        return F.pad(x, (p, p, p, p), mode="circular")
+    return F.pad(F.pad(x, (p, p, 0, 0), mode="circular"), (0, 0, p, p))
+
+
+@pytest.mark.parametrize("mode", ["circular", "circular_1d"])
+def test_wrap_mode_front_ends_forward_data_gradient_weight_gradient(ops_w, mode):
+    """Every convolution kind of the network in the two wrap modes: forward against the reference's construction (explicit pad +
+    unpadded conv; for the upsampler pad 2 + transposed conv cropping 5, VDDP:164-216), the data gradient through the ADJOINT
+    front-end (3x3 -> 3x3 with the flipped pack, down -> up, up -> down: the adjoint of a wrap-mode conv is a wrap-mode conv),
+    and the weight gradient tap tables."""
+    ops = ops_w
+    g = torch.Generator().manual_seed(21)
+    bf, h, w = 2, 8, 12
+    # 3x3, two concatenated sources
+    cins, cout = [8, 24], 16
+    xs = [torch.randn(bf, c, h, w, generator=g) for c in cins]
+    wt = (torch.randn(cout, sum(cins), 1, 3, 3, generator=g) * 0.1).requires_grad_(True)
+    x = torch.cat(xs, 1).requires_grad_(True)
+    y = F.conv2d(_ref_pad(x, 1, mode), wt[:, :, 0])
+    out = torch.zeros(bf, h, w, cout)
+    ops.conv3x3([cl(t) for t in xs], ops.pack_conv_taps(wt.detach()[:, :, 0], cins, torch.float32), cout, out, mode=mode)
+    assert close(out, cl(y))
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dx = torch.zeros(bf, h, w, sum(cins))
+    ops.conv3x3([cl(dy)], ops.pack_conv_taps(wt.detach()[:, :, 0].flip(2, 3).permute(1, 0, 2, 3), [cout], torch.float32), sum(cins), dx, mode=mode)
+    assert close(dx, cl(x.grad), 1e-4)
+    dw = torch.zeros_like(wt.detach())
+    ops.wgrad_conv3x3(cl(dy), [cl(t) for t in xs], dw, mode=mode)
+    assert close(dw, wt.grad, 1e-4)
+    # Downsample / Upsample
+    c = 12
+    x = torch.randn(bf, c, h, w, generator=g, requires_grad=True)
+    wd_ = (torch.randn(c, c, 1, 4, 4, generator=g) * 0.1).requires_grad_(True)
+    yd = F.conv2d(_ref_pad(x, 1, mode), wd_[:, :, 0], None, stride=2)
+    out = torch.zeros(bf, h // 2, w // 2, c)
+    ops.conv_down(cl(x.detach()), ops.pack_conv_taps(wd_.detach()[:, :, 0], [c], torch.float32), c, out, mode=mode)
+    assert close(out, cl(yd))
+    dyd = torch.randn_like(yd)
+    yd.backward(dyd)
+    dx = torch.zeros(bf, h, w, c)
+    ops.conv_up(cl(dyd), ops.pack_conv_taps(wd_.detach()[:, :, 0].permute(1, 0, 2, 3), [c], torch.float32), c, dx, mode=mode)
+    assert close(dx, cl(x.grad), 1e-4)
+    dwd = torch.zeros_like(wd_.detach())
+    ops.wgrad_down(cl(dyd), cl(x.detach()), dwd, mode=mode)
+    assert close(dwd, wd_.grad, 1e-4)
+    x2 = torch.randn(bf, c, h, w, generator=g, requires_grad=True)
+    wu_ = (torch.randn(c, c, 1, 4, 4, generator=g) * 0.1).requires_grad_(True)
+    yu = F.conv_transpose2d(_ref_pad(x2, 2, mode), wu_[:, :, 0], None, stride=2, padding=5)
+    assert yu.shape[-2:] == (2 * h, 2 * w)
+    out = torch.zeros(bf, 2 * h, 2 * w, c)
+    ops.conv_up(cl(x2.detach()), ops.pack_conv_up(wu_.detach(), torch.float32), c, out, mode=mode)
+    assert close(out, cl(yu))
+    dyu = torch.randn_like(yu)
+    yu.backward(dyu)
+    dx2 = torch.zeros(bf, h, w, c)
+    ops.conv_down(cl(dyu), ops.pack_conv_taps(wu_.detach()[:, :, 0], [c], torch.float32), c, dx2, mode=mode)
+    assert close(dx2, cl(x2.grad), 1e-4)
+    dwu = torch.zeros_like(wu_.detach())
+    ops.wgrad_up(cl(dyu), cl(x2.detach()), dwu, mode=mode)
+    assert close(dwu, wu_.grad, 1e-4)
+    # init_conv (1,7,7) through the wrapped prepared layout
+    ch, n = 3, 16
+    xi = torch.randn(bf, ch, h, w, generator=g)
+    wi = (torch.randn(n, ch, 1, 7, 7, generator=g) * 0.1).requires_grad_(True)
+    yi = F.conv2d(_ref_pad(xi, 3, mode), wi[:, :, 0])
+    xin = torch.zeros(bf, h, w + 6, 8)
+    xin[:, :, 3:3 + w, :ch] = cl(xi)
+    xin = ops.wrap_prepared_input(torch.cat((xin.reshape(-1), torch.zeros(8))), bf, h, w, mode)
+    out = torch.zeros(bf, h, w, n)
+    ops.init_conv(xin, bf, h, w, ops.pack_init_conv(wi.detach(), torch.float32), n, out, mode=mode)
+    assert close(out, cl(yi))
+    dyi = torch.randn_like(yi)
+    yi.backward(dyi)
+    dwi = torch.zeros_like(wi.detach())
+    ops.wgrad_init_conv(cl(dyi), xin, dwi, ch, mode=mode)
+    assert close(dwi, wi.grad, 1e-4)

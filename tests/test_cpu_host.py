@@ -67,8 +67,8 @@ def test_unsupported_configurations_raise():
     from videometamaterials_b200 import Unet3D
     with pytest.raises(NotImplementedError):
         Unet3D(dim=16, per_frame_cond=False)
-    with pytest.raises(NotImplementedError):
-        Unet3D(dim=16, per_frame_cond=True, use_temporal_attention_cond=True, padding_mode='circular')
+    with pytest.raises(ValueError):
+        Unet3D(dim=16, per_frame_cond=True, use_temporal_attention_cond=True, padding_mode='reflect')
     with pytest.raises(NotImplementedError, match="attn_heads"):          # at construction, not at the first kernel call
         Unet3D(dim=16, per_frame_cond=True, use_temporal_attention_cond=True, attn_heads=4)
 
@@ -217,7 +217,7 @@ def test_main_config_wiring(golden_dir, tmp_path):
     assert (diffusion.image_size, diffusion.num_frames, diffusion.channels) == (96, 11, 3)
     _, ddim = main.build_model(dict(cfg, sampling_timesteps=250))
     assert ddim.is_ddim_sampling
-    for key, val in (("padding_mode", "circular"), ("padding_mode", "circular_1d"), ("per_frame_cond", False), ("unet_cond_to_time", "concat"),
+    for key, val in (("per_frame_cond", False), ("unet_cond_to_time", "concat"),
                      ("unet_cond_att_GRU", True), ("unet_temporal_att_cond", False)):
         with pytest.raises(NotImplementedError):
             main.build_model(dict(cfg, **{key: val}))
@@ -282,3 +282,21 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out
     assert out.stdout.split()[0] == "1" and out.stdout.split()[2] == "err-ok"
+
+
+@pytest.mark.parametrize("mode", ["circular", "circular_1d"])
+def test_padding_mode_state_dict_matches_reference_layout(golden_dir, mode):
+    """The circular padding modes rename the keys of the wrapped convolutions (`...proj.conv.weight`, `ups.i.4.conv_transpose.weight`,
+    VDDP:181, 204, 223): same keys, order and shapes as the unmodified reference (tests/golden/padding_modes.pt), and the block code
+    sees them under their zero-padding names."""
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import Unet3D, blocks
+    gold = torch.load(os.path.join(golden_dir, "padding_modes.pt"))[mode]
+    m = Unet3D(dim=16, dim_mults=(1, 2), channels=3, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True,
+               per_frame_cond=True, padding_mode=mode)
+    assert list(m.state_dict().keys()) == gold["keys"]
+    m.load_state_dict(O.synthetic_state_dict(O.UnetCfg(dim=16, dim_mults=(1, 2), padding_mode=mode), seed=gold["seed"]), strict=True)
+    zeros = Unet3D(dim=16, dim_mults=(1, 2), channels=3, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True,
+                   per_frame_cond=True)
+    assert list(blocks.param_dict(m).keys()) == [k for k, _ in zeros.named_parameters()]
+    assert set(blocks.pack_all(m, torch.float32)) == set(blocks.pack_all(zeros, torch.float32))

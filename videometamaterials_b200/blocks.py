@@ -8,6 +8,7 @@ Each *_fwd returns `(out, saved)`; `saved` is what the matching backward needs.
 from __future__ import annotations
 
 import math
+import re
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -75,10 +76,24 @@ def resnet_splits(model) -> Dict[str, List[int]]:
     return sp
 
 
+_WRAPPED_CONV = re.compile(r"(init_conv|\.proj|\.4)\.(conv|conv_transpose)\.(weight|bias)$")
+
+
+def canonical_key(name: str) -> str:
+    """state_dict key of a convolution without the wrapper level the reference adds in the circular padding modes
+    (`...proj.conv.weight`, `ups.i.4.conv_transpose.weight`): the key the same tensor has with padding_mode='zeros'."""
+    return _WRAPPED_CONV.sub(r"\1.\3", name)
+
+
+def param_dict(model) -> Dict[str, Tensor]:
+    """named_parameters() under canonical keys, so that the block code is independent of the padding mode's key renames."""
+    return {canonical_key(k): v for k, v in model.named_parameters()}
+
+
 def pack_all(model, dtype, sd=None) -> Dict[str, Tensor]:
     """fp32 master parameters -> K-major GEMM operands (forward and data-gradient forms).  `sd` overrides the
     parameter values (pack_plan() runs this once on tensors holding their own arena indices)."""
-    sd = dict(model.named_parameters()) if sd is None else sd
+    sd = param_dict(model) if sd is None else sd
     P: Dict[str, Tensor] = {}
     sp = resnet_splits(model)
     for pre, splits in sp.items():
@@ -131,7 +146,7 @@ def pack_plan(model, arena):
         k = p.numel()
         index_of[id(p)] = (o, k)
         o += k
-    for name, p in model.named_parameters():
+    for name, p in param_dict(model).items():
         if id(p) in index_of:
             o0, k = index_of[id(p)]
             sd[name] = (torch.arange(o0 + 1, o0 + k + 1, dtype=torch.float64, device=p.device)).view(p.shape)
@@ -295,7 +310,7 @@ def conditioning(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: i
     rotary embedding, [0] pre-multiplied by the attention scale (queries), [1] plain (keys and the attention kernels).
     The per-block fan-out (18 ResnetBlock MLPs, 17 to_k / to_v pairs) is batched: parameters are gathered from the arena,
     results are split by one permutation, so the path is ~40 kernels forward instead of several hundred."""
-    sd = dict(model.named_parameters())
+    sd = param_dict(model)
     heads = model.heads
     hd = heads * 32
     dev = time.device
@@ -347,8 +362,8 @@ def _flat(x: Tensor) -> Tensor:
     return x.reshape(-1, x.shape[-1])
 
 
-def resnet_fwd(P, sd, pre: str, xs: Sequence[Tensor], ss: Optional[Tensor], groups: int):
-    """ResnetBlock VDDP:299-311 on an implicit channel-concat of xs."""
+def resnet_fwd(P, sd, pre: str, xs: Sequence[Tensor], ss: Optional[Tensor], groups: int, mode: str = "zeros"):
+    """ResnetBlock VDDP:299-311 on an implicit channel-concat of xs; `mode` = the padding mode of the two 3x3 convs."""
     B, Fr, H, W, _ = xs[0].shape
     cout = sd[pre + "block1.proj.bias"].shape[0]
     dt, dev = xs[0].dtype, xs[0].device
@@ -356,13 +371,13 @@ def resnet_fwd(P, sd, pre: str, xs: Sequence[Tensor], ss: Optional[Tensor], grou
     pix = Fr * H * W
     h1 = torch.empty(B, Fr, H, W, cout, dtype=dt, device=dev)
     st1 = torch.zeros(B, groups, 2, dtype=torch.float64, device=dev)
-    ops.conv3x3(xv, P[pre + "block1.w"], cout, h1, bias=sd[pre + "block1.proj.bias"], gn_stats=st1, gn_group=cout // groups,
+    ops.conv3x3(xv, P[pre + "block1.w"], cout, h1, mode=mode, bias=sd[pre + "block1.proj.bias"], gn_stats=st1, gn_group=cout // groups,
                 frames_per_sample=Fr)
     a1 = torch.empty_like(h1)
     ops.gn_silu_fwd(h1, a1, st1, sd[pre + "block1.norm.weight"], sd[pre + "block1.norm.bias"], ss, B, pix, cout, groups)
     h2 = torch.empty_like(h1)
     st2 = torch.zeros(B, groups, 2, dtype=torch.float64, device=dev)
-    ops.conv3x3([ops.as_bfhwc(a1)], P[pre + "block2.w"], cout, h2, bias=sd[pre + "block2.proj.bias"], gn_stats=st2,
+    ops.conv3x3([ops.as_bfhwc(a1)], P[pre + "block2.w"], cout, h2, mode=mode, bias=sd[pre + "block2.proj.bias"], gn_stats=st2,
                 gn_group=cout // groups, frames_per_sample=Fr)
     out = torch.empty_like(h1)
     if (pre + "res.w") in P:
@@ -410,17 +425,17 @@ def attn_block_fwd(P, sd, pre: str, kind: str, x: Tensor, ekv: Optional[Tensor],
     return out, (xn, qkv, ao, extra)
 
 
-def down_fwd(P, sd, pre: str, x: Tensor):
+def down_fwd(P, sd, pre: str, x: Tensor, mode: str = "zeros"):
     B, Fr, H, W, Cc = x.shape
     out = torch.empty(B, Fr, H // 2, W // 2, Cc, dtype=x.dtype, device=x.device)
-    ops.conv_down(ops.as_bfhwc(x), P[pre + "w"], Cc, out, bias=sd[pre + "bias"])
+    ops.conv_down(ops.as_bfhwc(x), P[pre + "w"], Cc, out, mode=mode, bias=sd[pre + "bias"])
     return out
 
 
-def up_fwd(P, sd, pre: str, x: Tensor):
+def up_fwd(P, sd, pre: str, x: Tensor, mode: str = "zeros"):
     B, Fr, H, W, Cc = x.shape
     out = torch.empty(B, Fr, 2 * H, 2 * W, Cc, dtype=x.dtype, device=x.device)
-    ops.conv_up(ops.as_bfhwc(x), P[pre + "w"], Cc, out, bias=sd[pre + "bias"])
+    ops.conv_up(ops.as_bfhwc(x), P[pre + "w"], Cc, out, mode=mode, bias=sd[pre + "bias"])
     return out
 
 
@@ -432,7 +447,10 @@ def init_fwd(P, sd, model, x: Tensor, noise: Optional[Tensor], qcoef):
     a, c, s = qcoef if qcoef is not None else (None, None, None)
     ops.prep_input(x.contiguous(), noise, a, c, s, xin, B, Cc, Fr, H, W)
     out = torch.empty(B, Fr, H, W, model.dim, dtype=dt, device=x.device)
-    ops.init_conv(xin, B * Fr, H, W, P["init_conv.w"], model.dim, out, bias=sd["init_conv.bias"])
+    mode = model.padding_mode
+    if mode != "zeros":
+        xin = ops.wrap_prepared_input(xin, B * Fr, H, W, mode)          # [bf][h+6][w+6][8]: the border of the wrap mode filled in
+    ops.init_conv(xin, B * Fr, H, W, P["init_conv.w"], model.dim, out, mode=mode, bias=sd["init_conv.bias"])
     return out, xin
 
 
@@ -452,9 +470,9 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
     if not x.is_cuda:
         raise RuntimeError("videometamaterials_b200 has no CPU path: move the model and inputs to a CUDA device")
     P = model.packed()
-    sd = dict(model.named_parameters())
+    sd = param_dict(model)
     L = len(model.dim_mults)
-    g, heads = model.groups, model.heads
+    g, heads, pm = model.groups, model.heads, model.padding_mode
     frames = x.shape[2]
     ss, ekv, bias, rot = conditioning(model, time, cond, null_mask, frames)
     h, _ = init_fwd(P, sd, model, x.float(), noise, qcoef)
@@ -463,24 +481,24 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
     skips = []
     for i in range(L):
         p = f"downs.{i}."
-        h, _ = resnet_fwd(P, sd, p + "0.", [h], ss[p + "0."], g)
-        h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g)
+        h, _ = resnet_fwd(P, sd, p + "0.", [h], ss[p + "0."], g, pm)
+        h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g, pm)
         h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads)
         h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads)
         skips.append(h)
         if i < L - 1:
-            h = down_fwd(P, sd, p + "4.", h)
-    h, _ = resnet_fwd(P, sd, "mid_block1.", [h], ss["mid_block1."], g)
+            h = down_fwd(P, sd, p + "4.", h, pm)
+    h, _ = resnet_fwd(P, sd, "mid_block1.", [h], ss["mid_block1."], g, pm)
     h, _ = attn_block_fwd(P, sd, "mid_spatial_attn.fn.fn.fn.", "spatial", h, ekv["mid_spatial_attn.fn.fn.fn."], None, None, heads)
     h, _ = attn_block_fwd(P, sd, "mid_temporal_attn.fn.fn.fn.", "temporal", h, ekv["mid_temporal_attn.fn.fn.fn."], bias, rot, heads)
-    h, _ = resnet_fwd(P, sd, "mid_block2.", [h], ss["mid_block2."], g)
+    h, _ = resnet_fwd(P, sd, "mid_block2.", [h], ss["mid_block2."], g, pm)
     for i in range(L):
         p = f"ups.{i}."
-        h, _ = resnet_fwd(P, sd, p + "0.", [h, skips.pop()], ss[p + "0."], g)
-        h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g)
+        h, _ = resnet_fwd(P, sd, p + "0.", [h, skips.pop()], ss[p + "0."], g, pm)
+        h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g, pm)
         h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads)
         h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads)
         if i < L - 1:
-            h = up_fwd(P, sd, p + "4.", h)
-    h, _ = resnet_fwd(P, sd, "final_conv.0.", [h, r], None, g)
+            h = up_fwd(P, sd, p + "4.", h, pm)
+    h, _ = resnet_fwd(P, sd, "final_conv.0.", [h, r], None, g, pm)
     return final_fwd(P, sd, model, h)

@@ -76,7 +76,8 @@ class _Env:
     def __init__(self, model):
         self.model = model
         self.P = model.packed()
-        self.sd = dict(model.named_parameters())
+        self.sd = blocks.param_dict(model)
+        self.mode = model.padding_mode
         self.groups = model.groups
         self.heads = model.heads
 
@@ -88,7 +89,7 @@ class ResnetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, env: _Env, pre: str, ss: Optional[Tensor], *xs: Tensor):
         xs = tuple(x.contiguous() for x in xs)
-        out, saved = blocks.resnet_fwd(env.P, env.sd, pre, xs, ss, env.groups)
+        out, saved = blocks.resnet_fwd(env.P, env.sd, pre, xs, ss, env.groups, env.mode)
         ctx.env, ctx.pre, ctx.n_src, ctx.has_ss = env, pre, len(xs), ss is not None
         ctx.save_for_backward(*xs, *saved, *( (ss,) if ss is not None else ()))
         return out
@@ -118,21 +119,21 @@ class ResnetFn(torch.autograd.Function):
         ops.gn_silu_bwd(h2, dout, dh2, st2, sd[pre + "block2.norm.weight"], sd[pre + "block2.norm.bias"], None, B, pix, cout, g,
                         sd[pre + "block2.norm.weight"].grad, sd[pre + "block2.norm.bias"].grad, None,
                         dx_colsum=sd[pre + "block2.proj.bias"].grad)       # conv bias gradient = column sums of dh2
-        ops.wgrad_conv3x3(ops.as_bfhwc(dh2), [ops.as_bfhwc(a1)], sd[pre + "block2.proj.weight"].grad)
+        ops.wgrad_conv3x3(ops.as_bfhwc(dh2), [ops.as_bfhwc(a1)], sd[pre + "block2.proj.weight"].grad, mode=env.mode)
         da1 = torch.empty_like(a1)
-        ops.conv3x3([ops.as_bfhwc(dh2)], P[pre + "block2.wd"], cout, da1)
+        ops.conv3x3([ops.as_bfhwc(dh2)], P[pre + "block2.wd"], cout, da1, mode=env.mode)      # the adjoint of a wrap-mode conv is one too
         # block1
         dh1 = dh2   # reuse the buffer
         dss = torch.zeros_like(ss) if ss is not None else None
         ops.gn_silu_bwd(h1, da1, dh1, st1, sd[pre + "block1.norm.weight"], sd[pre + "block1.norm.bias"], ss, B, pix, cout, g,
                         sd[pre + "block1.norm.weight"].grad, sd[pre + "block1.norm.bias"].grad, dss,
                         dx_colsum=sd[pre + "block1.proj.bias"].grad)
-        ops.wgrad_conv3x3(ops.as_bfhwc(dh1), [ops.as_bfhwc(x) for x in xs], sd[pre + "block1.proj.weight"].grad)
+        ops.wgrad_conv3x3(ops.as_bfhwc(dh1), [ops.as_bfhwc(x) for x in xs], sd[pre + "block1.proj.weight"].grad, mode=env.mode)
         if has_res:
             res, res2 = dxs[0], (dxs[1] if len(xs) > 1 else None)     # in-place accumulate on the res_conv gradient
         else:
             res, res2 = dout, None                                      # identity skip
-        ops.conv3x3([ops.as_bfhwc(dh1)], P[pre + "block1.wd"], cin, dxs[0],
+        ops.conv3x3([ops.as_bfhwc(dh1)], P[pre + "block1.wd"], cin, dxs[0], mode=env.mode,
                     out2=dxs[1] if len(xs) > 1 else None, nsplit=cins[0], res=res, res2=res2)
         return (None, None, dss, *dxs)
 
@@ -212,7 +213,7 @@ class DownFn(torch.autograd.Function):
         x = x.contiguous()
         ctx.env, ctx.pre = env, pre
         ctx.save_for_backward(x)
-        return blocks.down_fwd(env.P, env.sd, pre, x)
+        return blocks.down_fwd(env.P, env.sd, pre, x, env.mode)
 
     @staticmethod
     def backward(ctx, dout: Tensor):
@@ -221,8 +222,8 @@ class DownFn(torch.autograd.Function):
         dout = dout.contiguous()
         Cc = x.shape[-1]
         dx = torch.empty_like(x)
-        ops.conv_up(ops.as_bfhwc(dout), env.P[pre + "wd"], Cc, dx)
-        ops.wgrad_down(ops.as_bfhwc(dout), ops.as_bfhwc(x), env.sd[pre + "weight"].grad)
+        ops.conv_up(ops.as_bfhwc(dout), env.P[pre + "wd"], Cc, dx, mode=env.mode)
+        ops.wgrad_down(ops.as_bfhwc(dout), ops.as_bfhwc(x), env.sd[pre + "weight"].grad, mode=env.mode)
         ops.colsum(_flat(dout), env.sd[pre + "bias"].grad)
         return None, None, dx
 
@@ -233,7 +234,7 @@ class UpFn(torch.autograd.Function):
         x = x.contiguous()
         ctx.env, ctx.pre = env, pre
         ctx.save_for_backward(x)
-        return blocks.up_fwd(env.P, env.sd, pre, x)
+        return blocks.up_fwd(env.P, env.sd, pre, x, env.mode)
 
     @staticmethod
     def backward(ctx, dout: Tensor):
@@ -242,8 +243,8 @@ class UpFn(torch.autograd.Function):
         dout = dout.contiguous()
         Cc = x.shape[-1]
         dx = torch.empty_like(x)
-        ops.conv_down(ops.as_bfhwc(dout), env.P[pre + "wd"], Cc, dx)
-        ops.wgrad_up(ops.as_bfhwc(dout), ops.as_bfhwc(x), env.sd[pre + "weight"].grad)
+        ops.conv_down(ops.as_bfhwc(dout), env.P[pre + "wd"], Cc, dx, mode=env.mode)
+        ops.wgrad_up(ops.as_bfhwc(dout), ops.as_bfhwc(x), env.sd[pre + "weight"].grad, mode=env.mode)
         ops.colsum(_flat(dout), env.sd[pre + "bias"].grad)
         return None, None, dx
 
@@ -266,7 +267,7 @@ class InitFn(torch.autograd.Function):
         (xin,) = ctx.saved_tensors
         dout = dout.contiguous()
         B, Cc, Fr, H, W = ctx.shape
-        ops.wgrad_init_conv(ops.as_bfhwc(dout), xin, env.sd["init_conv.weight"].grad, Cc)
+        ops.wgrad_init_conv(ops.as_bfhwc(dout), xin, env.sd["init_conv.weight"].grad, Cc, mode=env.mode)
         ops.colsum(_flat(dout), env.sd["init_conv.bias"].grad)
         return None, torch.zeros(1, device=dout.device), None, None, None, None, None
 

@@ -255,10 +255,28 @@ def linear_rows(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch
           gn_group=gn_group, frames_per_sample=frames_per_sample, out2=out2, nsplit=nsplit, res2=res2, alpha=alpha, rot=rot)
 
 
-def conv3x3(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch.Tensor, **kw) -> None:
-    """xs: list of (bf, h, w, c_i) sources (implicit channel concat); 'zeros' padding 1."""
-    taps, _ = taps_conv(3, 3, [x.shape[3] for x in xs], 1)
+def wrap_pad(x: torch.Tensor, p: int, mode: str) -> torch.Tensor:
+    """(bf, h, w, c) -> (bf, h + 2p, w + 2p, c) for the reference's non-zero padding modes (model.yaml:13): 'circular' wraps both
+    pixel axes (nn.Conv3d(padding_mode='circular'), VDDP:240,271), 'circular_1d' wraps the horizontal axis and zero-fills the
+    vertical one (Circular_1d_Conv3d, VDDP:219-236).  vmm_cgemm / vmm_wgrad read such a copy with non-negative tap offsets: their
+    views are independent of the output grid, so the convolution (and its GroupNorm sums) still runs over the h x w grid."""
+    xw = torch.cat((x[:, :, -p:], x, x[:, :, :p]), dim=2)
+    if mode == "circular":
+        return torch.cat((xw[:, -p:], xw, xw[:, :p]), dim=1).contiguous()
+    if mode == "circular_1d":
+        z = xw.new_zeros(xw.shape[0], p, xw.shape[2], xw.shape[3])
+        return torch.cat((z, xw, z), dim=1).contiguous()
+    raise ValueError(f"unknown padding mode {mode!r}")
+
+
+def conv3x3(xs: Sequence[torch.Tensor], wp: torch.Tensor, n: int, out: torch.Tensor, mode: str = "zeros", **kw) -> None:
+    """xs: list of (bf, h, w, c_i) sources (implicit channel concat); padding 1, 'zeros' or a wrap mode (see wrap_pad)."""
     bf, h, w, _ = xs[0].shape
+    if mode != "zeros":
+        taps, _ = taps_conv(3, 3, [x.shape[3] for x in xs], 0)
+        cgemm([wrap_pad(x, 1, mode) for x in xs], [taps], wp, n, out, (bf, h, w), **kw)
+        return
+    taps, _ = taps_conv(3, 3, [x.shape[3] for x in xs], 1)
     if kw.get("tile") is None and h % 16 == 0 and w % 8 == 0 and n <= HALO_MAX_N:
         kw["tile"] = (1, 16, 8)      # vmm_cgemm switches to its halo mode on this tile (one A slab per kx instead of one tile per tap)
     cgemm(list(xs), [taps], wp, n, out, (bf, h, w), **kw)
@@ -277,9 +295,17 @@ def parity_views(x: torch.Tensor):
     return [x[:, py::2, px::2, :] for py in range(2) for px in range(2)]
 
 
-def conv_down(x: torch.Tensor, wp: torch.Tensor, n: int, out: torch.Tensor, **kw) -> None:
-    """(1,4,4) stride (1,2,2) pad (0,1,1) conv, VDDP:241.  x (bf, h, w, c) -> out (bf, h/2, w/2, n)."""
+def down_taps_padded(c: int):
+    """Taps of the strided 4x4 conv over the parity views of a copy padded by one pixel: padded row 2y + ky = parity ky % 2, row y + ky // 2."""
+    return [((ky % 2) * 2 + kx % 2, ky // 2, kx // 2, (ky * 4 + kx) * ceil64(c), c) for ky in range(4) for kx in range(4)]
+
+
+def conv_down(x: torch.Tensor, wp: torch.Tensor, n: int, out: torch.Tensor, mode: str = "zeros", **kw) -> None:
+    """(1,4,4) stride (1,2,2) pad (0,1,1) conv, VDDP:238-243.  x (bf, h, w, c) -> out (bf, h/2, w/2, n)."""
     bf, h, w, c = x.shape
+    if mode != "zeros":
+        cgemm(parity_views(wrap_pad(x, 1, mode)), [down_taps_padded(c)], wp, n, out, (bf, h // 2, w // 2), **kw)
+        return
     cgemm(parity_views(x), [down_taps(c)], wp, n, out, (bf, h // 2, w // 2), **kw)
 
 
@@ -296,10 +322,16 @@ def up_taps(c: int):
     return phases, offs
 
 
-def conv_up(x: torch.Tensor, wp: torch.Tensor, n: int, out: torch.Tensor, **kw) -> None:
-    """ConvTranspose (1,4,4)/(1,2,2)/(0,1,1), VDDP:155, as 4 output phases of 2x2 taps.  out (bf, 2h, 2w, n)."""
+def conv_up(x: torch.Tensor, wp: torch.Tensor, n: int, out: torch.Tensor, mode: str = "zeros", **kw) -> None:
+    """ConvTranspose (1,4,4)/(1,2,2)/(0,1,1), VDDP:153-160, as 4 output phases of 2x2 taps.  out (bf, 2h, 2w, n).  The circular
+    upsamplers of the reference (pad the input by 2, crop 5 output pixels per side, VDDP:164-216) are the same phase formula read
+    from the wrapped input; a one-pixel pad covers the tap offsets -1 .. 1."""
     bf, h, w, c = x.shape
     phases, offs = up_taps(c)
+    if mode != "zeros":
+        phases = [[(src, dy + 1, dx + 1, kofs, cc) for (src, dy, dx, kofs, cc) in ph] for ph in phases]
+        cgemm([wrap_pad(x, 1, mode)], phases, wp, n, out, (bf, h, w), out_geom=(2 * h, 2 * w, 2, 2), phase_off=offs, **kw)
+        return
     cgemm([x], phases, wp, n, out, (bf, h, w), out_geom=(2 * h, 2 * w, 2, 2), phase_off=offs, **kw)
 
 
@@ -317,9 +349,22 @@ def pack_init_conv(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return _pad_rows16(out.reshape(n, kh * 64).to(dtype))
 
 
-def init_conv(xin: torch.Tensor, bf: int, h: int, w: int, wp: torch.Tensor, n: int, out: torch.Tensor, ksize: int = 7, **kw) -> None:
-    """xin: flat 16-bit buffer [bf][h][w+6][8] (+8 slack) from prep_input; (1,7,7) conv VDDP:626."""
+def wrap_prepared_input(xin: torch.Tensor, bf: int, h: int, w: int, mode: str) -> torch.Tensor:
+    """The prepared network input [bf][h][w+6][8] (zero border in x, zero fill above / below by the TMA) re-laid as
+    [bf][h+6][w+6][8] with the three-pixel border of a wrap mode filled in (+8 slack elements)."""
+    inner = xin[: bf * h * (w + 6) * 8].view(bf, h, w + 6, 8)[:, :, 3:3 + w]
+    return torch.cat((wrap_pad(inner, 3, mode).reshape(-1), xin.new_zeros(8)))
+
+
+def init_conv(xin: torch.Tensor, bf: int, h: int, w: int, wp: torch.Tensor, n: int, out: torch.Tensor, ksize: int = 7,
+              mode: str = "zeros", **kw) -> None:
+    """xin: flat 16-bit buffer [bf][h][w+6][8] (+8 slack) from prep_input; (1,7,7) conv VDDP:624-628.  With a wrap mode xin is
+    the [bf][h+6][w+6][8] buffer of wrap_prepared_input and the seven row taps start at the padded row y + ky."""
     assert ksize == 7
+    if mode != "zeros":
+        view = xin.as_strided((bf, h + 6, w, 64), ((h + 6) * (w + 6) * 8, (w + 6) * 8, 8, 1))
+        cgemm([view], [[(0, ky, 0, ky * 64, 64) for ky in range(7)]], wp, n, out, (bf, h, w), **kw)
+        return
     view = xin.as_strided((bf, h, w, 64), (h * (w + 6) * 8, (w + 6) * 8, 8, 1))
     taps = [(0, ky - 3, 0, ky * 64, 64) for ky in range(7)]
     cgemm([view], [taps], wp, n, out, (bf, h, w), **kw)
@@ -458,7 +503,7 @@ def colsum(x2d: torch.Tensor, out: torch.Tensor) -> None:
     check(lib.vmm_colsum(_p(x2d), rows, n, x2d.stride(0), fmt_of(x2d), _p(out), stream_ptr()), "vmm_colsum")
 
 
-def wgrad_conv3x3(dy: torch.Tensor, xs: Sequence[torch.Tensor], dw: torch.Tensor) -> None:
+def wgrad_conv3x3(dy: torch.Tensor, xs: Sequence[torch.Tensor], dw: torch.Tensor, mode: str = "zeros") -> None:
     """dw: (Cout, Cin_total, 1, 3, 3) fp32.  dy (bf,h,w,Cout); xs: concat sources (bf,h,w,c_i)."""
     cout, cin_tot = dw.shape[0], dw.shape[1]
     taps, coff = [], 0
@@ -468,6 +513,10 @@ def wgrad_conv3x3(dy: torch.Tensor, xs: Sequence[torch.Tensor], dw: torch.Tensor
                 taps.append((0, s, ky - 1, kx - 1, x.shape[3], coff * 9 + ky * 3 + kx))
         coff += x.shape[3]
     bf, h, w, _ = dy.shape
+    if mode != "zeros":
+        taps = [(a, b, ddy + 1, ddx + 1, c, wofs) for (a, b, ddy, ddx, c, wofs) in taps]
+        wgrad([dy], [wrap_pad(x, 1, mode) for x in xs], taps, cout, dw, cin_tot * 9, 9, (bf, h, w))
+        return
     wgrad([dy], list(xs), taps, cout, dw, cin_tot * 9, 9, (bf, h, w))
 
 
@@ -488,7 +537,7 @@ def wgrad_linear(dy2d: torch.Tensor, xs2d: Sequence[torch.Tensor], dw: torch.Ten
     wgrad([rows_view(dy2d)], [rows_view(x) for x in xs2d], taps, n, dw, ktot, 1, (1, 1, m))
 
 
-def wgrad_down(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
+def wgrad_down(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, mode: str = "zeros") -> None:
     """Strided (1,4,4) conv: dw (Cout, Cin, 1, 4, 4); dy (bf, h/2, w/2, Cout); x (bf, h, w, Cin)."""
     cout, cin = dw.shape[0], dw.shape[1]
     taps = []
@@ -497,10 +546,14 @@ def wgrad_down(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
             py, px = (ky + 1) % 2, (kx + 1) % 2
             taps.append((0, py * 2 + px, (ky - 1) // 2, (kx - 1) // 2, cin, ky * 4 + kx))
     bf, h2, w2, _ = dy.shape
+    if mode != "zeros":
+        taps = [(0, (ky % 2) * 2 + kx % 2, ky // 2, kx // 2, cin, ky * 4 + kx) for ky in range(4) for kx in range(4)]
+        wgrad([dy], parity_views(wrap_pad(x, 1, mode)), taps, cout, dw, cin * 16, 16, (bf, h2, w2))
+        return
     wgrad([dy], parity_views(x), taps, cout, dw, cin * 16, 16, (bf, h2, w2))
 
 
-def wgrad_up(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
+def wgrad_up(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, mode: str = "zeros") -> None:
     """Transposed conv: dw (Cin, Cout, 1, 4, 4); dy (bf, 2h, 2w, Cout); x (bf, h, w, Cin)."""
     cin, cout = dw.shape[0], dw.shape[1]
     taps = []
@@ -510,13 +563,23 @@ def wgrad_up(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
                 for kx, ddx in (((1, 0), (3, -1)) if px == 0 else ((0, 1), (2, 0))):
                     taps.append((py * 2 + px, 0, ddy, ddx, cin, ky * 4 + kx))
     bf, h, w, _ = x.shape
+    if mode != "zeros":
+        taps = [(a, b, ddy + 1, ddx + 1, c, wofs) for (a, b, ddy, ddx, c, wofs) in taps]
+        wgrad(parity_views(dy), [wrap_pad(x, 1, mode)], taps, cout, dw, 16, cout * 16, (bf, h, w))
+        return
     wgrad(parity_views(dy), [x], taps, cout, dw, 16, cout * 16, (bf, h, w))
 
 
-def wgrad_init_conv(dy: torch.Tensor, xin: torch.Tensor, dw: torch.Tensor, channels: int) -> None:
-    """init_conv: dw (N, C, 1, 7, 7); dy (bf, h, w, N); xin the padded 8-channel buffer of prep_input."""
+def wgrad_init_conv(dy: torch.Tensor, xin: torch.Tensor, dw: torch.Tensor, channels: int, mode: str = "zeros") -> None:
+    """init_conv: dw (N, C, 1, 7, 7); dy (bf, h, w, N); xin the padded 8-channel buffer of prep_input (of wrap_prepared_input
+    with a wrap mode)."""
     n = dw.shape[0]
     bf, h, w, _ = dy.shape
+    if mode != "zeros":
+        view = xin.as_strided((bf, h + 6, w, 64), ((h + 6) * (w + 6) * 8, (w + 6) * 8, 8, 1))
+        wgrad([dy], [view], [(0, 0, ky, 0, 64, ky * 7) for ky in range(7)], n, dw, channels * 49, 49, (bf, h, w), s_c2=1, cmod=8,
+              c_valid=channels, k_valid=7)
+        return
     view = xin.as_strided((bf, h, w, 64), (h * (w + 6) * 8, (w + 6) * 8, 8, 1))
     taps = [(0, 0, ky - 3, 0, 64, ky * 7) for ky in range(7)]
     # column j of the 64-wide window = (kx = j // 8, ch = j % 8) -> dw[n][ch][ky][kx]

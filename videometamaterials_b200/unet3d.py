@@ -75,22 +75,28 @@ class _LinearAttention(nn.Module):     # VDDP:313-329
         self.to_out = nn.Conv2d(hidden, dim, 1)
 
 
+def _conv_module(conv: nn.Module, padding_mode: str) -> nn.Module:
+    """The reference wraps its convolutions in a module for 'circular_1d' (Circular_1d_Conv3d.conv, VDDP:219-236), which puts a
+    `.conv.` level into their state_dict keys; the other modes register the convolution directly."""
+    return _Holder(conv=conv) if padding_mode == 'circular_1d' else conv
+
+
 class _Block(nn.Module):               # VDDP:267-275
-    def __init__(self, dim, dim_out, groups):
+    def __init__(self, dim, dim_out, groups, padding_mode='zeros'):
         super().__init__()
-        self.proj = nn.Conv3d(dim, dim_out, (1, 3, 3), padding=(0, 1, 1))
+        self.proj = _conv_module(nn.Conv3d(dim, dim_out, (1, 3, 3), padding=(0, 1, 1)), padding_mode)
         self.norm = nn.GroupNorm(groups, dim_out)
 
 
 class _ResnetBlock(nn.Module):         # VDDP:287-297
-    def __init__(self, dim, dim_out, *, time_emb_dim=None, groups=8):
+    def __init__(self, dim, dim_out, *, time_emb_dim=None, groups=8, padding_mode='zeros'):
         super().__init__()
         if time_emb_dim is not None:
             self.mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_emb_dim, dim_out * 2))
         else:
             self.mlp = None
-        self.block1 = _Block(dim, dim_out, groups)
-        self.block2 = _Block(dim_out, dim_out, groups)
+        self.block1 = _Block(dim, dim_out, groups, padding_mode)
+        self.block2 = _Block(dim_out, dim_out, groups, padding_mode)
         self.res_conv = nn.Conv3d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
         self.dim, self.dim_out = dim, dim_out
 
@@ -126,8 +132,8 @@ class Unet3D(nn.Module):
             unsupported.append("use_temporal_attention_cond=False")
         if cond_to_time != 'add':
             unsupported.append(f"cond_to_time={cond_to_time!r}")
-        if padding_mode != 'zeros':
-            unsupported.append(f"padding_mode={padding_mode!r}")
+        if padding_mode not in ('zeros', 'circular', 'circular_1d'):
+            raise ValueError(f"unknown padding_mode {padding_mode!r}")
         if not use_sparse_linear_attn:
             unsupported.append("use_sparse_linear_attn=False")
         if attn_dim_head != 32:
@@ -162,7 +168,8 @@ class Unet3D(nn.Module):
         self.time_rel_pos_bias = _Holder(relative_attention_bias=nn.Embedding(32, attn_heads))
         init_dim = init_dim if init_dim is not None else dim
         pad = init_kernel_size // 2
-        self.init_conv = nn.Conv3d(channels, init_dim, (1, init_kernel_size, init_kernel_size), padding=(0, pad, pad))
+        self.init_conv = _conv_module(nn.Conv3d(channels, init_dim, (1, init_kernel_size, init_kernel_size), padding=(0, pad, pad)),
+                                      padding_mode)
         self.init_temporal_attn = temporal(init_dim)
         dims = [init_dim, *[dim * m for m in dim_mults]]
         in_out = list(zip(dims[:-1], dims[1:]))
@@ -175,14 +182,17 @@ class Unet3D(nn.Module):
         self.downs = nn.ModuleList([])
         self.ups = nn.ModuleList([])
         n_res = len(in_out)
-        rb = partial(_ResnetBlock, groups=resnet_groups)
+        rb = partial(_ResnetBlock, groups=resnet_groups, padding_mode=padding_mode)
+        # both circular upsamplers of the reference hold their transposed conv as `.conv_transpose` (VDDP:181, 204)
+        up = lambda d: (nn.ConvTranspose3d(d, d, (1, 4, 4), (1, 2, 2), (0, 1, 1)) if padding_mode == 'zeros'
+                        else _Holder(conv_transpose=nn.ConvTranspose3d(d, d, (1, 4, 4), (1, 2, 2), (0, 1, 1))))
         rbc = partial(rb, time_emb_dim=time_dim)
         lin = lambda d: _residual_prenorm(d, _LinearAttention(d, attn_heads, 32, time_dim), False)
         for ind, (di, do) in enumerate(in_out):
             last = ind >= n_res - 1
             self.downs.append(nn.ModuleList([
                 rbc(di, do), rbc(do, do), lin(do), temporal(do),
-                nn.Conv3d(do, do, (1, 4, 4), (1, 2, 2), (0, 1, 1)) if not last else nn.Identity()]))
+                _conv_module(nn.Conv3d(do, do, (1, 4, 4), (1, 2, 2), (0, 1, 1)), padding_mode) if not last else nn.Identity()]))
         mid = dims[-1]
         self.mid_block1 = rbc(mid, mid)
         self.mid_spatial_attn = _residual_prenorm(mid, _Attention(mid, attn_heads, attn_dim_head, time_dim, None), True)
@@ -192,7 +202,7 @@ class Unet3D(nn.Module):
             last = ind >= n_res - 1
             self.ups.append(nn.ModuleList([
                 rbc(do * 2, di), rbc(di, di), lin(di), temporal(di),
-                nn.ConvTranspose3d(di, di, (1, 4, 4), (1, 2, 2), (0, 1, 1)) if not last else nn.Identity()]))
+                up(di) if not last else nn.Identity()]))
         self.final_conv = nn.Sequential(rb(dim * 2, dim), nn.Conv3d(dim, channels, 1))
         self.null_text_token = nn.Parameter(torch.randn(1, self.cond_attention_tokens, time_dim))
         self.null_text_hidden = nn.Parameter(torch.randn(1, time_dim))
