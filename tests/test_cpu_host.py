@@ -300,3 +300,23 @@ def test_padding_mode_state_dict_matches_reference_layout(golden_dir, mode):
                    per_frame_cond=True)
     assert list(blocks.param_dict(m).keys()) == [k for k, _ in zeros.named_parameters()]
     assert set(blocks.pack_all(m, torch.float32)) == set(blocks.pack_all(zeros, torch.float32))
+
+
+@pytest.mark.parametrize("mode", ["zeros", "circular", "circular_1d"])
+def test_pack_plan_gather_equals_slicing_pack(mode):
+    """The one-launch weight repack gathers every packed GEMM operand from the flat parameter arena through a precomputed index
+    (blocks.pack_plan; vmm_gather_cast does dst[i] = idx[i] < 0 ? 0 : src[idx[i]]).  With the gather done in torch the result must
+    equal the slicing pack (blocks.pack_all) element for element, in every padding mode (the wrap modes rename parameters)."""
+    from videometamaterials_b200 import Unet3D, blocks
+    from videometamaterials_b200.blocks_bwd import GradArena
+    torch.manual_seed(0)
+    m = Unet3D(dim=16, dim_mults=(1, 2), channels=3, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True,
+               per_frame_cond=True, padding_mode=mode)
+    arena = GradArena(m)
+    idx, layout = blocks.pack_plan(m, arena)
+    flat = torch.where(idx < 0, torch.zeros(()), arena.flat_param[idx.clamp(min=0).long()])
+    want = blocks.pack_all(m, torch.float32)
+    assert set(layout) == set(want)
+    for name, (off, shape) in layout.items():
+        got = flat[off:off + int(torch.Size(shape).numel())].view(shape)
+        assert torch.equal(got, want[name]), name
