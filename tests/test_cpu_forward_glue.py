@@ -176,3 +176,37 @@ def test_sampler_glue_matches_oracle(monkeypatch, golden_dir):
         st["x"] = torch.Tensor(gde._ddim_step_core(st, 5.0)).as_subclass(_ClaimsCuda)
     assert rel((st["x"] + 1) * 0.5, want) < 1e-4
     assert float((torch.Tensor(got) - O.ddim_sample(sd, cfg, S, noises[0], cond, 5.0, 4)).abs().max()) > 1e-3      # eta changes the sample
+
+
+def test_trainer_steps_reduce_the_loss(monkeypatch, tmp_path):
+    """The whole optimisation step on the CPU: Trainer.train_step -> p_losses -> block Functions -> gradients in the arena ->
+    fused Adam (+EMA) -> weight repack -> next forward, with the kernels replaced by their contract statements and the optimiser
+    kernel by the oracle's.  On a fixed batch with a fixed (t, noise, mask) draw the loss must go down step after step."""
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import Accelerator, GaussianDiffusion, Trainer, Unet3D, ops
+    emu_ops.install_training(monkeypatch, ops)
+    monkeypatch.setattr(ops, "adam_ema_step", lambda p, g, m, v, ema, lr, b1, b2, eps, step, gs, mode, beta:
+                        O.adam_ema_step(p, g, m, v, ema, step, lr=lr, beta1=b1, beta2=b2, eps=eps, grad_scale=gs, ema_mode=mode, ema_beta=beta))
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    m = Unet3D(dim=16, dim_mults=(1, 2), channels=3, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, per_frame_cond=True)
+    gd = GaussianDiffusion(m, image_size=8, channels=3, num_frames=11, timesteps=8, use_dynamic_thres=True, sampling_timesteps=8)
+    t = Trainer(gd, None, None, [0, 1, 3], train_batch_size=2, test_batch_size=4, train_lr=3e-3, results_folder='run', log=True,
+                null_cond_prob=0.1, per_frame_cond=True, reference_frame='lagrangian', accelerator=Accelerator(cpu=True),
+                update_ema_every=2, step_start_ema=4)
+    t.use_cuda_graph = False                                   # the input below only claims to be a CUDA tensor
+    m.compute_dtype, m._packed = torch.float32, None
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(2, 3, 11, 8, 8, generator=g).as_subclass(_ClaimsCuda)
+    cond = torch.rand(2, 11, generator=g) * 2 - 1
+    w0 = m.init_conv.weight.detach().clone()
+    losses = []
+    for i in range(8):
+        torch.manual_seed(100)                                 # the same t / noise / conditioning-drop draw every step
+        t.step = i
+        losses.append(float(t.train_step(x, cond)))
+    assert all(b < a for a, b in zip(losses, losses[1:])), losses
+    assert losses[-1] < 0.8 * losses[0]
+    assert not torch.equal(m.init_conv.weight.detach(), w0)
+    ema_w = t.ema_model.denoise_fn.init_conv.weight.detach()
+    assert not torch.equal(ema_w, w0) and not torch.equal(ema_w, m.init_conv.weight.detach())      # copied at steps 0, 2; averaged at 4, 6
