@@ -210,3 +210,33 @@ def test_trainer_steps_reduce_the_loss(monkeypatch, tmp_path):
     assert not torch.equal(m.init_conv.weight.detach(), w0)
     ema_w = t.ema_model.denoise_fn.init_conv.weight.detach()
     assert not torch.equal(ema_w, w0) and not torch.equal(ema_w, m.init_conv.weight.detach())      # copied at steps 0, 2; averaged at 4, 6
+
+
+def test_interpolate_glue(monkeypatch):
+    """GaussianDiffusion.interpolate (VDDP:1020-1034) with the conditioning the reference forgets to pass: two q_sample draws at step
+    t, a blend, then p_sample from t - 1 to 0, against the same composition of the oracle's pieces on the recorded noise."""
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import GaussianDiffusion, Unet3D, ops
+    emu_ops.install_sampler(monkeypatch, ops)
+    cfg = O.UnetCfg(dim=16, dim_mults=(1, 2))
+    sd = O.synthetic_state_dict(cfg, seed=16)
+    model = Unet3D(dim=16, dim_mults=(1, 2), channels=3, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True,
+                   per_frame_cond=True)
+    model.load_state_dict(sd)
+    model.compute_dtype, model._packed = torch.float32, None
+    gd = GaussianDiffusion(model, image_size=12, channels=3, num_frames=11, timesteps=8, use_dynamic_thres=True, sampling_timesteps=8)
+    g = torch.Generator().manual_seed(6)
+    b, t, lam = 2, 3, 0.3
+    x1, x2 = (torch.rand(b, 3, 11, 12, 12, generator=g) * 2 - 1 for _ in range(2))
+    cond = torch.rand(b, 11, generator=g) * 2 - 1
+    noises = [torch.randn(b, 3, 11, 12, 12, generator=g) for _ in range(2 + t)]
+    with _Replay(noises):
+        got = gd.interpolate(x1.as_subclass(_ClaimsCuda), x2.as_subclass(_ClaimsCuda), t=t, lam=lam, cond=cond, guidance_scale=5.0)
+    S = O.schedule(8)
+    tb = torch.full((b,), t)
+    img = (1 - lam) * O.q_sample(S, x1, tb, noises[0]) + lam * O.q_sample(S, x2, tb, noises[1])
+    for k, i in enumerate(reversed(range(t))):
+        img = O.p_sample(sd, cfg, S, img, torch.full((b,), i), cond, 5.0, noises[2 + k])
+    assert float((torch.Tensor(got) - img).norm() / img.norm()) < 1e-4
+    with pytest.raises(ValueError):
+        gd.interpolate(x1, x2, t=t)

@@ -286,10 +286,21 @@ class GaussianDiffusion(nn.Module):
         return unnormalize_img(img)
 
     @torch.inference_mode()
-    def interpolate(self, x1, x2, t=None, lam=0.5):
-        """VDDP:1020-1034 (unconditional p_sample calls, as in the reference)."""
-        raise NotImplementedError("interpolate() calls p_sample without cond, which the per_frame_cond network cannot serve "
-                                  "(the reference fails the same way at VDDP:753)")
+    def interpolate(self, x1, x2, t=None, lam=0.5, cond=None, guidance_scale=1.):
+        """VDDP:1020-1034: noise both clips to step t (two q_sample draws), blend them, denoise from t - 1 down to 0.  The reference
+        calls p_sample without a conditioning, which its own per-frame-conditioned network rejects (VDDP:753); `cond` and
+        `guidance_scale` are therefore accepted here (keyword extensions) and `cond=None` fails the same way, with a ValueError."""
+        b = x1.shape[0]
+        t = self.num_timesteps - 1 if t is None else t
+        assert x1.shape == x2.shape
+        if cond is None:
+            raise ValueError("cond is required (per_frame_cond=True): pass the (b, frames) conditioning of the interpolated clip")
+        t_batched = torch.full((b,), t, device=x1.device, dtype=torch.long)
+        xt1, xt2 = (self.q_sample(x, t=t_batched) for x in (x1, x2))
+        img = (1 - lam) * xt1 + lam * xt2
+        for i in reversed(range(0, t)):
+            img = self.p_sample(img, torch.full((b,), i, device=x1.device, dtype=torch.long), cond=cond, guidance_scale=guidance_scale)
+        return img
 
     # ------------------------------------------------------------------ training
     def p_losses(self, x_start, t, cond=None, noise=None, **kwargs):
