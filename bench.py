@@ -2,7 +2,11 @@
 """Benchmark of the VideoMetamaterials hot path (driver contract: see the repository task statement).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]         own arm: B200 kernels
-  python bench.py --impl reference [...]                       reference arm: the CPU oracle port of the reference algorithm
+  python bench.py --impl reference [...]                       reference arm: the UNMODIFIED reference (baseline/_ref) on the host CPU
+  python bench.py --impl torch-gpu                             the UNMODIFIED reference's own torch path on the B200 (fp32 and bf16
+                                                               autocast, b=8): the number the kernels have to beat; the own arm runs
+                                                               it in a subprocess and reports it as `torch_gpu_baseline`
+  python bench.py --global-batch 32 [--gpus N]                 BASELINE configs[3]: strong scaling, 32/N clips per GPU
 
 Metric (BASELINE.json): UNet3D fwd+bwd video-clips/s at 96x96x11 (+ p_sample steps/s as an extra key).
 Workload at every N: configs[1] = "Unet3D fwd+bwd bf16, batch=8, 96x96x11" per GPU (weak scaling, global batch 8N);
@@ -71,6 +75,40 @@ def oracle_step_fn():
     return step
 
 
+def reference_step_fn(batch: int = 1, device: str = "cpu", autocast_dtype=None):
+    """One forward+backward of the UNMODIFIED reference (baseline/_ref, staged by baseline/stage_ref.py) through its own public
+    API: GaussianDiffusion.forward(x, cond=..., null_cond_prob=0.1) -> loss; loss.backward().  Returns (step, kind)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import stage_ref
+    cwd = os.getcwd()
+    vddp = stage_ref.import_reference()
+    os.chdir(cwd)
+    torch.manual_seed(0)
+    model = vddp.Unet3D(dim=64, dim_mults=(1, 2, 4, 8), channels=3, attn_heads=8, attn_dim_head=32, init_dim=None, init_kernel_size=7,
+                        use_sparse_linear_attn=True, resnet_groups=8, cond_bias=True, cond_attention='self-stacked',
+                        cond_attention_tokens=16, cond_att_GRU=False, use_temporal_attention_cond=True, cond_to_time='add',
+                        per_frame_cond=True, padding_mode='zeros')
+    gd = vddp.GaussianDiffusion(model, image_size=96, channels=3, num_frames=11, timesteps=256, loss_type='l1', use_dynamic_thres=True,
+                                sampling_timesteps=256).to(device)
+    torch.manual_seed(1)
+    x01 = torch.rand(batch, 3, 11, 96, 96, device=device)
+    cond = torch.rand(batch, 11, device=device) * 2 - 1
+
+    def step():
+        for p in gd.parameters():
+            p.grad = None
+        if autocast_dtype is not None:
+            with torch.autocast(device_type="cuda", dtype=autocast_dtype):
+                loss = gd(x01, cond=cond, null_cond_prob=0.1)
+        else:
+            loss = gd(x01, cond=cond, null_cond_prob=0.1)
+        loss.backward()
+        return loss
+
+    return step, gd
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -78,7 +116,13 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = oracle_step_fn()
+    kind = "reference"
+    try:
+        step, _ = reference_step_fn(1)
+        what = "the UNMODIFIED reference (baseline/_ref), GaussianDiffusion.forward + backward"
+    except Exception as e:  # noqa: BLE001     baseline/_ref not staged: the oracle port is the same algorithm
+        step, kind = oracle_step_fn(), "port"
+        what = f"oracle port (baseline/_ref unavailable: {str(e)[:80]})"
     t0 = time.perf_counter()
     step()                                   # first warm-up also gives the per-step cost
     est = time.perf_counter() - t0
@@ -86,8 +130,8 @@ def run_reference(args):
     budget = 170.0
     steps = args.steps
     if est * (warm + steps) > budget:        # keep the whole run within a few minutes
-        warm = 0
-        steps = max(1, int(budget / est))
+        warm = 1 if est * 3 <= budget else 0
+        steps = max(1, int(budget / est) - warm)
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
@@ -98,24 +142,77 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Unet3D fwd+bwd, 96x96x11, reference algorithm (oracle port) on host CPU", "sample": "1 clip per step"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": "1 clip forward+backward per step, fp32"},
+        "config": {"workload": "Unet3D fwd+bwd, 96x96x11 (BASELINE configs[1] shape), " + what + " on the host CPU",
+                   "sample": "1 clip per step (the own arm runs 8 per step per GPU; a CPU step of 8 clips takes minutes)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": "1 clip forward+backward per step, fp32, all host threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def run_torch_gpu(args):
+    """The reference's own PyTorch path (cuDNN / cuBLAS / ATen eager) on this GPU: SURVEY.md section 8d "the number to beat"."""
+    import torch
+    assert torch.cuda.is_available()
+    out = {"impl": "torch-gpu", "what": "UNMODIFIED reference (baseline/_ref) in torch eager on cuda:0, GaussianDiffusion.forward + backward, "
+                                        "b=8, 96x96x11, random-init weights, synthetic data", "unit": UNIT, "torch": torch.__version__}
+    B = 8
+
+    def timed(step, n_warm=2, n=3):
+        for _ in range(n_warm):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for name, dt in (("fp32", None), ("bf16_autocast", torch.bfloat16), ("fp16_autocast", torch.float16)):
+        try:
+            step, gd = reference_step_fn(B, "cuda", dt)
+            ms = timed(step)
+            out[name] = {"ms_per_step": ms, "value": B / (ms * 1e-3), "tflops": B * FWD_BWD_GFLOP_PER_CLIP / ms,
+                         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                         "tf32": {"matmul": torch.backends.cuda.matmul.allow_tf32, "cudnn": torch.backends.cudnn.allow_tf32}}
+            if name == "fp32":
+                # the reference's sampling step (fp32, guidance w = 5: two sequential forwards + torch.quantile), b = 4
+                cond = torch.rand(4, 11, device="cuda") * 2 - 1
+                img = torch.randn(4, 3, 11, 96, 96, device="cuda")
+                t = torch.full((4,), 128, device="cuda", dtype=torch.long)
+                ms_s = timed(lambda: gd.p_sample(img, t, cond=cond, guidance_scale=5.0), 2, 4)
+                out["p_sample_fp32"] = {"ms_per_step": ms_s, "value": 1e3 / ms_s, "unit": "p_sample steps/s", "batch": 4, "guidance_scale": 5.0}
+            del step, gd
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats()
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": str(e)[:300]}
+    print(json.dumps(out), flush=True)
+
+
 def cpu_baseline_bounded():
-    """One clip forward+backward of the oracle port on all host cores (~10-30 s of CPU work)."""
+    """One clip forward+backward of the unmodified reference (else the oracle port) on all host cores: one warm-up run, one
+    timed run (~20-30 s of CPU work)."""
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = oracle_step_fn()
+    cwd, path = os.getcwd(), list(sys.path)
+    try:
+        step, _ = reference_step_fn(1)
+        kind = "reference"
+    except Exception:  # noqa: BLE001
+        step, kind = oracle_step_fn(), "port"
+    step()
     t0 = time.perf_counter()
     step()
     dt = time.perf_counter() - t0
-    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": "1 clip (b=1) forward+backward, fp32, single run"}
+    os.chdir(cwd)
+    sys.path[:] = path
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "1 clip (b=1) forward+backward, fp32, all host threads, second of two runs"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,7 +298,10 @@ def run_own(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
     acc = Accelerator(mixed_precision="bf16")
     dev = acc.device
-    B = 8
+    strong = args.global_batch is not None
+    if strong and args.global_batch % world != 0:
+        raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+    B = args.global_batch // world if strong else 8
     torch.manual_seed(0)
     model = Unet3D(dim=64, dim_mults=(1, 2, 4, 8), channels=3, attn_heads=8, attn_dim_head=32, init_dim=None, init_kernel_size=7,
                    use_sparse_linear_attn=True, resnet_groups=8, cond_bias=True, cond_attention='self-stacked', cond_attention_tokens=16,
@@ -274,6 +374,55 @@ def run_own(args):
         step_resident()                      # Trainer falls back to eager launches while ops.PROFILE is set
     barrier()
     prof, ops.PROFILE, ops.PROFILE_TAGS = ops.PROFILE, None, False
+
+    # BASELINE configs[3] next to the weak-scaling line: global batch 32 split over the ranks (strong scaling), same step
+    strong_leg = None
+    if not strong and not args.no_strong and 32 % world == 0:
+        try:
+            import gc
+            trainer.__dict__.pop("_graph_states", None)      # release the CUDA graph (and its private activation pool) of the b=8 shape
+            trainer.__dict__.pop("_graph_state", None)
+            gc.collect()
+            torch.cuda.empty_cache()
+            B2 = 32 // world
+            torch.manual_seed(100 + rank)
+            x2 = torch.rand(B2, 3, 11, 96, 96, device=dev)
+            c2 = torch.rand(B2, 11, device=dev) * 2 - 1
+
+            def step2():
+                trainer.step += 1
+                return trainer.train_step(x2, c2)
+            for _ in range(3):
+                step2()                       # two eager steps, then the capture
+                torch.cuda.synchronize()
+            for _ in range(4):
+                step2()
+                torch.cuda.synchronize()
+            barrier()
+            n2 = max(3, min(args.steps, 10))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n2):
+                step2()
+            e1.record()
+            barrier()
+            ms2 = e0.elapsed_time(e1) / n2
+            if world > 1:
+                t = torch.tensor([ms2], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms2 = float(t[0])
+            strong_leg = {"workload": "BASELINE configs[3]: full Trainer step, global batch 32 (strong scaling)", "global_batch": 32,
+                          "per_gpu_batch": B2, "n_gpus": world, "steps": n2, "ms_per_step": ms2, "value": 32 / (ms2 * 1e-3), "unit": UNIT,
+                          "scaling": "strong", "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+            del x2, c2
+            trainer.__dict__.pop("_graph_states", None)
+            trainer.__dict__.pop("_graph_state", None)
+            gc.collect()
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            strong_leg = {"error": str(e)[:300]}
+            if world > 1:
+                raise                        # a rank that fails here would leave the others waiting in a collective
     if rank != 0:
         return
     pk = peaks()
@@ -303,6 +452,22 @@ def run_own(args):
         t = d[0] / d[1] / 1e12
         return {"achieved": t, "frac": t / pk["tflops_sustained"], "launches_per_step": d[2] // 2, "share_of_step": (d[1] / 2) / (ms * 1e-3)}
     top = sorted(((k, v) for k, v in by.items() if "|" in k and k.startswith("cgemm")), key=lambda kv: -kv[1][1])[:6]
+    def mem_kernel(keys):
+        """HBM-bound kernels: algorithmic bytes / summed CUDA-event durations against the measured copy bandwidth."""
+        tot = [0.0, 0.0, 0, 0.0]
+        for k in keys:
+            d = by.get(k)
+            if d:
+                tot = [tot[0] + d[0], tot[1] + d[1], tot[2] + d[2], tot[3] + d[3]]
+        if tot[1] <= 0:
+            return None
+        gbs = tot[3] / tot[1] / 1e9
+        return {"bound": "hbm", "achieved": gbs, "unit": "GB/s", "peak": pk["hbm"], "frac": gbs / pk["hbm"], "tflops": tot[0] / tot[1] / 1e12,
+                "launches_per_step": tot[2] // 2, "share_of_step": (tot[1] / 2) / (ms * 1e-3)}
+    others = {"tattn_fwd": mem_kernel(["tattn_fwd"]), "tattn_bwd": mem_kernel(["tattn_bwd"]), "tattn_fused_fwd": mem_kernel(["ftattn_fwd"]),
+              "lattn_fwd": mem_kernel(["lattn_fwd"]), "lattn_bwd": mem_kernel(["lattn_bwd"]),
+              "sattn": mem_kernel(["sattn_fwd", "sattn_bwd"]), "groupnorm": mem_kernel(["gn_silu_fwd", "gn_silu_bwd"]),
+              "layernorm": mem_kernel(["ln_fwd", "ln_bwd"])}
     roof = {"bound": "tensor", "kernel": "vmm::cgemm_kernel (all launches of a step)", "achieved": achieved, "peak": pk["tflops_sustained"],
             "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
             "traffic_note": "average DRAM bytes per launch, ncu (profiles/r1_gemm_dram.json); algorithmic_bytes_per_launch = operands read once + output written once",
@@ -313,7 +478,10 @@ def run_own(args):
             "conv3x3": sub("cgemm/conv3x3"), "other_gemm": sub("cgemm/other"),
             "top_shapes": [{"shape": k.partition("|")[2], "tflops": v[0] / v[1] / 1e12, "ms_per_step": v[1] / 2 * 1e3} for k, v in top],
             "wgrad": {"achieved": by["wgrad"][0] / by["wgrad"][1] / 1e12 if "wgrad" in by else None,
-                      "share_of_step": (by["wgrad"][1] / 2) / (ms * 1e-3) if "wgrad" in by else None}}
+                      "frac": by["wgrad"][0] / by["wgrad"][1] / 1e12 / pk["tflops_sustained"] if "wgrad" in by else None,
+                      "share_of_step": (by["wgrad"][1] / 2) / (ms * 1e-3) if "wgrad" in by else None},
+            "other_kernels": {k: v for k, v in others.items() if v is not None},
+            "note": "shares are eager per-launch CUDA-event times over the graph-replayed step time; they need not sum to 1"}
     # sampling metric (second half of BASELINE.json's metric): ancestral p_sample with guidance, b=4, replayed from a CUDA graph,
     # timed on the device; plus BASELINE configs[2], one full 250-step DDIM sample() of the 4 conditionings
     ps = None
@@ -351,12 +519,26 @@ def run_own(args):
     except Exception as e:  # noqa: BLE001
         ps = dict(ps or {}, error=str(e)[:200])
     cpu = cpu_baseline_bounded() if world == 1 and not args.no_cpu_baseline else None
+    # the reference's own torch path on this GPU (subprocess: its package name collides with the drop-in re-export of this repo)
+    tgb = None
+    if world == 1 and not args.no_torch_gpu and os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "denoising_diffusion_pytorch")):
+        try:
+            import gc
+            ema._graphs.clear()               # the sampler's step graphs (and their pools) are no longer needed
+            gc.collect()
+            torch.cuda.empty_cache()          # cached blocks go back to the driver: the child process needs ~60 GB for b=8 in fp32
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "torch-gpu"], capture_output=True, text=True, timeout=900)
+            rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            tgb = json.loads(rows[-1]) if rows else {"error": (r.stderr or "no output")[-300:]}
+        except Exception as e:  # noqa: BLE001
+            tgb = {"error": str(e)[:300]}
     value = world * B / (ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Unet3D fwd+bwd bf16, batch=8 per GPU, 96x96x11 (BASELINE configs[1]); step = forward + backward + "
-                               "gradient all-reduce + fused Adam/EMA + weight repack", "global_batch": world * B,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": (f"Unet3D fwd+bwd bf16, global batch {world * B} = {B} per GPU, 96x96x11 (BASELINE configs[3]); " if strong else
+                                "Unet3D fwd+bwd bf16, batch=8 per GPU, 96x96x11 (BASELINE configs[1]); ") +
+                               "step = forward + backward + gradient all-reduce + fused Adam/EMA + weight repack", "global_batch": world * B,
                    "l2": "activation working set per step (>20 GB) is far larger than the 126 MB L2; no explicit flush",
                    "launch": "forward + backward replayed from one CUDA graph per step; all-reduce, Adam/EMA and repack launched eagerly",
                    "parallelism": f"dp{world}", "model_tflops_per_gpu": B * FWD_BWD_GFLOP_PER_CLIP / ms},
@@ -366,6 +548,16 @@ def run_own(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if strong_leg is not None:
+        line["config4_strong_scaling"] = strong_leg
+    if tgb is not None:
+        line["torch_gpu_baseline"] = tgb
+        try:
+            line["speedup_vs_torch_gpu"] = {k: value / tgb[k]["value"] for k in ("fp32", "bf16_autocast", "fp16_autocast") if "value" in tgb.get(k, {})}
+            if ps and "value" in ps and "p_sample_fp32" in tgb and "value" in tgb["p_sample_fp32"]:
+                line["speedup_vs_torch_gpu"]["p_sample_fp32"] = ps["value"] / tgb["p_sample_fp32"]["value"]
+        except Exception:  # noqa: BLE001
+            pass
     print(json.dumps(line), flush=True)
 
 
@@ -374,12 +566,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--impl", default="own", choices=["own", "reference", "torch-gpu"])
+    ap.add_argument("--global-batch", type=int, default=None, help="strong scaling: this many clips per step over all ranks (BASELINE configs[3]: 32)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the extra global-batch-32 leg of the default run")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the reference-torch-on-this-GPU baseline")
     ap.add_argument("--no-ddim", dest="no_ddim", action="store_true", help="skip the 250-step DDIM sample() timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-gpu":
+        run_torch_gpu(args)
     else:
         run_own(args)
     try:

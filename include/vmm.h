@@ -155,6 +155,20 @@ int vmm_ln_bwd(const void* x, const void* dy, const void* dres, void* dx, int fm
 /* pre_rotated != 0: the q / k columns of qkv already carry the rotary embedding and q the scale (vmm_cgemm rotary epilogue) */
 int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bias, const float* rot, void* out, int fmt, int B, int frames,
                   int HW, int heads, float scale, int pre_rotated, void* stream);
+/* The whole Residual(PreNorm(temporal Attention)) block of a 64-channel level in one kernel (VDDP:131-137, 245-264, 381-535):
+ * TMA x tile -> channel LayerNorm -> to_qkv on tcgen05 (TMEM) -> rotary -> 11 x 22 attention per (pixel, head) on mma.sync ->
+ * to_out on tcgen05 -> + x -> bulk tensor store.  x, out: [B][frames][HW][64] 16-bit; wqkv [768][64] / wout [64][256]: packed
+ * K-major operands of vmm_cgemm; gamma [64]; ekv / bias as vmm_tattn_fwd; rot [2][frames][16][2] (table 0 carries the query scale).
+ * xn_save [rows][64], qkv_save [rows][768] (q, k rotated, q scaled), ao_save [rows][256]: optional outputs for the backward
+ * kernels (NULL when sampling: then qkv never reaches HBM).  frames == 11, heads == 8, C == 64, else VMM_ERR_UNSUPPORTED. */
+size_t vmm_ftattn_workspace(int B);   /* bytes of `workspace`: the per-(sample, head) attention fragments a small pre-kernel prepares */
+int vmm_ftattn_fwd(const void* x, void* out, const void* wqkv, const void* wout, const float* gamma, const float* ekv, const float* bias,
+                   const float* rot, void* xn_save, void* qkv_save, void* ao_save, void* workspace, size_t workspace_bytes, int fmt,
+                   int B, int frames, int HW, int C, int heads, float eps, void* stream);
+/* resident CTAs per SM of the fused kernel on the current device (2 expected; diagnostics) */
+int vmm_ftattn_ctas_per_sm(void);
+/* diagnostics (12 ints): registers, static / max dynamic shared memory, device limits, occupancy at several shared-memory sizes */
+int vmm_ftattn_diag(int* out);
 int vmm_lattn_fwd(const void* qkv, const float* ekv, int T, void* out, float* ctx, float* kstat, int fmt, int BF, int frames,
                   int HW, int heads, float scale, void* stream);
 int vmm_sattn_fwd(const void* qkv, const float* ekv, void* out, float* lse, int fmt, int BF, int frames, int HW, int heads,

@@ -96,7 +96,7 @@ def main(argv=None):
                       train_lr=config['learning_rate'], save_and_sample_every=args.save_and_sample_every, train_num_steps=args.train_steps,
                       ema_decay=0.995, log=True, null_cond_prob=0.1, per_frame_cond=config['per_frame_cond'],
                       reference_frame=config['reference_frame'], run_name=args.run_name, accelerator=accelerator,
-                      wandb_username=args.wandb_username, preload_data=args.preload_data)
+                      wandb_username=args.wandb_username, preload_data=args.preload_data, synthetic_data=args.synthetic_data)
     trainer.train(load_model_step=load_step, num_samples=3, num_preds=args.num_preds)
     trainer.eval_target(args.targets or root + 'data/target_responses.csv', guidance_scale=args.guidance_scale, num_preds=args.num_preds)
     return 0

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/vmm.h but not exported"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert _lib.lib.vmm_abi_version() == 1
+    assert _lib.lib.vmm_abi_version() == _lib.ABI_VERSION
 
 
 def test_compute_call_without_gpu_fails_loudly():
@@ -281,7 +281,7 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
                     "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out
-    assert out.stdout.split()[0] == "1" and out.stdout.split()[2] == "err-ok"
+    assert out.stdout.split()[0] == str(_lib.ABI_VERSION) and out.stdout.split()[2] == "err-ok"
 
 
 @pytest.mark.parametrize("mode", ["circular", "circular_1d"])

@@ -607,3 +607,93 @@ def test_qkv_projection_rotary_epilogue(ops, dt):
     ops.tattn_bwd(plain, ekv, bias, rot, dout, g1, de1, db1, B, Fr, HW, heads)
     ops.tattn_bwd(rotd, ekv, bias, rot, dout, g2, de2, db2, B, Fr, HW, heads, pre_rotated=True)
     assert rel(g2, g1) < 2.5 * TOL[dt] and rel(de2, de1) < TOL[dt] and rel(db2, db1) < TOL[dt]
+
+
+# ------------------------------------------------------------------------------------------------
+# fused temporal-attention block (csrc/ftattn.cu): LayerNorm -> to_qkv (tcgen05) -> rotary -> attention (mma.sync) -> to_out
+# (tcgen05) -> + residual, one kernel.  Checked against plain fp32 torch math of VDDP:131-137, 245-264, 396-535 and against the
+# unfused kernel chain it replaces (ln_fwd -> cgemm with rotary epilogue -> tattn_fwd -> cgemm with residual).
+# ------------------------------------------------------------------------------------------------
+def _fused_block_case(ops, dt, B, H, W, with_cond, keep, seed):
+    from oracle import vdm_oracle as O
+    Fr, heads, Cc = 11, 8, 64
+    hd = heads * 32
+    torch.manual_seed(seed)
+    x = torch.randn(B, Fr, H, W, Cc, device="cuda").to(dt)
+    gamma = (1 + 0.2 * torch.randn(Cc, device="cuda")).contiguous()
+    wq = torch.randn(3 * hd, Cc, device="cuda") * Cc ** -0.5
+    wo = torch.randn(Cc, hd, device="cuda") * hd ** -0.5
+    ekv = torch.randn(B, 11, 2 * hd, device="cuda") if with_cond else None
+    bias = torch.randn(heads, Fr, Fr, device="cuda")
+    freqs = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32)).cuda()
+    ang = torch.arange(Fr, device="cuda").float()[:, None] * freqs[None, :]
+    rot = ops.rotary_tables(torch.stack((ang.cos(), ang.sin()), -1).contiguous(), 32 ** -0.5)
+    wqp, wop = ops.pack_linear(wq, dt), ops.pack_linear(wo, dt)
+    rows = B * Fr * H * W
+    out = torch.empty_like(x)
+    xn = torch.empty(rows, Cc, device="cuda", dtype=dt) if keep else None
+    qkv = torch.empty(rows, 3 * hd, device="cuda", dtype=dt) if keep else None
+    ao = torch.empty(rows, hd, device="cuda", dtype=dt) if keep else None
+    ops.ftattn_fwd(x, out, wqp, wop, gamma, ekv, bias, rot, xn, qkv, ao, B, Fr, H * W, heads)
+    torch.cuda.synchronize()
+    # ---- the unfused kernel chain
+    x2 = x.reshape(-1, Cc)
+    xn_u = torch.empty_like(x2)
+    ops.ln_fwd(x2, xn_u, gamma)
+    qkv_u = torch.empty(rows, 3 * hd, device="cuda", dtype=dt)
+    ops.linear_rows([xn_u], wqp, 3 * hd, qkv_u, rot=(rot, Fr, H * W, 2 * hd, hd))
+    ao_u = torch.empty(rows, hd, device="cuda", dtype=dt)
+    ops.tattn_fwd(qkv_u, ekv, bias, rot[1], ao_u, B, Fr, H * W, heads, pre_rotated=True)
+    out_u = torch.empty_like(x)
+    ops.linear_rows([ao_u], wop, Cc, out_u.reshape(-1, Cc), res=x2)
+    # ---- fp32 torch statement (weights rounded to the 16-bit operand format, everything else fp32)
+    xf = x.float()
+    mean = xf.mean(-1, keepdim=True)
+    var = xf.var(-1, unbiased=False, keepdim=True)
+    xnf = (xf - mean) / (var + 1e-5).sqrt() * gamma
+    qkvf = xnf @ wq.to(dt).float().t()
+    q, k, v = (t.permute(0, 2, 3, 1, 4).reshape(B, H * W, Fr, heads, 32).transpose(2, 3) for t in qkvf.chunk(3, dim=-1))
+    k = O.rotary(k, freqs)
+    if with_cond:
+        ek = ekv[..., :hd].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
+        ev = ekv[..., hd:].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
+        k = torch.cat((ek, k), -2)
+        v = torch.cat((ev, v), -2)
+    sim = torch.einsum("...id,...jd->...ij", O.rotary(q * 32 ** -0.5, freqs), k)
+    sim = sim + (torch.cat((bias, bias), -1) if with_cond else bias)
+    aof = torch.einsum("...ij,...jd->...id", sim.softmax(-1), v).transpose(2, 3).reshape(B, H, W, Fr, hd).permute(0, 3, 1, 2, 4)
+    want = aof @ wo.to(dt).float().t() + xf
+    e = dict(out_vs_torch=rel(out, want), unfused_vs_torch=rel(out_u, want), out_vs_unfused=rel(out, out_u))
+    # the block output is dominated by the residual x: also compare the attention branch alone
+    e["branch_vs_torch"] = rel(out.float() - xf, want - xf)
+    e["branch_unfused_vs_torch"] = rel(out_u.float() - xf, want - xf)
+    if keep:
+        e["xn"] = rel(xn, xn_u)
+        e["qkv"] = rel(qkv, qkv_u)
+        e["ao"] = rel(ao, ao_u)
+    return e
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("case", [(2, 5, 7, True, True), (1, 16, 16, True, False), (3, 3, 3, False, True), (2, 12, 11, False, False),
+                                  (1, 1, 1, True, True)])
+def test_fused_temporal_attention_block(ops, dt, case):
+    """Ragged pixel counts (35, 9, 132 = 12 tiles exactly, 256, 1) against 11-pixel tiles; with / without conditioning keys;
+    with / without the rows kept for the backward kernels."""
+    B, H, W, with_cond, keep = case
+    e = _fused_block_case(ops, dt, B, H, W, with_cond, keep, seed=31)
+    print("fused temporal block:", dt, case, {k: round(v, 5) for k, v in e.items()})
+    assert e["out_vs_torch"] < TOL[dt], e
+    # the attention branch alone: qkv and the attention rows pass through 16 bit twice (as in the unfused chain)
+    assert e["branch_vs_torch"] < 3 * TOL[dt], e
+    assert e["branch_vs_torch"] < 1.5 * e["branch_unfused_vs_torch"] + 1e-4, e
+    if keep:
+        assert e["xn"] < 1e-6 + (2e-3 if dt == torch.bfloat16 else 3e-4), e        # same formula; rsqrt / rounding ties only
+        assert e["qkv"] < TOL[dt] and e["ao"] < TOL[dt], e
+
+
+def test_fused_temporal_attention_occupancy(ops):
+    """One 512-thread CTA per SM (two independent 8-warp groups, 112 KB of shared memory and 256 TMEM columns each): the kernel
+    must be launchable with its 225 KB of dynamic shared memory."""
+    from videometamaterials_b200 import _lib
+    assert _lib.lib.vmm_ftattn_ctas_per_sm() == 1

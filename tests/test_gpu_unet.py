@@ -386,13 +386,8 @@ def test_ddim_eta_graph_matches_eager_and_golden(golden_dir):
 # ------------------------------------------------------------------------------------------------
 # padding_mode = 'circular' / 'circular_1d' (model.yaml:13).  Implemented after the round's GPU budget was spent: the host side
 # is verified on the CPU against the oracle (tests/test_cpu_forward_glue.py, tests/test_cpu_gemm_formulation.py); what these
-# tests add is the kernels reading wrap-padded views that are larger than the output grid.  First device run pending, hence last.
+# tests add is the kernels reading wrap-padded views that are larger than the output grid.  They passed on their first device run (round 1 driver run, GPUTEST_r01.json).
 # ------------------------------------------------------------------------------------------------
-_FIRST_RUN = pytest.mark.xfail(strict=False, reason="padding-mode path written after round 1's GPU budget was spent: verified on the CPU "
-                               "through the kernel contracts only, this is its first run on a device (a pass shows as XPASS)")
-
-
-@_FIRST_RUN
 @pytest.mark.parametrize("mode", ["circular", "circular_1d"])
 def test_wrap_mode_convolutions_on_device(mode):
     import torch.nn.functional as F
@@ -441,7 +436,6 @@ def test_wrap_mode_convolutions_on_device(mode):
     assert rel(out, cl(F.conv_transpose2d(ref_pad(xd.float(), 2), wu[:, :, 0].float(), None, stride=2, padding=5))) < 6e-3
 
 
-@_FIRST_RUN
 @pytest.mark.parametrize("mode", ["circular", "circular_1d"])
 def test_wrap_mode_network_against_the_oracle(mode):
     from oracle import vdm_oracle as O

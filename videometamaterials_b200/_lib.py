@@ -62,20 +62,38 @@ class VmmError(RuntimeError):
     pass
 
 
+ABI_VERSION = 2          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
+
+
 def _load() -> C.CDLL:
-    if not os.path.exists(LIB_PATH):
-        try:
-            from . import build as _build
-            _build.build()
-        except Exception as e:  # noqa: BLE001
+    # Where nvcc exists the build is always consulted: it is a no-op when the source digest matches the stamp, and it replaces a
+    # stale .so (older csrc, drifted struct layouts) otherwise.  Ranks of one node serialise on a file lock.
+    try:
+        from . import build as _build
+        if os.path.exists(_build.NVCC) or not os.path.exists(LIB_PATH):
+            import fcntl
+            os.makedirs(_build.OBJ, exist_ok=True)
+            with open(os.path.join(_build.OBJ, ".lock"), "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                try:
+                    _build.build()
+                finally:
+                    fcntl.flock(lock, fcntl.LOCK_UN)
+    except Exception as e:  # noqa: BLE001
+        if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"libvmm_sm100.so is missing at {LIB_PATH} and could not be built ({e}). "
                 "This package has no CPU or PyTorch fallback: build it with "
                 "`python -m videometamaterials_b200.build` where nvcc is available.") from e
+        import warnings
+        warnings.warn(f"videometamaterials_b200: could not verify / rebuild libvmm_sm100.so ({e}); loading the existing file")
     lib = C.CDLL(LIB_PATH)
     lib.vmm_last_error.restype = C.c_char_p
     lib.vmm_abi_version.restype = C.c_int
     lib.vmm_launch_count.restype = C.c_uint64
+    if int(lib.vmm_abi_version()) != ABI_VERSION:
+        raise ImportError(f"libvmm_sm100.so reports ABI version {int(lib.vmm_abi_version())}, this package expects {ABI_VERSION}: "
+                          "rebuild it with `python -m videometamaterials_b200.build --force`")
     return lib
 
 
@@ -93,6 +111,10 @@ _SIGNATURES = {
     "vmm_ln_fwd": [_P, _P, _I, _L, _I, _P, _F, _P, _P],
     "vmm_ln_bwd": [_P, _P, _P, _P, _I, _L, _I, _P, _F, _P, _P],
     "vmm_tattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "vmm_ftattn_workspace": [_I],
+    "vmm_ftattn_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _F, _P],
+    "vmm_ftattn_ctas_per_sm": [],
+    "vmm_ftattn_diag": [_P],
     "vmm_lattn_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vmm_sattn_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vmm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
@@ -107,7 +129,7 @@ _SIGNATURES = {
     "vmm_gather_cast": [_P, _P, _P, _L, _I, _P],
     "vmm_adam_ema_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _I, _F, _P],
 }
-_RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t}
+_RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t, "vmm_ftattn_workspace": C.c_size_t}
 for _name, _args in _SIGNATURES.items():
     _fn = getattr(lib, _name)     # AttributeError here == the .so is stale: rebuild it
     _fn.argtypes = _args

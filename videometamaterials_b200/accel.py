@@ -26,20 +26,37 @@ from torch.utils import data as tdata
 class _DeviceLoader:
     """DataLoader wrapper that moves batches to the device (what accelerate's prepared loaders do)."""
 
-    def __init__(self, loader, device):
+    def __init__(self, loader, device, sampler=None, total=None):
         self.loader, self.device = loader, device
+        self.sampler = sampler        # DistributedSampler of a multi-process run (None otherwise)
+        self.total = total            # dataset length: gather_for_metrics trims the sampler's padding duplicates with it
+        self.epoch = 0
+        self.remainder = -1           # samples of the LAST gathered batch that are not padding (-1: no trimming needed)
 
     def __len__(self):
         return len(self.loader)
 
     def __iter__(self):
-        for batch in self.loader:
-            if isinstance(batch, (list, tuple)):
-                yield type(batch)(b.to(self.device, non_blocking=True) if torch.is_tensor(b) else b for b in batch)
-            elif torch.is_tensor(batch):
-                yield batch.to(self.device, non_blocking=True)
-            else:
-                yield batch
+        if self.sampler is not None:
+            # a new permutation per pass, as accelerate's prepared loader reshuffles every epoch (the sampler seeds with seed + epoch)
+            self.sampler.set_epoch(self.epoch)
+            self.epoch += 1
+        n_batches = len(self.loader)
+        for i, batch in enumerate(self.loader):
+            # accelerate's GradientState: on the last batch of a sharded loader `remainder` = the number of genuine samples in the
+            # gathered global batch (the DistributedSampler pads every rank's shard to equal length with repeated samples)
+            self.remainder = -1
+            if self.sampler is not None and i == n_batches - 1 and self.total is not None and self.loader.batch_size:
+                self.remainder = self.total % (self.loader.batch_size * self.sampler.num_replicas)
+            yield self._to_device(batch)
+        self.remainder = -1
+
+    def _to_device(self, batch):
+        if isinstance(batch, (list, tuple)):
+            return type(batch)(b.to(self.device, non_blocking=True) if torch.is_tensor(b) else b for b in batch)
+        if torch.is_tensor(batch):
+            return batch.to(self.device, non_blocking=True)
+        return batch
 
 
 class Accelerator:
@@ -69,6 +86,7 @@ class Accelerator:
         self.num_processes = dist.get_world_size() if dist.is_initialized() else 1
         self.process_index = dist.get_rank() if dist.is_initialized() else 0
         self._models: List[torch.nn.Module] = []
+        self._loaders: List[_DeviceLoader] = []
 
     # ------------------------------------------------------------------ properties
     @property
@@ -110,13 +128,18 @@ class Accelerator:
                     self.broadcast_parameters(o)
                 self._models.append(o)
             elif isinstance(o, tdata.DataLoader):
+                sampler = None
                 if self.num_processes > 1:
                     shuffle = isinstance(o.sampler, tdata.RandomSampler)
                     sampler = tdata.distributed.DistributedSampler(o.dataset, num_replicas=self.num_processes, rank=self.process_index,
                                                                    shuffle=shuffle)
+                    extra = dict(collate_fn=o.collate_fn, worker_init_fn=o.worker_init_fn, timeout=o.timeout, generator=o.generator)
+                    if o.num_workers > 0:
+                        extra.update(persistent_workers=o.persistent_workers, prefetch_factor=o.prefetch_factor)
                     o = tdata.DataLoader(o.dataset, batch_size=o.batch_size, sampler=sampler, pin_memory=o.pin_memory,
-                                         num_workers=o.num_workers, drop_last=o.drop_last)
-                o = _DeviceLoader(o, self.device)
+                                         num_workers=o.num_workers, drop_last=o.drop_last, **extra)
+                o = _DeviceLoader(o, self.device, sampler=sampler, total=len(o.dataset))
+                self._loaders.append(o)
             out.append(o)
         return out[0] if len(out) == 1 else tuple(out)
 
@@ -137,21 +160,28 @@ class Accelerator:
         loss.backward()
         self.all_reduce_gradients()
 
-    def all_reduce_gradients(self) -> None:
-        """SUM the gradient arenas over ranks and divide by the world size (what DDP's averaging does)."""
+    def all_reduce_gradients(self, average: bool = True) -> float:
+        """SUM the gradient arenas over ranks and divide by the world size (what DDP's averaging does).  With average=False the
+        division is left to the caller (the fused optimiser kernel takes it as `grad_scale`, which saves one pass over the
+        158 MB arena); the factor still to be applied is returned."""
         if self.num_processes <= 1:
-            return
+            return 1.0
+        pending = 1.0
         for m in self._models:
             inner = getattr(m, "denoise_fn", m)
             arena = getattr(inner, "_vmm_arena", None)
             if arena is not None:
                 dist.all_reduce(arena.flat_grad, op=dist.ReduceOp.SUM, group=self.grad_group)
-                arena.flat_grad.mul_(1.0 / self.num_processes)
+                if average:
+                    arena.flat_grad.mul_(1.0 / self.num_processes)
+                else:
+                    pending = 1.0 / self.num_processes
             else:
                 for p in m.parameters():
                     if p.grad is not None:
                         dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.grad_group)
                         p.grad.mul_(1.0 / self.num_processes)
+        return pending
 
     def clip_grad_norm_(self, parameters, max_norm, norm_type=2):
         return torch.nn.utils.clip_grad_norm_(parameters, max_norm, norm_type=norm_type)
@@ -170,7 +200,14 @@ class Accelerator:
         return torch.cat(outs, dim=0)
 
     def gather_for_metrics(self, tensor: torch.Tensor) -> torch.Tensor:
-        return self.gather(tensor)
+        """gather() minus the samples a sharded loader duplicated to fill its last global batch (accelerate truncates the gathered
+        tensor to `remainder` entries on that batch; a per-rank scalar counts as one entry, as in accelerate)."""
+        out = self.gather(tensor)
+        if self.num_processes > 1:
+            for ld in self._loaders:
+                if ld.remainder > 0 and out.dim() > 0 and out.shape[0] > ld.remainder:
+                    return out[:ld.remainder]
+        return out
 
     def pad_across_processes(self, tensor: torch.Tensor, dim: int = 0, pad_index: float = 0) -> torch.Tensor:
         if self.num_processes <= 1:

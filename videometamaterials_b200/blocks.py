@@ -19,6 +19,7 @@ from . import ops
 
 Tensor = torch.Tensor
 ROTARY_IN_EPILOGUE = os.environ.get("VMM_NO_ROT_EPILOGUE") is None     # debugging switch: rotate q / k inside the attention kernels
+FUSED_TATTN = os.environ.get("VMM_NO_FUSED_TATTN") is None              # debugging switch: 64-channel temporal blocks through the unfused kernels
 
 
 def prob_mask_like(shape, prob, device):
@@ -137,31 +138,44 @@ def pack_all(model, dtype, sd=None) -> Dict[str, Tensor]:
     return P
 
 
+_PACK_PLANS: Dict[tuple, Tuple[Tensor, dict]] = {}
+
+
 def pack_plan(model, arena):
     """The packing as ONE gather: run pack_all on tensors that hold (their own arena index + 1) and read the layout
-    back.  Returns (int32 gather index over the arena, -1 = structural zero; {name: (offset, shape)})."""
-    sd, o = {}, 0
-    index_of = {}
-    for p in arena.params:
-        k = p.numel()
-        index_of[id(p)] = (o, k)
-        o += k
-    for name, p in param_dict(model).items():
-        if id(p) in index_of:
-            o0, k = index_of[id(p)]
-            sd[name] = (torch.arange(o0 + 1, o0 + k + 1, dtype=torch.float64, device=p.device)).view(p.shape)
-        else:
-            sd[name] = torch.zeros(p.shape, dtype=torch.float64, device=p.device)
-    packed = pack_all(model, torch.float64, sd=sd)
-    layout, chunks, off = {}, [], 0
-    for name, t in packed.items():
-        n = t.numel()
-        assert n % 8 == 0
-        layout[name] = (off, tuple(t.shape))
-        chunks.append(t.reshape(-1))
-        off += n
-    idx = (torch.cat(chunks).round().to(torch.int64) - 1).to(torch.int32)
-    return idx, layout
+    back.  Returns (int32 gather index over the arena on the arena's device, -1 = structural zero; {name: (offset, shape)}).
+    The plan is built on the HOST with integer tensors (no device launches) and depends only on the architecture, so it is
+    cached per structure: the EMA copy, a resumed Trainer or the next test reuse it."""
+    names = list(param_dict(model).items())
+    key = (model.dim, model.dim_mults, model.channels, model.heads, model.groups, model.padding_mode,
+           tuple((k, tuple(v.shape)) for k, v in names), tuple(p.numel() for p in arena.params))
+    dev = arena.flat_param.device
+    hit = _PACK_PLANS.get(key)
+    if hit is None:
+        sd, o = {}, 0
+        index_of = {}
+        for p in arena.params:
+            k = p.numel()
+            index_of[id(p)] = (o, k)
+            o += k
+        assert o < 2 ** 31 - 1
+        for name, p in names:
+            if id(p) in index_of:
+                o0, k = index_of[id(p)]
+                sd[name] = torch.arange(o0 + 1, o0 + k + 1, dtype=torch.int32).view(p.shape)
+            else:
+                sd[name] = torch.zeros(p.shape, dtype=torch.int32)
+        packed = pack_all(model, torch.int32, sd=sd)
+        layout, chunks, off = {}, [], 0
+        for name, t in packed.items():
+            n = t.numel()
+            assert n % 8 == 0
+            layout[name] = (off, tuple(t.shape))
+            chunks.append(t.reshape(-1))
+            off += n
+        hit = _PACK_PLANS[key] = (torch.cat(chunks) - 1, layout)
+    idx, layout = hit
+    return idx.to(dev), layout
 
 
 # ------------------------------------------------------------------------------------------------
@@ -391,14 +405,24 @@ def resnet_fwd(P, sd, pre: str, xs: Sequence[Tensor], ss: Optional[Tensor], grou
 
 
 def attn_block_fwd(P, sd, pre: str, kind: str, x: Tensor, ekv: Optional[Tensor], bias: Optional[Tensor], rot: Optional[Tensor],
-                   heads: int):
-    """Residual(PreNorm(attention)) for the three attention flavours.  VDDP:131-137, 256-264, 313-535."""
+                   heads: int, keep: bool = True):
+    """Residual(PreNorm(attention)) for the three attention flavours.  VDDP:131-137, 256-264, 313-535.
+    keep=False (sampling): nothing is saved for a backward pass."""
     B, Fr, H, W, Cc = x.shape
     dt, dev = x.dtype, x.device
     hd = heads * 32
     norm_pre = pre[: pre.index("fn.fn.") + 3]                     # "....fn."  -> PreNorm owns `norm`
     gamma = sd[norm_pre + "norm.gamma"].reshape(-1)
     x2 = _flat(x)
+    if (kind == "temporal" and FUSED_TATTN and ROTARY_IN_EPILOGUE and x.is_cuda and Cc == 64 and Fr == 11 and heads == 8
+            and x.is_contiguous()):
+        # one kernel for the whole block (csrc/ftattn.cu); qkv / attention rows reach HBM only when a backward pass needs them
+        out = torch.empty_like(x)
+        xn = torch.empty_like(x2) if keep else None
+        qkv = torch.empty(x2.shape[0], 3 * hd, dtype=dt, device=dev) if keep else None
+        ao = torch.empty(x2.shape[0], hd, dtype=dt, device=dev) if keep else None
+        ops.ftattn_fwd(x, out, P[pre + "qkv.w"], P[pre + "out.w"], gamma, ekv, bias, rot, xn, qkv, ao, B, Fr, H * W, heads)
+        return out, (xn, qkv, ao, None)
     xn = torch.empty_like(x2)
     ops.ln_fwd(x2, xn, gamma)
     qkv = torch.empty(x2.shape[0], 3 * hd, dtype=dt, device=dev)
@@ -476,7 +500,7 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
     frames = x.shape[2]
     ss, ekv, bias, rot = conditioning(model, time, cond, null_mask, frames)
     h, _ = init_fwd(P, sd, model, x.float(), noise, qcoef)
-    h, _ = attn_block_fwd(P, sd, "init_temporal_attn.fn.fn.fn.", "temporal", h, None, bias, rot, heads)
+    h, _ = attn_block_fwd(P, sd, "init_temporal_attn.fn.fn.fn.", "temporal", h, None, bias, rot, heads, keep=False)
     r = h
     skips = []
     for i in range(L):
@@ -484,20 +508,20 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
         h, _ = resnet_fwd(P, sd, p + "0.", [h], ss[p + "0."], g, pm)
         h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g, pm)
         h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads)
-        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads)
+        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads, keep=False)
         skips.append(h)
         if i < L - 1:
             h = down_fwd(P, sd, p + "4.", h, pm)
     h, _ = resnet_fwd(P, sd, "mid_block1.", [h], ss["mid_block1."], g, pm)
     h, _ = attn_block_fwd(P, sd, "mid_spatial_attn.fn.fn.fn.", "spatial", h, ekv["mid_spatial_attn.fn.fn.fn."], None, None, heads)
-    h, _ = attn_block_fwd(P, sd, "mid_temporal_attn.fn.fn.fn.", "temporal", h, ekv["mid_temporal_attn.fn.fn.fn."], bias, rot, heads)
+    h, _ = attn_block_fwd(P, sd, "mid_temporal_attn.fn.fn.fn.", "temporal", h, ekv["mid_temporal_attn.fn.fn.fn."], bias, rot, heads, keep=False)
     h, _ = resnet_fwd(P, sd, "mid_block2.", [h], ss["mid_block2."], g, pm)
     for i in range(L):
         p = f"ups.{i}."
         h, _ = resnet_fwd(P, sd, p + "0.", [h, skips.pop()], ss[p + "0."], g, pm)
         h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g, pm)
         h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads)
-        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads)
+        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads, keep=False)
         if i < L - 1:
             h = up_fwd(P, sd, p + "4.", h, pm)
     h, _ = resnet_fwd(P, sd, "final_conv.0.", [h, r], None, g, pm)

@@ -37,12 +37,13 @@ class GradArena:
         self.params = params
         n = sum(p.numel() for p in params)
         dev = params[0].device
-        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            # ONE concatenation kernel (not one copy per parameter: model load must not bury the vmm kernels under ~400 tiny launches)
+            self.flat_param = torch.cat([p.data.reshape(-1).to(torch.float32) for p in params])
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         o = 0
         for p in params:
             k = p.numel()
-            self.flat_param[o:o + k].copy_(p.data.reshape(-1))
             p.data = self.flat_param[o:o + k].view(p.shape)
             p.grad = self.flat_grad[o:o + k].view(p.shape)
             o += k

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import csv
 import os
+import threading
 from pathlib import Path
 from typing import Optional, Sequence
 
@@ -147,9 +148,12 @@ class Dataset(data.Dataset):
     decode_cache_bytes = 32 << 30
 
     def __init__(self, folder, image_size, labels_scaling=None, selected_channels=[0, 1, 2, 3], num_frames=16, horizontal_flip=False,
-                 force_num_frames=True, exts=['gif'], per_frame_cond=False, reference_frame='eulerian'):
+                 force_num_frames=True, exts=['gif'], per_frame_cond=False, reference_frame='eulerian', decode_cache_bytes=None):
         super().__init__()
         self._cache, self._cache_used = {}, 0
+        self._cache_lock = threading.Lock()          # preload() fills the cache from a thread pool
+        if decode_cache_bytes is not None:
+            self.decode_cache_bytes = int(decode_cache_bytes)
         if reference_frame not in ('eulerian', 'lagrangian'):
             raise ValueError(f'unknown reference_frame {reference_frame!r}')
         folder = str(folder)
@@ -204,14 +208,25 @@ class Dataset(data.Dataset):
     def __len__(self):
         return len(self.paths['topo'])
 
+    def __getstate__(self):          # DataLoader workers started with 'spawn' pickle the dataset: locks do not pickle
+        st = dict(self.__dict__)
+        st.pop('_cache_lock', None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._cache_lock = threading.Lock()
+
     def _frames_u8(self, sub, index) -> torch.Tensor:
         key = (sub, int(index))
         u8 = self._cache.get(key)
         if u8 is None:
             u8 = _gif_frames_u8(self.paths[sub][index], self.image_size, self.horizontal_flip)
-            if not self.horizontal_flip and self._cache_used + u8.numel() <= self.decode_cache_bytes:
-                self._cache[key] = u8
-                self._cache_used += u8.numel()
+            if not self.horizontal_flip:
+                with self._cache_lock:
+                    if key not in self._cache and self._cache_used + u8.numel() <= self.decode_cache_bytes:
+                        self._cache[key] = u8
+                        self._cache_used += u8.numel()
         return u8
 
     def _frames(self, sub, index) -> torch.Tensor:

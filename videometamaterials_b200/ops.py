@@ -378,42 +378,73 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def gn_silu_fwd(x, y, stats, gamma, beta, scale_shift, B, pix, C_, groups, act=True, eps=1e-5, res=None):
+    e0 = _prof_begin()
     check(lib.vmm_gn_silu_fwd(_p(x), _p(res), _p(y), fmt_of(x), B, pix, C_, groups, _p(stats), _p(gamma), _p(beta), _p(scale_shift),
                               eps, 1 if act else 0, stream_ptr()), "vmm_gn_silu_fwd")
+    _prof_end("gn_silu_fwd", 0.0, e0, 2.0 * B * pix * C_ * (3 if res is not None else 2))
 
 
 def gn_silu_bwd(x, dy, dx, stats, gamma, beta, scale_shift, B, pix, C_, groups, dgamma, dbeta, dss, act=True, eps=1e-5, dx_colsum=None):
     nbytes = int(lib.vmm_gn_silu_bwd_workspace(B, C_, groups))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    e0 = _prof_begin()
     check(lib.vmm_gn_silu_bwd(_p(x), _p(dy), _p(dx), fmt_of(x), B, pix, C_, groups, _p(stats), _p(gamma), _p(beta),
                               _p(scale_shift), eps, 1 if act else 0, _p(dgamma), _p(dbeta), _p(dss), _p(dx_colsum), _p(ws), nbytes,
                               stream_ptr()), "vmm_gn_silu_bwd")
+    _prof_end("gn_silu_bwd", 0.0, e0, 2.0 * B * pix * C_ * 5)        # two passes: (x, dy) read twice, dx written once
 
 
 def ln_fwd(x2d, y2d, gamma, eps=1e-5):
     rows, C_ = x2d.shape
+    e0 = _prof_begin()
     check(lib.vmm_ln_fwd(_p(x2d), _p(y2d), fmt_of(x2d), rows, C_, _p(gamma), eps, None, stream_ptr()), "vmm_ln_fwd")
+    _prof_end("ln_fwd", 0.0, e0, 2.0 * rows * C_ * 2)
 
 
 def ln_bwd(x2d, dy2d, dres2d, dx2d, gamma, dgamma, eps=1e-5):
     rows, C_ = x2d.shape
+    e0 = _prof_begin()
     check(lib.vmm_ln_bwd(_p(x2d), _p(dy2d), _p(dres2d), _p(dx2d), fmt_of(x2d), rows, C_, _p(gamma), eps, _p(dgamma),
                          stream_ptr()), "vmm_ln_bwd")
+    _prof_end("ln_bwd", 0.0, e0, 2.0 * rows * C_ * 4)
 
 
 def tattn_fwd(qkv, ekv, bias, rot, out, B, frames, HW, heads, pre_rotated=False):
+    e0 = _prof_begin()
     check(lib.vmm_tattn_fwd(_p(qkv), _p(ekv), _p(bias), _p(rot), _p(out), fmt_of(qkv), B, frames, HW, heads, 32 ** -0.5,
                             1 if pre_rotated else 0, stream_ptr()), "vmm_tattn_fwd")
+    rows = B * frames * HW
+    _prof_end("tattn_fwd", 2.0 * rows * heads * 32 * (2 * frames if ekv is not None else frames) * 2, e0, 2.0 * rows * heads * 32 * 4)
+
+
+def ftattn_fwd(x, out, wqkv, wout, gamma, ekv, bias, rot, xn, qkv, ao, B, frames, HW, heads, eps=1e-5):
+    """Fused Residual(PreNorm(temporal attention)) forward of a 64-channel level; xn / qkv / ao = None when nothing is kept."""
+    C_ = x.shape[-1]
+    nbytes_ws = int(lib.vmm_ftattn_workspace(B))
+    ws = torch.empty(nbytes_ws, dtype=torch.uint8, device=x.device)
+    e0 = _prof_begin()
+    check(lib.vmm_ftattn_fwd(_p(x), _p(out), _p(wqkv), _p(wout), _p(gamma), _p(ekv), _p(bias), _p(rot), _p(xn), _p(qkv), _p(ao), _p(ws),
+                             nbytes_ws, fmt_of(x), B, frames, HW, C_, heads, eps, stream_ptr()), "vmm_ftattn_fwd")
+    rows, hd = B * frames * HW, heads * 32
+    keys = 2 * frames if ekv is not None else frames
+    flops = 2.0 * rows * (C_ * 3 * hd + hd * C_) + 2.0 * rows * hd * keys * 2
+    nbytes = 2.0 * rows * (2 * C_ + (C_ + 4 * hd if qkv is not None else 0))
+    _prof_end("ftattn_fwd", flops, e0, nbytes)
 
 
 def lattn_fwd(qkv, ekv, T, out, ctx, kstat, BF, frames, HW, heads):
+    e0 = _prof_begin()
     check(lib.vmm_lattn_fwd(_p(qkv), _p(ekv), T, _p(out), _p(ctx), _p(kstat), fmt_of(qkv), BF, frames, HW, heads, 32 ** -0.5,
                             stream_ptr()), "vmm_lattn_fwd")
+    rows = BF * HW
+    _prof_end("lattn_fwd", 2.0 * rows * heads * 32 * 32 * 2, e0, 2.0 * rows * heads * 32 * 4)
 
 
 def sattn_fwd(qkv, ekv, out, lse, BF, frames, HW, heads):
+    e0 = _prof_begin()
     check(lib.vmm_sattn_fwd(_p(qkv), _p(ekv), _p(out), _p(lse), fmt_of(qkv), BF, frames, HW, heads, 32 ** -0.5, stream_ptr()),
           "vmm_sattn_fwd")
+    _prof_end("sattn_fwd", 2.0 * BF * HW * heads * 32 * (HW + 1) * 2, e0, 2.0 * BF * HW * heads * 32 * 4)
 
 
 def prep_input(x, noise, a, c, s, xin, B, C_, F_, H, W):
@@ -587,18 +618,26 @@ def wgrad_init_conv(dy: torch.Tensor, xin: torch.Tensor, dw: torch.Tensor, chann
 
 
 def tattn_bwd(qkv, ekv, bias, rot, dout, dqkv, dekv, dbias, B, frames, HW, heads, pre_rotated=False):
+    e0 = _prof_begin()
     check(lib.vmm_tattn_bwd(_p(qkv), _p(ekv), _p(bias), _p(rot), _p(dout), _p(dqkv), _p(dekv), _p(dbias), fmt_of(qkv), B, frames, HW,
                             heads, 32 ** -0.5, 1 if pre_rotated else 0, stream_ptr()), "vmm_tattn_bwd")
+    rows = B * frames * HW
+    _prof_end("tattn_bwd", 2.0 * rows * heads * 32 * (2 * frames if ekv is not None else frames) * 5, e0, 2.0 * rows * heads * 32 * 7)
 
 
 def lattn_bwd(qkv, ekv, T, dout, ctx, kstat, dctx, dqkv, dekv, BF, frames, HW, heads):
+    e0 = _prof_begin()
     check(lib.vmm_lattn_bwd(_p(qkv), _p(ekv), T, _p(dout), _p(ctx), _p(kstat), _p(dctx), _p(dqkv), _p(dekv), fmt_of(qkv), BF, frames,
                             HW, heads, 32 ** -0.5, 1.0 / HW, stream_ptr()), "vmm_lattn_bwd")
+    rows = BF * HW
+    _prof_end("lattn_bwd", 2.0 * rows * heads * 32 * 32 * 5, e0, 2.0 * rows * heads * 32 * 7)
 
 
 def sattn_bwd(qkv, ekv, aout, dout, lse, dqkv, dekv, BF, HW, heads):
+    e0 = _prof_begin()
     check(lib.vmm_sattn_bwd(_p(qkv), _p(ekv), _p(aout), _p(dout), _p(lse), _p(dqkv), _p(dekv), fmt_of(qkv), BF, HW, heads, 32 ** -0.5,
                             stream_ptr()), "vmm_sattn_bwd")
+    _prof_end("sattn_bwd", 2.0 * BF * HW * heads * 32 * (HW + 1) * 5, e0, 2.0 * BF * HW * heads * 32 * 8)
 
 
 def gather_cast(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> None:

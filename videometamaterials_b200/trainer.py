@@ -113,7 +113,8 @@ class Trainer(object):
     def __init__(self, diffusion_model, folder, validation_folder, selected_channels, *, ema_decay=0.995, train_batch_size=4,
                  test_batch_size=2, train_lr=1.e-4, train_num_steps=100000, step_start_ema=2000, update_ema_every=10,
                  save_and_sample_every=1000, results_folder='./', max_grad_norm=None, log=True, null_cond_prob=0., per_frame_cond=False,
-                 reference_frame='eulerian', run_name=None, accelerator=None, wandb_username=None, log_every=50, preload_data=False):
+                 reference_frame='eulerian', run_name=None, accelerator=None, wandb_username=None, log_every=50, preload_data=False,
+                 synthetic_data=False, decode_cache_bytes=None):
         super().__init__()
         self.accelerator = accelerator if accelerator is not None else Accelerator()
         if log:
@@ -146,19 +147,33 @@ class Trainer(object):
         self.selected_channels = selected_channels
         self.per_frame_cond = per_frame_cond
         self.reference_frame = reference_frame
-        if folder is not None and os.path.isdir(str(folder)):
+        # decoded-frame cache budget per Dataset object: the per-rank default is divided by the ranks sharing this host's memory
+        ds_kw = {}
+        if decode_cache_bytes is None:
+            local = max(int(os.environ.get("LOCAL_WORLD_SIZE", self.accelerator.num_processes)), 1)
+            decode_cache_bytes = (32 << 30) // local
+        ds_kw["decode_cache_bytes"] = int(decode_cache_bytes)
+        # synthetic clips only on request (folder=None or synthetic_data=True): a mistyped path must not train on noise
+        synthetic_train = synthetic_data or folder is None
+        if not synthetic_train and not os.path.isdir(str(folder)):
+            raise FileNotFoundError(f"training folder {folder!r} does not exist (pass synthetic_data=True or folder=None for synthetic clips)")
+        if not synthetic_train:
             self.ds = Dataset(folder, image_size, labels_scaling=None, selected_channels=selected_channels, num_frames=num_frames,
-                              per_frame_cond=per_frame_cond, reference_frame=reference_frame)
+                              per_frame_cond=per_frame_cond, reference_frame=reference_frame, **ds_kw)
         else:
             self.ds = SyntheticLagrangianDataset(1024, image_size, len(selected_channels), num_frames)
         if preload_data and hasattr(self.ds, 'preload'):
             self.ds.preload()             # decode every GIF once, in threads; otherwise the cache fills during the first epoch
         self.dl = cycle(self.accelerator.prepare(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=True, pin_memory=True)))
-        self.accelerator.print(f'found {len(self.ds)} videos in {folder}')
+        self.accelerator.print(f'found {len(self.ds)} videos in {folder}' if not synthetic_train
+                               else f'using {len(self.ds)} SYNTHETIC clips (SyntheticLagrangianDataset), no training folder')
         assert len(self.ds) > 0, 'could not find any gif files in folder'
-        if validation_folder is not None and os.path.isdir(str(validation_folder)):
+        synthetic_val = synthetic_data or validation_folder is None
+        if not synthetic_val and not os.path.isdir(str(validation_folder)):
+            raise FileNotFoundError(f"validation folder {validation_folder!r} does not exist (pass synthetic_data=True or None for synthetic clips)")
+        if not synthetic_val:
             self.ds_test = Dataset(validation_folder, image_size, labels_scaling=self.ds.labels_scaling, selected_channels=selected_channels,
-                                   num_frames=num_frames, per_frame_cond=per_frame_cond, reference_frame=reference_frame)
+                                   num_frames=num_frames, per_frame_cond=per_frame_cond, reference_frame=reference_frame, **ds_kw)
         else:
             self.ds_test = SyntheticLagrangianDataset(8, image_size, len(selected_channels), num_frames, seed=1)
         self.dl_test = self.accelerator.prepare(data.DataLoader(self.ds_test, batch_size=self.test_batch_size, shuffle=False, pin_memory=True))
@@ -284,6 +299,7 @@ class Trainer(object):
             if _warn is not None:
                 _warn(False)
             torch.cuda.synchronize()
+            torch.cuda.empty_cache()         # the eager warm-up's cached activation blocks: the graph allocates its own private pool
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with torch.cuda.graph(g):
@@ -300,13 +316,17 @@ class Trainer(object):
     def train_step(self, x, cond):
         """One optimisation step on a device batch: forward, backward, gradient all-reduce, fused Adam (+EMA)."""
         loss = self._fwd_bwd(x, cond)
-        self.accelerator.all_reduce_gradients()
+        # the 1/P of the gradient average rides in the optimiser kernel's grad_scale unless the clipped norm needs averaged gradients
+        reduce = getattr(self.accelerator, "all_reduce_gradients", None)      # a genuine HF Accelerator has no such member: its
+        grad_scale = 1.0                                                        # prepared (DDP) model averages during backward
+        if reduce is not None:
+            grad_scale = reduce(average=self.max_grad_norm is not None) or 1.0
         if self.max_grad_norm is not None:
             self.accelerator.clip_grad_norm_(get_arena(self.model.denoise_fn).params, self.max_grad_norm)
         ema_mode = 0
         if self.step % self.update_ema_every == 0:
             ema_mode = 1 if self.step < self.step_start_ema else 2
-        self.opt.step(ema_flat=self._ema_flat() if ema_mode else None, ema_mode=ema_mode, ema_beta=self.ema_decay)
+        self.opt.step(ema_flat=self._ema_flat() if ema_mode else None, ema_mode=ema_mode, ema_beta=self.ema_decay, grad_scale=grad_scale)
         if ema_mode:
             self.ema_model.denoise_fn.repack()
         return loss

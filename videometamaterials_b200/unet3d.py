@@ -224,8 +224,13 @@ class Unet3D(nn.Module):
         """Rebuild every packed weight (call after an optimizer step or a load_state_dict).  With a parameter
         arena (training) this is ONE gather+cast launch over the arena; otherwise the torch slicing path."""
         with torch.no_grad():
-            arena = getattr(self, "_vmm_arena", None)
             dev = next(self.parameters()).device
+            if dev.type == "cuda":
+                # on a device the parameters always live in a flat arena (created here on first use, ONE concatenation), so that
+                # packing is the one-launch gather also at model load and for sampling-only models
+                from .blocks_bwd import get_arena
+                get_arena(self)
+            arena = getattr(self, "_vmm_arena", None)
             if arena is not None and arena.flat_param.device == dev and dev.type == "cuda":
                 plan = getattr(self, "_pack_plan", None)
                 if plan is None or plan[0].device != dev or plan[3] is not arena:
