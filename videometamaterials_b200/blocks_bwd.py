@@ -304,12 +304,40 @@ class LossFn(torch.autograd.Function):
         return None, dh, None, None
 
 
+class FinalFn(torch.autograd.Function):
+    """final 1x1x1 conv (VDDP:708) as a differentiable output: fp32 channels-last prediction (b, f, h, w, c).  Used when the network
+    itself is called under autograd (Unet3D.forward with gradients enabled); the training step fuses this conv with the loss (LossFn)."""
+
+    @staticmethod
+    def forward(ctx, env: _Env, h: Tensor):
+        h = h.contiguous()
+        ctx.env = env
+        ctx.save_for_backward(h)
+        return blocks.final_fwd(env.P, env.sd, env.model, h)
+
+    @staticmethod
+    def backward(ctx, dpred: Tensor):
+        env = ctx.env
+        (h,) = ctx.saved_tensors
+        model = env.model
+        Cc = model.channels
+        dp8 = torch.zeros(h.numel() // h.shape[-1], 8, dtype=h.dtype, device=h.device)      # rows carry 8 (zero padded) channels
+        dp8[:, :Cc] = dpred.reshape(-1, Cc).to(h.dtype)
+        dh = torch.empty_like(h)
+        ops.linear_rows([dp8], env.P["final.wd"], h.shape[-1], _flat(dh))
+        ops.wgrad_linear(dp8, [_flat(h)], env.sd["final_conv.1.weight"].grad)
+        db8 = torch.zeros(8, dtype=torch.float32, device=h.device)
+        ops.colsum(dp8, db8)
+        env.sd["final_conv.1.bias"].grad.add_(db8[:Cc])
+        return None, dh
+
+
 # ------------------------------------------------------------------------------------------------
 # whole network, training form
 # ------------------------------------------------------------------------------------------------
-def training_loss(model, x0: Tensor, noise: Tensor, qcoef, t: Tensor, cond: Tensor, null_mask: Tensor, l2: bool = False) -> Tensor:
-    """loss(noise, Unet3D(q_sample(x0, t, noise), t, cond)) with gradients accumulated into the parameter arena.
-    x0, noise: fp32 (b, c, f, h, w).  qcoef = (a[b], c[b] or None, s[b]): x_t = a x0 + c + s noise."""
+def _trunk(model, x0: Tensor, noise: Optional[Tensor], qcoef, t: Tensor, cond: Tensor, null_mask: Tensor):
+    """Everything of Unet3D.forward (VDDP:730-820) up to the input of the final 1x1x1 conv, as autograd Functions whose
+    backward kernels accumulate parameter gradients into the arena.  Returns (env, hidden activations)."""
     if not x0.is_cuda:
         raise RuntimeError("videometamaterials_b200 has no CPU path: move the model and inputs to a CUDA device")
     get_arena(model)
@@ -318,7 +346,7 @@ def training_loss(model, x0: Tensor, noise: Tensor, qcoef, t: Tensor, cond: Tens
     frames = x0.shape[2]
     ss, ekv, bias, rot = blocks.conditioning(model, t, cond, null_mask, frames)
     anchor = torch.zeros(1, device=x0.device, requires_grad=True)
-    a, c, s = qcoef
+    a, c, s = qcoef if qcoef is not None else (None, None, None)
     h = InitFn.apply(env, anchor, x0, noise, a, c, s)
     h = AttnBlockFn.apply(env, "init_temporal_attn.fn.fn.fn.", "temporal", h, None, bias, rot)
     r = h
@@ -345,4 +373,19 @@ def training_loss(model, x0: Tensor, noise: Tensor, qcoef, t: Tensor, cond: Tens
         if i < L - 1:
             h = UpFn.apply(env, p + "4.", h)
     h = ResnetFn.apply(env, "final_conv.0.", None, h, r)
+    return env, h
+
+
+def training_loss(model, x0: Tensor, noise: Tensor, qcoef, t: Tensor, cond: Tensor, null_mask: Tensor, l2: bool = False) -> Tensor:
+    """loss(noise, Unet3D(q_sample(x0, t, noise), t, cond)) with gradients accumulated into the parameter arena.
+    x0, noise: fp32 (b, c, f, h, w).  qcoef = (a[b], c[b] or None, s[b]): x_t = a x0 + c + s noise."""
+    env, h = _trunk(model, x0, noise, qcoef, t, cond, null_mask)
     return LossFn.apply(env, h, noise, l2)
+
+
+def unet_forward_autograd(model, x: Tensor, t: Tensor, cond: Tensor, null_mask: Tensor) -> Tensor:
+    """Unet3D.forward under autograd: fp32 channels-last prediction (b, f, h, w, c) whose backward accumulates every parameter
+    gradient into `param.grad` (views of the arena), like nn.Module parameters under torch autograd.  The input `x` itself
+    receives no gradient (nothing in the reference's training or sampling paths asks for one)."""
+    env, h = _trunk(model, x.contiguous().float(), None, None, t, cond, null_mask)
+    return FinalFn.apply(env, h)

@@ -566,7 +566,10 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
         dot += __shfl_xor_sync(0xffffffffu, dot, 1);
         dot += __shfl_xor_sync(0xffffffffu, dot, 2);
         if (live) {
-          uint16_t* orow = dqkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD + h * 32 + 2 * t;
+          // in place over the staged row: the p / wn values of these very elements were read just above, the MMAs of this 16-row
+          // block are done, and the 32 columns of head h in each segment belong to this warp alone.  The CTA then copies whole
+          // rows to dqkv with 16-byte stores (4-byte stores from the fragments split into eight pieces per warp instruction).
+          uint16_t* orow = tile + r * LP3 + h * 32 + 2 * t;
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
             *reinterpret_cast<uint32_t*>(orow + 8 * nt) =
@@ -579,6 +582,12 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
       }
     }
     __syncthreads();
+    for (int i = tid; i < cnt * 96; i += 256) {           // coalesced copy-out: 96 x 16 bytes per 768-wide row
+      const int r = i / 96, c8 = i - r * 96;
+      *reinterpret_cast<uint4*>(dqkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD + c8 * 8) =
+          *reinterpret_cast<const uint4*>(tile + r * LP3 + c8 * 8);
+    }
+    __syncthreads();       // the next step's staging overwrites the tile
   }
 }
 

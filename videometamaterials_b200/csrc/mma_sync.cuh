@@ -19,6 +19,14 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, uint32_t addr) {
                : "r"(addr));
 }
 
+// transpose of an 8 x 8 matrix of 16-bit elements held one 32-bit register per lane (lane = 4 * row + column pair): the layout of an
+// accumulator block packed to 16 bit, and of every 8 x 8 block of an A / B fragment
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
 // D(16x8, fp32) += A(16x16, row) * B(16x8, col); FMT 0 = fp16, 1 = bf16 operands
 template <int FMT>
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, const uint32_t* b) {

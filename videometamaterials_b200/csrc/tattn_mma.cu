@@ -266,7 +266,7 @@ extern "C" int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bia
 // Backward.  Same CTA shape (8 warps = 8 heads, TPXB pixels per iteration).  Per pixel and head:
 //   pass A (rows = queries): S, P, dP = dO V^T, D = rowsum(P dP), dS = P (dP - D), dQ = dS K      -> dq, log-sum-exp / D
 //   pass B (rows = keys, once for the 16 cond slots, once for the 16 frame slots):
-//            S^T = K Q^T, P^T = exp(S^T + bias^T - lse), dP^T = V dO^T, dS^T = P^T (dP^T - D),
+//            P^T and dS^T = the 16-bit P / dS fragments of pass A transposed in registers (movmatrix, 8 x 8 blocks),
 //            dK = dS^T Q, dV = P^T dO                                                            -> dk, dv | cond grads
 // Gradients of the cond keys / values and of the position bias are summed over the CTA's pixels in accumulator
 // fragments and added atomically once per CTA.  The cond keys / values sit in shared memory as a 16-bit tile so that
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
   uint16_t* ctile = dtile0 + 2 * BPXB * TNF * DPITCH;       // [TNF][CPITCH]            cond ek | ev
   uint16_t* zrow = ctile + TNF * CPITCH;                    // [TPITCH] zeros
   float* RT = reinterpret_cast<float*>(zrow + TPITCH);      // [TNF][16][2]
-  float* ST = RT + TNF * 32;                                // [8 warps][2][16]  lse, D per query
+
   const int HD = heads * 32;
   const int b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
       ctile[j * CPITCH + c] = FMT ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
     }
   }
-  float bs[2][2][2], bsT[2][2][2];
+  float bs[2][2][2];
 #pragma unroll
   for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
@@ -333,8 +333,6 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
       for (int c = 0; c < 2; ++c) {
         const int i = g + 8 * rh, j = 8 * nt + 2 * t + c;                    // pass A: row = query i, col = key j
         bs[rh][nt][c] = (j < TNF) ? ((i < TNF) ? bias[(h * TNF + i) * TNF + j] : 0.f) : -1e30f;
-        const int jj = g + 8 * rh, ii = 8 * nt + 2 * t + c;                  // pass B: row = key jj, col = query ii
-        bsT[rh][nt][c] = (jj < TNF && ii < TNF) ? bias[(h * TNF + ii) * TNF + jj] : -1e30f;
       }
   float gb[2][2][2];
   float gEK[4][4], gEV[4][4];
@@ -349,8 +347,6 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
   fa.lm = lane >> 3;
   fa.lr = lane & 7;
   const uint32_t ctile_s = smem_u32(ctile);
-  float* lse_s = ST + warp * 32;
-  float* dd_s = lse_s + 16;
   const int groups = (HW + BPXB - 1) / BPXB;
   auto stage_load = [&](int st, int grp) {
     const int p0 = grp * BPXB;
@@ -460,11 +456,12 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
         Dr[rh] += __shfl_xor_sync(0xffffffffu, Dr[rh], 1);
         Dr[rh] += __shfl_xor_sync(0xffffffffu, Dr[rh], 2);
       }
-      if (t == 0) {
-        lse_s[g] = mx[0] + __logf(sum[0]);
-        lse_s[g + 8] = mx[1] + __logf(sum[1]);
-        dd_s[g] = Dr[0];
-        dd_s[g + 8] = Dr[1];
+      // P as 16-bit fragments [key tile][query rows g | g + 8]: pass B transposes them instead of recomputing S^T
+      uint32_t pk[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        pk[nt][0] = pack2<FMT>(S[nt][0], S[nt][1]);
+        pk[nt][1] = pack2<FMT>(S[nt][2], S[nt][3]);
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
@@ -474,11 +471,12 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
           dP[nt][c] = ds;                          // dS
           gb[c >> 1][nt & 1][c & 1] += ds;
         }
+      uint32_t sa[2][4];                         // dS as 16-bit A fragments per key tile (also transposed in pass B)
+      uint32_t dqp[2][4];                        // dq of rows g | g + 8, written over the q slice once pass B no longer reads it
       {   // dQ_rot = dS K  (k-step 0: cond keys, k-step 1: frame keys)
         float dQ[4][4];
 #pragma unroll
         for (int x = 0; x < 16; ++x) (&dQ[0][0])[x] = 0.f;
-        uint32_t sa[2][4];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           sa[ks][0] = pack2<FMT>(dP[2 * ks][0], dP[2 * ks][1]);
@@ -501,16 +499,13 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
         // dq = scale R^T dQ_rot
 #pragma unroll
         for (int rh = 0; rh < 2; ++rh) {
-          const int i = g + 8 * rh;
-          if (i < TNF) {
-            uint16_t* orow = dqkv + ((static_cast<long long>(b) * TNF + i) * HW + p0 + p) * 3 * HD + h * 32 + 2 * t;
+          const int i = min(g + 8 * rh, TNF - 1);
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-              const int k = 4 * nt + t;
-              const float cs = RT[(i * 16 + k) * 2], sn = RT[(i * 16 + k) * 2 + 1];
-              const float a = dQ[nt][2 * rh], c = dQ[nt][2 * rh + 1];
-              *reinterpret_cast<uint32_t*>(orow + 8 * nt) = pack2<FMT>((a * cs + c * sn) * scale, (c * cs - a * sn) * scale);
-            }
+          for (int nt = 0; nt < 4; ++nt) {
+            const int k = 4 * nt + t;
+            const float cs = RT[(i * 16 + k) * 2], sn = RT[(i * 16 + k) * 2 + 1];
+            const float a = dQ[nt][2 * rh], c = dQ[nt][2 * rh + 1];
+            dqp[rh][nt] = pack2<FMT>((a * cs + c * sn) * scale, (c * cs - a * sn) * scale);
           }
         }
       }
@@ -519,38 +514,11 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         if (mt == 0 && !cond) continue;
-        const uint32_t kbase = mt == 0 ? ctile_s : tp;
-        const int kpitch = mt == 0 ? CPITCH : TPITCH;
-        const int kcol = (mt == 0 ? 0 : HD) + h * 32;
-        const int vcol = (mt == 0 ? HD : 2 * HD) + h * 32;
-        float STt[2][4], dPT[2][4];
-#pragma unroll
-        for (int x = 0; x < 8; ++x) (&STt[0][0])[x] = (&dPT[0][0])[x] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t ka[4], va[4], qb[4], db[4];
-          ldsm_x4(ka, fa.a(kbase, kpitch, kcol + 16 * ks));
-          ldsm_x4(va, fa.a(kbase, kpitch, vcol + 16 * ks));
-          ldsm_x4(qb, fa.b(tp, TPITCH, h * 32 + 16 * ks));
-          ldsm_x4(db, fa.b(dp_s, DPITCH, h * 32 + 16 * ks));
-          mma16816<FMT>(STt[0], ka, qb);
-          mma16816<FMT>(STt[1], ka, qb + 2);
-          mma16816<FMT>(dPT[0], va, db);
-          mma16816<FMT>(dPT[1], va, db + 2);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int qi = 8 * nt + 2 * t + (c & 1);
-            const float pt = __expf(STt[nt][c] + bsT[c >> 1][nt][c & 1] - lse_s[qi]);     // 0 on padded keys / queries
-            STt[nt][c] = pt;                                   // P^T
-            dPT[nt][c] = pt * (dPT[nt][c] - dd_s[qi]);         // dS^T
-          }
-        uint32_t pa[4] = {pack2<FMT>(STt[0][0], STt[0][1]), pack2<FMT>(STt[0][2], STt[0][3]), pack2<FMT>(STt[1][0], STt[1][1]),
-                          pack2<FMT>(STt[1][2], STt[1][3])};
-        uint32_t sa[4] = {pack2<FMT>(dPT[0][0], dPT[0][1]), pack2<FMT>(dPT[0][2], dPT[0][3]), pack2<FMT>(dPT[1][0], dPT[1][1]),
-                          pack2<FMT>(dPT[1][2], dPT[1][3])};
+        // rows = keys of tile mt, k = queries: block (keys 8a.., queries 8b..) is the transpose of block (queries 8b.., keys 8a..)
+        const uint32_t pa[4] = {movmatrix_trans(pk[2 * mt][0]), movmatrix_trans(pk[2 * mt + 1][0]), movmatrix_trans(pk[2 * mt][1]),
+                                movmatrix_trans(pk[2 * mt + 1][1])};
+        const uint32_t sat[4] = {movmatrix_trans(sa[mt][0]), movmatrix_trans(sa[mt][2]), movmatrix_trans(sa[mt][1]),
+                                 movmatrix_trans(sa[mt][3])};
         float dK[4][4], dV[4][4];
 #pragma unroll
         for (int x = 0; x < 16; ++x) (&dK[0][0])[x] = (&dV[0][0])[x] = 0.f;
@@ -559,8 +527,8 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
           uint32_t qb[4], db[4];
           ldsm_x4_trans(qb, fa.bt(tp, TPITCH, h * 32 + 16 * dh));
           ldsm_x4_trans(db, fa.bt(dp_s, DPITCH, h * 32 + 16 * dh));
-          mma16816<FMT>(dK[2 * dh], sa, qb);
-          mma16816<FMT>(dK[2 * dh + 1], sa, qb + 2);
+          mma16816<FMT>(dK[2 * dh], sat, qb);
+          mma16816<FMT>(dK[2 * dh + 1], sat, qb + 2);
           mma16816<FMT>(dV[2 * dh], pa, db);
           mma16816<FMT>(dV[2 * dh + 1], pa, db + 2);
         }
@@ -571,19 +539,24 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
             (&gEV[0][0])[x] += (&dV[0][0])[x];
           }
         } else {
+          // Gradients go over the staged rows in place: K and V of this pixel are no longer read (dQ was taken in pass A), Q is read
+          // by the dK MMAs just above, and the 32 columns of head h in each of the q | k | v segments belong to this warp alone.
+          // The CTA then copies whole 1536-byte rows to dqkv with 16-byte stores (4-byte stores straight from the fragments cost
+          // eight 16-byte pieces per warp instruction).
+          __syncwarp();
 #pragma unroll
           for (int rh = 0; rh < 2; ++rh) {
             const int j = g + 8 * rh;
             if (j < TNF) {
-              uint16_t* krow = dqkv + ((static_cast<long long>(b) * TNF + j) * HW + p0 + p) * 3 * HD + HD + h * 32 + 2 * t;
-              uint16_t* vrow = krow + HD;
+              uint16_t* qrow = tile + (p * TNF + j) * TPITCH + h * 32 + 2 * t;
 #pragma unroll
               for (int nt = 0; nt < 4; ++nt) {
                 const int k = 4 * nt + t;
                 const float cs = RT[(j * 16 + k) * 2], sn = RT[(j * 16 + k) * 2 + 1];
                 const float a = dK[nt][2 * rh], c = dK[nt][2 * rh + 1];
-                *reinterpret_cast<uint32_t*>(krow + 8 * nt) = pack2<FMT>(a * cs + c * sn, c * cs - a * sn);
-                *reinterpret_cast<uint32_t*>(vrow + 8 * nt) = pack2<FMT>(dV[nt][2 * rh], dV[nt][2 * rh + 1]);
+                *reinterpret_cast<uint32_t*>(qrow + 8 * nt) = dqp[rh][nt];
+                *reinterpret_cast<uint32_t*>(qrow + HD + 8 * nt) = pack2<FMT>(a * cs + c * sn, c * cs - a * sn);
+                *reinterpret_cast<uint32_t*>(qrow + 2 * HD + 8 * nt) = pack2<FMT>(dV[nt][2 * rh], dV[nt][2 * rh + 1]);
               }
             }
           }
@@ -592,6 +565,15 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
       __syncwarp();
     }
     __syncthreads();
+    // coalesced copy-out of the gradient rows (dq | dk | dv now sit where q | k | v were): 96 x 16 bytes per row
+    for (int i = tid; i < BPXB * TNF * 96; i += 256) {
+      const int c = i % 96, f = (i / 96) % TNF, p = i / (96 * TNF);
+      if (p0 + p < HW) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + (p * TNF + f) * TPITCH + c * 8);
+        *reinterpret_cast<uint4*>(dqkv + ((static_cast<long long>(b) * TNF + f) * HW + p0 + p) * 3 * HD + c * 8) = v;
+      }
+    }
+    __syncthreads();       // the next iteration's prefetch refills this buffer
   }
   // ---- flush the per-CTA sums
   if (cond && dekv) {

@@ -6,6 +6,12 @@
 // the shared-memory descriptors are built with the MN-major flag.  One work item = (tap, 128-wide slice of n,
 // <=128-wide slice of c, K range of pixel tiles); partial sums are added atomically into the fp32 gradient in
 // the parameter's own (master) layout, so no unpack pass is needed.
+//
+// Slab mode (3x3 stride-1 taps on a 1 x 16 x 8 pixel tile, the level-0 / level-1 convolutions): the three ky taps of one
+// (kx, 64-channel chunk) read pixel tiles that overlap in 14 of their 16 rows, so ONE box of 18 pixel rows is loaded per column
+// block and the three 64-channel chunks of the B operand are addressed 1024 bytes (one pixel row = one swizzle atom) apart
+// through the descriptor's leading-dimension stride.  B traffic per block drops from 3 to 1.125 tiles: these launches are
+// bound by the L2 -> shared-memory fill, not by the MMAs.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -26,6 +32,8 @@ constexpr int kWgMaxChunks = 3;
 struct WgColDev {     // one column block of the accumulator = up to 3 chunks of 64 B-operand channels, possibly of different taps
   int16_t n_chunks;
   int16_t a_src;      // all chunks of a block share the A view
+  int16_t slab;       // 1: the chunks are the taps dy0, dy0 + 1, dy0 + 2 of one slab load (see above)
+  int16_t pad;
   int16_t tap[kWgMaxChunks];
   int16_t c0[kWgMaxChunks];
 };
@@ -33,6 +41,8 @@ struct WgColDev {     // one column block of the accumulator = up to 3 chunks of
 struct WgradDev {
   CUtensorMap amap[VMM_MAX_VIEWS];
   CUtensorMap bmap[VMM_MAX_VIEWS];
+  CUtensorMap bslab[VMM_MAX_VIEWS];   // box of th + 2 pixel rows (slab mode)
+  uint32_t slab_bytes;
   WgTapDev taps[VMM_MAX_TAPS];
   WgColDev cols[kWgMaxCols];
   int n_cols, m_tiles, ksplit, total_items;
@@ -124,12 +134,17 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           wg_pix(p, kt, bf0, y0, x0);
           mbar_wait(&ctl->empty[s], ph ^ 1);
           uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
-          mbar_expect_tx(&ctl->full[s], (p.a_chunks + cd.n_chunks) * kChunkBytes);
+          mbar_expect_tx(&ctl->full[s], cd.slab ? p.a_chunks * kChunkBytes + p.slab_bytes : (p.a_chunks + cd.n_chunks) * kChunkBytes);
           for (int a = 0; a < p.a_chunks; ++a)
             tma_load_4d(st + a * kChunkBytes, &p.amap[cd.a_src], &ctl->full[s], mt * 128 + a * 64, x0, y0, bf0);
-          for (int b = 0; b < cd.n_chunks; ++b) {
-            const WgTapDev T = p.taps[cd.tap[b]];
-            tma_load_4d(st + (p.a_chunks + b) * kChunkBytes, &p.bmap[T.b_src], &ctl->full[s], cd.c0[b], x0 + T.dx, y0 + T.dy, bf0);
+          if (cd.slab) {
+            const WgTapDev T = p.taps[cd.tap[0]];       // first (lowest dy) tap of the slab
+            tma_load_4d(st + p.a_chunks * kChunkBytes, &p.bslab[T.b_src], &ctl->full[s], cd.c0[0], x0 + T.dx, y0 + T.dy, bf0);
+          } else {
+            for (int b = 0; b < cd.n_chunks; ++b) {
+              const WgTapDev T = p.taps[cd.tap[b]];
+              tma_load_4d(st + (p.a_chunks + b) * kChunkBytes, &p.bmap[T.b_src], &ctl->full[s], cd.c0[b], x0 + T.dx, y0 + T.dy, bf0);
+            }
           }
           if (++s == p.stages) {
             s = 0;
@@ -151,6 +166,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
       const uint32_t idesc = p.idesc_by_chunks[p.cols[col].n_chunks];
+      const uint32_t b_lbo = p.cols[col].slab ? 1024u : static_cast<uint32_t>(kChunkBytes);
       uint32_t accumulate = 0;
       for (int kt = kt0; kt < kt1; ++kt) {
         mbar_wait(&ctl->full[s], ph);
@@ -161,7 +177,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
 #pragma unroll
           for (int k = 0; k < 8; ++k) {   // 8 x 16 pixels
             const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, kChunkBytes, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, kChunkBytes, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, b_lbo, 1024);
             umma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
             accumulate = 1;
           }
@@ -317,18 +333,73 @@ extern "C" int vmm_wgrad(const vmm_wgrad_params* hp, void* stream_) {
     d.taps[t].dx = static_cast<int16_t>(T.dx);
     d.taps[t].c = T.c;
     d.taps[t].wofs = T.wofs;
-    for (int c0 = 0; c0 < T.c; c0 += 64) {
-      WgColDev* blk = ncols > 0 ? &d.cols[ncols - 1] : nullptr;
-      if (!blk || blk->n_chunks >= max_chunks || blk->a_src != T.a_src) {
-        if (ncols >= kWgMaxCols) return set_error(VMM_ERR_UNSUPPORTED, "vmm_wgrad: too many column blocks");
-        blk = &d.cols[ncols++];
-        blk->n_chunks = 0;
-        blk->a_src = static_cast<int16_t>(T.a_src);
+  }
+  // slab mode: every tap must belong to a triple (same views, dx, c; dy = d0, d0 + 1, d0 + 2) on the 1 x 16 x 8 tile
+  static const bool no_slab = getenv("VMM_WGRAD_NO_SLAB") != nullptr;
+  bool slab = !no_slab && h.tf == 1 && h.th == 16 && h.tw == 8 && (h.n_taps % 3) == 0;
+  int trip[VMM_MAX_TAPS][3];
+  int n_trip = 0;
+  if (slab) {
+    bool used[VMM_MAX_TAPS] = {false};
+    for (int t = 0; t < h.n_taps && slab; ++t) {
+      if (used[t]) continue;
+      // t must be the lowest dy of its triple: find the partners
+      int t1 = -1, t2 = -1, lower = -1;
+      for (int u = 0; u < h.n_taps; ++u) {
+        if (u == t || used[u]) continue;
+        const vmm_wgrad_tap &A = h.taps[t], &Bt = h.taps[u];
+        if (A.a_src != Bt.a_src || A.b_src != Bt.b_src || A.dx != Bt.dx || A.c != Bt.c) continue;
+        if (Bt.dy == A.dy + 1) t1 = u;
+        if (Bt.dy == A.dy + 2) t2 = u;
+        if (Bt.dy == A.dy - 1) lower = u;
       }
-      blk->tap[blk->n_chunks] = static_cast<int16_t>(t);
-      blk->c0[blk->n_chunks] = static_cast<int16_t>(c0);
-      ++blk->n_chunks;
-      if (64 * blk->n_chunks > d.BNc) d.BNc = 64 * blk->n_chunks;
+      if (lower >= 0) continue;            // not the first of its triple: it is picked up from there
+      if (t1 < 0 || t2 < 0) {
+        slab = false;
+        break;
+      }
+      used[t] = used[t1] = used[t2] = true;
+      trip[n_trip][0] = t;
+      trip[n_trip][1] = t1;
+      trip[n_trip][2] = t2;
+      ++n_trip;
+    }
+    for (int t = 0; t < h.n_taps && slab; ++t)
+      if (!used[t]) slab = false;
+  }
+  if (slab) {
+    for (int g = 0; g < n_trip; ++g) {
+      const vmm_wgrad_tap& T = h.taps[trip[g][0]];
+      for (int c0 = 0; c0 < T.c; c0 += 64) {
+        if (ncols >= kWgMaxCols) return set_error(VMM_ERR_UNSUPPORTED, "vmm_wgrad: too many column blocks");
+        WgColDev* blk = &d.cols[ncols++];
+        blk->n_chunks = 3;
+        blk->slab = 1;
+        blk->a_src = static_cast<int16_t>(T.a_src);
+        for (int j = 0; j < 3; ++j) {
+          blk->tap[j] = static_cast<int16_t>(trip[g][j]);
+          blk->c0[j] = static_cast<int16_t>(c0);
+        }
+      }
+    }
+    d.BNc = 192;
+  } else {
+    for (int t = 0; t < h.n_taps; ++t) {
+      const vmm_wgrad_tap& T = h.taps[t];
+      for (int c0 = 0; c0 < T.c; c0 += 64) {
+        WgColDev* blk = ncols > 0 ? &d.cols[ncols - 1] : nullptr;
+        if (!blk || blk->n_chunks >= max_chunks || blk->a_src != T.a_src) {
+          if (ncols >= kWgMaxCols) return set_error(VMM_ERR_UNSUPPORTED, "vmm_wgrad: too many column blocks");
+          blk = &d.cols[ncols++];
+          blk->n_chunks = 0;
+          blk->slab = 0;
+          blk->a_src = static_cast<int16_t>(T.a_src);
+        }
+        blk->tap[blk->n_chunks] = static_cast<int16_t>(t);
+        blk->c0[blk->n_chunks] = static_cast<int16_t>(c0);
+        ++blk->n_chunks;
+        if (64 * blk->n_chunks > d.BNc) d.BNc = 64 * blk->n_chunks;
+      }
     }
   }
   d.n_cols = ncols;
@@ -363,7 +434,10 @@ extern "C" int vmm_wgrad(const vmm_wgrad_params* hp, void* stream_) {
   }
   d.ksplit = ksplit;
   d.total_items = base_items * ksplit;
-  d.stage_bytes = (d.a_chunks + (d.BNc >> 6)) * kChunkBytes;
+  d.slab_bytes = static_cast<uint32_t>((h.th + 2) * h.tw * 128);
+  // slab mode: A chunks + one slab, padded to whole 1024-byte atoms; the MMA of the last k-step reads chunk 2 up to 2 atoms past
+  // the 16-row tile, i.e. exactly to the end of the 18-row slab
+  d.stage_bytes = slab ? (d.a_chunks * kChunkBytes + ((d.slab_bytes + 1023u) & ~1023u)) : (d.a_chunks + (d.BNc >> 6)) * kChunkBytes;
   d.stages = (200 * 1024) / static_cast<int>(d.stage_bytes);
   if (d.stages > 8) d.stages = 8;
   for (int nc = 1; nc <= kWgMaxChunks; ++nc) d.idesc_by_chunks[nc] = make_idesc_f16(128, 64 * nc, h.fmt, 1, 1);
@@ -389,6 +463,11 @@ extern "C" int vmm_wgrad(const vmm_wgrad_params* hp, void* stream_) {
     uint64_t gsb[3] = {(uint64_t)vb.strides[0] * 2, (uint64_t)vb.strides[1] * 2, (uint64_t)vb.strides[2] * 2};
     rc = encode_tensor_map(&d.bmap[i], dt, 4, vb.ptr, gdb, gsb, box, false);
     if (rc) return rc;
+    if (slab) {
+      const uint32_t sbox[4] = {64, (uint32_t)h.tw, (uint32_t)h.th + 2, (uint32_t)h.tf};
+      rc = encode_tensor_map(&d.bslab[i], dt, 4, vb.ptr, gdb, gsb, sbox, false);
+      if (rc) return rc;
+    }
   }
   const size_t smem = static_cast<size_t>(d.stages) * d.stage_bytes + sizeof(WgSmemCtl) + 1024;
   static bool attr_set = false;

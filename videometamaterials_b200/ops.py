@@ -197,27 +197,28 @@ def _pad_rows16(w2d: torch.Tensor) -> torch.Tensor:
 
 
 def pack_linear(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """(N, K) -> [N_pad16, ceil64(K)]."""
+    """(N, K) -> [N_pad16, ceil64(K)] (one zero fill + one strided copy; the copy casts)."""
     n, k = w.shape
-    out = w.new_zeros(n, ceil64(k))
-    out[:, :k] = w
-    return _pad_rows16(out.to(dtype))
+    out = torch.zeros((n + 15) // 16 * 16, ceil64(k), dtype=dtype, device=w.device)
+    out[:n, :k] = w
+    return out
 
 
 def pack_conv_taps(w: torch.Tensor, splits: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
-    """(N, Cin, kh, kw) with Cin = sum(splits) -> [N_pad16, kh*kw*sum(ceil64(split))], tap-major then source-major."""
+    """(N, Cin, kh, kw) with Cin = sum(splits) -> [N_pad16, kh*kw*sum(ceil64(split))], tap-major then source-major
+    (one zero fill + one strided copy per source; the copy casts)."""
     n, cin, kh, kw = w.shape
     assert sum(splits) == cin
-    blocks = []
-    for ky in range(kh):
-        for kx in range(kw):
-            c0 = 0
-            for c in splits:
-                blk = w.new_zeros(n, ceil64(c))
-                blk[:, :c] = w[:, c0:c0 + c, ky, kx]
-                blocks.append(blk)
-                c0 += c
-    return _pad_rows16(torch.cat(blocks, dim=1).to(dtype))
+    widths = [ceil64(c) for c in splits]
+    per_tap = sum(widths)
+    out = torch.zeros((n + 15) // 16 * 16, kh * kw * per_tap, dtype=dtype, device=w.device)
+    o3 = out[:n].view(n, kh * kw, per_tap)
+    c0 = k0 = 0
+    for c, wd in zip(splits, widths):
+        o3[:, :, k0:k0 + c] = w[:, c0:c0 + c].reshape(n, c, kh * kw).permute(0, 2, 1)
+        c0 += c
+        k0 += wd
+    return out
 
 
 def taps_conv(kh: int, kw: int, splits: Sequence[int], pad: int) -> Tuple[List[Tuple[int, int, int, int, int]], int]:
@@ -544,11 +545,13 @@ def wgrad_conv3x3(dy: torch.Tensor, xs: Sequence[torch.Tensor], dw: torch.Tensor
                 taps.append((0, s, ky - 1, kx - 1, x.shape[3], coff * 9 + ky * 3 + kx))
         coff += x.shape[3]
     bf, h, w, _ = dy.shape
+    # 1 x 16 x 8 pixel tiles switch vmm_wgrad to its slab mode (one 18-row box of X per (kx, 64-channel chunk) serves the three ky taps)
+    tile = (1, 16, 8) if (h % 16 == 0 and w % 8 == 0) else None
     if mode != "zeros":
         taps = [(a, b, ddy + 1, ddx + 1, c, wofs) for (a, b, ddy, ddx, c, wofs) in taps]
-        wgrad([dy], [wrap_pad(x, 1, mode) for x in xs], taps, cout, dw, cin_tot * 9, 9, (bf, h, w))
+        wgrad([dy], [wrap_pad(x, 1, mode) for x in xs], taps, cout, dw, cin_tot * 9, 9, (bf, h, w), tile=tile)
         return
-    wgrad([dy], list(xs), taps, cout, dw, cin_tot * 9, 9, (bf, h, w))
+    wgrad([dy], list(xs), taps, cout, dw, cin_tot * 9, 9, (bf, h, w), tile=tile)
 
 
 def wgrad_linear(dy2d: torch.Tensor, xs2d: Sequence[torch.Tensor], dw: torch.Tensor) -> None:

@@ -284,5 +284,11 @@ class Unet3D(nn.Module):
         return self._forward_masked(x, time, cond, mask)
 
     def _forward_masked(self, x, time, cond, null_mask):
-        eps_cl = blocks.unet_forward(self, x, None, None, time, cond, null_mask)   # (b, f, h, w, c) fp32
+        if torch.is_grad_enabled() and x.is_cuda and any(p.requires_grad for p in self.parameters()):
+            # called under autograd (the reference's nn.Module supports `model(x, t, cond=c).backward()`, VDDP:730-821): route through
+            # the block Functions of the training path so that the call is differentiable instead of silently detached
+            from . import blocks_bwd
+            eps_cl = blocks_bwd.unet_forward_autograd(self, x, time, cond, null_mask)
+        else:
+            eps_cl = blocks.unet_forward(self, x, None, None, time, cond, null_mask)   # (b, f, h, w, c) fp32
         return eps_cl.permute(0, 4, 1, 2, 3).contiguous()
