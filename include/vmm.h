@@ -215,6 +215,44 @@ int vmm_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, 
                       float eps, int step, float grad_scale, int ema_mode, float ema_beta, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Conditioning / time path of Unet3D.forward in one forward kernel and two backward kernels (fp32, CUDA cores):
+ *   SinusoidalPosEmb + time_mlp (VDDP:139-151, 637-642, 745), sign_emb tokens (VDDP:653, 753-755), cond_token_to_hidden
+ *   (VDDP:656-661, 757-759), classifier-free-guidance null tokens (VDDP:772-784), t + hidden (VDDP:786-788), every
+ *   ResnetBlock.mlp (VDDP:290-293, 304-306), every to_k / to_v on the tokens with the rotary embedding of the temporal
+ *   blocks' keys (VDDP:349-353, 457-474), the relative position bias (VDDP:70-108, 741) and the rotary cos / sin tables.
+ * Parameters are read from / gradients accumulated into flat fp32 arenas at the given element offsets.  `out` (forward) is one
+ * flat fp32 buffer: per ResnetBlock (B, 2C) at res_out[j]; per attention block keys|values (B, T, 512) at att_out[a]; the bias
+ * [heads][frames][frames] at bias_out; rotary tables [2][frames][16][2] at rot_out (table 0 x dim_head^-1/2).  For
+ * vmm_cond_bwd `out` holds the gradients w.r.t. those outputs in the same layout; `ws` (vmm_cond_workspace bytes) carries
+ * the saved intermediates from the forward call.  B <= 32, T <= 16, td <= 256, heads == 8.
+ * ------------------------------------------------------------------------------------------ */
+#define VMM_COND_MAX_BLOCKS 24
+typedef struct {
+  int32_t B, T, dim, td, heads, frames, n_res, n_attn;
+  const int64_t* time;             /* (B) timesteps */
+  const float* cond;               /* (B, T) */
+  const unsigned char* null_mask;  /* (B) 1 = conditioning dropped */
+  const float* param;              /* parameter arena */
+  float* grad;                     /* gradient arena (vmm_cond_bwd) */
+  const float* freqs;              /* rotary frequencies [16] */
+  const int32_t* buckets;          /* relative position bucket of (i, j), [frames][frames] */
+  int64_t o_w1, o_b1, o_w2, o_b2;  /* time_mlp.1 / time_mlp.3 */
+  int64_t o_wse, o_bse;            /* sign_emb */
+  int64_t o_lng, o_lnb, o_w3, o_b3, o_w4, o_b4;   /* cond_token_to_hidden.0 / .1 / .3 */
+  int64_t o_ntok, o_nhid, o_table; /* null_text_token, null_text_hidden, time_rel_pos_bias table [32][heads] */
+  int64_t res_w[VMM_COND_MAX_BLOCKS], res_b[VMM_COND_MAX_BLOCKS], res_out[VMM_COND_MAX_BLOCKS];
+  int32_t res_c2[VMM_COND_MAX_BLOCKS];
+  int64_t att_wk[VMM_COND_MAX_BLOCKS], att_wv[VMM_COND_MAX_BLOCKS], att_out[VMM_COND_MAX_BLOCKS];
+  int32_t att_temporal[VMM_COND_MAX_BLOCKS];
+  int64_t bias_out, rot_out;
+  float* out;
+  float* ws;
+} vmm_cond_params;
+size_t vmm_cond_workspace(int B, int T, int dim, int td);
+int vmm_cond_fwd(const vmm_cond_params* p, void* stream);
+int vmm_cond_bwd(const vmm_cond_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Weight gradients on tcgen05 tensor cores:  dW[n, tap, c] += sum_pix dY[pix, n] * X[pix + d_tap, c].
  * The gradient of every layer vmm_cgemm runs forward (VDDP:271,297,319,325,413,421,241,155,626,708).
  * a[]: views of the output gradient (one, or the 4 parity views for the transposed conv);

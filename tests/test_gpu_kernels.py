@@ -697,3 +697,68 @@ def test_fused_temporal_attention_occupancy(ops):
     must be launchable with its 225 KB of dynamic shared memory."""
     from videometamaterials_b200 import _lib
     assert _lib.lib.vmm_ftattn_ctas_per_sm() == 1
+
+
+# ------------------------------------------------------------------------------------------------
+# conditioning / time path (csrc/cond.cu): one forward kernel + two backward kernels against the torch statement of the same
+# path (blocks.conditioning(_torch_path=True), itself pinned to the oracle on the CPU in tests/test_cpu_host.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(64, (1, 2, 4, 8), 8, [False, True, False, False, True, False, False, False]),
+                                  (64, (1, 2, 4, 8), 32, None), (16, (1, 2), 3, [True, False, False]), (64, (1, 2), 1, [False])])
+def test_conditioning_kernels_match_the_torch_path(case, monkeypatch):
+    from videometamaterials_b200 import Unet3D, blocks
+    from videometamaterials_b200.blocks_bwd import get_arena
+    dim, mults, B, mask = case
+    monkeypatch.setattr(blocks, "COND_KERNEL_MAX_B", 32)      # the product routes batches above 8 to the torch statement (speed); the kernels handle 32
+    torch.manual_seed(7)
+    model = Unet3D(dim=dim, dim_mults=mults, channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
+                   cond_bias=True, cond_attention='self-stacked', cond_attention_tokens=16, use_temporal_attention_cond=True,
+                   cond_to_time='add', per_frame_cond=True, padding_mode='zeros').cuda()
+    with torch.no_grad():        # parameters that start at zero / one in the reference's init would hide errors
+        for k, p in model.named_parameters():
+            if "null_text" in k or "cond_token_to_hidden.0" in k or "relative_attention_bias" in k:
+                p.add_(0.3 * torch.randn_like(p))
+    arena = get_arena(model)
+    time = torch.randint(0, 256, (B,), device="cuda")
+    cond = torch.rand(B, 11, device="cuda") * 2 - 1
+    null = torch.tensor(mask, device="cuda") if mask is not None else (torch.rand(B, device="cuda") < 0.25)
+    assert blocks.cond_kernel_eligible(model, time, cond)
+    # torch path with autograd
+    ss_t, ekv_t, bias_t, rot_t = blocks.conditioning(model, time, cond, null, 11, _torch_path=True)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    g_ss = {k: torch.randn(v.shape, device="cuda", generator=gen) for k, v in ss_t.items()}
+    g_ekv = {k: torch.randn(v.shape, device="cuda", generator=gen) for k, v in ekv_t.items()}
+    g_bias = torch.randn(bias_t.shape, device="cuda", generator=gen)
+    arena.zero_grad()
+    loss = sum((ss_t[k] * g_ss[k]).sum() for k in ss_t) + sum((ekv_t[k] * g_ekv[k]).sum() for k in ekv_t) + (bias_t * g_bias).sum()
+    loss.backward()
+    want = arena.flat_grad.clone()
+    # kernel path
+    arena.zero_grad()
+    ss_k, ekv_k, bias_k, rot_k, st = blocks.conditioning_state(model, time, cond, null, 11)
+    assert st is not None
+    worst = max([rel(ss_k[k], ss_t[k].detach()) for k in ss_t] + [rel(ekv_k[k], ekv_t[k].detach()) for k in ekv_t])
+    assert worst < 2e-5, worst
+    assert rel(bias_k, bias_t.detach()) < 1e-6 and rel(rot_k, rot_t.detach()) < 1e-6
+    d_ss, d_ekv, d_bias = st.grad_views()
+    for k in g_ss:
+        d_ss[k].copy_(g_ss[k])
+    for k in g_ekv:
+        d_ekv[k].copy_(g_ekv[k])
+    d_bias.copy_(g_bias)
+    st.backward()
+    torch.cuda.synchronize()
+    got = arena.flat_grad
+    # per parameter, so that a wrong small tensor cannot hide behind the large ones
+    o, errs = 0, {}
+    names = {id(p): k for k, p in model.named_parameters()}
+    for p in arena.params:
+        n = p.numel()
+        w = want[o:o + n]
+        if float(w.abs().max()) > 0 or float(got[o:o + n].abs().max()) > 0:
+            errs[names[id(p)]] = rel(got[o:o + n], w)
+        o += n
+    bad = {k: v for k, v in errs.items() if v > 2e-4}
+    print("conditioning kernels: forward worst", worst, "| parameters with gradient", len(errs), "| worst gradient",
+          max(errs.items(), key=lambda kv: kv[1]))
+    assert len(errs) > 20 and not bad, bad

@@ -58,11 +58,31 @@ class WgradParams(C.Structure):
     ]
 
 
+COND_MAX_BLOCKS = 24
+
+
+class CondParams(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("T", C.c_int32), ("dim", C.c_int32), ("td", C.c_int32), ("heads", C.c_int32), ("frames", C.c_int32),
+        ("n_res", C.c_int32), ("n_attn", C.c_int32),
+        ("time", C.c_void_p), ("cond", C.c_void_p), ("null_mask", C.c_void_p), ("param", C.c_void_p), ("grad", C.c_void_p),
+        ("freqs", C.c_void_p), ("buckets", C.c_void_p),
+        ("o_w1", C.c_int64), ("o_b1", C.c_int64), ("o_w2", C.c_int64), ("o_b2", C.c_int64), ("o_wse", C.c_int64), ("o_bse", C.c_int64),
+        ("o_lng", C.c_int64), ("o_lnb", C.c_int64), ("o_w3", C.c_int64), ("o_b3", C.c_int64), ("o_w4", C.c_int64), ("o_b4", C.c_int64),
+        ("o_ntok", C.c_int64), ("o_nhid", C.c_int64), ("o_table", C.c_int64),
+        ("res_w", C.c_int64 * COND_MAX_BLOCKS), ("res_b", C.c_int64 * COND_MAX_BLOCKS), ("res_out", C.c_int64 * COND_MAX_BLOCKS),
+        ("res_c2", C.c_int32 * COND_MAX_BLOCKS),
+        ("att_wk", C.c_int64 * COND_MAX_BLOCKS), ("att_wv", C.c_int64 * COND_MAX_BLOCKS), ("att_out", C.c_int64 * COND_MAX_BLOCKS),
+        ("att_temporal", C.c_int32 * COND_MAX_BLOCKS),
+        ("bias_out", C.c_int64), ("rot_out", C.c_int64), ("out", C.c_void_p), ("ws", C.c_void_p),
+    ]
+
+
 class VmmError(RuntimeError):
     pass
 
 
-ABI_VERSION = 2          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
+ABI_VERSION = 3          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
 
 
 def _load() -> C.CDLL:
@@ -115,6 +135,9 @@ _SIGNATURES = {
     "vmm_ftattn_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _F, _P],
     "vmm_ftattn_ctas_per_sm": [],
     "vmm_ftattn_diag": [_P],
+    "vmm_cond_workspace": [_I, _I, _I, _I],
+    "vmm_cond_fwd": [C.POINTER(CondParams), _P],
+    "vmm_cond_bwd": [C.POINTER(CondParams), _P],
     "vmm_lattn_fwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vmm_sattn_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "vmm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
@@ -129,7 +152,7 @@ _SIGNATURES = {
     "vmm_gather_cast": [_P, _P, _P, _L, _I, _P],
     "vmm_adam_ema_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _I, _F, _P],
 }
-_RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t, "vmm_ftattn_workspace": C.c_size_t}
+_RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t, "vmm_ftattn_workspace": C.c_size_t, "vmm_cond_workspace": C.c_size_t}
 for _name, _args in _SIGNATURES.items():
     _fn = getattr(lib, _name)     # AttributeError here == the .so is stale: rebuild it
     _fn.argtypes = _args

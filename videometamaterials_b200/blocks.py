@@ -20,6 +20,8 @@ from . import ops
 Tensor = torch.Tensor
 ROTARY_IN_EPILOGUE = os.environ.get("VMM_NO_ROT_EPILOGUE") is None     # debugging switch: rotate q / k inside the attention kernels
 FUSED_TATTN = os.environ.get("VMM_NO_FUSED_TATTN") is None              # debugging switch: 64-channel temporal blocks through the unfused kernels
+COND_KERNEL = os.environ.get("VMM_NO_COND_KERNEL") is None              # debugging switch: conditioning path through torch ops
+COND_KERNEL_MAX_B = int(os.environ.get("VMM_COND_KERNEL_MAX_B", "8"))
 
 
 def prob_mask_like(shape, prob, device):
@@ -319,11 +321,136 @@ def _build_cond_plan(model, sd, b: int, frames_tok: int, device, arena):
     return plan
 
 
-def conditioning(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: int):
+class CondState:
+    """One forward call of the conditioning kernels: the parameter block, the flat output buffer and (training) the flat buffer
+    the block backward kernels accumulate d(scale|shift), d(ek|ev) and d(bias) into; `backward()` launches vmm_cond_bwd."""
+
+    def __init__(self, p, out, ws, keep, arena, layout):
+        self.p, self.out, self.ws, self.keep, self.arena, self.layout = p, out, ws, keep, arena, layout
+        self.dout = None
+        self.done = False
+
+    def views(self, buf):
+        L = self.layout
+        ss = {q: buf[o:o + n].view(L["B"], c2) for q, (o, n, c2) in L["ss"].items()}
+        ekv = {q: buf[o:o + n].view(L["B"], L["T"], 512) for q, (o, n) in L["ekv"].items()}
+        f = L["frames"]
+        bias = buf[L["bias"]:L["bias"] + 8 * f * f].view(8, f, f)
+        rot = buf[L["rot"]:L["rot"] + 2 * f * 32].view(2, f, 16, 2)
+        return ss, ekv, bias, rot
+
+    def grad_views(self):
+        """(d ss, d ekv, d bias) views of the zero-initialised gradient buffer (created on first use in a backward pass)."""
+        if self.dout is None:
+            self.dout = torch.zeros_like(self.out)
+            self._gv = self.views(self.dout)
+        return self._gv[0], self._gv[1], self._gv[2]
+
+    def backward(self):
+        if self.done or self.dout is None:
+            return
+        self.done = True
+        p = self.p
+        p.out = self.dout.data_ptr()
+        p.grad = self.arena.flat_grad.data_ptr()
+        ops.check(ops.lib.vmm_cond_bwd(ops.C.byref(p), ops.stream_ptr()), "vmm_cond_bwd")
+
+
+def _cond_kernel_plan(model, sd, arena, B: int, T: int, frames: int, device):
+    """Offsets of every conditioning parameter in the arena and the layout of the flat output buffer (cached per shape)."""
+    key = ("kernel", B, T, frames, str(device), id(arena))
+    cache = model.__dict__.setdefault("_vmm_cond_plans", {})
+    plan = cache.get(key)
+    if plan is not None:
+        return plan
+    off, o = {}, 0
+    for q in arena.params:
+        off[id(q)] = o
+        o += q.numel()
+    at = lambda name: off[id(sd[name])]
+    rn, an = resnet_names(model), attn_names(model)
+    lay = dict(B=B, T=T, frames=frames, ss={}, ekv={})
+    pos = 0
+    for q in rn:
+        c2 = int(sd[q + "mlp.1.bias"].shape[0])
+        lay["ss"][q] = (pos, B * c2, c2)
+        pos += B * c2
+    for q, _ in an:
+        lay["ekv"][q] = (pos, B * T * 512)
+        pos += B * T * 512
+    lay["bias"] = pos
+    pos += 8 * frames * frames
+    lay["rot"] = pos
+    pos += 2 * frames * 32
+    lay["total"] = pos
+    with torch.inference_mode(False):
+        buckets = rel_pos_buckets(frames, device).to(torch.int32).contiguous()
+    plan = cache[key] = dict(at=at, rn=rn, an=an, lay=lay, buckets=buckets)
+    return plan
+
+
+def _conditioning_kernel(model, sd, arena, time: Tensor, cond: Tensor, null_mask: Tensor, frames: int):
+    from ._lib import CondParams
+    dev = time.device
+    B, T = cond.shape
+    plan = _cond_kernel_plan(model, sd, arena, B, T, frames, dev)
+    at, rn, an, lay = plan["at"], plan["rn"], plan["an"], plan["lay"]
+    p = CondParams()
+    p.B, p.T, p.dim, p.td, p.heads, p.frames, p.n_res, p.n_attn = B, T, model.dim, model.cond_dim, model.heads, frames, len(rn), len(an)
+    time_c = time.contiguous().to(torch.int64)
+    cond_c = cond.contiguous().float()
+    mask_c = null_mask.contiguous().to(torch.bool)
+    freqs = sd["init_temporal_attn.fn.fn.fn.rotary_emb.freqs"]
+    p.time, p.cond, p.null_mask = time_c.data_ptr(), cond_c.data_ptr(), mask_c.data_ptr()
+    p.param = arena.flat_param.data_ptr()
+    p.freqs, p.buckets = freqs.data_ptr(), plan["buckets"].data_ptr()
+    p.o_w1, p.o_b1, p.o_w2, p.o_b2 = at("time_mlp.1.weight"), at("time_mlp.1.bias"), at("time_mlp.3.weight"), at("time_mlp.3.bias")
+    p.o_wse, p.o_bse = at("sign_emb.weight"), at("sign_emb.bias")
+    p.o_lng, p.o_lnb = at("cond_token_to_hidden.0.weight"), at("cond_token_to_hidden.0.bias")
+    p.o_w3, p.o_b3 = at("cond_token_to_hidden.1.weight"), at("cond_token_to_hidden.1.bias")
+    p.o_w4, p.o_b4 = at("cond_token_to_hidden.3.weight"), at("cond_token_to_hidden.3.bias")
+    p.o_ntok, p.o_nhid = at("null_text_token"), at("null_text_hidden")
+    p.o_table = at("time_rel_pos_bias.relative_attention_bias.weight")
+    for j, q in enumerate(rn):
+        p.res_w[j], p.res_b[j] = at(q + "mlp.1.weight"), at(q + "mlp.1.bias")
+        p.res_out[j], _, p.res_c2[j] = lay["ss"][q]
+    for a, (q, kind) in enumerate(an):
+        p.att_wk[a], p.att_wv[a] = at(q + "to_k.weight"), at(q + "to_v.weight")
+        p.att_out[a] = lay["ekv"][q][0]
+        p.att_temporal[a] = 1 if kind == "temporal" else 0
+    p.bias_out, p.rot_out = lay["bias"], lay["rot"]
+    out = torch.empty(lay["total"], dtype=torch.float32, device=dev)
+    ws = torch.empty(int(ops.lib.vmm_cond_workspace(B, T, model.dim, model.cond_dim)) // 4, dtype=torch.float32, device=dev)
+    p.out, p.ws = out.data_ptr(), ws.data_ptr()
+    ops.check(ops.lib.vmm_cond_fwd(ops.C.byref(p), ops.stream_ptr()), "vmm_cond_fwd")
+    st = CondState(p, out, ws, (time_c, cond_c, mask_c, freqs, plan["buckets"]), arena, lay)
+    ss, ekv, bias, rot = st.views(out)
+    return ss, ekv, bias, rot, st
+
+
+def cond_kernel_eligible(model, time: Tensor, cond: Tensor) -> bool:
+    arena = getattr(model, "_vmm_arena", None)
+    # (the kernels block their loops over at most 8 samples in registers; 2 x 4 guided sampling and 8-clip training steps qualify,
+    # larger batches take the torch statement below: measured, the kernels lose to it beyond 8 samples)
+    return (COND_KERNEL and time.is_cuda and arena is not None and arena.flat_param.device == time.device and cond.shape[0] <= COND_KERNEL_MAX_B
+            and cond.shape[1] <= 16 and model.cond_dim <= 256 and model.cond_dim % 4 == 0 and model.dim % 4 == 0 and model.dim >= 4
+            and model.heads == 8)
+
+
+def conditioning_state(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: int):
+    """conditioning() plus the CondState of the kernel path (None on the torch path)."""
+    if cond_kernel_eligible(model, time, cond):
+        return _conditioning_kernel(model, param_dict(model), model._vmm_arena, time, cond, null_mask, frames)
+    return (*conditioning(model, time, cond, null_mask, frames, _torch_path=True), None)
+
+
+def conditioning(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: int, _torch_path: bool = False):
     """Returns (scale_shift per resnet block, ekv per attention block, bias (h,f,f), rot (2,f,16,2): cos/sin tables of the
     rotary embedding, [0] pre-multiplied by the attention scale (queries), [1] plain (keys and the attention kernels).
     The per-block fan-out (18 ResnetBlock MLPs, 17 to_k / to_v pairs) is batched: parameters are gathered from the arena,
     results are split by one permutation, so the path is ~40 kernels forward instead of several hundred."""
+    if not _torch_path and cond_kernel_eligible(model, time, cond):
+        return _conditioning_kernel(model, param_dict(model), model._vmm_arena, time, cond, null_mask, frames)[:4]
     sd = param_dict(model)
     heads = model.heads
     hd = heads * 32

@@ -81,6 +81,7 @@ class _Env:
         self.mode = model.padding_mode
         self.groups = model.groups
         self.heads = model.heads
+        self.cond = None                 # blocks.CondState when the conditioning path runs on its kernels
 
 
 # ------------------------------------------------------------------------------------------------
@@ -125,7 +126,10 @@ class ResnetFn(torch.autograd.Function):
         ops.conv3x3([ops.as_bfhwc(dh2)], P[pre + "block2.wd"], cout, da1, mode=env.mode)      # the adjoint of a wrap-mode conv is one too
         # block1
         dh1 = dh2   # reuse the buffer
-        dss = torch.zeros_like(ss) if ss is not None else None
+        if ss is not None and env.cond is not None:
+            dss = env.cond.grad_views()[0][pre]          # accumulated in place; vmm_cond_bwd consumes the whole buffer after the pass
+        else:
+            dss = torch.zeros_like(ss) if ss is not None else None
         ops.gn_silu_bwd(h1, da1, dh1, st1, sd[pre + "block1.norm.weight"], sd[pre + "block1.norm.bias"], ss, B, pix, cout, g,
                         sd[pre + "block1.norm.weight"].grad, sd[pre + "block1.norm.bias"].grad, dss,
                         dx_colsum=sd[pre + "block1.proj.bias"].grad)
@@ -136,7 +140,7 @@ class ResnetFn(torch.autograd.Function):
             res, res2 = dout, None                                      # identity skip
         ops.conv3x3([ops.as_bfhwc(dh1)], P[pre + "block1.wd"], cin, dxs[0], mode=env.mode,
                     out2=dxs[1] if len(xs) > 1 else None, nsplit=cins[0], res=res, res2=res2)
-        return (None, None, dss, *dxs)
+        return (None, None, None if env.cond is not None else dss, *dxs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -184,10 +188,14 @@ class AttnBlockFn(torch.autograd.Function):
             ops.colsum(d2, sd[pre + "to_out.bias"].grad)
         # attention core
         dqkv = torch.empty_like(qkv)
-        dekv = torch.zeros_like(ekv) if ekv is not None else None
         dbias = None
+        if env.cond is not None:
+            _, d_ekv, d_bias = env.cond.grad_views()
+            dekv = d_ekv[pre] if ekv is not None else None
+        else:
+            dekv = torch.zeros_like(ekv) if ekv is not None else None
         if kind == "temporal":
-            dbias = torch.zeros_like(bias)
+            dbias = d_bias if env.cond is not None else torch.zeros_like(bias)
             ops.tattn_bwd(qkv, ekv, bias, rot[1], dao, dqkv, dekv, dbias, B, Fr, H * W, heads, pre_rotated=blocks.ROTARY_IN_EPILOGUE)
         elif kind == "linear":
             ctxm, kstat = extra
@@ -205,6 +213,8 @@ class AttnBlockFn(torch.autograd.Function):
         gamma = sd[norm_pre + "norm.gamma"]
         dx = torch.empty_like(x)
         ops.ln_bwd(_flat(x), dxn, d2, _flat(dx), gamma.reshape(-1), gamma.grad.reshape(-1))
+        if env.cond is not None:
+            return None, None, None, dx, None, None, None
         return None, None, None, dx, dekv, dbias, None
 
 
@@ -273,6 +283,14 @@ class InitFn(torch.autograd.Function):
         return None, torch.zeros(1, device=dout.device), None, None, None, None, None
 
 
+def _queue_cond_backward(env: _Env) -> None:
+    """The conditioning kernels' backward runs once, after every block has accumulated its d(scale|shift) / d(ek|ev) / d(bias)
+    into the CondState buffer: queued on the autograd engine from the FIRST backward node of the pass (loss / final conv)."""
+    if env.cond is not None:
+        st = env.cond
+        torch.autograd.Variable._execution_engine.queue_callback(st.backward)
+
+
 class LossFn(torch.autograd.Function):
     """final 1x1x1 conv (VDDP:708) + F.l1_loss / F.mse_loss against the noise (VDDP:1053-1056)."""
 
@@ -294,6 +312,7 @@ class LossFn(torch.autograd.Function):
         env = ctx.env
         h, dpred = ctx.saved_tensors
         model = env.model
+        _queue_cond_backward(env)
         dpred = dpred * gout.to(dpred.dtype)                                # loss scale (1 in bf16 training)
         dh = torch.empty_like(h)
         ops.linear_rows([dpred], env.P["final.wd"], h.shape[-1], _flat(dh))
@@ -320,6 +339,7 @@ class FinalFn(torch.autograd.Function):
         env = ctx.env
         (h,) = ctx.saved_tensors
         model = env.model
+        _queue_cond_backward(env)
         Cc = model.channels
         dp8 = torch.zeros(h.numel() // h.shape[-1], 8, dtype=h.dtype, device=h.device)      # rows carry 8 (zero padded) channels
         dp8[:, :Cc] = dpred.reshape(-1, Cc).to(h.dtype)
@@ -344,7 +364,7 @@ def _trunk(model, x0: Tensor, noise: Optional[Tensor], qcoef, t: Tensor, cond: T
     env = _Env(model)
     L = len(model.dim_mults)
     frames = x0.shape[2]
-    ss, ekv, bias, rot = blocks.conditioning(model, t, cond, null_mask, frames)
+    ss, ekv, bias, rot, env.cond = blocks.conditioning_state(model, t, cond, null_mask, frames)
     anchor = torch.zeros(1, device=x0.device, requires_grad=True)
     a, c, s = qcoef if qcoef is not None else (None, None, None)
     h = InitFn.apply(env, anchor, x0, noise, a, c, s)

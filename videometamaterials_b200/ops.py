@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import CgemmParams, FMT_BF16, FMT_F16, WgradParams, check, lib
+from ._lib import CgemmParams, FMT_BF16, FMT_F16, WgradParams, check, lib  # noqa: F401  (C, check, lib are used by blocks.py)
 
 
 # bench.py sets PROFILE = [] to collect (kernel, algorithmic flops, start event, end event) per GEMM launch
