@@ -561,6 +561,78 @@ def run_own(args):
     print(json.dumps(line), flush=True)
 
 
+def run_sweep(args):
+    """BASELINE configs[4]: resolution sweep 64 / 96 / 128 px (x 11 frames; 22-frame rows when --sweep-frames lists them: no
+    reference value exists there, the reference raises at 22 frames under per_frame_cond).  Per row: the
+    full training step (graph replayed), model TFLOP/s against the sustained tensor peak, and the per-kernel roofline fractions
+    of two eager steps timed with CUDA events per launch."""
+    import gc
+    import torch
+    from videometamaterials_b200 import Accelerator, GaussianDiffusion, Trainer, Unet3D, ops
+    pk = peaks()
+    fwd_gflop = {64: 172.10, 96: 387.26, 128: 688.73}            # SURVEY.md section 8d (11 frames); scales linearly with frames
+    rows = []
+    B = args.sweep_batch
+    for frames in [int(f) for f in args.sweep_frames.split(",")]:
+        for px in (64, 96, 128):
+            row = {"px": px, "frames": frames, "batch": B, "reference_parity": frames == 11}
+            try:
+                torch.manual_seed(0)
+                kw = {} if frames == 11 else {"num_frames": frames}
+                model = Unet3D(dim=64, dim_mults=(1, 2, 4, 8), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True,
+                               resnet_groups=8, cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True,
+                               cond_to_time='add', per_frame_cond=True, **kw)
+                gd = GaussianDiffusion(model, image_size=px, channels=3, num_frames=frames, timesteps=256, use_dynamic_thres=True,
+                                       sampling_timesteps=256)
+                tr = Trainer(gd, None, None, [0, 1, 3], train_batch_size=B, results_folder=os.path.join(ROOT, "gpurun_out", "bench_run"),
+                             log=False, null_cond_prob=0.1, per_frame_cond=True, reference_frame='lagrangian', accelerator=Accelerator("bf16"))
+                x = torch.rand(B, 3, frames, px, px, device="cuda")
+                c = torch.rand(B, frames, device="cuda") * 2 - 1
+                for _ in range(12):
+                    tr.step += 1
+                    loss = tr.train_step(x, c)
+                    torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    tr.step += 1
+                    tr.train_step(x, c)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / args.steps
+                gflop = fwd_gflop[px] * frames / 11.0 * (FWD_BWD_GFLOP_PER_CLIP / FWD_GFLOP_PER_CLIP)
+                tf = B * gflop / ms
+                row.update(ms_per_step=ms, clips_per_s=B / ms * 1e3, model_tflops=tf, frac_of_sustained_tensor_peak=tf / pk["tflops_sustained"],
+                           loss_finite=bool(torch.isfinite(loss)))
+                ops.PROFILE, ops.PROFILE_TAGS = [], False
+                for _ in range(2):
+                    tr.step += 1
+                    tr.train_step(x, c)
+                torch.cuda.synchronize()
+                prof, ops.PROFILE = ops.PROFILE, None
+                by = {}
+                for name, flops, a, b, nbytes in prof:
+                    d = by.setdefault(name, [0.0, 0.0, 0.0])
+                    d[0] += flops
+                    d[1] += a.elapsed_time(b) * 1e-3
+                    d[2] += nbytes
+                kern = {}
+                for k, (fl, sec, nb) in by.items():
+                    if k in ("cgemm", "wgrad"):
+                        kern[k] = {"tflops": fl / sec / 1e12, "frac_tensor": fl / sec / 1e12 / pk["tflops_sustained"], "share": sec / 2 / (ms * 1e-3)}
+                    else:
+                        kern[k] = {"gbs": nb / sec / 1e9, "frac_hbm": nb / sec / 1e9 / pk["hbm"], "share": sec / 2 / (ms * 1e-3)}
+                row["kernels"] = kern
+                del tr, gd, model, x, c
+            except Exception as e:  # noqa: BLE001
+                row["error"] = str(e)[:200]
+            gc.collect()
+            torch.cuda.empty_cache()
+            rows.append(row)
+    print(json.dumps({"metric": "resolution sweep (BASELINE configs[4]): Trainer step, bf16", "unit": UNIT, "peak_tflops_sustained": pk["tflops_sustained"],
+                      "peak_hbm_gbs": pk["hbm"], "rows": rows}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -570,10 +642,15 @@ def main():
     ap.add_argument("--global-batch", type=int, default=None, help="strong scaling: this many clips per step over all ranks (BASELINE configs[3]: 32)")
     ap.add_argument("--no-strong", action="store_true", help="skip the extra global-batch-32 leg of the default run")
     ap.add_argument("--no-torch-gpu", action="store_true", help="skip the reference-torch-on-this-GPU baseline")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: resolution sweep 64 / 96 / 128 px with per-row roofline fractions")
+    ap.add_argument("--sweep-frames", default="11", help="comma list of frame counts for --sweep (22: no reference parity)")
+    ap.add_argument("--sweep-batch", type=int, default=8)
     ap.add_argument("--no-ddim", dest="no_ddim", action="store_true", help="skip the 250-step DDIM sample() timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "torch-gpu":
         run_torch_gpu(args)

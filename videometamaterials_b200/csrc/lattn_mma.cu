@@ -591,32 +591,41 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
   }
 }
 
-// cond-token gradients (tiny): thread = (bf, h, token j); summed over frames with atomics
-__global__ void lattn_bwd_tokens_kernel(const float* __restrict__ ekv, int T, const float* __restrict__ ctx, const float* __restrict__ dctx,
-                                        const float* __restrict__ kstat, float* __restrict__ dekv, int BF, int frames, float vscale) {
-  // one WARP per (frame-image, head, token): a thread per unit walked the 32 x 32 matrices serially (1024 dependent steps,
-  // 60 us per launch whatever the batch); now lane = d for the key gradient and lane = e for the value gradient, 64 steps
+// cond-token gradients (tiny).  CTA = (frame-image, head): the 32 x 32 ctx / dctx matrices go to shared memory with coalesced
+// loads (rows padded to 33 floats: lane = d walks a row without bank conflicts), then one warp per token:
+//   lane = d:  dk[d] = w[d] * sum_e dctx[d][e] (vscale v[e] - ctx[d][e]),   lane = e:  dv[e] = vscale * sum_d w[d] dctx[d][e]
+// summed over the frames of a sample with atomics.  (Round 1 ran one warp per (frame-image, head, token) straight from global
+// memory: 68 us per launch at any size, 0.5 ms per step.)
+__global__ void __launch_bounds__(256) lattn_bwd_tokens_kernel(const float* __restrict__ ekv, int T, const float* __restrict__ ctx,
+                                                               const float* __restrict__ dctx, const float* __restrict__ kstat,
+                                                               float* __restrict__ dekv, int BF, int frames, float vscale) {
+  __shared__ float Cs[32][33], Gs[32][33];
   const int HD = 256;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (wid >= BF * 8 * T) return;
-  const int j = wid % T, h = (wid / T) % 8, bf = wid / (T * 8);
+  const int h = blockIdx.x & 7, bf = blockIdx.x >> 3;
   const int b = bf / frames;
-  const float* src = ekv + (static_cast<long long>(b) * T + j) * 2 * HD + h * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* ch = ctx + (static_cast<long long>(bf) * 8 + h) * 1024;
   const float* gh = dctx + (static_cast<long long>(bf) * 8 + h) * 1024;
+  for (int i = threadIdx.x; i < 1024; i += 256) {
+    Cs[i >> 5][i & 31] = __ldg(ch + i);
+    Gs[i >> 5][i & 31] = __ldg(gh + i);
+  }
   const float* ks = kstat + (static_cast<long long>(bf) * HD + h * 32) * 2;
-  float* dst = dekv + (static_cast<long long>(b) * T + j) * 2 * HD + h * 32;
-  // lane = d:  dk[d] = w[d] * sum_e dctx[d][e] (vscale v[e] - ctx[d][e])
-  const float w = __expf(src[lane] - ks[lane * 2]) / ks[lane * 2 + 1];
-  float r = 0.f;
-#pragma unroll 8
-  for (int e = 0; e < 32; ++e) r = fmaf(gh[lane * 32 + e], fmaf(vscale, src[HD + e], -ch[lane * 32 + e]), r);
-  atomicAdd(dst + lane, w * r);
-  // lane = e:  dv[e] = vscale * sum_d w[d] dctx[d][e]
-  float dv = 0.f;
-#pragma unroll 8
-  for (int d = 0; d < 32; ++d) dv = fmaf(__shfl_sync(0xffffffffu, w, d), gh[d * 32 + lane], dv);
-  atomicAdd(dst + HD + lane, dv * vscale);
+  const float mx = ks[lane * 2], zi = 1.f / ks[lane * 2 + 1];
+  __syncthreads();
+  for (int j = warp; j < T; j += 8) {
+    const float* src = ekv + (static_cast<long long>(b) * T + j) * 2 * HD + h * 32;
+    float* dst = dekv + (static_cast<long long>(b) * T + j) * 2 * HD + h * 32;
+    const float w = __expf(src[lane] - mx) * zi;
+    const float vl = vscale * src[HD + lane];            // lane = e
+    float r = 0.f, dv = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) r = fmaf(Gs[lane][e], __shfl_sync(0xffffffffu, vl, e) - Cs[lane][e], r);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) dv = fmaf(__shfl_sync(0xffffffffu, w, d), Gs[d][lane], dv);
+    atomicAdd(dst + lane, w * r);
+    atomicAdd(dst + HD + lane, dv * vscale);
+  }
 }
 
 static int lat_rows_per_cta(int HW, int BF) {
@@ -707,8 +716,7 @@ extern "C" int vmm_lattn_bwd(const void* qkv, const float* ekv, int T, const voi
                                                                        static_cast<uint16_t*>(dqkv), HW, scale, vscale, rpc);
   }
   count_launch();
-  const int ntok = BF * 8 * T;
-  lattn_bwd_tokens_kernel<<<(ntok + 3) / 4, 128, 0, stream>>>(ekv, T, ctx, dctx, kstat, dekv, BF, frames, vscale);
+  lattn_bwd_tokens_kernel<<<BF * 8, 256, 0, stream>>>(ekv, T, ctx, dctx, kstat, dekv, BF, frames, vscale);
   count_launch();
   return check_launch("vmm_lattn_bwd");
 }
