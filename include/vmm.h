@@ -169,6 +169,17 @@ int vmm_ftattn_fwd(const void* x, void* out, const void* wqkv, const void* wout,
 int vmm_ftattn_ctas_per_sm(void);
 /* diagnostics (12 ints): registers, static / max dynamic shared memory, device limits, occupancy at several shared-memory sizes */
 int vmm_ftattn_diag(int* out);
+/* The whole Residual(PreNorm(SpatialLinearAttention)) block of a 64-channel level without materialising qkv (inference form:
+ * nothing is kept for a backward pass), VDDP:131-137, 245-264, 313-378: per 128-pixel tile TMA -> channel LayerNorm ->
+ * K^T / V projections on tcgen05 (the column softmax of k becomes a per-thread reduction) -> tile context on tcgen05 -> online
+ * combination; a small kernel merges the per-CTA partials with the T conditioning tokens; a third kernel projects q, applies
+ * the row softmax, multiplies by the block-diagonal context and by to_out on tcgen05, adds bias and x and stores.
+ * x, out: [BF][HW][64] 16-bit; wqkv [768][64], wout [64][256] packed operands; ekv fp32 [B][T][512]; ctx [BF][8][32][32] and
+ * kstat [BF][256][2] (may be NULL) are outputs as of vmm_lattn_fwd.  HW % 128 == 0, heads == 8, C == 64. */
+size_t vmm_flattn_workspace(int BF);
+int vmm_flattn_fwd(const void* x, void* out, const void* wqkv, const void* wout, const float* gamma, const float* bias_out,
+                   const float* ekv, int T, float* ctx, float* kstat, void* workspace, size_t workspace_bytes, int fmt, int BF,
+                   int frames, int HW, int C, int heads, float scale, float eps, void* stream);
 int vmm_lattn_fwd(const void* qkv, const float* ekv, int T, void* out, float* ctx, float* kstat, int fmt, int BF, int frames,
                   int HW, int heads, float scale, void* stream);
 int vmm_sattn_fwd(const void* qkv, const float* ekv, void* out, float* lse, int fmt, int BF, int frames, int HW, int heads,

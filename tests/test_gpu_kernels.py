@@ -762,3 +762,63 @@ def test_conditioning_kernels_match_the_torch_path(case, monkeypatch):
     print("conditioning kernels: forward worst", worst, "| parameters with gradient", len(errs), "| worst gradient",
           max(errs.items(), key=lambda kv: kv[1]))
     assert len(errs) > 20 and not bad, bad
+
+
+# ------------------------------------------------------------------------------------------------
+# fused linear-attention block, inference form (csrc/flattn.cu): three kernels, qkv never in HBM.  Against plain fp32 torch math of
+# VDDP:131-137, 245-264, 313-378 and against the unfused kernel chain (ln_fwd -> cgemm -> lattn_fwd (5 kernels) -> cgemm).
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("case", [(1, 11, 16, 16), (2, 11, 16, 24), (1, 2, 48, 48)])
+def test_fused_linear_attention_block(ops, dt, case):
+    B, Fr, H, W = case
+    heads, Cc, T = 8, 64, 11
+    hd = heads * 32
+    n = H * W
+    torch.manual_seed(41)
+    x = torch.randn(B, Fr, H, W, Cc, device="cuda").to(dt)
+    gamma = (1 + 0.2 * torch.randn(Cc, device="cuda")).contiguous()
+    wq = torch.randn(3 * hd, Cc, device="cuda") * Cc ** -0.5
+    wo = torch.randn(Cc, hd, device="cuda") * hd ** -0.5
+    bo = torch.randn(Cc, device="cuda") * 0.1
+    ekv = torch.randn(B, T, 2 * hd, device="cuda")
+    wqp, wop = ops.pack_linear(wq, dt), ops.pack_linear(wo, dt)
+    rows = B * Fr * n
+    out = torch.empty_like(x)
+    ctx = torch.empty(B * Fr, heads, 32, 32, device="cuda")
+    kstat = torch.empty(B * Fr, heads, 32, 2, device="cuda")
+    ops.flattn_fwd(x, out, wqp, wop, gamma, bo, ekv, ctx, kstat, B * Fr, Fr, n, heads)
+    torch.cuda.synchronize()
+    # unfused chain
+    x2 = x.reshape(-1, Cc)
+    xn = torch.empty_like(x2)
+    ops.ln_fwd(x2, xn, gamma)
+    qkv = torch.empty(rows, 3 * hd, device="cuda", dtype=dt)
+    ops.linear_rows([xn], wqp, 3 * hd, qkv)
+    ao = torch.empty(rows, hd, device="cuda", dtype=dt)
+    ctx_u = torch.empty_like(ctx)
+    kstat_u = torch.empty_like(kstat)
+    ops.lattn_fwd(qkv, ekv, T, ao, ctx_u, kstat_u, B * Fr, Fr, n, heads)
+    out_u = torch.empty_like(x)
+    ops.linear_rows([ao], wop, Cc, out_u.reshape(-1, Cc), bias=bo, res=x2)
+    # fp32 torch statement (16-bit weights, everything else fp32)
+    xf = x.float()
+    mean = xf.mean(-1, keepdim=True)
+    var = xf.var(-1, unbiased=False, keepdim=True)
+    xnf = (xf - mean) / (var + 1e-5).sqrt() * gamma
+    qkvf = (xnf @ wq.to(dt).float().t()).reshape(B * Fr, n, 3 * hd)
+    q, k, v = (t.reshape(B * Fr, n, heads, 32).permute(0, 2, 3, 1) for t in qkvf.chunk(3, dim=-1))          # (bf, h, d, n)
+    ek = ekv[..., :hd].reshape(B, 1, T, heads, 32).expand(B, Fr, T, heads, 32).permute(0, 1, 3, 4, 2).reshape(B * Fr, heads, 32, T)
+    ev = ekv[..., hd:].reshape(B, 1, T, heads, 32).expand(B, Fr, T, heads, 32).permute(0, 1, 3, 4, 2).reshape(B * Fr, heads, 32, T)
+    kk = torch.cat((ek, k), -1).softmax(-1)
+    vv = torch.cat((ev, v), -1) / n
+    c = torch.einsum("bhdn,bhen->bhde", kk, vv)
+    aof = torch.einsum("bhde,bhdn->bhen", c, q.softmax(-2) * 32 ** -0.5).permute(0, 3, 1, 2).reshape(B, Fr, H, W, hd)
+    want = aof @ wo.to(dt).float().t() + bo + xf
+    e = dict(ctx=rel(ctx, c), ctx_unfused=rel(ctx_u, c), out=rel(out, want), branch=rel(out.float() - xf, want - xf),
+             branch_unfused=rel(out_u.float() - xf, want - xf), kstat_max=float((kstat[..., 0] - kstat_u[..., 0]).abs().max()))
+    print("fused linear block:", dt, case, {k_: round(v_, 5) for k_, v_ in e.items()})
+    assert e["ctx"] < 1.5 * TOL[dt] and e["out"] < TOL[dt], e
+    assert e["branch"] < 3 * TOL[dt] and e["branch"] < 1.5 * e["branch_unfused"] + 1e-4, e
+    # the column maxima come from the fp32 accumulators here and from the 16-bit k rows in the unfused chain
+    assert e["kstat_max"] < (0.05 if dt == torch.bfloat16 else 0.01), e

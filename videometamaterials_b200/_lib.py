@@ -135,6 +135,8 @@ _SIGNATURES = {
     "vmm_ftattn_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _F, _P],
     "vmm_ftattn_ctas_per_sm": [],
     "vmm_ftattn_diag": [_P],
+    "vmm_flattn_workspace": [_I],
+    "vmm_flattn_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _F, _F, _P],
     "vmm_cond_workspace": [_I, _I, _I, _I],
     "vmm_cond_fwd": [C.POINTER(CondParams), _P],
     "vmm_cond_bwd": [C.POINTER(CondParams), _P],
@@ -152,7 +154,8 @@ _SIGNATURES = {
     "vmm_gather_cast": [_P, _P, _P, _L, _I, _P],
     "vmm_adam_ema_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _I, _F, _P],
 }
-_RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t, "vmm_ftattn_workspace": C.c_size_t, "vmm_cond_workspace": C.c_size_t}
+_RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t, "vmm_ftattn_workspace": C.c_size_t, "vmm_cond_workspace": C.c_size_t,
+             "vmm_flattn_workspace": C.c_size_t}
 for _name, _args in _SIGNATURES.items():
     _fn = getattr(lib, _name)     # AttributeError here == the .so is stale: rebuild it
     _fn.argtypes = _args

@@ -20,6 +20,7 @@ from . import ops
 Tensor = torch.Tensor
 ROTARY_IN_EPILOGUE = os.environ.get("VMM_NO_ROT_EPILOGUE") is None     # debugging switch: rotate q / k inside the attention kernels
 FUSED_TATTN = os.environ.get("VMM_NO_FUSED_TATTN") is None              # debugging switch: 64-channel temporal blocks through the unfused kernels
+FUSED_LATTN = os.environ.get("VMM_NO_FUSED_LATTN") is None              # debugging switch: 64-channel linear blocks (inference) unfused
 COND_KERNEL = os.environ.get("VMM_NO_COND_KERNEL") is None              # debugging switch: conditioning path through torch ops
 COND_KERNEL_MAX_B = int(os.environ.get("VMM_COND_KERNEL_MAX_B", "8"))
 
@@ -550,6 +551,13 @@ def attn_block_fwd(P, sd, pre: str, kind: str, x: Tensor, ekv: Optional[Tensor],
         ao = torch.empty(x2.shape[0], hd, dtype=dt, device=dev) if keep else None
         ops.ftattn_fwd(x, out, P[pre + "qkv.w"], P[pre + "out.w"], gamma, ekv, bias, rot, xn, qkv, ao, B, Fr, H * W, heads)
         return out, (xn, qkv, ao, None)
+    if (kind == "linear" and FUSED_LATTN and not keep and x.is_cuda and Cc == 64 and heads == 8 and (H * W) % 128 == 0
+            and x.is_contiguous()):
+        # inference: three kernels for the whole block (csrc/flattn.cu), q / k / v never reach HBM
+        out = torch.empty_like(x)
+        ctx = torch.empty(B * Fr, heads, 32, 32, dtype=torch.float32, device=dev)
+        ops.flattn_fwd(x, out, P[pre + "qkv.w"], P[pre + "out.w"], gamma, sd.get(pre + "to_out.bias"), ekv, ctx, None, B * Fr, Fr, H * W, heads)
+        return out, (None, None, None, None)
     xn = torch.empty_like(x2)
     ops.ln_fwd(x2, xn, gamma)
     qkv = torch.empty(x2.shape[0], 3 * hd, dtype=dt, device=dev)
@@ -634,7 +642,7 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
         p = f"downs.{i}."
         h, _ = resnet_fwd(P, sd, p + "0.", [h], ss[p + "0."], g, pm)
         h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g, pm)
-        h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads)
+        h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads, keep=False)
         h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads, keep=False)
         skips.append(h)
         if i < L - 1:
@@ -647,7 +655,7 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
         p = f"ups.{i}."
         h, _ = resnet_fwd(P, sd, p + "0.", [h, skips.pop()], ss[p + "0."], g, pm)
         h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g, pm)
-        h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads)
+        h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads, keep=False)
         h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads, keep=False)
         if i < L - 1:
             h = up_fwd(P, sd, p + "4.", h, pm)

@@ -433,6 +433,18 @@ def ftattn_fwd(x, out, wqkv, wout, gamma, ekv, bias, rot, xn, qkv, ao, B, frames
     _prof_end("ftattn_fwd", flops, e0, nbytes)
 
 
+def flattn_fwd(x, out, wqkv, wout, gamma, bias_out, ekv, ctx, kstat, BF, frames, HW, heads, eps=1e-5):
+    """Fused Residual(PreNorm(linear attention)) forward of a 64-channel level (inference form, nothing kept)."""
+    C_ = x.shape[-1]
+    nbytes_ws = int(lib.vmm_flattn_workspace(BF))
+    ws = torch.empty(nbytes_ws, dtype=torch.uint8, device=x.device)
+    e0 = _prof_begin()
+    check(lib.vmm_flattn_fwd(_p(x), _p(out), _p(wqkv), _p(wout), _p(gamma), _p(bias_out), _p(ekv), ekv.shape[1], _p(ctx), _p(kstat), _p(ws),
+                             nbytes_ws, fmt_of(x), BF, frames, HW, C_, heads, 32 ** -0.5, eps, stream_ptr()), "vmm_flattn_fwd")
+    rows, hd = BF * HW, heads * 32
+    _prof_end("flattn_fwd", 2.0 * rows * (C_ * 4 * hd + hd * C_) + 2.0 * rows * hd * 32 * 2, e0, 2.0 * rows * 3 * C_)
+
+
 def lattn_fwd(qkv, ekv, T, out, ctx, kstat, BF, frames, HW, heads):
     e0 = _prof_begin()
     check(lib.vmm_lattn_fwd(_p(qkv), _p(ekv), T, _p(out), _p(ctx), _p(kstat), fmt_of(qkv), BF, frames, HW, heads, 32 ** -0.5,
