@@ -573,10 +573,18 @@ extern "C" int vmm_flattn_fwd(const void* x, void* out, const void* wqkv, const 
   d.BF = BF;
   d.HW = HW;
   d.tiles_per_bf = HW / 128;
-  int chunks = (2 * num_sms() + BF - 1) / BF;
-  if (chunks > 8) chunks = 8;
-  if (chunks > d.tiles_per_bf) chunks = d.tiles_per_bf;
-  if (chunks < 1) chunks = 1;
+  // CTAs per frame-image: every CTA walks a contiguous range of the frame-image's tiles.  Pick the split (1..8) that minimises
+  // waves x tiles per CTA (352 CTAs of 18 tiles on 148 SMs run as three waves; 440 CTAs of 15 tiles also do)
+  int chunks = 1;
+  long long best = -1;
+  for (int c = 1; c <= 8 && c <= d.tiles_per_bf; ++c) {
+    const long long waves = (1LL * BF * c + num_sms() - 1) / num_sms();
+    const long long cost = waves * ((d.tiles_per_bf + c - 1) / c) * 16 + c;        // + c: fewer partials on ties
+    if (best < 0 || cost < best) {
+      best = cost;
+      chunks = c;
+    }
+  }
   d.tiles_per_chunk = (d.tiles_per_bf + chunks - 1) / chunks;
   chunks = (d.tiles_per_bf + d.tiles_per_chunk - 1) / d.tiles_per_chunk;
   d.chunks = chunks;
