@@ -480,6 +480,9 @@ def run_own(args):
             "wgrad": {"achieved": by["wgrad"][0] / by["wgrad"][1] / 1e12 if "wgrad" in by else None,
                       "frac": by["wgrad"][0] / by["wgrad"][1] / 1e12 / pk["tflops_sustained"] if "wgrad" in by else None,
                       "share_of_step": (by["wgrad"][1] / 2) / (ms * 1e-3) if "wgrad" in by else None},
+            "wgrad_top_shapes": [{"shape": k.partition("|")[2], "tflops": v[0] / v[1] / 1e12, "gbs": v[3] / v[1] / 1e9, "ms_per_step": v[1] / 2 * 1e3,
+                                  "launches_per_step": v[2] // 2}
+                                 for k, v in sorted(((k, v) for k, v in by.items() if "|" in k and k.startswith("wgrad")), key=lambda kv: -kv[1][1])[:10]],
             "other_kernels": {k: v for k, v in others.items() if v is not None},
             "note": "shares are eager per-launch CUDA-event times over the graph-replayed step time; they need not sum to 1"}
     # sampling metric (second half of BASELINE.json's metric): ancestral p_sample with guidance, b=4, replayed from a CUDA graph,

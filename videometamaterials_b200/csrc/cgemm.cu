@@ -939,7 +939,8 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   // Narrow tiles (BN <= 128) are bound by the latency of the per-tile epilogue, not by the MMAs: two groups of eight
   // epilogue warps then drain alternate tiles (4 TMEM accumulators).  Costs 24 KB more static shared memory.
   static const bool one_group = getenv("VMM_ONE_EPI_GROUP") != nullptr;
-  const bool two_groups = !one_group && d.fast_epi && BN > 64 && BN <= 128;   // BN = 64 is bound by the operand reads of the MMAs (48 clk each)
+  static const bool groups64 = getenv("VMM_TWO_GROUPS_64") != nullptr;
+  const bool two_groups = !one_group && d.fast_epi && (BN > 64 || (groups64 && BN == 64)) && BN <= 128;   // BN = 64 is bound by the operand reads of the MMAs (48 clk each)
   const int smem_budget = (two_groups ? 170 : 194) * 1024;   // + 12 / 20 KB static (bias, GroupNorm slots) + 16 / 32 KB store staging + control block
   // Halo mode: 3x3 stride-1 taps in (ky, kx, source) order on a 1 x th x 8 tile.  Each (64-channel chunk, kx) stage loads ONE
   // slab of th + 2 pixel rows; the three ky taps read it at +0 / +1 / +2 swizzle atoms.  A traffic drops from 9 to 3.4 tiles
