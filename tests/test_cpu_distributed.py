@@ -48,7 +48,7 @@ def _worker(rank, world, port, q):
     from videometamaterials_b200.trainer import Trainer
     chunks = Trainer.cond_to_gpu(T, torch.arange(10).reshape(5, 2))
     acc.wait_for_everyone()
-    q.put((rank, w0, ok_grad, g.tolist(), tuple(padded.shape), tuple(gathered.shape), obj, [c.tolist() for c in chunks]))
+    q.put((rank, w0.numpy(), ok_grad, g.tolist(), tuple(padded.shape), tuple(gathered.shape), obj, [c.tolist() for c in chunks]))
     dist.destroy_process_group()
 
 
@@ -64,7 +64,7 @@ def test_two_rank_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     (r0, w0, ok0, g0, ps0, gs0, o0, c0), (r1, w1, ok1, g1, ps1, gs1, o1, c1) = res
-    assert torch.equal(w0, w1)                                    # parameters broadcast from rank 0
+    assert torch.equal(torch.from_numpy(w0), torch.from_numpy(w1))                                    # parameters broadcast from rank 0
     assert ok0 and ok1                                            # averaged gradient on both ranks
     assert g0 == g1 == [0.0, 1.0]
     assert ps0 == ps1 == (2, 2) and gs0 == gs1 == (4, 2)
@@ -190,8 +190,10 @@ def _train_worker(rank, world, port, workdir, q):
             yield x, c
     t.dl = recording()
     t.train(num_samples=0)
-    q.put((rank, w0, t.model.denoise_fn.init_conv.weight.detach().clone(), t.ema_model.denoise_fn.init_conv.weight.detach().clone(),
-           torch.cat(seen), os.path.isfile("run/model/step_4/checkpoint.pt")))
+    # numpy arrays are pickled by value: a torch tensor on an mp.Queue travels as a shared-memory file that is gone when this process
+    # exits before the parent has read it (seen once as FileNotFoundError on a loaded machine)
+    q.put((rank, w0.numpy(), t.model.denoise_fn.init_conv.weight.detach().numpy().copy(), t.ema_model.denoise_fn.init_conv.weight.detach().numpy().copy(),
+           torch.cat(seen).numpy(), os.path.isfile("run/model/step_4/checkpoint.pt")))
     dist.destroy_process_group()
 
 
@@ -209,6 +211,7 @@ def test_two_rank_training_loop(tmp_path):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = [tuple(torch.from_numpy(v) if hasattr(v, "dtype") and not torch.is_tensor(v) else v for v in r) for r in res]
     (_, w0a, wa, ea, ca, cka), (_, w0b, wb, eb, cb, ckb) = res
     assert torch.equal(w0a, w0b) and torch.equal(wa, wb) and torch.equal(ea, eb)
     assert cka and ckb                                          # rank 0 wrote it; both see the same folder

@@ -13,6 +13,8 @@
 namespace vmm {
 
 constexpr int LROWS = 64;        // pixel rows staged per step
+constexpr int LSR = 32;          // rows per step and buffer of the ctx / out / dctx kernels (two buffers, cp.async)
+constexpr int LBR = 16;          // rows per step and buffer of lattn_bwd_mma_kernel (two buffers)
 constexpr int LP3 = 776;         // pitch of a full qkv row (768 + 8)
 constexpr int LP2 = 520;         // pitch of a k|v row pair (512 + 8)
 constexpr int LP1 = 264;         // pitch of a 256-wide row (256 + 8)
@@ -94,13 +96,32 @@ __global__ void __launch_bounds__(256) lattn_ctx_mma_kernel(const uint16_t* __re
                                                             float* __restrict__ acc, float* __restrict__ kstat, int HW, int frames,
                                                             int rows_per_cta) {
   extern __shared__ __align__(16) uint16_t lsm[];
-  uint16_t* tile = lsm;                              // [LROWS][LP2]   w | v
-  uint16_t* zrow = tile + LROWS * LP2;               // [256] zeros
+  constexpr int R = LSR;
+  uint16_t* tile0 = lsm;                             // [2][R][LP2]   k -> w | v      (cp.async double buffer, see lattn_bwd_mma_kernel)
+  uint16_t* zrow = tile0 + 2 * R * LP2;              // [256] zeros
   float* Ms = reinterpret_cast<float*>(zrow + 256);  // [256] column maxima
   const int HD = 256;
   const int bf = blockIdx.y, b = bf / frames;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3, h = warp;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(r_begin + rows_per_cta, HW);
+  const uint32_t tile_s0 = smem_u32(tile0);
+  auto prefetch = [&](int s0, int buf) {
+    const int cnt = min(R, r_end - s0);
+#pragma unroll
+    for (int u = 0; u < R * 64 / 256; ++u) {
+      const int i = u * 256 + tid;
+      const int r = i >> 6, c8 = i & 63;
+      const bool ok = r < cnt;
+      cp_async16(tile_s0 + static_cast<uint32_t>((buf * R + r) * LP2 + c8 * 8) * 2,
+                 qkv + (static_cast<long long>(bf) * HW + s0 + (ok ? r : 0)) * 3 * HD + HD + c8 * 8, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  // the first CTA of each frame-image also owns the T cond tokens (fp32 rows of ekv): staged through buffer 1 before the pixel
+  // rows start to arrive in buffer 0
+  if (r_begin < r_end) prefetch(r_begin, 0);
   for (int i = tid; i < 256; i += 256) {
     zrow[i] = 0;
     Ms[i] = kstat[(static_cast<long long>(bf) * HD + i) * 2];
@@ -110,79 +131,20 @@ __global__ void __launch_bounds__(256) lattn_ctx_mma_kernel(const uint16_t* __re
   fa.zrow = smem_u32(zrow);
   fa.lm = lane >> 3;
   fa.lr = lane & 7;
-  const uint32_t tile_s = smem_u32(tile);
   float C[2][5][4];
 #pragma unroll
   for (int x = 0; x < 40; ++x) (&C[0][0][0])[x] = 0.f;
   const uint32_t ones = pack2<FMT>(1.f, 1.f);
   const uint32_t bones[2] = {ones, ones};
-  const int r_begin = blockIdx.x * rows_per_cta;
-  const int r_end = min(r_begin + rows_per_cta, HW);
-  // the first CTA of each frame-image also owns the T cond tokens: they are handled as "rows" -T..-1
-  const int first = (blockIdx.x == 0) ? -T : 0;
-  for (int s0 = r_begin + first; s0 < r_end; s0 += LROWS) {
-    const int cnt = min(LROWS, r_end - s0);
-    // stage + exponentiate: thread -> (row, 8 channels) of k ; plain copy of v.  Loads are issued in batches of 8
-    // before any use: one dependent global load per iteration made this loop latency-bound.
-    for (int base = 0; base < LROWS * 64; base += 256 * 8) {
-      uint4 raw[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = base + u * 256 + tid;
-        const int r = i >> 6, c8 = i & 63;
-        const int m = s0 + r;
-        raw[u] = make_uint4(0, 0, 0, 0);
-        if (r < cnt && m >= 0) raw[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + m) * 3 * HD + HD) + c8);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = base + u * 256 + tid;
-        const int r = i >> 6, c8 = i & 63;
-        const int m = s0 + r;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (r < cnt) {
-          float v[8];
-          if (m < 0) {
-            const float* src = ekv + (static_cast<long long>(b) * T + (m + T)) * 2 * HD + c8 * 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = src[j];
-          } else {
-            const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack2<FMT>(w[j]);
-              v[2 * j] = f.x;
-              v[2 * j + 1] = f.y;
-            }
-          }
-          if (c8 < 32) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __expf(v[j] - Ms[c8 * 8 + j]);
-            o.x = pack2<FMT>(v[0], v[1]);
-            o.y = pack2<FMT>(v[2], v[3]);
-            o.z = pack2<FMT>(v[4], v[5]);
-            o.w = pack2<FMT>(v[6], v[7]);
-          } else if (m < 0) {
-            o.x = pack2<FMT>(v[0], v[1]);
-            o.y = pack2<FMT>(v[2], v[3]);
-            o.z = pack2<FMT>(v[4], v[5]);
-            o.w = pack2<FMT>(v[6], v[7]);
-          } else {
-            o = raw[u];
-          }
-        }
-        *reinterpret_cast<uint4*>(tile + r * LP2 + c8 * 8) = o;
-      }
-    }
-    __syncthreads();
+  auto accumulate = [&](uint32_t tile_s, int cnt) {
     for (int r0 = 0; r0 < cnt; r0 += 16) {
       uint32_t vb[2][4];
-      ldsm_x4_trans(vb[0], fa.bt(tile_s, LP2, r0, HD + h * 32, LROWS));
-      ldsm_x4_trans(vb[1], fa.bt(tile_s, LP2, r0, HD + h * 32 + 16, LROWS));
+      ldsm_x4_trans(vb[0], fa.bt(tile_s, LP2, r0, HD + h * 32, R));
+      ldsm_x4_trans(vb[1], fa.bt(tile_s, LP2, r0, HD + h * 32 + 16, R));
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         uint32_t wa[4];
-        ldsm_x4_trans(wa, fa.at(tile_s, LP2, r0, h * 32 + 16 * mt, LROWS));
+        ldsm_x4_trans(wa, fa.at(tile_s, LP2, r0, h * 32 + 16 * mt, R));
         mma16816<FMT>(C[mt][0], wa, vb[0]);
         mma16816<FMT>(C[mt][1], wa, vb[0] + 2);
         mma16816<FMT>(C[mt][2], wa, vb[1]);
@@ -190,7 +152,60 @@ __global__ void __launch_bounds__(256) lattn_ctx_mma_kernel(const uint16_t* __re
         mma16816<FMT>(C[mt][4], wa, bones);
       }
     }
+  };
+  if (blockIdx.x == 0) {
+    uint16_t* tk = tile0 + R * LP2;
+    for (int j0 = 0; j0 < T; j0 += R) {
+      const int cnt = min(R, T - j0);
+      for (int i = tid; i < R * 64; i += 256) {
+        const int r = i >> 6, c8 = i & 63;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (r < cnt) {
+          const float* src = ekv + (static_cast<long long>(b) * T + j0 + r) * 2 * HD + c8 * 8;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = src[j];
+          if (c8 < 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __expf(v[j] - Ms[c8 * 8 + j]);
+          }
+          o = make_uint4(pack2<FMT>(v[0], v[1]), pack2<FMT>(v[2], v[3]), pack2<FMT>(v[4], v[5]), pack2<FMT>(v[6], v[7]));
+        }
+        *reinterpret_cast<uint4*>(tk + r * LP2 + c8 * 8) = o;
+      }
+      __syncthreads();
+      accumulate(tile_s0 + static_cast<uint32_t>(R * LP2) * 2, cnt);
+      __syncthreads();
+    }
+  }
+  int buf = 0;
+  for (int s0 = r_begin; s0 < r_end; s0 += R, buf ^= 1) {
+    const int cnt = min(R, r_end - s0);
+    uint16_t* tile = tile0 + buf * R * LP2;
+    cp_async_wait<0>();
+    __syncthreads();       // rows of this step have landed; the MMAs of the previous step are done with the other buffer
+    if (s0 + R < r_end) prefetch(s0 + R, buf ^ 1);
+    // k -> w = exp(k - M) in place: thread -> (row, 8 channels)
+#pragma unroll
+    for (int u = 0; u < R * 32 / 256; ++u) {
+      const int i = u * 256 + tid;
+      const int r = i >> 5, c8 = i & 31;
+      if (r < cnt) {
+        uint4* kp = reinterpret_cast<uint4*>(tile + r * LP2 + c8 * 8);
+        const uint4 v = *kp;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack2<FMT>(w[j]);
+          const int c = c8 * 8 + 2 * j;
+          o[j] = pack2<FMT>(__expf(f.x - Ms[c]), __expf(f.y - Ms[c + 1]));
+        }
+        *kp = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
     __syncthreads();
+    accumulate(tile_s0 + static_cast<uint32_t>(buf * R * LP2) * 2, cnt);
   }
   float* ab = acc + (static_cast<long long>(bf) * 8 + h) * 1024;
 #pragma unroll
@@ -216,9 +231,9 @@ __global__ void lattn_ctx_finalize_kernel(float* __restrict__ ctx, const float* 
 // out = qs ctx   (and, with dout given, dctx += qs^T dout for the backward)
 // ------------------------------------------------------------------------------------------------
 template <int FMT>
-__device__ __forceinline__ void softmax_rows_inplace(uint16_t* tile, int pitch, int col0, int cnt, float scale, int tid) {
+__device__ __forceinline__ void softmax_rows_inplace(uint16_t* tile, int pitch, int col0, int cnt, float scale, int tid, int rows = LROWS) {
   // thread -> (row, head): softmax over the head's 32 values, result * scale written back in place
-  for (int i = tid; i < LROWS * 8; i += 256) {
+  for (int i = tid; i < rows * 8; i += 256) {
     const int r = i >> 3, hh = i & 7;
     if (r >= cnt) continue;
     uint32_t* p = reinterpret_cast<uint32_t*>(tile + r * pitch + col0 + hh * 32);
@@ -248,13 +263,29 @@ template <int FMT>
 __global__ void __launch_bounds__(256) lattn_out_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ctx,
                                                             uint16_t* __restrict__ out, int HW, float scale, int rows_per_cta) {
   extern __shared__ __align__(16) uint16_t lsm[];
+  constexpr int R = LSR;
   const float hw = static_cast<float>(HW);
-  uint16_t* tile = lsm;                      // [LROWS][LP1]  q -> qs
-  uint16_t* zrow = tile + LROWS * LP1;
+  uint16_t* tile0 = lsm;                     // [2][R][LP1]  q -> qs -> out rows   (cp.async double buffer)
+  uint16_t* zrow = tile0 + 2 * R * LP1;
   const int HD = 256;
   const int bf = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3, h = warp;
+  const int r_begin = blockIdx.x * rows_per_cta, r_end = min(r_begin + rows_per_cta, HW);
+  const uint32_t tile_s0 = smem_u32(tile0);
+  auto prefetch = [&](int s0, int buf) {
+    const int cnt = min(R, r_end - s0);
+#pragma unroll
+    for (int u = 0; u < R * 32 / 256; ++u) {
+      const int i = u * 256 + tid;
+      const int r = i >> 5, c8 = i & 31;
+      const bool ok = r < cnt;
+      cp_async16(tile_s0 + static_cast<uint32_t>((buf * R + r) * LP1 + c8 * 8) * 2,
+                 qkv + (static_cast<long long>(bf) * HW + s0 + (ok ? r : 0)) * 3 * HD + c8 * 8, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  if (r_begin < r_end) prefetch(r_begin, 0);
   for (int i = tid; i < 256; i += 256) zrow[i] = 0;
   // B[k = d][n = e] = ctx[d][e]
   uint32_t cb[2][4][2];
@@ -275,28 +306,15 @@ __global__ void __launch_bounds__(256) lattn_out_mma_kernel(const uint16_t* __re
   fa.zrow = smem_u32(zrow);
   fa.lm = lane >> 3;
   fa.lr = lane & 7;
-  const uint32_t tile_s = smem_u32(tile);
-  const int r_begin = blockIdx.x * rows_per_cta, r_end = min(r_begin + rows_per_cta, HW);
-  __syncthreads();
-  for (int s0 = r_begin; s0 < r_end; s0 += LROWS) {
-    const int cnt = min(LROWS, r_end - s0);
-    {
-      uint4 raw[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = u * 256 + tid;
-        const int r = i >> 5, c8 = i & 31;
-        raw[u] = make_uint4(0, 0, 0, 0);
-        if (r < cnt) raw[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD) + c8);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = u * 256 + tid;
-        *reinterpret_cast<uint4*>(tile + (i >> 5) * LP1 + (i & 31) * 8) = raw[u];
-      }
-    }
-    __syncthreads();
-    softmax_rows_inplace<FMT>(tile, LP1, 0, cnt, scale, tid);
+  int buf = 0;
+  for (int s0 = r_begin; s0 < r_end; s0 += R, buf ^= 1) {
+    const int cnt = min(R, r_end - s0);
+    uint16_t* tile = tile0 + buf * R * LP1;
+    const uint32_t tile_s = tile_s0 + static_cast<uint32_t>(buf * R * LP1) * 2;
+    cp_async_wait<0>();
+    __syncthreads();       // rows landed; the copy-out of the previous step is done with the other buffer
+    if (s0 + R < r_end) prefetch(s0 + R, buf ^ 1);
+    softmax_rows_inplace<FMT>(tile, LP1, 0, cnt, scale, tid, R);
     __syncthreads();
     for (int r0 = 0; r0 < cnt; r0 += 16) {
       float O[4][4];
@@ -305,15 +323,17 @@ __global__ void __launch_bounds__(256) lattn_out_mma_kernel(const uint16_t* __re
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         uint32_t qa[4];
-        ldsm_x4(qa, fa.a(tile_s, LP1, r0, h * 32 + 16 * ks, LROWS));
+        ldsm_x4(qa, fa.a(tile_s, LP1, r0, h * 32 + 16 * ks, R));
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) mma16816<FMT>(O[nt], qa, cb[ks][nt]);
       }
+      // in place over this warp's own 32 columns of the 16 rows it has just consumed; whole rows leave with 16-byte stores below
+      __syncwarp();
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
         const int r = r0 + g + 8 * rh;
         if (r < cnt) {
-          uint16_t* orow = out + (static_cast<long long>(bf) * HW + s0 + r) * HD + h * 32 + 2 * t;
+          uint16_t* orow = tile + r * LP1 + h * 32 + 2 * t;
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt)
             *reinterpret_cast<uint32_t*>(orow + 8 * nt) = pack2<FMT>(O[nt][2 * rh] * inv_hw, O[nt][2 * rh + 1] * inv_hw);
@@ -321,6 +341,10 @@ __global__ void __launch_bounds__(256) lattn_out_mma_kernel(const uint16_t* __re
       }
     }
     __syncthreads();
+    for (int i = tid; i < cnt * 32; i += 256) {
+      const int r = i >> 5, c8 = i & 31;
+      *reinterpret_cast<uint4*>(out + (static_cast<long long>(bf) * HW + s0 + r) * HD + c8 * 8) = *reinterpret_cast<const uint4*>(tile + r * LP1 + c8 * 8);
+    }
   }
 }
 
@@ -328,63 +352,61 @@ template <int FMT>
 __global__ void __launch_bounds__(256) lattn_dctx_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ dout,
                                                              float* __restrict__ dctx, int HW, float scale, int rows_per_cta) {
   extern __shared__ __align__(16) uint16_t lsm[];
-  uint16_t* qt = lsm;                        // [LROWS][LP1] qs
-  uint16_t* dt = qt + LROWS * LP1;           // [LROWS][LP1] dout
-  uint16_t* zrow = dt + LROWS * LP1;
+  constexpr int R = LSR;
+  uint16_t* qt0 = lsm;                       // [2][R][LP1] q -> qs        (cp.async double buffer)
+  uint16_t* dt0 = qt0 + 2 * R * LP1;         // [2][R][LP1] dout
+  uint16_t* zrow = dt0 + 2 * R * LP1;
   const int HD = 256;
   const int bf = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3, h = warp;
+  const int r_begin = blockIdx.x * rows_per_cta, r_end = min(r_begin + rows_per_cta, HW);
+  const uint32_t qt_s0 = smem_u32(qt0), dt_s0 = smem_u32(dt0);
+  auto prefetch = [&](int s0, int buf) {
+    const int cnt = min(R, r_end - s0);
+#pragma unroll
+    for (int u = 0; u < R * 64 / 256; ++u) {
+      const int i = u * 256 + tid;
+      const int r = i >> 6, c8 = i & 63;
+      const bool ok = r < cnt;
+      const long long row = static_cast<long long>(bf) * HW + s0 + (ok ? r : 0);
+      if (c8 < 32) cp_async16(qt_s0 + static_cast<uint32_t>((buf * R + r) * LP1 + c8 * 8) * 2, qkv + row * 3 * HD + c8 * 8, ok ? 16 : 0);
+      else cp_async16(dt_s0 + static_cast<uint32_t>((buf * R + r) * LP1 + (c8 - 32) * 8) * 2, dout + row * HD + (c8 - 32) * 8, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  if (r_begin < r_end) prefetch(r_begin, 0);
   for (int i = tid; i < 256; i += 256) zrow[i] = 0;
   LFrag fa;
   fa.zrow = smem_u32(zrow);
   fa.lm = lane >> 3;
   fa.lr = lane & 7;
-  const uint32_t qt_s = smem_u32(qt), dt_s = smem_u32(dt);
   float C[2][4][4];
 #pragma unroll
   for (int x = 0; x < 32; ++x) (&C[0][0][0])[x] = 0.f;
-  const int r_begin = blockIdx.x * rows_per_cta, r_end = min(r_begin + rows_per_cta, HW);
-  __syncthreads();
-  for (int s0 = r_begin; s0 < r_end; s0 += LROWS) {
-    const int cnt = min(LROWS, r_end - s0);
-    for (int base = 0; base < LROWS * 64; base += 256 * 8) {
-      uint4 raw[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = base + u * 256 + tid;
-        const int r = i >> 6, c8 = i & 63;
-        raw[u] = make_uint4(0, 0, 0, 0);
-        if (r < cnt) {
-          if (c8 < 32) raw[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD) + c8);
-          else raw[u] = __ldg(reinterpret_cast<const uint4*>(dout + (static_cast<long long>(bf) * HW + s0 + r) * HD) + (c8 - 32));
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = base + u * 256 + tid;
-        const int r = i >> 6, c8 = i & 63;
-        *reinterpret_cast<uint4*>((c8 < 32 ? qt : dt) + r * LP1 + (c8 & 31) * 8) = raw[u];
-      }
-    }
+  int buf = 0;
+  for (int s0 = r_begin; s0 < r_end; s0 += R, buf ^= 1) {
+    const int cnt = min(R, r_end - s0);
+    const uint32_t qt_s = qt_s0 + static_cast<uint32_t>(buf * R * LP1) * 2, dt_s = dt_s0 + static_cast<uint32_t>(buf * R * LP1) * 2;
+    cp_async_wait<0>();
     __syncthreads();
-    softmax_rows_inplace<FMT>(qt, LP1, 0, cnt, scale, tid);
+    if (s0 + R < r_end) prefetch(s0 + R, buf ^ 1);
+    softmax_rows_inplace<FMT>(qt0 + buf * R * LP1, LP1, 0, cnt, scale, tid, R);
     __syncthreads();
     for (int r0 = 0; r0 < cnt; r0 += 16) {
       uint32_t db[2][4];
-      ldsm_x4_trans(db[0], fa.bt(dt_s, LP1, r0, h * 32, LROWS));
-      ldsm_x4_trans(db[1], fa.bt(dt_s, LP1, r0, h * 32 + 16, LROWS));
+      ldsm_x4_trans(db[0], fa.bt(dt_s, LP1, r0, h * 32, R));
+      ldsm_x4_trans(db[1], fa.bt(dt_s, LP1, r0, h * 32 + 16, R));
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         uint32_t qa[4];
-        ldsm_x4_trans(qa, fa.at(qt_s, LP1, r0, h * 32 + 16 * mt, LROWS));
+        ldsm_x4_trans(qa, fa.at(qt_s, LP1, r0, h * 32 + 16 * mt, R));
         mma16816<FMT>(C[mt][0], qa, db[0]);
         mma16816<FMT>(C[mt][1], qa, db[0] + 2);
         mma16816<FMT>(C[mt][2], qa, db[1]);
         mma16816<FMT>(C[mt][3], qa, db[1] + 2);
       }
     }
-    __syncthreads();
   }
   float* ab = dctx + (static_cast<long long>(bf) * 8 + h) * 1024;
 #pragma unroll
@@ -409,16 +431,35 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
                                                             const float* __restrict__ kstat, uint16_t* __restrict__ dqkv, int HW,
                                                             float scale, float vscale, int rows_per_cta) {
   extern __shared__ __align__(16) uint16_t lsm[];
-  constexpr int R = 32;                      // rows per step (full qkv rows are wide)
-  uint16_t* tile = lsm;                      // [R][LP3]  q -> p | k -> wn | v
-  uint16_t* dt = tile + R * LP3;             // [R][LP1]  dout
-  uint16_t* zrow = dt + R * LP1;             // [256]
+  // Two buffers of R = 16 rows: cp.async fills buffer (s + 1) & 1 with the rows of the next step while the CTA turns the rows of
+  // step s into p / wn, runs the MMAs and copies the gradients out.  (One buffer of 32 rows and register-staged loads left every
+  // phase of a step waiting on HBM: 989 us for the level-0 block, 2.9 TB/s.)
+  constexpr int R = LBR;
+  uint16_t* tile0 = lsm;                     // [2][R][LP3]  q -> p | k -> wn | v    (then dq | dk | dv in place)
+  uint16_t* dt0 = tile0 + 2 * R * LP3;       // [2][R][LP1]  dout
+  uint16_t* zrow = dt0 + 2 * R * LP1;        // [256]
   float* Ms = reinterpret_cast<float*>(zrow + 256);   // [256] max
   float* Zi = Ms + 256;                                // [256] 1 / Z
   const int HD = 256;
   const int bf = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3, h = warp;
+  const int r_begin = blockIdx.x * rows_per_cta, r_end = min(r_begin + rows_per_cta, HW);
+  const uint32_t tile_s0 = smem_u32(tile0), dt_s0 = smem_u32(dt0);
+  auto prefetch = [&](int s0, int buf) {
+    const int cnt = min(R, r_end - s0);
+#pragma unroll
+    for (int u = 0; u < R * 128 / 256; ++u) {
+      const int i = u * 256 + tid;
+      const int r = i >> 7, c8 = i & 127;
+      const bool ok = r < cnt;
+      const long long row = static_cast<long long>(bf) * HW + s0 + (ok ? r : 0);
+      if (c8 < 96) cp_async16(tile_s0 + static_cast<uint32_t>((buf * R + r) * LP3 + c8 * 8) * 2, qkv + row * 3 * HD + c8 * 8, ok ? 16 : 0);
+      else cp_async16(dt_s0 + static_cast<uint32_t>((buf * R + r) * LP1 + (c8 - 96) * 8) * 2, dout + row * HD + (c8 - 96) * 8, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  if (r_begin < r_end) prefetch(r_begin, 0);
   for (int i = tid; i < 256; i += 256) {
     zrow[i] = 0;
     Ms[i] = kstat[(static_cast<long long>(bf) * HD + i) * 2];
@@ -456,74 +497,70 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
   fa.zrow = smem_u32(zrow);
   fa.lm = lane >> 3;
   fa.lr = lane & 7;
-  const uint32_t tile_s = smem_u32(tile), dt_s = smem_u32(dt);
-  const int r_begin = blockIdx.x * rows_per_cta, r_end = min(r_begin + rows_per_cta, HW);
-  __syncthreads();
-  for (int s0 = r_begin; s0 < r_end; s0 += R) {
+  int buf = 0;
+  for (int s0 = r_begin; s0 < r_end; s0 += R, buf ^= 1) {
     const int cnt = min(R, r_end - s0);
-    for (int base = 0; base < R * 128; base += 256 * 8) {
-      uint4 raw[8];
+    uint16_t* tile = tile0 + buf * R * LP3;
+    const uint32_t tile_s = tile_s0 + static_cast<uint32_t>(buf * R * LP3) * 2, dt_s = dt_s0 + static_cast<uint32_t>(buf * R * LP1) * 2;
+    cp_async_wait<0>();
+    __syncthreads();       // rows of this step have landed; every thread is done with the other buffer (copy-out of the previous step)
+    if (s0 + R < r_end) prefetch(s0 + R, buf ^ 1);
+    if (tid < 128) {
+      // q -> p = softmax_d(q) (scale applied at the end): thread -> (row, head)
+      const int r = tid >> 3, hh = tid & 7;
+      if (r < cnt) {
+        uint4* p4 = reinterpret_cast<uint4*>(tile + r * LP3 + hh * 32);
+        float v[32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = base + u * 256 + tid;
-        const int r = i >> 7, c8 = i & 127;
-        raw[u] = make_uint4(0, 0, 0, 0);
-        if (r < cnt) {
-          if (c8 < 96) raw[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD) + c8);
-          else raw[u] = __ldg(reinterpret_cast<const uint4*>(dout + (static_cast<long long>(bf) * HW + s0 + r) * HD) + (c8 - 96));
-        }
-      }
+        for (int j = 0; j < 4; ++j) {
+          const uint4 q4 = p4[j];
+          const uint32_t w4[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = base + u * 256 + tid;
-        const int r = i >> 7, c8 = i & 127;
-        uint4 v = raw[u];
-        if (c8 < 96) {
-          if (c8 >= 32 && c8 < 64 && r < cnt) {      // k -> wn = exp(k - M) / Z
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack2<FMT>(w[j]);
-              const int c = (c8 - 32) * 8 + 2 * j;
-              o[j] = pack2<FMT>(__expf(f.x - Ms[c]) * Zi[c], __expf(f.y - Ms[c + 1]) * Zi[c + 1]);
-            }
-            v = make_uint4(o[0], o[1], o[2], o[3]);
+          for (int x = 0; x < 4; ++x) {
+            const float2 f = unpack2<FMT>(w4[x]);
+            v[8 * j + 2 * x] = f.x;
+            v[8 * j + 2 * x + 1] = f.y;
           }
-          *reinterpret_cast<uint4*>(tile + r * LP3 + c8 * 8) = v;
-        } else {
-          *reinterpret_cast<uint4*>(dt + r * LP1 + (c8 - 96) * 8) = v;
+        }
+        float mx = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __expf(v[j] - mx);
+          sum += v[j];
+        }
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          p4[j] = make_uint4(pack2<FMT>(v[8 * j] * inv, v[8 * j + 1] * inv), pack2<FMT>(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
+                             pack2<FMT>(v[8 * j + 4] * inv, v[8 * j + 5] * inv), pack2<FMT>(v[8 * j + 6] * inv, v[8 * j + 7] * inv));
+      }
+    } else {
+      // k -> wn = exp(k - M) / Z: thread -> (row, 8 channels), 16 rows x 32 vectors over 128 threads
+#pragma unroll
+      for (int u = 0; u < R * 32 / 128; ++u) {
+        const int i = u * 128 + (tid - 128);
+        const int r = i >> 5, c8 = i & 31;
+        if (r < cnt) {
+          uint4* kp = reinterpret_cast<uint4*>(tile + r * LP3 + HD + c8 * 8);
+          const uint4 v = *kp;
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2<FMT>(w[j]);
+            const int c = c8 * 8 + 2 * j;
+            o[j] = pack2<FMT>(__expf(f.x - Ms[c]) * Zi[c], __expf(f.y - Ms[c + 1]) * Zi[c + 1]);
+          }
+          *kp = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
     }
     __syncthreads();
-    // q -> p = softmax_d(q) (scale applied at the end)
-    for (int i = tid; i < R * 8; i += 256) {
-      const int r = i >> 3, hh = i & 7;
-      if (r >= cnt) continue;
-      uint32_t* p = reinterpret_cast<uint32_t*>(tile + r * LP3 + hh * 32);
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float2 f = unpack2<FMT>(p[j]);
-        v[2 * j] = f.x;
-        v[2 * j + 1] = f.y;
-      }
-      float mx = v[0];
-#pragma unroll
-      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = __expf(v[j] - mx);
-        sum += v[j];
-      }
-      const float inv = 1.f / sum;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) p[j] = pack2<FMT>(v[2 * j] * inv, v[2 * j + 1] * inv);
-    }
-    __syncthreads();
-    for (int r0 = 0; r0 < cnt; r0 += 16) {
+    {
+      constexpr int r0 = 0;
       float DQ[4][4], DV[4][4], DW[4][4];
 #pragma unroll
       for (int x = 0; x < 16; ++x) (&DQ[0][0])[x] = (&DV[0][0])[x] = (&DW[0][0])[x] = 0.f;
@@ -587,7 +624,6 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
       *reinterpret_cast<uint4*>(dqkv + (static_cast<long long>(bf) * HW + s0 + r) * 3 * HD + c8 * 8) =
           *reinterpret_cast<const uint4*>(tile + r * LP3 + c8 * 8);
     }
-    __syncthreads();       // the next step's staging overwrites the tile
   }
 }
 
@@ -636,6 +672,34 @@ static int lat_rows_per_cta(int HW, int BF) {
   return rows;
 }
 
+// Rows per CTA for a kernel with `slots` co-resident CTAs on the device: the kernel's time is (waves of CTAs) x (rows per CTA + a
+// prologue worth ~48 rows: fragments, statistics), so pick the chunk count that minimises it instead of a fixed "3 CTAs per SM"
+// (level 0, b = 8: 6 chunks x 88 frame-images = 528 CTAs = 1.8 waves of 296 paid as 2; 10 chunks = 2.97 waves, 9 % less time).
+static int lat_rows_waves(int HW, int BF, int slots) {
+  long long best_cost = -1;
+  int best_rows = HW;
+  const int max_chunks = (HW + LROWS - 1) / LROWS;
+  for (int c = 1; c <= max_chunks && c <= 96; ++c) {
+    int rows = (HW + c - 1) / c;
+    rows = (rows + LROWS - 1) / LROWS * LROWS;
+    const int chunks = (HW + rows - 1) / rows;
+    const long long waves = (static_cast<long long>(chunks) * BF + slots - 1) / slots;
+    const long long cost = waves * (rows + 48);
+    if (best_cost < 0 || cost < best_cost) best_cost = cost, best_rows = rows;
+  }
+  return best_rows;
+}
+
+template <typename K>
+static int lat_slots(K kern, size_t smem, int& cache) {
+  if (cache == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 256, smem) != cudaSuccess || n < 1) n = 1;
+    cache = n * num_sms();
+  }
+  return cache;
+}
+
 }  // namespace vmm
 
 using namespace vmm;
@@ -653,8 +717,8 @@ extern "C" int vmm_lattn_fwd(const void* qkv, const float* ekv, int T, void* out
   if (heads != 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_lattn_fwd: heads must be 8");
   if (T > 48) return set_error(VMM_ERR_UNSUPPORTED, "vmm_lattn_fwd: too many cond tokens");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t sm_ctx = (static_cast<size_t>(LROWS) * LP2 + 256) * 2 + 256 * 4;
-  const size_t sm_out = (static_cast<size_t>(LROWS) * LP1 + 256) * 2;
+  const size_t sm_ctx = (static_cast<size_t>(2 * LSR) * LP2 + 256) * 2 + 256 * 4;
+  const size_t sm_out = (static_cast<size_t>(2 * LSR) * LP1 + 256) * 2;
   static bool attr = false;
   if (!attr) {
     LAT_SET_ATTR(lattn_ctx_mma_kernel, 100 * 1024);
@@ -666,10 +730,13 @@ extern "C" int vmm_lattn_fwd(const void* qkv, const float* ekv, int T, void* out
   if (e != cudaSuccess) return set_cuda_error(e, "vmm_lattn_fwd: memset");
   lattn_kstat_init_kernel<<<static_cast<int>((nstat + 255) / 256), 256, 0, stream>>>(kstat, ekv, T, 256, frames, nstat);
   count_launch();
-  const int rpc = lat_rows_per_cta(HW, BF);
-  const int chunks = (HW + rpc - 1) / rpc;
+  int rpc = lat_rows_per_cta(HW, BF);
+  int chunks = (HW + rpc - 1) / rpc;
   lattn_kmax_kernel<<<dim3(chunks, BF), 256, 0, stream>>>(static_cast<const uint16_t*>(qkv), kstat, fmt, HW, 256, rpc);
   count_launch();
+  static int slots_ctx = 0, slots_out = 0;
+  rpc = lat_rows_waves(HW, BF, lat_slots(lattn_ctx_mma_kernel<1>, sm_ctx, slots_ctx));
+  chunks = (HW + rpc - 1) / rpc;
   if (fmt == VMM_FMT_F16)
     lattn_ctx_mma_kernel<0><<<dim3(chunks, BF), 256, sm_ctx, stream>>>(static_cast<const uint16_t*>(qkv), ekv, T, ctx, kstat, HW, frames, rpc);
   else
@@ -678,6 +745,8 @@ extern "C" int vmm_lattn_fwd(const void* qkv, const float* ekv, int T, void* out
   const long long nctx = static_cast<long long>(BF) * 8 * 1024;
   lattn_ctx_finalize_kernel<<<static_cast<int>((nctx + 255) / 256), 256, 0, stream>>>(ctx, kstat, nctx, 1.f / static_cast<float>(HW));
   count_launch();
+  rpc = lat_rows_waves(HW, BF, lat_slots(lattn_out_mma_kernel<1>, sm_out, slots_out));
+  chunks = (HW + rpc - 1) / rpc;
   if (fmt == VMM_FMT_F16)
     lattn_out_mma_kernel<0><<<dim3(chunks, BF), 256, sm_out, stream>>>(static_cast<const uint16_t*>(qkv), ctx, static_cast<uint16_t*>(out), HW, scale, rpc);
   else
@@ -692,8 +761,8 @@ extern "C" int vmm_lattn_bwd(const void* qkv, const float* ekv, int T, const voi
   if (!qkv || !ekv || !dout || !ctx || !kstat || !dctx || !dqkv || !dekv) return set_error(VMM_ERR_ARG, "vmm_lattn_bwd: null pointer");
   if (heads != 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_lattn_bwd: heads must be 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t sm_dctx = (static_cast<size_t>(2) * LROWS * LP1 + 256) * 2;
-  const size_t sm_bwd = (static_cast<size_t>(32) * (LP3 + LP1) + 256) * 2 + 512 * 4;
+  const size_t sm_dctx = (static_cast<size_t>(4 * LSR) * LP1 + 256) * 2;
+  const size_t sm_bwd = (static_cast<size_t>(2 * LBR) * (LP3 + LP1) + 256) * 2 + 512 * 4;
   static bool attr = false;
   if (!attr) {
     LAT_SET_ATTR(lattn_dctx_mma_kernel, 100 * 1024);
@@ -702,18 +771,20 @@ extern "C" int vmm_lattn_bwd(const void* qkv, const float* ekv, int T, const voi
   }
   cudaError_t e = cudaMemsetAsync(dctx, 0, static_cast<size_t>(BF) * 8 * 1024 * sizeof(float), stream);
   if (e != cudaSuccess) return set_cuda_error(e, "vmm_lattn_bwd: memset");
-  const int rpc = lat_rows_per_cta(HW, BF);
-  const int chunks = (HW + rpc - 1) / rpc;
+  static int slots_dctx = 0, slots_bwd = 0;
+  const int rpc_d = lat_rows_waves(HW, BF, lat_slots(lattn_dctx_mma_kernel<1>, sm_dctx, slots_dctx));
+  const int rpc_b = lat_rows_waves(HW, BF, lat_slots(lattn_bwd_mma_kernel<1>, sm_bwd, slots_bwd));
+  const dim3 grid_d((HW + rpc_d - 1) / rpc_d, BF), grid_b((HW + rpc_b - 1) / rpc_b, BF);
   if (fmt == VMM_FMT_F16) {
-    lattn_dctx_mma_kernel<0><<<dim3(chunks, BF), 256, sm_dctx, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(dout), dctx, HW, scale, rpc);
+    lattn_dctx_mma_kernel<0><<<grid_d, 256, sm_dctx, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(dout), dctx, HW, scale, rpc_d);
     count_launch();
-    lattn_bwd_mma_kernel<0><<<dim3(chunks, BF), 256, sm_bwd, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(dout), ctx, dctx, kstat,
-                                                                       static_cast<uint16_t*>(dqkv), HW, scale, vscale, rpc);
+    lattn_bwd_mma_kernel<0><<<grid_b, 256, sm_bwd, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(dout), ctx, dctx, kstat,
+                                                             static_cast<uint16_t*>(dqkv), HW, scale, vscale, rpc_b);
   } else {
-    lattn_dctx_mma_kernel<1><<<dim3(chunks, BF), 256, sm_dctx, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(dout), dctx, HW, scale, rpc);
+    lattn_dctx_mma_kernel<1><<<grid_d, 256, sm_dctx, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(dout), dctx, HW, scale, rpc_d);
     count_launch();
-    lattn_bwd_mma_kernel<1><<<dim3(chunks, BF), 256, sm_bwd, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(dout), ctx, dctx, kstat,
-                                                                       static_cast<uint16_t*>(dqkv), HW, scale, vscale, rpc);
+    lattn_bwd_mma_kernel<1><<<grid_b, 256, sm_bwd, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(dout), ctx, dctx, kstat,
+                                                             static_cast<uint16_t*>(dqkv), HW, scale, vscale, rpc_b);
   }
   count_launch();
   lattn_bwd_tokens_kernel<<<BF * 8, 256, 0, stream>>>(ekv, T, ctx, dctx, kstat, dekv, BF, frames, vscale);
