@@ -183,6 +183,20 @@ class Accelerator:
                         p.grad.mul_(1.0 / self.num_processes)
         return pending
 
+    def reduce_gradient_chunks(self, arena, n_chunks: int = 4):
+        """SUM all-reduce of one gradient arena as `n_chunks` asynchronous collectives over contiguous pieces.  Returns
+        ([(start, end, work), ...], factor still to be applied = 1 / world size).  The caller waits on piece i and runs the optimiser
+        over it while piece i + 1 is still on the wire (Trainer.train_step), so that only the first piece's transfer and the last
+        piece's update are exposed instead of the whole all-reduce followed by the whole update."""
+        n = arena.flat_grad.numel()
+        step = -(-n // max(1, n_chunks))
+        step = -(-step // 1024) * 1024                       # 4 KB boundaries keep every piece 16-byte aligned
+        out = []
+        for a in range(0, n, step):
+            b = min(n, a + step)
+            out.append((a, b, dist.all_reduce(arena.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.grad_group, async_op=True)))
+        return out, 1.0 / self.num_processes
+
     def clip_grad_norm_(self, parameters, max_norm, norm_type=2):
         return torch.nn.utils.clip_grad_norm_(parameters, max_norm, norm_type=norm_type)
 

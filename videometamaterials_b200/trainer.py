@@ -26,6 +26,9 @@ from .accel import Accelerator, broadcast_object_list
 from .blocks_bwd import get_arena
 from .dataset import Dataset, SyntheticLagrangianDataset, clean_pred, video_tensor_to_gif
 
+# pieces of the gradient all-reduce that are pipelined with the optimiser update (1 = one collective, then one update)
+REDUCE_CHUNKS = int(os.environ.get("VMM_REDUCE_CHUNKS", "4"))
+
 
 def cycle(dl):
     while True:
@@ -67,6 +70,18 @@ class FusedAdam:
         self.step_count += 1
         ops.adam_ema_step(self.arena.flat_param, self.arena.flat_grad, self.m, self.v, ema_flat, self.lr, self.betas[0], self.betas[1],
                           self.eps, self.step_count, grad_scale, ema_mode, ema_beta)
+        self.model.repack()
+
+    def step_chunks(self, chunks, ema_flat: Optional[torch.Tensor] = None, ema_mode: int = 0, ema_beta: float = 0.995, grad_scale: float = 1.0):
+        """The same update as step(), piece by piece: `chunks` = [(start, end, work)] from Accelerator.reduce_gradient_chunks; the update
+        of piece i is queued behind its all-reduce only, so it overlaps the transfer of the pieces after it."""
+        self._ensure()
+        self.step_count += 1
+        a_ = self.arena
+        for a, b, work in chunks:
+            work.wait()                                      # stream-ordered for NCCL (no host block); blocks the host for gloo
+            ops.adam_ema_step(a_.flat_param[a:b], a_.flat_grad[a:b], self.m[a:b], self.v[a:b], None if ema_flat is None else ema_flat[a:b],
+                              self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, grad_scale, ema_mode, ema_beta)
         self.model.repack()
 
     def _torch_indices(self):
@@ -319,13 +334,23 @@ class Trainer(object):
         # the 1/P of the gradient average rides in the optimiser kernel's grad_scale unless the clipped norm needs averaged gradients
         reduce = getattr(self.accelerator, "all_reduce_gradients", None)      # a genuine HF Accelerator has no such member: its
         grad_scale = 1.0                                                        # prepared (DDP) model averages during backward
+        ema_mode = 0
+        if self.step % self.update_ema_every == 0:
+            ema_mode = 1 if self.step < self.step_start_ema else 2
+        chunked = getattr(self.accelerator, "reduce_gradient_chunks", None)
+        if (chunked is not None and REDUCE_CHUNKS > 1 and self.max_grad_norm is None and getattr(self.accelerator, "num_processes", 1) > 1
+                and hasattr(self.opt, "step_chunks")):
+            # all-reduce piece i + 1 runs under the optimiser update of piece i (no clipping: the global norm would need every piece first)
+            chunks, grad_scale = chunked(get_arena(self.model.denoise_fn), REDUCE_CHUNKS)
+            self.opt.step_chunks(chunks, ema_flat=self._ema_flat() if ema_mode else None, ema_mode=ema_mode, ema_beta=self.ema_decay,
+                                 grad_scale=grad_scale)
+            if ema_mode:
+                self.ema_model.denoise_fn.repack()
+            return loss
         if reduce is not None:
             grad_scale = reduce(average=self.max_grad_norm is not None) or 1.0
         if self.max_grad_norm is not None:
             self.accelerator.clip_grad_norm_(get_arena(self.model.denoise_fn).params, self.max_grad_norm)
-        ema_mode = 0
-        if self.step % self.update_ema_every == 0:
-            ema_mode = 1 if self.step < self.step_start_ema else 2
         self.opt.step(ema_flat=self._ema_flat() if ema_mode else None, ema_mode=ema_mode, ema_beta=self.ema_decay, grad_scale=grad_scale)
         if ema_mode:
             self.ema_model.denoise_fn.repack()
