@@ -169,6 +169,8 @@ def _train_worker(rank, world, port, workdir, q):
     from oracle import vdm_oracle as O
     from videometamaterials_b200 import Accelerator, GaussianDiffusion, Trainer, Unet3D, ops
     os.chdir(workdir)
+    import videometamaterials_b200.trainer as trainer_mod
+    trainer_mod.REDUCE_CHUNKS = 3                     # the pipelined all-reduce / optimiser path (default 1 = one collective, covered by test_two_rank_gloo)
     GaussianDiffusion.forward = _rank_loss
     GaussianDiffusion.sample = lambda self, cond=None, batch_size=16, guidance_scale=1.: _stub_sample(cond, guidance_scale)
     ops.adam_ema_step = lambda p, g, m, v, ema, lr, b1, b2, eps, step, gs, mode, beta: \

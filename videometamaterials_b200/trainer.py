@@ -26,8 +26,11 @@ from .accel import Accelerator, broadcast_object_list
 from .blocks_bwd import get_arena
 from .dataset import Dataset, SyntheticLagrangianDataset, clean_pred, video_tensor_to_gif
 
-# pieces of the gradient all-reduce that are pipelined with the optimiser update (1 = one collective, then one update)
-REDUCE_CHUNKS = int(os.environ.get("VMM_REDUCE_CHUNKS", "4"))
+# Pieces of the gradient all-reduce that are pipelined with the optimiser update (1 = one collective, then one update).
+# Measured on B200s over NVSwitch (bench.py, b = 8 per GPU): the whole 158 MB all-reduce costs only ~0.35 ms per step, and splitting it
+# does not hide it: 2 GPUs 32.23 ms (1 piece) vs 32.38 ms (4 pieces), 4 GPUs 32.16 vs 32.51 ms; both kernels are HBM-bound and contend.
+# The default therefore stays at one piece; the pipelined form is kept for fabrics where the transfer dominates (VMM_REDUCE_CHUNKS=4).
+REDUCE_CHUNKS = int(os.environ.get("VMM_REDUCE_CHUNKS", "1"))
 
 
 def cycle(dl):
