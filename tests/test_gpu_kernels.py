@@ -60,21 +60,22 @@ def test_layernorm_fwd(ops, dt, C):
     assert rel(y, want) < TOL[dt]
 
 
-def _attn_inputs(B, Fr, H, W, heads, dt, seed):
+def _attn_inputs(B, Fr, H, W, heads, dt, seed, T=11):
     torch.manual_seed(seed)
     hd = heads * 32
     qkv = torch.randn(B, Fr, H, W, 3 * hd, device="cuda").to(dt)
-    ekv = torch.randn(B, 11, 2 * hd, device="cuda")
+    ekv = torch.randn(B, T, 2 * hd, device="cuda")
     return qkv, ekv
 
 
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("with_cond", [True, False])
-def test_temporal_attention_core(ops, dt, with_cond):
+@pytest.mark.parametrize("Fr", [11, 22, 7])        # 11: tensor-core kernel; other frame counts (tokens == frames): csrc/tattn_generic.cu
+def test_temporal_attention_core(ops, dt, with_cond, Fr):
     from oracle import vdm_oracle as O
-    B, Fr, H, W, heads = 2, 11, 5, 7, 8
+    B, H, W, heads = 2, 5, 7, 8
     hd = heads * 32
-    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 2)
+    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 2, T=Fr)
     bias = torch.randn(heads, Fr, Fr, device="cuda")
     freqs = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32)).cuda()
     ang = torch.arange(Fr, device="cuda").float()[:, None] * freqs[None, :]
@@ -85,8 +86,8 @@ def test_temporal_attention_core(ops, dt, with_cond):
     q, k, v = (t.float().permute(0, 2, 3, 1, 4).reshape(B, H * W, Fr, heads, 32).transpose(2, 3) for t in qkv.chunk(3, dim=-1))
     k = O.rotary(k, freqs)
     if with_cond:
-        ek = ekv[..., :hd].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
-        ev = ekv[..., hd:].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
+        ek = ekv[..., :hd].reshape(B, 1, Fr, heads, 32).transpose(2, 3).expand(B, H * W, heads, Fr, 32)
+        ev = ekv[..., hd:].reshape(B, 1, Fr, heads, 32).transpose(2, 3).expand(B, H * W, heads, Fr, 32)
         k = torch.cat((ek, k), -2)
         v = torch.cat((ev, v), -2)
     qq = O.rotary(q * 32 ** -0.5, freqs)
@@ -417,11 +418,12 @@ def _rot_tables(Fr):
 
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("with_cond", [True, False])
-def test_temporal_attention_bwd(ops, dt, with_cond):
+@pytest.mark.parametrize("Fr", [11, 22, 7])
+def test_temporal_attention_bwd(ops, dt, with_cond, Fr):
     from oracle import vdm_oracle as O
-    B, Fr, H, W, heads = 2, 11, 5, 7, 8
+    B, H, W, heads = 2, 5, 7, 8
     hd = heads * 32
-    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 20)
+    qkv, ekv = _attn_inputs(B, Fr, H, W, heads, dt, 20, T=Fr)
     dout = torch.randn(B, Fr, H, W, hd, device="cuda").to(dt)
     bias = torch.randn(heads, Fr, Fr, device="cuda")
     freqs, rot = _rot_tables(Fr)
@@ -431,8 +433,8 @@ def test_temporal_attention_bwd(ops, dt, with_cond):
     q, k, v = (t.permute(0, 2, 3, 1, 4).reshape(B, H * W, Fr, heads, 32).transpose(2, 3) for t in qf.chunk(3, dim=-1))
     k = O.rotary(k, freqs)
     if with_cond:
-        ek = ef[..., :hd].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
-        ev = ef[..., hd:].reshape(B, 1, 11, heads, 32).transpose(2, 3).expand(B, H * W, heads, 11, 32)
+        ek = ef[..., :hd].reshape(B, 1, Fr, heads, 32).transpose(2, 3).expand(B, H * W, heads, Fr, 32)
+        ev = ef[..., hd:].reshape(B, 1, Fr, heads, 32).transpose(2, 3).expand(B, H * W, heads, Fr, 32)
         k = torch.cat((ek, k), -2)
         v = torch.cat((ev, v), -2)
     sim = torch.einsum("...id,...jd->...ij", O.rotary(q * 32 ** -0.5, freqs), k)

@@ -203,6 +203,56 @@ def test_ragged_sizes_against_the_oracle(size, b, check_grads):
     assert worst[0] < 0.08, worst            # same bound family as test_small_training_loss_and_gradients (sign flips of the L1 loss)
 
 
+@pytest.mark.parametrize("frames,b", [(22, 2), (7, 1)])
+def test_other_frame_counts_against_the_oracle(frames, b):
+    """BASELINE configs[4] names 22 frames.  The reference's shipped configuration cannot run there (11 hard-coded tokens, VDDP:603 /
+    VDDP:777), so this package's `num_frames` extension sets tokens == frames and the temporal attention runs on the
+    generic kernels (csrc/tattn_generic.cu).  No reference parity exists for these rows: the check is against this repo's oracle,
+    which is pinned to the reference at 11 frames and generic in the frame count.  Forward, guided forward, loss, gradient norms."""
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import GaussianDiffusion, Unet3D
+    size = 16
+    cfg = O.UnetCfg(dim=16, dim_mults=(1, 2), frames=frames)
+    model = Unet3D(dim=16, dim_mults=(1, 2), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
+                   cond_bias=True, cond_attention='self-stacked', cond_attention_tokens=16, use_temporal_attention_cond=True,
+                   cond_to_time='add', per_frame_cond=True, padding_mode='zeros', num_frames=frames)
+    sd = O.synthetic_state_dict(cfg, seed=5)
+    model.load_state_dict(sd, strict=True)
+    model.set_compute_dtype(torch.float16)
+    gd = GaussianDiffusion(model, image_size=size, channels=3, num_frames=frames, timesteps=8, loss_type='l1', use_dynamic_thres=True,
+                           sampling_timesteps=8).cuda()
+    g = torch.Generator().manual_seed(frames * 10 + b)
+    x = torch.randn(b, 3, frames, size, size, generator=g)
+    cond = torch.rand(b, frames, generator=g) * 2 - 1
+    t = torch.randint(0, 8, (b,), generator=g)
+    noise = torch.randn(b, 3, frames, size, size, generator=g)
+    with torch.no_grad():
+        y = model(x.cuda(), t.cuda(), cond=cond.cuda(), null_cond_prob=0.0)
+        yg = model.forward_with_guidance_scale(x.cuda(), t.cuda(), cond=cond.cuda(), guidance_scale=3.0)
+        y_ref = O.unet_forward(sd, cfg, x, t, cond, torch.zeros(b, dtype=torch.bool))
+        yg_ref = O.unet_forward_guided(sd, cfg, x, t, cond, 3.0)
+    e = (rel(y, y_ref), rel(yg, yg_ref))
+    print("frames forward rel-L2:", frames, b, e)
+    assert e[0] < FWD_TOL[torch.float16] and e[1] < 5 * FWD_TOL[torch.float16]
+    x01 = torch.rand(b, 3, frames, size, size, generator=g)
+    P = {k: v.clone().requires_grad_(v.is_floating_point() and "freqs" not in k) for k, v in sd.items()}
+    loss_ref = O.p_losses(P, cfg, O.schedule(8), x01, t, cond, noise, torch.zeros(b, dtype=torch.bool))
+    loss_ref.backward()
+    loss = gd.p_losses((x01 * 2 - 1).cuda(), t.cuda(), cond=cond.cuda(), noise=noise.cuda(), null_cond_prob=0.0)
+    (loss * 4096.0).backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 2e-3
+    params = dict(model.named_parameters())
+    worst = max((abs(float(params[k].grad.norm()) / 4096.0 - float(p.grad.norm())) / (float(p.grad.norm()) + 1e-7 / 0.08), k)
+                for k, p in P.items() if p.requires_grad and p.grad is not None and float(p.grad.norm()) > 0)
+    print("frames worst grad-norm deviation:", frames, b, worst)
+    assert worst[0] < 0.08, worst
+    # one guided sampling step through the public sampler
+    with torch.no_grad():
+        img = gd.p_sample(x.cuda(), t.cuda(), cond=cond.cuda(), guidance_scale=3.0)
+    assert tuple(img.shape) == (b, 3, frames, size, size) and bool(torch.isfinite(img).all())
+
+
 def test_forward_needs_cuda():
     from videometamaterials_b200 import Unet3D
     m = Unet3D(dim=16, dim_mults=(1, 2), per_frame_cond=True, use_temporal_attention_cond=True, cond_attention='self-stacked')

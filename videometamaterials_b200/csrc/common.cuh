@@ -18,6 +18,12 @@ int check_launch(const char* where);
 void count_launch();
 int num_sms();
 
+// temporal attention for frame counts other than 11 (tattn_generic.cu), reached through vmm_tattn_fwd / vmm_tattn_bwd
+int tattn_generic_fwd(const void* qkv, const float* ekv, const float* bias, const float* rot, void* out, int fmt, int B, int frames, int HW,
+                      float scale, int pre_rotated, cudaStream_t stream);
+int tattn_generic_bwd(const void* qkv, const float* ekv, const float* bias, const float* rot, const void* dout, void* dqkv, float* dekv,
+                      float* dbias, int fmt, int B, int frames, int HW, float scale, int pre_rotated, cudaStream_t stream);
+
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency, so the
 // library also loads on a machine without a driver).  128-byte swizzle (or 64), zero fill out of bounds.
 int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* gdim,

@@ -239,9 +239,10 @@ using namespace vmm;
 extern "C" int vmm_tattn_fwd(const void* qkv, const float* ekv, const float* bias, const float* rot, void* out, int fmt, int B,
                              int frames, int HW, int heads, float scale, int pre_rotated, void* stream_) {
   if (!qkv || !bias || !rot || !out) return set_error(VMM_ERR_ARG, "vmm_tattn_fwd: null pointer");
-  if (frames != TNF) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: only 11 frames (the reference hard-codes 11 cond tokens, VDDP:603)");
   if (heads != 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_fwd: heads must be 8 (one warp per head, rows of 3*8*32 channels)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // the reference's shipped configuration is 11 frames (VDDP:603); other frame counts run on the generic kernels of tattn_generic.cu
+  if (frames != TNF) return tattn_generic_fwd(qkv, ekv, bias, rot, out, fmt, B, frames, HW, scale, pre_rotated, stream);
   const size_t smem = (static_cast<size_t>(2) * TPXB * TNF * TPITCH + TPITCH) * sizeof(uint16_t) + TNF * 32 * sizeof(float);
   static bool attr = false;
   if (!attr) {
@@ -612,9 +613,9 @@ extern "C" int vmm_tattn_bwd(const void* qkv, const float* ekv, const float* bia
                              void* stream_) {
   using namespace vmm;
   if (!qkv || !bias || !rot || !dout || !dqkv) return set_error(VMM_ERR_ARG, "vmm_tattn_bwd: null pointer");
-  if (frames != TNF) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: only 11 frames");
   if (heads != 8) return set_error(VMM_ERR_UNSUPPORTED, "vmm_tattn_bwd: heads must be 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (frames != TNF) return tattn_generic_bwd(qkv, ekv, bias, rot, dout, dqkv, dekv, dbias, fmt, B, frames, HW, scale, pre_rotated, stream);
   const size_t smem = (static_cast<size_t>(2) * BPXB * TNF * (TPITCH + DPITCH) + TNF * CPITCH + TPITCH) * sizeof(uint16_t) +
                       (TNF * 32 + 8 * 32) * sizeof(float);
   static bool attr = false;

@@ -121,7 +121,7 @@ class Unet3D(nn.Module):
     def __init__(self, dim, out_dim=None, dim_mults=(1, 2, 4, 8), channels=3, attn_heads=8, attn_dim_head=32, init_dim=None,
                  init_kernel_size=7, use_sparse_linear_attn=True, resnet_groups=8, cond_bias=False, cond_attention='none',
                  cond_attention_tokens=6, cond_att_GRU=False, use_temporal_attention_cond=False, cond_to_time='add',
-                 per_frame_cond=False, padding_mode='zeros'):
+                 per_frame_cond=False, padding_mode='zeros', num_frames=11):
         super().__init__()
         unsupported = []
         if not per_frame_cond:
@@ -155,7 +155,11 @@ class Unet3D(nn.Module):
         self.groups = resnet_groups
         self.cond_bias = cond_bias
         self.cond_attention = 'self-stacked'           # VDDP:602
-        self.cond_attention_tokens = 11                # VDDP:603
+        # VDDP:603 hard-codes 11 tokens (one per frame of the 11-frame clips); `num_frames` is an extension of this package for
+        # BASELINE configs[4]'s 22-frame rows: tokens == frames (the reference itself raises at 22 frames, VDDP:777)
+        if not 1 <= int(num_frames) <= 24:
+            raise NotImplementedError("num_frames must be between 1 and 24 (11: tensor-core attention kernels; others: generic kernels)")
+        self.cond_attention_tokens = int(num_frames)
         self.cond_att_GRU = cond_att_GRU
         self.cond_dim = time_dim
         self.use_temporal_attention_cond = use_temporal_attention_cond
