@@ -40,7 +40,7 @@ __device__ __forceinline__ void g_load32(const uint16_t* p, float* v) {
 
 template <int FMT>
 __device__ __forceinline__ float g_dot32(const uint16_t* p, const float* q) {
-  float s = 0.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};     // four independent chains: with 8 warps per SM a single 32-deep FMA chain is latency-bound
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint4 u = *reinterpret_cast<const uint4*>(p + 8 * j);
@@ -48,11 +48,11 @@ __device__ __forceinline__ float g_dot32(const uint16_t* p, const float* q) {
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
       const float2 f = unpack2<FMT>(w[x]);
-      s = fmaf(f.x, q[8 * j + 2 * x], s);
-      s = fmaf(f.y, q[8 * j + 2 * x + 1], s);
+      s[x] = fmaf(f.x, q[8 * j + 2 * x], s[x]);
+      s[x] = fmaf(f.y, q[8 * j + 2 * x + 1], s[x]);
     }
   }
-  return s;
+  return (s[0] + s[1]) + (s[2] + s[3]);
 }
 
 template <int FMT>
@@ -144,13 +144,16 @@ __global__ void __launch_bounds__(256) tattn_gen_fwd_kernel(const uint16_t* __re
         for (int j = 0; j < F; ++j) {
           const uint16_t* kr = kbase + j * kp;
           const float s = g_dot32<FMT>(kr, q) + brow[j];
-          const float mn = fmaxf(m, s);
-          const float corr = __expf(m - mn), p = __expf(s - mn);
-          l = l * corr + p;
+          if (s > m) {                                      // rescale only when the running maximum moves (rare after the first keys)
+            const float corr = __expf(m - s);
+            l *= corr;
 #pragma unroll
-          for (int x = 0; x < 32; ++x) o[x] *= corr;
+            for (int x = 0; x < 32; ++x) o[x] *= corr;
+            m = s;
+          }
+          const float p = __expf(s - m);
+          l += p;
           g_axpy32<FMT>(kr + 256, p, o);                   // v row sits 256 columns after the k row in both tiles
-          m = mn;
         }
       }
       const float inv = 1.f / l;
