@@ -253,6 +253,22 @@ def test_other_frame_counts_against_the_oracle(frames, b):
     assert tuple(img.shape) == (b, 3, frames, size, size) and bool(torch.isfinite(img).all())
 
 
+def test_focus_present_mask_like_the_reference(gold_small):
+    """N4: an all-False focus_present_mask is inert (VDDP:514); any True entry raises, as the unmodified reference does in the
+    shipped configuration (its (n, n) self-mask meets the (n, 2n) similarity of stacked cond + frame keys, VDDP:514-524)."""
+    g = gold_small
+    model, gd, _ = build(16, (1, 2), g["T"], g["size"], g["T"], torch.float16, g["seed"])
+    x, t, cond = g["x"].cuda(), g["t"].cuda(), g["cond"].cuda()
+    with torch.no_grad():
+        y0 = model(x, t, cond=cond, null_cond_prob=0.0)
+        y1 = model(x, t, cond=cond, null_cond_prob=0.0, focus_present_mask=torch.zeros(x.shape[0], dtype=torch.bool, device="cuda"))
+    assert rel(y1, y0) < 1e-3          # same path twice (fp32 atomics in the linear-attention context sums are not order-stable)
+    with pytest.raises(RuntimeError, match="focus_present_mask"):
+        model(x, t, cond=cond, null_cond_prob=0.0, focus_present_mask=torch.ones(x.shape[0], dtype=torch.bool, device="cuda"))
+    with pytest.raises(RuntimeError, match="focus_present_mask"):
+        model(x, t, cond=cond, null_cond_prob=0.0, prob_focus_present=0.5)
+
+
 def test_forward_needs_cuda():
     from videometamaterials_b200 import Unet3D
     m = Unet3D(dim=16, dim_mults=(1, 2), per_frame_cond=True, use_temporal_attention_cond=True, cond_attention='self-stacked')

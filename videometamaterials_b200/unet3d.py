@@ -279,8 +279,14 @@ class Unet3D(nn.Module):
 
     def forward(self, x, time, cond=None, null_cond_prob=0., focus_present_mask=None, prob_focus_present=0.):
         """VDDP:730-821.  x (b, c, f, h, w) fp32, time (b,) long, cond (b, f) -> (b, c, f, h, w) fp32."""
-        if focus_present_mask is not None or prob_focus_present != 0.:
-            raise NotImplementedError("focus_present_mask / prob_focus_present are inert in the shipped path and not implemented")
+        # VDDP:738: an absent mask is drawn with prob_focus_present (0 -> all False, no RNG use).  All False is inert (VDDP:514).  With
+        # any True entry the REFERENCE ITSELF raises in this configuration: its (n, n) self-mask is applied to the (n, 2n) similarity
+        # of the stacked [cond | frame] keys (VDDP:514-524, "size of tensor a (11) must match the size of tensor b (22)"; measured
+        # against the unmodified reference, DESIGN.md section 6), so there is no behaviour to reproduce.
+        if prob_focus_present != 0. or (focus_present_mask is not None and bool(torch.as_tensor(focus_present_mask).any())):
+            raise RuntimeError("focus_present_mask with True entries / prob_focus_present > 0: the reference raises here under "
+                               "cond_attention='self-stacked' (VDDP:514-524: (n, n) mask against the (n, 2n) similarity); only the "
+                               "all-False mask of the shipped path is defined")
         if cond is None:
             raise ValueError("cond is required (per_frame_cond=True)")
         batch = x.shape[0]
