@@ -47,6 +47,7 @@ dekv = torch.zeros_like(ekv); dbias = torch.zeros_like(bias)
 npos = B * Fr * HW
 bench("tattn_fwd", lambda: ops.tattn_fwd(qkv, ekv, bias, rot, out, B, Fr, HW, heads), npos * (3 * hd + hd) * 2)
 bench("tattn_bwd", lambda: ops.tattn_bwd(qkv, ekv, bias, rot, dout, dqkv, dekv, dbias, B, Fr, HW, heads), npos * (3 * hd + hd + 3 * hd) * 2)
+bench("tattn_bwd_prerot", lambda: ops.tattn_bwd(qkv, ekv, bias, rot, dout, dqkv, dekv, dbias, B, Fr, HW, heads, pre_rotated=True), npos * (3 * hd + hd + 3 * hd) * 2)
 ctx = torch.empty(B * Fr, heads, 32, 32, device="cuda"); kstat = torch.empty(B * Fr, heads, 32, 2, device="cuda"); dctx = torch.empty_like(ctx)
 bench("lattn_fwd", lambda: ops.lattn_fwd(qkv, ekv, 11, out, ctx, kstat, B * Fr, Fr, HW, heads), npos * (2 * hd + 2 * hd + hd + hd) * 2)
 bench("lattn_bwd", lambda: ops.lattn_bwd(qkv, ekv, 11, dout, ctx, kstat, dctx, dqkv, dekv, B * Fr, Fr, HW, heads), npos * (3 * hd + hd + 3 * hd + hd) * 2)

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
   uint16_t* zrow = ctile + TNF * CPITCH;                    // [TPITCH] zeros
   float* RT = reinterpret_cast<float*>(zrow + TPITCH);      // [TNF][16][2]
 
-  const int HD = heads * 32;
+  constexpr int HD = 256;                                   // heads == 8 (host check)
   const int b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -318,6 +318,14 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
 
   for (int i = tid; i < TPITCH; i += 256) zrow[i] = 0;
   for (int i = tid; i < TNF * 32; i += 256) RT[i] = rot[i];
+  // (cos, sin) of the rows / pairs a lane un-rotates, laid out [nt][row half][lane] so that a warp reads 32 consecutive float2:
+  // indexing the [frame][pair] table directly put the 8 rows of a quad column on one bank (8-way conflicts on 32 loads per pixel)
+  float2* RL = reinterpret_cast<float2*>(RT + TNF * 32);
+  {
+    const int l = tid & 31, rh = (tid >> 5) & 1, nt = tid >> 6;
+    const int i = min((l >> 2) + 8 * rh, TNF - 1), k = 4 * nt + (l & 3);
+    RL[tid] = make_float2(rot[(i * 16 + k) * 2], rot[(i * 16 + k) * 2 + 1]);
+  }
   if (cond) {
     for (int i = tid; i < TNF * 2 * HD; i += 256) {
       const int j = i / (2 * HD), c = i % (2 * HD);
@@ -343,21 +351,44 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
   for (int x = 0; x < 16; ++x) (&gEK[0][0])[x] = (&gEV[0][0])[x] = 0.f;
   __syncthreads();
 
-  FragAddr fa;
-  fa.zrow = smem_u32(zrow);
-  fa.lm = lane >> 3;
-  fa.lr = lane & 7;
+  // ldmatrix row addresses = (per-pixel tile base or the zero row) + lane-constant offset + compile-time column offset:
+  //   A pattern (also B with .trans): matrices (r0-7, c0-7) (r8-15, c0-7) (r0-7, c8-15) (r8-15, c8-15)
+  //   B pattern, k contiguous (rows = n index): two n-tiles x (k lo, k hi)
+  const int lm = lane >> 3, lr = lane & 7;
+  const int rowA = lr + 8 * (lm & 1), cA = 8 * (lm >> 1);
+  const int rowB = lr + 8 * (lm >> 1), cB = 8 * (lm & 1);
+  const bool vA = rowA < TNF, vB = rowB < TNF;
+  const uint32_t zA = smem_u32(zrow) + static_cast<uint32_t>(cA + h * 32) * 2, zB = smem_u32(zrow) + static_cast<uint32_t>(cB + h * 32) * 2;
+  const uint32_t otA = static_cast<uint32_t>(rowA * TPITCH + cA + h * 32) * 2, otB = static_cast<uint32_t>(rowB * TPITCH + cB + h * 32) * 2;
+  const uint32_t odA = static_cast<uint32_t>(rowA * DPITCH + cA + h * 32) * 2;
   const uint32_t ctile_s = smem_u32(ctile);
+  const uint32_t cAb = vA ? ctile_s + static_cast<uint32_t>(rowA * CPITCH + cA + h * 32) * 2 : zA;    // cond tile, A pattern
+  const uint32_t cBb = vB ? ctile_s + static_cast<uint32_t>(rowB * CPITCH + cB + h * 32) * 2 : zB;    // cond tile, B pattern
   const int groups = (HW + BPXB - 1) / BPXB;
+  // Staging and copy-out: thread -> (16-byte column c = tid & 127 of a 1024-channel q | k | v | dO row, row parity tid >> 7); the rows
+  // of a stage are walked with pointer increments only (the former flat index needed a division by 11 and by 1408 per copy: the
+  // kernel is instruction-issue bound, and two thirds of its instructions were integer / address work).
+  const int sc = tid & 127, sr0 = tid >> 7;
+  const bool s_q = sc < 96;                                     // q | k | v columns; else dO
+  const uint16_t* s_src = s_q ? qkv + sc * 8 : dout + (sc - 96) * 8;
+  const long long s_ld = s_q ? 3 * HD : HD;                     // row length of the source
+  const uint32_t s_pitch2 = (s_q ? TPITCH : DPITCH) * 2;        // row pitch of the destination in bytes
+  const uint32_t s_dst0 = s_q ? smem_u32(tile0) + sc * 16 : smem_u32(dtile0) + (sc - 96) * 16;
+  const uint32_t s_stage = (s_q ? BPXB * TNF * TPITCH : BPXB * TNF * DPITCH) * 2;
   auto stage_load = [&](int st, int grp) {
     const int p0 = grp * BPXB;
-    const uint32_t t0 = smem_u32(tile0 + st * BPXB * TNF * TPITCH), d0 = smem_u32(dtile0 + st * BPXB * TNF * DPITCH);
-    for (int i = tid; i < BPXB * TNF * 128; i += 256) {
-      const int c = i & 127, f = (i >> 7) % TNF, p = i / (128 * TNF);
+#pragma unroll
+    for (int p = 0; p < BPXB; ++p) {
       const bool ok = p0 + p < HW;
-      const long long row = (static_cast<long long>(b) * TNF + f) * HW + (ok ? p0 + p : 0);
-      if (c < 96) cp_async16(t0 + static_cast<uint32_t>((p * TNF + f) * TPITCH + c * 8) * 2, qkv + row * 3 * HD + c * 8, ok ? 16 : 0);
-      else cp_async16(d0 + static_cast<uint32_t>((p * TNF + f) * DPITCH + (c - 96) * 8) * 2, dout + row * HD + (c - 96) * 8, ok ? 16 : 0);
+      const int fs = ((p * TNF) & 1) ? 1 - sr0 : sr0;            // alternate the frame parity per pixel: 11 rows per thread and stage
+      const uint16_t* src = s_src + ((static_cast<long long>(b) * TNF + fs) * HW + (ok ? p0 + p : 0)) * s_ld;
+      uint32_t dst = s_dst0 + st * s_stage + static_cast<uint32_t>(p * TNF + fs) * s_pitch2;
+      // unrolled with fresh address registers per copy: LDGSTS reads its address registers late, so a pointer that is bumped right
+      // after the copy stalls on the write-after-read hazard (ncu: long-scoreboard stalls on the increments)
+      const long long sstep = 2LL * HW * s_ld;
+#pragma unroll
+      for (int k = 0; k < (TNF + 1) / 2; ++k)
+        if (fs + 2 * k < TNF) cp_async16(dst + k * 2 * s_pitch2, src + k * sstep, ok ? 16 : 0);
     }
   };
   if (static_cast<int>(blockIdx.x) < groups) stage_load(0, blockIdx.x);
@@ -392,6 +423,7 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
       if (p0 + p >= HW) break;
       const uint32_t tp = tile_s + static_cast<uint32_t>(p * TNF * TPITCH) * 2;
       const uint32_t dp_s = dtile_s + static_cast<uint32_t>(p * TNF * DPITCH) * 2;
+      const uint32_t tA = vA ? tp + otA : zA, tB = vB ? tp + otB : zB, dA = vA ? dp_s + odA : zA;
       // =========================== pass A: rows = queries
       float S[4][4], dP[4][4];
 #pragma unroll
@@ -399,18 +431,18 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         uint32_t qa[4], da[4], kb[4], vb[4];
-        ldsm_x4(qa, fa.a(tp, TPITCH, h * 32 + 16 * ks));
-        ldsm_x4(da, fa.a(dp_s, DPITCH, h * 32 + 16 * ks));
+        ldsm_x4(qa, tA + 32 * ks);
+        ldsm_x4(da, dA + 32 * ks);
         if (cond) {
-          ldsm_x4(kb, fa.b(ctile_s, CPITCH, h * 32 + 16 * ks));
-          ldsm_x4(vb, fa.b(ctile_s, CPITCH, HD + h * 32 + 16 * ks));
+          ldsm_x4(kb, cBb + 32 * ks);
+          ldsm_x4(vb, cBb + 2 * HD + 32 * ks);
           mma16816<FMT>(S[0], qa, kb);
           mma16816<FMT>(S[1], qa, kb + 2);
           mma16816<FMT>(dP[0], da, vb);
           mma16816<FMT>(dP[1], da, vb + 2);
         }
-        ldsm_x4(kb, fa.b(tp, TPITCH, HD + h * 32 + 16 * ks));
-        ldsm_x4(vb, fa.b(tp, TPITCH, 2 * HD + h * 32 + 16 * ks));
+        ldsm_x4(kb, tB + 2 * HD + 32 * ks);
+        ldsm_x4(vb, tB + 4 * HD + 32 * ks);
         mma16816<FMT>(S[2], qa, kb);
         mma16816<FMT>(S[3], qa, kb + 2);
         mma16816<FMT>(dP[2], da, vb);
@@ -489,22 +521,21 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
         for (int dh = 0; dh < 2; ++dh) {
           uint32_t kb[4];
           if (cond) {
-            ldsm_x4_trans(kb, fa.bt(ctile_s, CPITCH, h * 32 + 16 * dh));
+            ldsm_x4_trans(kb, cAb + 32 * dh);
             mma16816<FMT>(dQ[2 * dh], sa[0], kb);
             mma16816<FMT>(dQ[2 * dh + 1], sa[0], kb + 2);
           }
-          ldsm_x4_trans(kb, fa.bt(tp, TPITCH, HD + h * 32 + 16 * dh));
+          ldsm_x4_trans(kb, tA + 2 * HD + 32 * dh);
           mma16816<FMT>(dQ[2 * dh], sa[1], kb);
           mma16816<FMT>(dQ[2 * dh + 1], sa[1], kb + 2);
         }
         // dq = scale R^T dQ_rot
 #pragma unroll
         for (int rh = 0; rh < 2; ++rh) {
-          const int i = min(g + 8 * rh, TNF - 1);
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
-            const int k = 4 * nt + t;
-            const float cs = RT[(i * 16 + k) * 2], sn = RT[(i * 16 + k) * 2 + 1];
+            const float2 rl = RL[(nt * 2 + rh) * 32 + lane];
+            const float cs = rl.x, sn = rl.y;
             const float a = dQ[nt][2 * rh], c = dQ[nt][2 * rh + 1];
             dqp[rh][nt] = pack2<FMT>((a * cs + c * sn) * scale, (c * cs - a * sn) * scale);
           }
@@ -526,8 +557,8 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
 #pragma unroll
         for (int dh = 0; dh < 2; ++dh) {
           uint32_t qb[4], db[4];
-          ldsm_x4_trans(qb, fa.bt(tp, TPITCH, h * 32 + 16 * dh));
-          ldsm_x4_trans(db, fa.bt(dp_s, DPITCH, h * 32 + 16 * dh));
+          ldsm_x4_trans(qb, tA + 32 * dh);
+          ldsm_x4_trans(db, dA + 32 * dh);
           mma16816<FMT>(dK[2 * dh], sat, qb);
           mma16816<FMT>(dK[2 * dh + 1], sat, qb + 2);
           mma16816<FMT>(dV[2 * dh], pa, db);
@@ -552,8 +583,8 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
               uint16_t* qrow = tile + (p * TNF + j) * TPITCH + h * 32 + 2 * t;
 #pragma unroll
               for (int nt = 0; nt < 4; ++nt) {
-                const int k = 4 * nt + t;
-                const float cs = RT[(j * 16 + k) * 2], sn = RT[(j * 16 + k) * 2 + 1];
+                const float2 rl = RL[(nt * 2 + rh) * 32 + lane];
+                const float cs = rl.x, sn = rl.y;
                 const float a = dK[nt][2 * rh], c = dK[nt][2 * rh + 1];
                 *reinterpret_cast<uint32_t*>(qrow + 8 * nt) = dqp[rh][nt];
                 *reinterpret_cast<uint32_t*>(qrow + HD + 8 * nt) = pack2<FMT>(a * cs + c * sn, c * cs - a * sn);
@@ -567,11 +598,21 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
     }
     __syncthreads();
     // coalesced copy-out of the gradient rows (dq | dk | dv now sit where q | k | v were): 96 x 16 bytes per row
-    for (int i = tid; i < BPXB * TNF * 96; i += 256) {
-      const int c = i % 96, f = (i / 96) % TNF, p = i / (96 * TNF);
-      if (p0 + p < HW) {
-        const uint4 v = *reinterpret_cast<const uint4*>(tile + (p * TNF + f) * TPITCH + c * 8);
-        *reinterpret_cast<uint4*>(dqkv + ((static_cast<long long>(b) * TNF + f) * HW + p0 + p) * 3 * HD + c * 8) = v;
+    if (s_q) {
+#pragma unroll
+      for (int p = 0; p < BPXB; ++p) {
+        if (p0 + p >= HW) break;
+        const int fs = ((p * TNF) & 1) ? 1 - sr0 : sr0;
+        const uint16_t* srow = tile + (p * TNF + fs) * TPITCH + sc * 8;
+        uint16_t* drow = dqkv + ((static_cast<long long>(b) * TNF + fs) * HW + p0 + p) * 3 * HD + sc * 8;
+        const long long dstep = 2LL * HW * 3 * HD;
+        uint4 v[(TNF + 1) / 2];
+#pragma unroll
+        for (int k = 0; k < (TNF + 1) / 2; ++k)
+          if (fs + 2 * k < TNF) v[k] = *reinterpret_cast<const uint4*>(srow + k * 2 * TPITCH);
+#pragma unroll
+        for (int k = 0; k < (TNF + 1) / 2; ++k)
+          if (fs + 2 * k < TNF) *reinterpret_cast<uint4*>(drow + k * dstep) = v[k];
       }
     }
     __syncthreads();       // the next iteration's prefetch refills this buffer
@@ -617,7 +658,7 @@ extern "C" int vmm_tattn_bwd(const void* qkv, const float* ekv, const float* bia
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (frames != TNF) return tattn_generic_bwd(qkv, ekv, bias, rot, dout, dqkv, dekv, dbias, fmt, B, frames, HW, scale, pre_rotated, stream);
   const size_t smem = (static_cast<size_t>(2) * BPXB * TNF * (TPITCH + DPITCH) + TNF * CPITCH + TPITCH) * sizeof(uint16_t) +
-                      (TNF * 32 + 8 * 32) * sizeof(float);
+                      (TNF * 32 + 512) * sizeof(float);      // rotary table + its per-lane copy (256 float2)
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tattn_bwd_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
