@@ -178,6 +178,10 @@ __global__ void __launch_bounds__(256) lattn_ctx_mma_kernel(const uint16_t* __re
       __syncthreads();
     }
   }
+  // the thread's 8 k channels are the same in every step (tid & 31 picks the 16-byte column): their maxima stay in registers
+  float mreg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mreg[j] = Ms[(tid & 31) * 8 + j];
   int buf = 0;
   for (int s0 = r_begin; s0 < r_end; s0 += R, buf ^= 1) {
     const int cnt = min(R, r_end - s0);
@@ -198,8 +202,7 @@ __global__ void __launch_bounds__(256) lattn_ctx_mma_kernel(const uint16_t* __re
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = unpack2<FMT>(w[j]);
-          const int c = c8 * 8 + 2 * j;
-          o[j] = pack2<FMT>(__expf(f.x - Ms[c]), __expf(f.y - Ms[c + 1]));
+          o[j] = pack2<FMT>(__expf(f.x - mreg[2 * j]), __expf(f.y - mreg[2 * j + 1]));
         }
         *kp = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -232,17 +235,24 @@ __global__ void lattn_ctx_finalize_kernel(float* __restrict__ ctx, const float* 
 // ------------------------------------------------------------------------------------------------
 template <int FMT>
 __device__ __forceinline__ void softmax_rows_inplace(uint16_t* tile, int pitch, int col0, int cnt, float scale, int tid, int rows = LROWS) {
-  // thread -> (row, head): softmax over the head's 32 values, result * scale written back in place
+  // thread -> (row, head): softmax over the head's 32 values, result * scale written back in place.  16-byte accesses from a
+  // per-head rotated start: the 8 lanes of a row sit 64 bytes apart and would otherwise share two bank groups
   for (int i = tid; i < rows * 8; i += 256) {
     const int r = i >> 3, hh = i & 7;
     if (r >= cnt) continue;
-    uint32_t* p = reinterpret_cast<uint32_t*>(tile + r * pitch + col0 + hh * 32);
+    uint4* p4 = reinterpret_cast<uint4*>(tile + r * pitch + col0 + hh * 32);
+    const int rotq = hh >> 1;
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float2 f = unpack2<FMT>(p[j]);
-      v[2 * j] = f.x;
-      v[2 * j + 1] = f.y;
+    for (int j = 0; j < 4; ++j) {
+      const uint4 q4 = p4[(j + rotq) & 3];
+      const uint32_t w4[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const float2 f = unpack2<FMT>(w4[x]);
+        v[8 * j + 2 * x] = f.x;
+        v[8 * j + 2 * x + 1] = f.y;
+      }
     }
     float mx = v[0];
 #pragma unroll
@@ -255,7 +265,9 @@ __device__ __forceinline__ void softmax_rows_inplace(uint16_t* tile, int pitch, 
     }
     const float inv = scale / sum;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) p[j] = pack2<FMT>(v[2 * j] * inv, v[2 * j + 1] * inv);
+    for (int j = 0; j < 4; ++j)
+      p4[(j + rotq) & 3] = make_uint4(pack2<FMT>(v[8 * j] * inv, v[8 * j + 1] * inv), pack2<FMT>(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
+                                      pack2<FMT>(v[8 * j + 4] * inv, v[8 * j + 5] * inv), pack2<FMT>(v[8 * j + 6] * inv, v[8 * j + 7] * inv));
   }
 }
 
@@ -462,8 +474,11 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
   if (r_begin < r_end) prefetch(r_begin, 0);
   for (int i = tid; i < 256; i += 256) {
     zrow[i] = 0;
-    Ms[i] = kstat[(static_cast<long long>(bf) * HD + i) * 2];
-    Zi[i] = 1.f / kstat[(static_cast<long long>(bf) * HD + i) * 2 + 1];
+    // stored as [channel half (0..3 | 4..7)][16-byte column (32)][4]: the thread that owns column c8 reads two consecutive-per-lane
+    // float4 of each table (the plain [256] layout put 8 lanes on every bank: 16 conflicting 4-byte loads per vector)
+    const int pi = (((i & 7) >> 2) * 32 + (i >> 3)) * 4 + (i & 3);
+    Ms[pi] = kstat[(static_cast<long long>(bf) * HD + i) * 2];
+    Zi[pi] = 1.f / kstat[(static_cast<long long>(bf) * HD + i) * 2 + 1];
   }
   const float* ch = ctx + (static_cast<long long>(bf) * 8 + h) * 1024;
   const float* gh = dctx + (static_cast<long long>(bf) * 8 + h) * 1024;
@@ -510,10 +525,11 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
       const int r = tid >> 3, hh = tid & 7;
       if (r < cnt) {
         uint4* p4 = reinterpret_cast<uint4*>(tile + r * LP3 + hh * 32);
-        float v[32];
+        const int rotq = hh >> 1;        // lanes hh = 0..7 of a row sit 64 bytes apart: walking the four 16-byte pieces from a rotated start
+        float v[32];                     // keeps the 8 lanes of a shared-memory phase on distinct bank groups
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint4 q4 = p4[j];
+          const uint4 q4 = p4[(j + rotq) & 3];
           const uint32_t w4[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
           for (int x = 0; x < 4; ++x) {
@@ -534,7 +550,7 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
         const float inv = 1.f / sum;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          p4[j] = make_uint4(pack2<FMT>(v[8 * j] * inv, v[8 * j + 1] * inv), pack2<FMT>(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
+          p4[(j + rotq) & 3] = make_uint4(pack2<FMT>(v[8 * j] * inv, v[8 * j + 1] * inv), pack2<FMT>(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
                              pack2<FMT>(v[8 * j + 4] * inv, v[8 * j + 5] * inv), pack2<FMT>(v[8 * j + 6] * inv, v[8 * j + 7] * inv));
       }
     } else {
@@ -546,15 +562,13 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
         if (r < cnt) {
           uint4* kp = reinterpret_cast<uint4*>(tile + r * LP3 + HD + c8 * 8);
           const uint4 v = *kp;
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack2<FMT>(w[j]);
-            const int c = c8 * 8 + 2 * j;
-            o[j] = pack2<FMT>(__expf(f.x - Ms[c]) * Zi[c], __expf(f.y - Ms[c + 1]) * Zi[c + 1]);
-          }
-          *kp = make_uint4(o[0], o[1], o[2], o[3]);
+          const float4 m0 = reinterpret_cast<const float4*>(Ms)[c8], m1 = reinterpret_cast<const float4*>(Ms)[32 + c8];
+          const float4 z0 = reinterpret_cast<const float4*>(Zi)[c8], z1 = reinterpret_cast<const float4*>(Zi)[32 + c8];
+          const float2 f0 = unpack2<FMT>(v.x), f1 = unpack2<FMT>(v.y), f2 = unpack2<FMT>(v.z), f3 = unpack2<FMT>(v.w);
+          *kp = make_uint4(pack2<FMT>(__expf(f0.x - m0.x) * z0.x, __expf(f0.y - m0.y) * z0.y),
+                           pack2<FMT>(__expf(f1.x - m0.z) * z0.z, __expf(f1.y - m0.w) * z0.w),
+                           pack2<FMT>(__expf(f2.x - m1.x) * z1.x, __expf(f2.y - m1.y) * z1.y),
+                           pack2<FMT>(__expf(f3.x - m1.z) * z1.z, __expf(f3.y - m1.w) * z1.w));
         }
       }
     }
