@@ -14,7 +14,9 @@
 // Two TMEM accumulators (four when 4 x BN <= 512 columns) let the epilogue of tile i overlap the main loop of the next tiles.
 // The ring of smem stages is shared across tiles (the producer runs ahead of the MMA warp).
 //
-// Debug / experiment switches (environment, read once): VMM_NO_HALO, VMM_NO_FAST_EPI, VMM_ONE_EPI_GROUP, VMM_TWO_ACC.
+// Debug / experiment switches (environment, read once): VMM_NO_HALO, VMM_NO_FAST_EPI, VMM_ONE_EPI_GROUP, VMM_TWO_ACC,
+// VMM_TWO_GROUPS_64 (two epilogue groups also at BN = 64; measured in round 2: 87.9 vs 84.1 us for the level-0 3x3, i.e. no gain:
+// with GroupNorm statistics and bias removed the same launch takes 80 us, so the epilogue is not what bounds it).
 #include "common.cuh"
 #include "mma_sync.cuh"
 #include "sm100_ptx.cuh"
