@@ -365,26 +365,26 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
   const uint32_t cAb = vA ? ctile_s + static_cast<uint32_t>(rowA * CPITCH + cA + h * 32) * 2 : zA;    // cond tile, A pattern
   const uint32_t cBb = vB ? ctile_s + static_cast<uint32_t>(rowB * CPITCH + cB + h * 32) * 2 : zB;    // cond tile, B pattern
   const int groups = (HW + BPXB - 1) / BPXB;
-  // Staging and copy-out: thread -> (16-byte column c = tid & 127 of a 1024-channel q | k | v | dO row, row parity tid >> 7); the rows
-  // of a stage are walked with pointer increments only (the former flat index needed a division by 11 and by 1408 per copy: the
-  // kernel is instruction-issue bound, and two thirds of its instructions were integer / address work).
-  const int sc = tid & 127, sr0 = tid >> 7;
-  const bool s_q = sc < 96;                                     // q | k | v columns; else dO
-  const uint16_t* s_src = s_q ? qkv + sc * 8 : dout + (sc - 96) * 8;
+  // Warp-private pipeline: warp h stages, transforms and copies out ONLY the 32 columns of its head in the q | k | v | dO rows
+  // (4 x 64 bytes per row), so the main loop needs no block barrier at all: the warps drift apart and hide each other's
+  // ldmatrix / mma / shuffle latencies (ncu before: 11 % of the warp samples waiting at the two block barriers of a stage).
+  // lane -> (segment q | k | v | dO, 16-byte piece, row parity); 22 rows per stage = 11 copies per lane, each with its own address
+  // registers (LDGSTS reads them late: a pointer bumped right after the copy stalls on the write-after-read hazard).
+  const int sseg = (lane & 15) >> 2, sv4 = lane & 3, shi = lane >> 4;
+  const bool s_q = sseg < 3;                                    // q | k | v segment; else dO
+  const uint16_t* s_src = s_q ? qkv + sseg * HD + h * 32 + sv4 * 8 : dout + h * 32 + sv4 * 8;
   const long long s_ld = s_q ? 3 * HD : HD;                     // row length of the source
   const uint32_t s_pitch2 = (s_q ? TPITCH : DPITCH) * 2;        // row pitch of the destination in bytes
-  const uint32_t s_dst0 = s_q ? smem_u32(tile0) + sc * 16 : smem_u32(dtile0) + (sc - 96) * 16;
+  const uint32_t s_dst0 = (s_q ? smem_u32(tile0) + static_cast<uint32_t>(sseg * HD) * 2 : smem_u32(dtile0)) + static_cast<uint32_t>(h * 32 + sv4 * 8) * 2;
   const uint32_t s_stage = (s_q ? BPXB * TNF * TPITCH : BPXB * TNF * DPITCH) * 2;
   auto stage_load = [&](int st, int grp) {
     const int p0 = grp * BPXB;
 #pragma unroll
     for (int p = 0; p < BPXB; ++p) {
       const bool ok = p0 + p < HW;
-      const int fs = ((p * TNF) & 1) ? 1 - sr0 : sr0;            // alternate the frame parity per pixel: 11 rows per thread and stage
+      const int fs = ((p * TNF) & 1) ? 1 - shi : shi;            // alternate the frame parity per pixel: 11 rows per lane and stage
       const uint16_t* src = s_src + ((static_cast<long long>(b) * TNF + fs) * HW + (ok ? p0 + p : 0)) * s_ld;
-      uint32_t dst = s_dst0 + st * s_stage + static_cast<uint32_t>(p * TNF + fs) * s_pitch2;
-      // unrolled with fresh address registers per copy: LDGSTS reads its address registers late, so a pointer that is bumped right
-      // after the copy stalls on the write-after-read hazard (ncu: long-scoreboard stalls on the increments)
+      const uint32_t dst = s_dst0 + st * s_stage + static_cast<uint32_t>(p * TNF + fs) * s_pitch2;
       const long long sstep = 2LL * HW * s_ld;
 #pragma unroll
       for (int k = 0; k < (TNF + 1) / 2; ++k)
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
     if (grp + static_cast<int>(gridDim.x) < groups) stage_load((it + 1) & 1, grp + gridDim.x);
     cp_async_commit();
     cp_async_wait<1>();
-    __syncthreads();
+    __syncwarp();          // the lanes of this warp see each other's copies; no other warp touches these columns
     uint16_t* tile = tile0 + (it & 1) * BPXB * TNF * TPITCH;
     const uint32_t tile_s = smem_u32(tile), dtile_s = smem_u32(dtile0 + (it & 1) * BPXB * TNF * DPITCH);
     // rotary in place (q scaled); skipped when the to_qkv epilogue already did it
@@ -596,15 +596,15 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
       }
       __syncwarp();
     }
-    __syncthreads();
-    // coalesced copy-out of the gradient rows (dq | dk | dv now sit where q | k | v were): 96 x 16 bytes per row
+    __syncwarp();
+    // copy-out of this warp's gradient columns (dq | dk | dv now sit where q | k | v were): 3 x 64 bytes per row
     if (s_q) {
 #pragma unroll
       for (int p = 0; p < BPXB; ++p) {
         if (p0 + p >= HW) break;
-        const int fs = ((p * TNF) & 1) ? 1 - sr0 : sr0;
-        const uint16_t* srow = tile + (p * TNF + fs) * TPITCH + sc * 8;
-        uint16_t* drow = dqkv + ((static_cast<long long>(b) * TNF + fs) * HW + p0 + p) * 3 * HD + sc * 8;
+        const int fs = ((p * TNF) & 1) ? 1 - shi : shi;
+        const uint16_t* srow = tile + (p * TNF + fs) * TPITCH + sseg * HD + h * 32 + sv4 * 8;
+        uint16_t* drow = dqkv + ((static_cast<long long>(b) * TNF + fs) * HW + p0 + p) * 3 * HD + sseg * HD + h * 32 + sv4 * 8;
         const long long dstep = 2LL * HW * 3 * HD;
         uint4 v[(TNF + 1) / 2];
 #pragma unroll
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
           if (fs + 2 * k < TNF) *reinterpret_cast<uint4*>(drow + k * dstep) = v[k];
       }
     }
-    __syncthreads();       // the next iteration's prefetch refills this buffer
+    __syncwarp();          // the next iteration's prefetch refills this buffer
   }
   // ---- flush the per-CTA sums
   if (cond && dekv) {
