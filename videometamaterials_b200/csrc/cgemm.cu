@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(128 + 256 * G, 1) cgemm_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < VMM_MAX_VIEWS; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__(128 + 256 * G, 1) cgemm_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();        // launched with programmatic serialisation (VMM_PDL): everything above overlapped the previous kernel's tail
   const uint32_t tmem_base = ctl->tmem_base;
   // one elected lane per warp issues the TMA / MMA / bulk-store instructions: behind elect.sync the compiler knows that a
   // single thread is active and keeps descriptors and addresses in uniform registers (no per-instruction waterfall loop)
@@ -1094,13 +1096,15 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
     attr_set = true;
   }
   const int grid = d.total_tiles < num_sms() ? d.total_tiles : num_sms();
+  cudaError_t le;
   if (two_groups) {
-    if (h.fmt == VMM_FMT_F16) cgemm_kernel<0, 2><<<grid, 640, smem, stream>>>(d);
-    else cgemm_kernel<1, 2><<<grid, 640, smem, stream>>>(d);
+    if (h.fmt == VMM_FMT_F16) le = launch_maybe_pdl(cgemm_kernel<0, 2>, dim3(grid), dim3(640), smem, stream, d);
+    else le = launch_maybe_pdl(cgemm_kernel<1, 2>, dim3(grid), dim3(640), smem, stream, d);
   } else {
-    if (h.fmt == VMM_FMT_F16) cgemm_kernel<0, 1><<<grid, 384, smem, stream>>>(d);
-    else cgemm_kernel<1, 1><<<grid, 384, smem, stream>>>(d);
+    if (h.fmt == VMM_FMT_F16) le = launch_maybe_pdl(cgemm_kernel<0, 1>, dim3(grid), dim3(384), smem, stream, d);
+    else le = launch_maybe_pdl(cgemm_kernel<1, 1>, dim3(grid), dim3(384), smem, stream, d);
   }
+  if (le != cudaSuccess) return set_cuda_error(le, "vmm_cgemm: launch");
   count_launch();
   return check_launch("vmm_cgemm");
 }

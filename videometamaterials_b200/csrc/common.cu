@@ -1,5 +1,7 @@
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <atomic>
 
 namespace vmm {
@@ -8,6 +10,14 @@ static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 
 char* error_buffer() { return g_err; }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VMM_PDL");
+    return e != nullptr && e[0] != '0';
+  }();
+  return on;
+}
 
 int set_error(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);

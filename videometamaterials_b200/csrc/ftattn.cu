@@ -119,6 +119,7 @@ __global__ void ftattn_prep_kernel(const float* __restrict__ ekv, const float* _
 
 template <int FMT>
 __global__ void __launch_bounds__(512, 1) ftattn_fwd_kernel(const __grid_constant__ FtattnDev p) {
+  pdl_trigger();
   extern __shared__ uint8_t ft_smem_raw[];
   uint8_t* sm0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
   const int grp = threadIdx.x >> 8;                       // warp group: an independent worker with its own tiles and buffers

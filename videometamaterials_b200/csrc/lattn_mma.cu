@@ -95,6 +95,7 @@ template <int FMT>
 __global__ void __launch_bounds__(256) lattn_ctx_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv, int T,
                                                             float* __restrict__ acc, float* __restrict__ kstat, int HW, int frames,
                                                             int rows_per_cta) {
+  pdl_trigger();
   extern __shared__ __align__(16) uint16_t lsm[];
   constexpr int R = LSR;
   uint16_t* tile0 = lsm;                             // [2][R][LP2]   k -> w | v      (cp.async double buffer, see lattn_bwd_mma_kernel)
@@ -274,6 +275,7 @@ __device__ __forceinline__ void softmax_rows_inplace(uint16_t* tile, int pitch, 
 template <int FMT>
 __global__ void __launch_bounds__(256) lattn_out_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ctx,
                                                             uint16_t* __restrict__ out, int HW, float scale, int rows_per_cta) {
+  pdl_trigger();
   extern __shared__ __align__(16) uint16_t lsm[];
   constexpr int R = LSR;
   const float hw = static_cast<float>(HW);
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(256) lattn_out_mma_kernel(const uint16_t* __re
 template <int FMT>
 __global__ void __launch_bounds__(256) lattn_dctx_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ dout,
                                                              float* __restrict__ dctx, int HW, float scale, int rows_per_cta) {
+  pdl_trigger();
   extern __shared__ __align__(16) uint16_t lsm[];
   constexpr int R = LSR;
   uint16_t* qt0 = lsm;                       // [2][R][LP1] q -> qs        (cp.async double buffer)
@@ -442,6 +445,7 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
                                                             const float* __restrict__ ctx, const float* __restrict__ dctx,
                                                             const float* __restrict__ kstat, uint16_t* __restrict__ dqkv, int HW,
                                                             float scale, float vscale, int rows_per_cta) {
+  pdl_trigger();
   extern __shared__ __align__(16) uint16_t lsm[];
   // Two buffers of R = 16 rows: cp.async fills buffer (s + 1) & 1 with the rows of the next step while the CTA turns the rows of
   // step s into p / wn, runs the MMAs and copies the gradients out.  (One buffer of 32 rows and register-staged loads left every
@@ -649,6 +653,7 @@ __global__ void __launch_bounds__(256) lattn_bwd_mma_kernel(const uint16_t* __re
 __global__ void __launch_bounds__(256) lattn_bwd_tokens_kernel(const float* __restrict__ ekv, int T, const float* __restrict__ ctx,
                                                                const float* __restrict__ dctx, const float* __restrict__ kstat,
                                                                float* __restrict__ dekv, int BF, int frames, float vscale) {
+  pdl_trigger();
   __shared__ float Cs[32][33], Gs[32][33];
   const int HD = 256;
   const int h = blockIdx.x & 7, bf = blockIdx.x >> 3;

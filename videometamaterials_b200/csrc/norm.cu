@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256, MINB) gn_silu_fwd_kernel(const uint16_t* 
                                                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, const float* __restrict__ scale_shift,
                                                                 float eps, int act) {
+  pdl_trigger();
   const int b = blockIdx.y;
   const int i00 = blockIdx.x * blockDim.x + threadIdx.x;          // 32-bit vector indices (host: nvec < 2^30)
   const int nvec = static_cast<int>(pix * C / 8);
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(256, MINB) gn_silu_bwd_reduce_kernel(const uin
                                                                        float* __restrict__ part, unsigned* __restrict__ counter,
                                                                        float* __restrict__ gm, float* __restrict__ dgamma,
                                                                        float* __restrict__ dbeta, float* __restrict__ dss) {
+  pdl_trigger();
   extern __shared__ float red[];   // [2][C] block partials | [2][groups] group sums of the last CTA
   __shared__ int s_last;
   const int b = blockIdx.y;
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(256, MINB) gn_silu_bwd_apply_kernel(const uint
                                                                       const float* __restrict__ beta, const float* __restrict__ scale_shift,
                                                                       float eps, int act, const float* __restrict__ gm,
                                                                       float* __restrict__ dx_colsum) {
+  pdl_trigger();
   extern __shared__ float cs[];    // [C] block partial of the column sums of dx
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -431,6 +434,7 @@ template <int VPT, int FMT>   // 16-byte vectors per thread (C = 8 * VPT * tpr);
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
                                                      long long rows, int C, int tpr, const float* __restrict__ gamma, float eps,
                                                      float* __restrict__ mean_rstd) {
+  pdl_trigger();
   const int rpb = blockDim.x / tpr;
   const int lr = threadIdx.x / tpr, lc = threadIdx.x % tpr;
   const float inv_c = 1.f / C;
@@ -484,6 +488,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
                                                      const uint16_t* __restrict__ dres, uint16_t* __restrict__ dx,
                                                      long long rows, int C, int tpr, const float* __restrict__ gamma, float eps,
                                                      float* __restrict__ dgamma) {
+  pdl_trigger();
   extern __shared__ float sdg[];   // [C] block partial of dgamma
   for (int c = threadIdx.x; c < C; c += blockDim.x) sdg[c] = 0.f;
   __syncthreads();

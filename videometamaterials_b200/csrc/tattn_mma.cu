@@ -20,6 +20,7 @@ template <int FMT>
 __global__ void __launch_bounds__(256) tattn_fwd_mma_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ ekv,
                                                             const float* __restrict__ bias, const float* __restrict__ rot,
                                                             uint16_t* __restrict__ out, int HW, int heads, float scale, int pre_rotated) {
+  pdl_trigger();
   extern __shared__ __align__(16) uint16_t tsm[];
   uint16_t* tile0 = tsm;                                  // [2 stages][TPXB][TNF][TPITCH]
   uint16_t* zrow = tile0 + 2 * TPXB * TNF * TPITCH;       // one row of zeros (frames >= 11)
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(256, 2) tattn_bwd_mma_kernel(const uint16_t* _
                                                                const uint16_t* __restrict__ dout, uint16_t* __restrict__ dqkv,
                                                                float* __restrict__ dekv, float* __restrict__ dbias, int HW, int heads,
                                                                float scale, int pre_rotated) {
+  pdl_trigger();
   extern __shared__ __align__(16) uint16_t tsm[];
   uint16_t* tile0 = tsm;                                    // [2][BPXB][TNF][TPITCH]   q | k | v   (q, k rotated in place)
   uint16_t* dtile0 = tile0 + 2 * BPXB * TNF * TPITCH;       // [2][BPXB][TNF][DPITCH]   dO

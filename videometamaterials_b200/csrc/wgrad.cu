@@ -89,6 +89,7 @@ __device__ __forceinline__ void wg_pix(const WgradDev& p, int kt, int& bf0, int&
 }
 
 __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradDev p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   WgSmemCtl* ctl = reinterpret_cast<WgSmemCtl*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();        // see cgemm.cu
   const uint32_t tmem_base = ctl->tmem_base;
   const bool leader = elect_one();   // see cgemm.cu: keeps the issue loops in uniform registers
 
@@ -477,7 +479,10 @@ extern "C" int vmm_wgrad(const vmm_wgrad_params* hp, void* stream_) {
     attr_set = true;
   }
   const int grid = d.total_items < num_sms() ? d.total_items : num_sms();
-  wgrad_kernel<<<grid, 256, smem, stream>>>(d);
+  {
+    cudaError_t le = launch_maybe_pdl(wgrad_kernel, dim3(grid), dim3(256), smem, stream, d);
+    if (le != cudaSuccess) return set_cuda_error(le, "vmm_wgrad: launch");
+  }
   count_launch();
   return check_launch("vmm_wgrad");
 }
