@@ -297,6 +297,67 @@ typedef struct {
 int vmm_wgrad(const vmm_wgrad_params* p, void* stream);
 int vmm_colsum(const void* x, long long rows, int n, long long ld, int fmt, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dataset on the device: GIF decode + the Dataset's normalisation.
+ *
+ * replaces: gif_to_tensor / seek_all_images  (PIL Image.open + seek + convert('L') + ToTensor)   VDDP:1076-1106
+ *           Dataset.__getitem__ (unnorm with the sample's range, void pixels -> 0, global normalise) VDDP:1302-1397
+ *
+ * vmm_gif_scan (HOST, no device work): walks one GIF file held in host memory and fills one vmm_gif_frame per image
+ * (offsets are relative to the start of that file).  Returns the number of frames (it keeps counting beyond
+ * max_frames without writing), or a negative code: VMM_ERR_ARG for a malformed file, VMM_ERR_UNSUPPORTED for a
+ * feature the device compositor does not reproduce (disposal method 3, a transparent FIRST frame, frames that
+ * leave the logical screen, more than 2^19 pixels per frame).
+ *
+ * vmm_gif_decode (DEVICE): `files` = the bytes of n_files GIF files back to back, file_ofs[i] = start of file i
+ * (n_files + 1 entries), frame_begin[i] .. frame_begin[i+1] = its rows in `frames` (n_files + 1 entries,
+ * frame_begin[n_files] = n_frames_total; the tables vmm_gif_scan produced, copied to the device).
+ * Kernel 1 (one warp per frame) walks the sub-block chain and decodes the LZW stream into `index_ws`
+ * (sum of w*h over all frames bytes; vmm_gif_frame.px_ofs = the frame's offset in it).  Kernel 2 (one CTA per
+ * file) composites the frames in order on the logical screen (frame rectangle, interlace, transparency, disposal
+ * 0 / 1 / 2) and writes out[file][frame][H][W] 8-bit luminance = ITU-R 601-2 luma of the palette colour, which is
+ * what PIL's convert('L') returns for every frame of such a file.  Every file has the logical screen H x W and at
+ * most `frames_per_file` frames; frames a file does not have are written as zeros.  err[0] is incremented for
+ * every frame whose LZW stream was short or invalid (the caller zeroes it).
+ *
+ * vmm_dataset_items (DEVICE): out[i][ch][f][h][w] fp32 for the n samples in `index`, from the decoded planes
+ * u8[sample][plane][f][h][w]: t = u8/255; if the channel has a range: t = t*(smax-smin) + smin (two roundings, the
+ * sample's range as fp32), 0 where the topology plane is 0, then (t - gmin) / (gmax - gmin).  Bit-identical to the
+ * reference's fp32 tensor arithmetic (every operation correctly rounded, no contraction into FMAs).
+ *   ch_plane[c]   plane read by output channel c            ch_has_range[c]  0 = pass-through (the topology itself)
+ *   sample_rng    [n_samples][n_ch][2] fp32 = {smin, smax - smin} per sample and channel
+ *   global_rng    [n_ch][2] fp32 = {gmin, gmax - gmin}
+ *   sample_frames [n_samples] frames the sample's files really hold (NULL: `frames`)
+ *   frames_out > the sample's frames: the extra frames are zero (cast_num_frames, VDDP:1114-1124); fewer: truncated.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  uint32_t data_ofs;     /* first data sub-block (the byte after the LZW minimum code size) */
+  uint32_t pal_ofs;      /* RGB palette used by this frame (local, else global); 0xffffffff = none (grey ramp) */
+  uint32_t px_ofs;       /* offset of this frame's index stream in the decode workspace (filled by the caller) */
+  uint16_t x, y, w, h;   /* frame rectangle on the logical screen */
+  uint16_t pal_size;     /* number of palette entries */
+  uint8_t min_code;      /* LZW minimum code size */
+  uint8_t interlace;
+  uint8_t disposal;      /* 0 / 1 keep, 2 restore to background (as PIL applies it: sticky when a frame leaves it unspecified) */
+  uint8_t has_transp;
+  uint8_t transp;        /* transparent colour index */
+  uint8_t background;    /* logical screen background colour index */
+  uint32_t reserved;     /* sizeof(vmm_gif_frame) == 32 */
+} vmm_gif_frame;
+
+typedef struct {
+  uint16_t width, height;  /* logical screen */
+  int32_t n_frames;
+} vmm_gif_info;
+
+int vmm_gif_scan(const uint8_t* file, size_t nbytes, vmm_gif_info* info, vmm_gif_frame* frames, int max_frames);
+int vmm_gif_decode(const uint8_t* files, const uint64_t* file_ofs, const int32_t* frame_begin, const vmm_gif_frame* frames,
+                   int n_files, int n_frames_total, int frames_per_file, int H, int W, uint8_t* index_ws, uint8_t* out, int32_t* err,
+                   void* stream);
+int vmm_dataset_items(const uint8_t* u8, const int64_t* index, int n, int n_planes, int topo_plane, int n_ch,
+                      const int32_t* ch_plane, const int32_t* ch_has_range, const float* sample_rng, const float* global_rng,
+                      const int32_t* sample_frames, int frames, int frames_out, int hw, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,92 @@
+"""Host side of the device dataset, without a GPU: the native container scanner `vmm_gif_scan` and the
+contract statements of `vmm_gif_decode` / `vmm_dataset_items` (tests/emu_gif.py) against PIL, which is what the reference decodes
+with (VDDP:1076-1106), and against `Dataset.__getitem__` (pinned bit-equal to the reference's Dataset by tests/golden/host_dataset.pt).
+The `-m gpu` twin (tests/test_gpu_dataset.py) holds the kernels to the same checkers on the same corpus."""
+import numpy as np
+import pytest
+import torch
+
+import emu_gif
+
+
+def _scan(blob):
+    from videometamaterials_b200.device_dataset import scan_gif
+    return scan_gif(blob)
+
+
+def test_scan_and_decode_statement_match_pil_on_the_corpus():
+    seen = dict(interlace=0, transp=0, disposal2=0, local_palette=0, partial=0, small_code=0)
+    for name, blob in emu_gif.corpus():
+        ref = emu_gif.pil_frames(blob)
+        if name == 'P_colour_transparency':
+            continue                                   # rejected, see test_scan_rejects_what_the_compositor_does_not_reproduce
+        (w, h), tab = _scan(blob)
+        assert (h, w) == ref.shape[1:] and len(tab) == len(ref), name
+        got = emu_gif.decode(blob, tab, (w, h))
+        assert np.array_equal(got, ref), name
+        seen['interlace'] += int(tab['interlace'].any())
+        seen['transp'] += int(tab['has_transp'].any())
+        seen['disposal2'] += int((tab['disposal'] == 2).any())
+        seen['local_palette'] += int((tab['pal_ofs'] != 13).any())
+        seen['partial'] += int(((tab['w'] != w) | (tab['h'] != h)).any())
+        seen['small_code'] += int((tab['min_code'] < 8).any())
+    assert all(v > 0 for v in seen.values()), seen     # the corpus really exercises every branch of the compositor
+
+
+def test_frames_beyond_a_files_count_are_zero_and_extra_frames_are_dropped():
+    name, blob = emu_gif.corpus()[2]
+    (w, h), tab = _scan(blob)
+    ref = emu_gif.pil_frames(blob)
+    more = emu_gif.decode(blob, tab, (w, h), frames_per_file=len(tab) + 2)
+    assert np.array_equal(more[:len(tab)], ref) and not more[len(tab):].any()
+    fewer = emu_gif.decode(blob, tab[:3], (w, h), frames_per_file=3)
+    assert np.array_equal(fewer, ref[:3])
+
+
+def test_scan_rejects_what_the_compositor_does_not_reproduce():
+    from videometamaterials_b200 import _lib
+    rng = np.random.default_rng(0)
+    gp = rng.integers(0, 256, (4, 3), dtype=np.uint8)
+    idx = rng.integers(0, 4, (8, 8), dtype=np.uint8)
+    cases = {
+        'transparent first frame': emu_gif.write_gif(8, 8, gp, [dict(x=0, y=0, idx=idx, transp=1)]),
+        'disposal method 3': emu_gif.write_gif(8, 8, gp, [dict(x=0, y=0, idx=idx), dict(x=0, y=0, idx=idx, disposal=3)]),
+        'outside the logical screen': emu_gif.write_gif(8, 8, gp, [dict(x=4, y=0, idx=idx)]),
+        'not a GIF': b'PNG' + bytes(40),
+        'no image': emu_gif.write_gif(8, 8, gp, []),
+    }
+    for what, blob in cases.items():
+        with pytest.raises(_lib.VmmError, match=what):
+            _scan(blob)
+    # a file cut inside its image data still yields its frame table (PIL opens such files too); the DEVICE decode reports the short stream
+    good = emu_gif.write_gif(8, 8, gp, [dict(x=0, y=0, idx=idx)] * 2)
+    (w, h), tab = _scan(good[:-12])
+    assert len(tab) == 2
+    _, complete = emu_gif.lzw(good[:-12], tab[1])
+    assert not complete
+
+
+@pytest.mark.parametrize("frame,num_frames,channels", [('lagrangian', 11, [0, 1, 2, 3]), ('lagrangian', 11, [0, 1, 3]), ('eulerian', 11, [0, 1, 2, 3]),
+                                                       ('lagrangian', 1, [0, 1]), ('lagrangian', 14, [1, 3]), ('lagrangian', 5, [0, 2])])
+def test_item_tables_and_statement_equal_dataset_items(tmp_path, frame, num_frames, channels):
+    """`item_tables` (product, host) + the statement of `vmm_dataset_items` reproduce Dataset.__getitem__ BIT FOR BIT: this pins the
+    fp32 table entries (float64 spans converted after the subtraction) and the order of the separately rounded operations."""
+    from videometamaterials_b200.dataset import Dataset, write_synthetic_dataset
+    from videometamaterials_b200.device_dataset import item_tables
+    folder = str(tmp_path / "d") + "/"
+    write_synthetic_dataset(folder, 5, image_size=16, num_frames=11, seed=3, reference_frame=frame)
+    ds = Dataset(folder, 16, selected_channels=list(channels), num_frames=num_frames, per_frame_cond=True, reference_frame=frame)
+    planes, ch_plane, ch_has, srng, grng = item_tables(ds)
+    assert planes[0] == 'topo'
+    u8 = np.stack([np.stack([ds._frames_u8(sub, i).numpy() for sub in planes]) for i in range(len(ds))])
+    frames = u8.shape[2]
+    got = emu_gif.dataset_items(u8, [4, 0, 2], 0, ch_plane, ch_has, srng.numpy(), grng.numpy(), np.full(len(ds), frames), num_frames)
+    want = torch.stack([ds[i][0] for i in (4, 0, 2)]).numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.int32), want.view(np.int32))
+
+
+def test_device_dataset_has_no_host_path():
+    from videometamaterials_b200.device_dataset import DeviceDataset
+    with pytest.raises(TypeError):
+        DeviceDataset(object())

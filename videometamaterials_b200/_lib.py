@@ -78,11 +78,22 @@ class CondParams(C.Structure):
     ]
 
 
+class GifFrame(C.Structure):        # vmm_gif_frame
+    _fields_ = [("data_ofs", C.c_uint32), ("pal_ofs", C.c_uint32), ("px_ofs", C.c_uint32),
+                ("x", C.c_uint16), ("y", C.c_uint16), ("w", C.c_uint16), ("h", C.c_uint16), ("pal_size", C.c_uint16),
+                ("min_code", C.c_uint8), ("interlace", C.c_uint8), ("disposal", C.c_uint8), ("has_transp", C.c_uint8),
+                ("transp", C.c_uint8), ("background", C.c_uint8), ("reserved", C.c_uint32)]
+
+
+class GifInfo(C.Structure):         # vmm_gif_info
+    _fields_ = [("width", C.c_uint16), ("height", C.c_uint16), ("n_frames", C.c_int32)]
+
+
 class VmmError(RuntimeError):
     pass
 
 
-ABI_VERSION = 3          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
+ABI_VERSION = 4          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
 
 
 def _load() -> C.CDLL:
@@ -153,6 +164,9 @@ _SIGNATURES = {
     "vmm_axpby": [_P, _P, _F, _F, _F, _P, _L, _P],
     "vmm_gather_cast": [_P, _P, _P, _L, _I, _P],
     "vmm_adam_ema_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _I, _F, _P],
+    "vmm_gif_scan": [_P, _Z, C.POINTER(GifInfo), C.POINTER(GifFrame), _I],
+    "vmm_gif_decode": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "vmm_dataset_items": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
 }
 _RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t, "vmm_ftattn_workspace": C.c_size_t, "vmm_cond_workspace": C.c_size_t,
              "vmm_flattn_workspace": C.c_size_t}

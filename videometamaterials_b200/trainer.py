@@ -132,7 +132,7 @@ class Trainer(object):
                  test_batch_size=2, train_lr=1.e-4, train_num_steps=100000, step_start_ema=2000, update_ema_every=10,
                  save_and_sample_every=1000, results_folder='./', max_grad_norm=None, log=True, null_cond_prob=0., per_frame_cond=False,
                  reference_frame='eulerian', run_name=None, accelerator=None, wandb_username=None, log_every=50, preload_data=False,
-                 synthetic_data=False, decode_cache_bytes=None):
+                 synthetic_data=False, decode_cache_bytes=None, device_dataset=False):
         super().__init__()
         self.accelerator = accelerator if accelerator is not None else Accelerator()
         if log:
@@ -182,7 +182,19 @@ class Trainer(object):
             self.ds = SyntheticLagrangianDataset(1024, image_size, len(selected_channels), num_frames)
         if preload_data and hasattr(self.ds, 'preload'):
             self.ds.preload()             # decode every GIF once, in threads; otherwise the cache fills during the first epoch
-        self.dl = cycle(self.accelerator.prepare(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=True, pin_memory=True)))
+        if device_dataset and not synthetic_train:
+            # keyword extension: the training GIFs are decoded ON the device once and stay resident in HBM as
+            # 8-bit planes; a batch is one gather + normalise launch (device_dataset.py), bit-identical to Dataset.__getitem__.  No host
+            # decode, no DataLoader workers, no H2D copy per step.  Every rank holds the whole set and walks its share of one permutation.
+            if self.device.type != 'cuda':
+                raise RuntimeError("device_dataset=True needs a CUDA device")
+            from .device_dataset import DeviceDataset
+            self.dds = DeviceDataset(self.ds, device=self.device)
+            self.dl = cycle(self.dds.loader(train_batch_size, shuffle=True, rank=self.accelerator.process_index,
+                                            world_size=self.accelerator.num_processes))
+        else:
+            self.dds = None
+            self.dl = cycle(self.accelerator.prepare(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=True, pin_memory=True)))
         self.accelerator.print(f'found {len(self.ds)} videos in {folder}' if not synthetic_train
                                else f'using {len(self.ds)} SYNTHETIC clips (SyntheticLagrangianDataset), no training folder')
         assert len(self.ds) > 0, 'could not find any gif files in folder'
