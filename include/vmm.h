@@ -308,6 +308,11 @@ int vmm_colsum(const void* x, long long rows, int n, long long ld, int fmt, floa
  * max_frames without writing), or a negative code: VMM_ERR_ARG for a malformed file, VMM_ERR_UNSUPPORTED for a
  * feature the device compositor does not reproduce (disposal method 3, a transparent FIRST frame, frames that
  * leave the logical screen, more than 2^19 pixels per frame).
+ * flags & VMM_GIF_PIL_COMPAT: Pillow (12.2 here, the decoder behind the reference's gif_to_tensor) opens a file whose
+ * first frame has the plain grey ramp as its palette in mode 'L' and decodes the FIRST later frame that brings a real
+ * palette as raw indices, ignoring that palette (it does not round-trip such files it wrote itself: measured,
+ * tests/test_cpu_gif.py); with the flag that frame gets the grey ramp here too, so the planes equal what the reference
+ * reads.  Without it every frame is mapped through its own palette (the image the file encodes).
  *
  * vmm_gif_decode (DEVICE): `files` = the bytes of n_files GIF files back to back, file_ofs[i] = start of file i
  * (n_files + 1 entries), frame_begin[i] .. frame_begin[i+1] = its rows in `frames` (n_files + 1 entries,
@@ -350,7 +355,8 @@ typedef struct {
   int32_t n_frames;
 } vmm_gif_info;
 
-int vmm_gif_scan(const uint8_t* file, size_t nbytes, vmm_gif_info* info, vmm_gif_frame* frames, int max_frames);
+#define VMM_GIF_PIL_COMPAT 1 /* reproduce Pillow's handling of a palette that arrives while the image is still in mode 'L' (above) */
+int vmm_gif_scan(const uint8_t* file, size_t nbytes, int flags, vmm_gif_info* info, vmm_gif_frame* frames, int max_frames);
 int vmm_gif_decode(const uint8_t* files, const uint64_t* file_ofs, const int32_t* frame_begin, const vmm_gif_frame* frames,
                    int n_files, int n_frames_total, int frames_per_file, int H, int W, uint8_t* index_ws, uint8_t* out, int32_t* err,
                    void* stream);

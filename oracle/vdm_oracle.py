@@ -52,6 +52,8 @@ class UnetCfg:
     init_kernel: int = 7
     frames: int = 11
     padding_mode: str = "zeros"          # 'zeros' (shipped) | 'circular' | 'circular_1d'  (model.yaml:13, VDDP:153-243)
+    temporal_cond: bool = True           # use_temporal_attention_cond (model.yaml:21, VDDP:792-795): False = no tokens in temporal attention
+    cond_to_time: str = "add"            # 'add' (shipped) | 'concat' (model.yaml:22, VDDP:786-790, 666)
 
     @property
     def dims(self) -> List[int]:
@@ -307,6 +309,8 @@ def conditioning(P: Params, cfg: UnetCfg, time: Tensor, cond: Tensor, null_mask:
     hid = F.linear(F.silu(hid), P["cond_token_to_hidden.3.weight"], P["cond_token_to_hidden.3.bias"])
     tok = torch.where(null_mask[:, None, None], P["null_text_token"], tok)               # VDDP:772-777
     hid = torch.where(null_mask[:, None], P["null_text_hidden"], hid)                    # VDDP:780-784
+    if cfg.cond_to_time == "concat":
+        return torch.cat((t, hid), dim=-1), tok                                          # VDDP:789-790
     return t + hid, tok                                                                  # VDDP:788
 
 
@@ -320,7 +324,9 @@ def unet_forward(P: Params, cfg: UnetCfg, x: Tensor, time: Tensor, cond: Tensor,
     x = conv_frames(x, P["init_conv." + ck + "weight"], P["init_conv." + ck + "bias"], pad=cfg.init_kernel // 2, mode=pm)
     x = temporal_block(P, "init_temporal_attn.", x, cfg, bias, None)       # no conditioning here  VDDP:743
     r = x
-    t, tok = conditioning(P, cfg, time, cond, null_mask)
+    t, tok_all = conditioning(P, cfg, time, cond, null_mask)
+    tok = tok_all
+    tok_t = tok_all if cfg.temporal_cond else None       # VDDP:792-795: label_emb_token_temporal
     skips = []
     L = cfg.levels
     for i in range(L):
@@ -328,13 +334,13 @@ def unet_forward(P: Params, cfg: UnetCfg, x: Tensor, time: Tensor, cond: Tensor,
         x = resnet_block(P, p + "0.", x, t, g, pm)
         x = resnet_block(P, p + "1.", x, t, g, pm)
         x = linear_block(P, p + "2.", x, cfg, tok)
-        x = temporal_block(P, p + "3.", x, cfg, bias, tok)
+        x = temporal_block(P, p + "3.", x, cfg, bias, tok_t)
         skips.append(x)
         if i < L - 1:
             x = conv_frames(x, P[p + "4." + ck + "weight"], P[p + "4." + ck + "bias"], stride=2, pad=1, mode=pm)   # Downsample VDDP:238-243
     x = resnet_block(P, "mid_block1.", x, t, g, pm)
     x = mid_spatial_block(P, "mid_spatial_attn.", x, cfg, tok)
-    x = temporal_block(P, "mid_temporal_attn.", x, cfg, bias, tok)
+    x = temporal_block(P, "mid_temporal_attn.", x, cfg, bias, tok_t)
     x = resnet_block(P, "mid_block2.", x, t, g, pm)
     for i in range(L):
         p = f"ups.{i}."
@@ -342,7 +348,7 @@ def unet_forward(P: Params, cfg: UnetCfg, x: Tensor, time: Tensor, cond: Tensor,
         x = resnet_block(P, p + "0.", x, t, g, pm)
         x = resnet_block(P, p + "1.", x, t, g, pm)
         x = linear_block(P, p + "2.", x, cfg, tok)
-        x = temporal_block(P, p + "3.", x, cfg, bias, tok)
+        x = temporal_block(P, p + "3.", x, cfg, bias, tok_t)
         if i < L - 1:
             x = convT_frames(x, P[p + "4." + uk + "weight"], P[p + "4." + uk + "bias"], pm)      # Upsample VDDP:153-160
     x = torch.cat((x, r), dim=1)
@@ -574,7 +580,7 @@ def unet_param_shapes(cfg: UnetCfg) -> Dict[str, Tuple[int, ...]]:
 
     def resnet(pre, ci, co, with_time=True):
         if with_time:
-            S[pre + "mlp.1.weight"] = (2 * co, td)
+            S[pre + "mlp.1.weight"] = (2 * co, 2 * td if cfg.cond_to_time == "concat" else td)        # VDDP:666
             S[pre + "mlp.1.bias"] = (2 * co,)
         for blk, c_in in (("block1.", ci), ("block2.", co)):
             S[pre + blk + "proj." + ck + "weight"] = (co, c_in, 1, 3, 3)

@@ -55,6 +55,8 @@ def main():
               for dt, sc in ((torch.bfloat16, 1.0), (torch.float16, 4096.0))]
     steps += [(f"ragged {a}", lambda a=a: T.test_ragged_sizes_against_the_oracle(*a)) for a in ((20, 3, True), (24, 1, True))]
     steps += [(f"wrap-mode network {m}", lambda m=m: T.test_wrap_mode_network_against_the_oracle(m)) for m in ("circular", "circular_1d")]
+    steps += [(f"config flags {a}", lambda a=a: T.test_config_flags_network_against_the_oracle(*a))
+              for a in ((False, "add", 16), (True, "concat", 16), (False, "concat", 64))]
     failed = 0
     for name, fn in steps:
         try:

@@ -183,6 +183,17 @@ def pil_frames(blob: bytes) -> np.ndarray:
     return np.stack(frames)
 
 
+def quirk_frames(rng, h: int = 48, w: int = 64):
+    """Three 'L' frames: the first holds all 256 grey values (Pillow's writer then keeps the plain ramp as the global palette and its
+    reader opens the file in mode 'L'), the second misses one value (the writer compacts its LOCAL palette and uses the freed index as
+    the transparent colour): the file Pillow's reader does not round-trip."""
+    a = rng.integers(0, 256, (3, h, w), dtype=np.uint8)
+    a[0].reshape(-1)[:256] = np.arange(256, dtype=np.uint8)
+    missing = int(rng.integers(1, 255))
+    a[1][a[1] == missing] = missing + 1
+    return [a[0], a[1], a[2]]
+
+
 def corpus(seed: int = 0):
     from PIL import Image
     rng = np.random.default_rng(seed)
@@ -241,6 +252,11 @@ def corpus(seed: int = 0):
     save('P_16_colours', paletted(grey(24, 24, 3, 0, 16)))
     save('one_bit', [Image.fromarray((rng.random((40, 40)) > 0.5)).convert('1') for _ in range(3)])
     save('RGB_quantised', [Image.fromarray(rng.integers(0, 256, (32, 32, 3), dtype=np.uint8), 'RGB') for _ in range(3)])
+    # small random 'L' frames: not every grey value occurs, so Pillow's writer keeps the full grey ramp for frame 0 (-> mode 'L' on
+    # reading) and gives later frames a compacted LOCAL palette + a transparent index: the case Pillow's reader does not round-trip
+    # (VMM_GIF_PIL_COMPAT, include/vmm.h)
+    for k in range(3):
+        save(f'L_pillow_quirk_{k}', [Image.fromarray(a, 'L') for a in quirk_frames(rng)])
     save('L_interlaced', grey(96, 96, 3), interlace=True)
     save('L_interlaced_odd', grey(37, 21, 3), interlace=True)
     # files from the writer below: small code sizes, interlaced partial frames, local palettes, transparency + disposal 2, deferred clear

@@ -13,15 +13,18 @@ class _ClaimsCuda(torch.Tensor):
     is_cuda = property(lambda self: True)
 
 
-@pytest.mark.parametrize("size,b,mode", [(16, 2, "zeros"), (12, 1, "zeros"), (16, 2, "circular"), (12, 2, "circular_1d")])
-def test_unet_forward_glue_matches_oracle(monkeypatch, size, b, mode):
+@pytest.mark.parametrize("size,b,mode,tcond,c2t", [(16, 2, "zeros", True, "add"), (12, 1, "zeros", True, "add"), (16, 2, "circular", True, "add"),
+                                                   (12, 2, "circular_1d", True, "add"), (12, 2, "zeros", False, "add"), (12, 2, "zeros", True, "concat"),
+                                                   (12, 2, "circular", False, "concat")])
+def test_unet_forward_glue_matches_oracle(monkeypatch, size, b, mode, tcond, c2t):
     from oracle import vdm_oracle as O
     from videometamaterials_b200 import Unet3D, blocks, ops
     emu_ops.install(monkeypatch, ops)
-    cfg = O.UnetCfg(dim=16, dim_mults=(1, 2), padding_mode=mode)          # the oracle's wrap modes are pinned to the reference
+    # the oracle's wrap modes and its use_temporal_attention_cond / cond_to_time branches are pinned to the reference (test_cpu_oracle.py)
+    cfg = O.UnetCfg(dim=16, dim_mults=(1, 2), padding_mode=mode, temporal_cond=tcond, cond_to_time=c2t)
     sd = O.synthetic_state_dict(cfg, seed=13)
     model = Unet3D(dim=16, dim_mults=(1, 2), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
-                   cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, cond_to_time='add', per_frame_cond=True,
+                   cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=tcond, cond_to_time=c2t, per_frame_cond=True,
                    padding_mode=mode)
     model.load_state_dict(sd)
     model.compute_dtype, model._packed = torch.float32, None          # fp32 "16-bit" operands: the glue is exact, tolerances tight
@@ -45,10 +48,12 @@ def test_unet_forward_glue_matches_oracle(monkeypatch, size, b, mode):
     assert rel(torch.Tensor(eps).permute(0, 4, 1, 2, 3), want) < 2e-5
 
 
-@pytest.mark.parametrize("channels,mults,l2,size,mode", [(3, (1, 2), False, 12, "zeros"), (4, (1, 2, 4), True, 16, "zeros"),
-                                                        (1, (1,), False, 8, "zeros"), (3, (1, 2), False, 12, "circular"),
-                                                        (3, (1, 2, 4), True, 16, "circular_1d")])
-def test_training_glue_matches_oracle_gradients(monkeypatch, channels, mults, l2, size, mode):
+@pytest.mark.parametrize("channels,mults,l2,size,mode,tcond,c2t", [(3, (1, 2), False, 12, "zeros", True, "add"), (4, (1, 2, 4), True, 16, "zeros", True, "add"),
+                                                                  (1, (1,), False, 8, "zeros", True, "add"), (3, (1, 2), False, 12, "circular", True, "add"),
+                                                                  (3, (1, 2, 4), True, 16, "circular_1d", True, "add"),
+                                                                  (3, (1, 2), False, 12, "zeros", False, "add"), (3, (1, 2), True, 12, "zeros", True, "concat"),
+                                                                  (3, (1, 2), False, 12, "zeros", False, "concat")])
+def test_training_glue_matches_oracle_gradients(monkeypatch, channels, mults, l2, size, mode, tcond, c2t):
     """The same for the training form: `blocks_bwd.training_loss` + backward (block-level autograd Functions, data gradients
     through the transformed weight packs with the fused concat split, weight gradients scattered into the master layout, bias
     gradients folded into the GroupNorm backward, the batched conditioning path) must give the oracle's loss and every parameter
@@ -57,10 +62,10 @@ def test_training_glue_matches_oracle_gradients(monkeypatch, channels, mults, l2
     from oracle import vdm_oracle as O
     from videometamaterials_b200 import Unet3D, blocks, blocks_bwd, ops
     emu_ops.install_training(monkeypatch, ops)
-    cfg = O.UnetCfg(dim=16, dim_mults=mults, channels=channels, padding_mode=mode)
+    cfg = O.UnetCfg(dim=16, dim_mults=mults, channels=channels, padding_mode=mode, temporal_cond=tcond, cond_to_time=c2t)
     sd = O.synthetic_state_dict(cfg, seed=14)
     model = Unet3D(dim=16, dim_mults=mults, channels=channels, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
-                   cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, cond_to_time='add', per_frame_cond=True,
+                   cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=tcond, cond_to_time=c2t, per_frame_cond=True,
                    padding_mode=mode)
     model.load_state_dict(sd)
     model.compute_dtype, model._packed = torch.float32, None

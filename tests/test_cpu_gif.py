@@ -33,8 +33,32 @@ def test_scan_and_decode_statement_match_pil_on_the_corpus():
     assert all(v > 0 for v in seen.values()), seen     # the corpus really exercises every branch of the compositor
 
 
+def test_pillow_mode_l_palette_quirk_is_reproduced_and_can_be_turned_off():
+    """A file whose first frame carries the plain grey ramp and whose second frame brings a compacted local palette: Pillow decodes the
+    second frame as raw indices (it does not round-trip the file it wrote); the scanner reproduces that by default, because the
+    reference reads through Pillow, and maps every frame through its own palette with pil_compat=False (= the encoded image)."""
+    from PIL import Image
+    import io
+    from videometamaterials_b200.device_dataset import scan_gif
+    rng = np.random.default_rng(5)
+    hit = 0
+    for _ in range(12):
+        arrs = emu_gif.quirk_frames(rng)
+        bio = io.BytesIO()
+        frames = [Image.fromarray(a, 'L') for a in arrs]
+        frames[0].save(bio, format='GIF', save_all=True, append_images=frames[1:], duration=200, loop=0)
+        blob = bio.getvalue()
+        ref = emu_gif.pil_frames(blob)
+        (w, h), tab = scan_gif(blob)
+        assert np.array_equal(emu_gif.decode(blob, tab, (w, h)), ref)
+        (w, h), tab_true = scan_gif(blob, pil_compat=False)
+        assert np.array_equal(emu_gif.decode(blob, tab_true, (w, h)), np.stack(arrs))
+        hit += int(not np.array_equal(ref, np.stack(arrs)))
+    assert hit > 0          # Pillow really mis-decodes some of these files: the quirk is exercised, not hypothetical
+
+
 def test_frames_beyond_a_files_count_are_zero_and_extra_frames_are_dropped():
-    name, blob = emu_gif.corpus()[2]
+    name, blob = [c for c in emu_gif.corpus() if c[0] == 'L_boxes'][0]
     (w, h), tab = _scan(blob)
     ref = emu_gif.pil_frames(blob)
     more = emu_gif.decode(blob, tab, (w, h), frames_per_file=len(tab) + 2)

@@ -55,6 +55,28 @@ def test_gif_decode_many_files_in_chunks_and_padded_frames():
         assert not got[i, k:].any()
 
 
+def test_pil_compat_off_decodes_the_encoded_image():
+    """The file Pillow does not round-trip (tests/test_cpu_gif.py): default = what Pillow (the reference) reads, pil_compat=False = the frames
+    that were written."""
+    from videometamaterials_b200.device_dataset import decode_gifs
+    from PIL import Image
+    import io
+    rng = np.random.default_rng(5)
+    differs = 0
+    for _ in range(8):
+        arrs = np.stack(emu_gif.quirk_frames(rng))
+        frames = [Image.fromarray(a, 'L') for a in arrs]
+        bio = io.BytesIO()
+        frames[0].save(bio, format='GIF', save_all=True, append_images=frames[1:], duration=200, loop=0)
+        blob = bio.getvalue()
+        ref = emu_gif.pil_frames(blob)
+        a = decode_gifs([blob], None, (48, 64), 'cuda')[0][0].cpu().numpy()
+        b = decode_gifs([blob], None, (48, 64), 'cuda', pil_compat=False)[0][0].cpu().numpy()
+        assert np.array_equal(a, ref) and np.array_equal(b, arrs)
+        differs += int(not np.array_equal(a, b))
+    assert differs > 0
+
+
 def test_short_lzw_stream_is_reported():
     from videometamaterials_b200 import _lib
     from videometamaterials_b200.device_dataset import decode_gifs

@@ -574,3 +574,49 @@ def test_module_forward_is_differentiable(gold_small):
                 for k, p in P.items() if p.requires_grad and p.grad is not None and float(p.grad.norm()) > 0)
     print("differentiable forward: worst grad-norm deviation", worst)
     assert worst[0] < 0.05, worst
+
+
+@pytest.mark.parametrize("tcond,c2t,dim", [(False, "add", 16), (True, "concat", 16), (False, "concat", 64)])
+def test_config_flags_network_against_the_oracle(tcond, c2t, dim):
+    """`use_temporal_attention_cond=False` / `cond_to_time='concat'` (model.yaml:21-22; the oracle's branches are pinned to the unmodified
+    reference by tests/golden/config_flags.pt): forward, guided forward, loss and every gradient norm on the kernels.  dim 64 puts the
+    fused temporal-attention kernel on the label-free path at level 0; 'concat' takes the torch statement of the conditioning path."""
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import GaussianDiffusion, Unet3D
+    cfg = O.UnetCfg(dim=dim, dim_mults=(1, 2), temporal_cond=tcond, cond_to_time=c2t)
+    sd = O.synthetic_state_dict(cfg, seed=43)
+    model = Unet3D(dim=dim, dim_mults=(1, 2), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
+                   cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=tcond, cond_to_time=c2t, per_frame_cond=True)
+    model.load_state_dict(sd, strict=True)
+    model.set_compute_dtype(torch.float16)
+    gd = GaussianDiffusion(model, image_size=16, channels=3, num_frames=11, timesteps=8, loss_type='l1', use_dynamic_thres=True,
+                           sampling_timesteps=8).cuda()
+    g = torch.Generator().manual_seed(44)
+    b = 2
+    x = torch.randn(b, 3, 11, 16, 16, generator=g)
+    cond = torch.rand(b, 11, generator=g) * 2 - 1
+    t = torch.tensor([1, 6])
+    noise = torch.randn(b, 3, 11, 16, 16, generator=g)
+    x01 = torch.rand(b, 3, 11, 16, 16, generator=g)
+    with torch.no_grad():
+        y = model(x.cuda(), t.cuda(), cond=cond.cuda(), null_cond_prob=0.0)
+        y_ref = O.unet_forward(sd, cfg, x, t, cond, torch.zeros(b, dtype=torch.bool))
+        yg = model.forward_with_guidance_scale(x.cuda(), t.cuda(), cond=cond.cuda(), guidance_scale=3.0)
+        yg_ref = O.unet_forward_guided(sd, cfg, x, t, cond, 3.0)
+    print("config flags forward rel-L2:", tcond, c2t, rel(y, y_ref), rel(yg, yg_ref))
+    assert rel(y, y_ref) < FWD_TOL[torch.float16] and rel(yg, yg_ref) < 2 * FWD_TOL[torch.float16]
+    P = {k: v.clone().requires_grad_(v.is_floating_point() and "freqs" not in k) for k, v in sd.items()}
+    loss_ref = O.p_losses(P, cfg, O.schedule(8), x01, t, cond, noise, torch.zeros(b, dtype=torch.bool))
+    loss_ref.backward()
+    loss = gd.p_losses((x01 * 2 - 1).cuda(), t.cuda(), cond=cond.cuda(), noise=noise.cuda(), null_cond_prob=0.0)
+    (loss * 4096.0).backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach()) < 2e-3
+    params = dict(model.named_parameters())
+    worst = max((abs(float(params[k].grad.norm()) / 4096.0 - float(p.grad.norm())) / (float(p.grad.norm()) + 1e-7 / 0.08), k)
+                for k, p in P.items() if p.requires_grad and p.grad is not None and float(p.grad.norm()) > 0)
+    print("config flags worst grad-norm deviation:", tcond, c2t, worst)
+    assert worst[0] < 0.08, worst
+    if not tcond:       # the temporal blocks' label projections are dead under the flag: no gradient here either
+        gk = params["downs.0.3.fn.fn.fn.to_k.weight"].grad
+        assert gk is None or float(gk.abs().max()) == 0.0

@@ -164,7 +164,7 @@ _SIGNATURES = {
     "vmm_axpby": [_P, _P, _F, _F, _F, _P, _L, _P],
     "vmm_gather_cast": [_P, _P, _P, _L, _I, _P],
     "vmm_adam_ema_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _I, _F, _P],
-    "vmm_gif_scan": [_P, _Z, C.POINTER(GifInfo), C.POINTER(GifFrame), _I],
+    "vmm_gif_scan": [_P, _Z, _I, C.POINTER(GifInfo), C.POINTER(GifFrame), _I],
     "vmm_gif_decode": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "vmm_dataset_items": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
 }

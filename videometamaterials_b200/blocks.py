@@ -433,7 +433,7 @@ def cond_kernel_eligible(model, time: Tensor, cond: Tensor) -> bool:
     arena = getattr(model, "_vmm_arena", None)
     # (the kernels block their loops over at most 8 samples in registers; 2 x 4 guided sampling and 8-clip training steps qualify,
     # larger batches take the torch statement below: measured, the kernels lose to it beyond 8 samples)
-    return (COND_KERNEL and time.is_cuda and arena is not None and arena.flat_param.device == time.device and cond.shape[0] <= COND_KERNEL_MAX_B
+    return (COND_KERNEL and model.cond_to_time == 'add' and time.is_cuda and arena is not None and arena.flat_param.device == time.device and cond.shape[0] <= COND_KERNEL_MAX_B
             and cond.shape[1] <= 16 and model.cond_dim <= 256 and model.cond_dim % 4 == 0 and model.dim % 4 == 0 and model.dim >= 4
             and model.heads == 8)
 
@@ -469,7 +469,7 @@ def conditioning(model, time: Tensor, cond: Tensor, null_mask: Tensor, frames: i
     hid = F.linear(F.silu(hid), sd["cond_token_to_hidden.3.weight"], sd["cond_token_to_hidden.3.bias"])
     tok = torch.where(null_mask[:, None, None], sd["null_text_token"], tok)
     hid = torch.where(null_mask[:, None], sd["null_text_hidden"], hid)
-    t = t + hid
+    t = torch.cat((t, hid), dim=-1) if model.cond_to_time == 'concat' else t + hid          # VDDP:786-790
     if arena is not None:
         anchor = torch.zeros(1, device=dev, requires_grad=torch.is_grad_enabled())
         wm = _GatherParams.apply(anchor, arena.flat_param, arena.flat_grad, plan["idx_wm"], sum(plan["ss_sizes"]))
@@ -634,6 +634,7 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
     g, heads, pm = model.groups, model.heads, model.padding_mode
     frames = x.shape[2]
     ss, ekv, bias, rot = conditioning(model, time, cond, null_mask, frames)
+    tkv = (lambda q: ekv[q]) if model.use_temporal_attention_cond else (lambda q: None)      # VDDP:792-795
     h, _ = init_fwd(P, sd, model, x.float(), noise, qcoef)
     h, _ = attn_block_fwd(P, sd, "init_temporal_attn.fn.fn.fn.", "temporal", h, None, bias, rot, heads, keep=False)
     r = h
@@ -643,20 +644,20 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
         h, _ = resnet_fwd(P, sd, p + "0.", [h], ss[p + "0."], g, pm)
         h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g, pm)
         h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads, keep=False)
-        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads, keep=False)
+        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, tkv(p + "3.fn.fn.fn."), bias, rot, heads, keep=False)
         skips.append(h)
         if i < L - 1:
             h = down_fwd(P, sd, p + "4.", h, pm)
     h, _ = resnet_fwd(P, sd, "mid_block1.", [h], ss["mid_block1."], g, pm)
     h, _ = attn_block_fwd(P, sd, "mid_spatial_attn.fn.fn.fn.", "spatial", h, ekv["mid_spatial_attn.fn.fn.fn."], None, None, heads)
-    h, _ = attn_block_fwd(P, sd, "mid_temporal_attn.fn.fn.fn.", "temporal", h, ekv["mid_temporal_attn.fn.fn.fn."], bias, rot, heads, keep=False)
+    h, _ = attn_block_fwd(P, sd, "mid_temporal_attn.fn.fn.fn.", "temporal", h, tkv("mid_temporal_attn.fn.fn.fn."), bias, rot, heads, keep=False)
     h, _ = resnet_fwd(P, sd, "mid_block2.", [h], ss["mid_block2."], g, pm)
     for i in range(L):
         p = f"ups.{i}."
         h, _ = resnet_fwd(P, sd, p + "0.", [h, skips.pop()], ss[p + "0."], g, pm)
         h, _ = resnet_fwd(P, sd, p + "1.", [h], ss[p + "1."], g, pm)
         h, _ = attn_block_fwd(P, sd, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None, heads, keep=False)
-        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot, heads, keep=False)
+        h, _ = attn_block_fwd(P, sd, p + "3.fn.fn.fn.", "temporal", h, tkv(p + "3.fn.fn.fn."), bias, rot, heads, keep=False)
         if i < L - 1:
             h = up_fwd(P, sd, p + "4.", h, pm)
     h, _ = resnet_fwd(P, sd, "final_conv.0.", [h, r], None, g, pm)

@@ -365,6 +365,7 @@ def _trunk(model, x0: Tensor, noise: Optional[Tensor], qcoef, t: Tensor, cond: T
     L = len(model.dim_mults)
     frames = x0.shape[2]
     ss, ekv, bias, rot, env.cond = blocks.conditioning_state(model, t, cond, null_mask, frames)
+    tkv = (lambda q: ekv[q]) if model.use_temporal_attention_cond else (lambda q: None)      # VDDP:792-795
     anchor = torch.zeros(1, device=x0.device, requires_grad=True)
     a, c, s = qcoef if qcoef is not None else (None, None, None)
     h = InitFn.apply(env, anchor, x0, noise, a, c, s)
@@ -376,20 +377,20 @@ def _trunk(model, x0: Tensor, noise: Optional[Tensor], qcoef, t: Tensor, cond: T
         h = ResnetFn.apply(env, p + "0.", ss[p + "0."], h)
         h = ResnetFn.apply(env, p + "1.", ss[p + "1."], h)
         h = AttnBlockFn.apply(env, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None)
-        h = AttnBlockFn.apply(env, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot)
+        h = AttnBlockFn.apply(env, p + "3.fn.fn.fn.", "temporal", h, tkv(p + "3.fn.fn.fn."), bias, rot)
         skips.append(h)
         if i < L - 1:
             h = DownFn.apply(env, p + "4.", h)
     h = ResnetFn.apply(env, "mid_block1.", ss["mid_block1."], h)
     h = AttnBlockFn.apply(env, "mid_spatial_attn.fn.fn.fn.", "spatial", h, ekv["mid_spatial_attn.fn.fn.fn."], None, None)
-    h = AttnBlockFn.apply(env, "mid_temporal_attn.fn.fn.fn.", "temporal", h, ekv["mid_temporal_attn.fn.fn.fn."], bias, rot)
+    h = AttnBlockFn.apply(env, "mid_temporal_attn.fn.fn.fn.", "temporal", h, tkv("mid_temporal_attn.fn.fn.fn."), bias, rot)
     h = ResnetFn.apply(env, "mid_block2.", ss["mid_block2."], h)
     for i in range(L):
         p = f"ups.{i}."
         h = ResnetFn.apply(env, p + "0.", ss[p + "0."], h, skips.pop())
         h = ResnetFn.apply(env, p + "1.", ss[p + "1."], h)
         h = AttnBlockFn.apply(env, p + "2.fn.fn.", "linear", h, ekv[p + "2.fn.fn."], None, None)
-        h = AttnBlockFn.apply(env, p + "3.fn.fn.fn.", "temporal", h, ekv[p + "3.fn.fn.fn."], bias, rot)
+        h = AttnBlockFn.apply(env, p + "3.fn.fn.fn.", "temporal", h, tkv(p + "3.fn.fn.fn."), bias, rot)
         if i < L - 1:
             h = UpFn.apply(env, p + "4.", h)
     h = ResnetFn.apply(env, "final_conv.0.", None, h, r)

@@ -240,7 +240,14 @@ __global__ void __launch_bounds__(256) dataset_items_kernel(const uint8_t* __res
 // ----------------------------------------------------------------------------------------------------------------------------
 // C ABI
 // ----------------------------------------------------------------------------------------------------------------------------
-extern "C" int vmm_gif_scan(const uint8_t* f, size_t n, vmm_gif_info* info, vmm_gif_frame* frames, int max_frames) {
+// PIL's GifImagePlugin._is_palette_needed: a palette that is exactly the grey ramp (entry i = (i, i, i)) is dropped
+static bool gif_palette_needed(const uint8_t* pal, uint32_t entries) {
+  for (uint32_t i = 0; i < entries; ++i)
+    if (pal[3 * i] != i || pal[3 * i + 1] != i || pal[3 * i + 2] != i) return true;
+  return false;
+}
+
+extern "C" int vmm_gif_scan(const uint8_t* f, size_t n, int flags, vmm_gif_info* info, vmm_gif_frame* frames, int max_frames) {
   using namespace vmm;
   if (!f || !info) return set_error(VMM_ERR_ARG, "vmm_gif_scan: null argument");
   if (n < 13 || (memcmp(f, "GIF87a", 6) != 0 && memcmp(f, "GIF89a", 6) != 0)) return set_error(VMM_ERR_ARG, "vmm_gif_scan: not a GIF file");
@@ -257,6 +264,12 @@ extern "C" int vmm_gif_scan(const uint8_t* f, size_t n, vmm_gif_info* info, vmm_
   }
   int count = 0;
   uint8_t sticky_disposal = 0, has_t = 0, t_index = 0;
+  // VMM_GIF_PIL_COMPAT: PIL opens a file whose first frame needs no palette in mode 'L' and stays there until a frame brings a palette
+  // it needs; THAT frame is decoded into the 'L' canvas as raw indices, its palette ignored (GifImagePlugin.load_prepare only builds a
+  // paletted frame image in the RGB modes), after which the image is 'P' / 'RGB' and palettes are honoured.  Reproduced by giving that one
+  // frame the grey ramp.
+  const bool pil_compat = (flags & VMM_GIF_PIL_COMPAT) != 0;
+  bool pil_mode_l = false;
   auto skip_blocks = [&](size_t& q) -> bool {     // false when the chain runs off the file
     while (true) {
       if (q >= n) return false;
@@ -298,6 +311,17 @@ extern "C" int vmm_gif_scan(const uint8_t* f, size_t n, vmm_gif_info* info, vmm_
       fr.pal_ofs = static_cast<uint32_t>(p);
       fr.pal_size = static_cast<uint16_t>(lsize);
       p += 3 * static_cast<size_t>(lsize);
+    }
+    if (p > n) return set_error(VMM_ERR_ARG, "vmm_gif_scan: truncated local colour table");
+    if (pil_compat) {
+      const bool needed = fr.pal_ofs != GIF_NO_PALETTE && gif_palette_needed(f + fr.pal_ofs, fr.pal_size);
+      if (count == 0) {
+        pil_mode_l = !needed;
+      } else if (pil_mode_l && needed) {
+        fr.pal_ofs = GIF_NO_PALETTE;
+        fr.pal_size = 0;
+        pil_mode_l = false;
+      }
     }
     if (p >= n) return set_error(VMM_ERR_ARG, "vmm_gif_scan: truncated image data");
     fr.min_code = f[p++];

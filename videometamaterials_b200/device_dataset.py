@@ -28,15 +28,17 @@ from . import ops
 from .dataset import _LAYOUT, Dataset
 
 
-def scan_gif(buf: bytes, max_frames: int = 4096) -> Tuple[Tuple[int, int], np.ndarray]:
-    """Frame table of one GIF file (host; `vmm_gif_scan`): ((width, height), structured array of vmm_gif_frame rows)."""
+def scan_gif(buf: bytes, max_frames: int = 4096, pil_compat: bool = True) -> Tuple[Tuple[int, int], np.ndarray]:
+    """Frame table of one GIF file (host; `vmm_gif_scan`): ((width, height), structured array of vmm_gif_frame rows).
+    pil_compat: reproduce Pillow's decode of a palette that arrives while the image is still in mode 'L' (include/vmm.h), so that the
+    planes equal what the reference's `gif_to_tensor` reads; False maps every frame through its own palette."""
     info = _lib.GifInfo()
     frames = (_lib.GifFrame * max_frames)()
-    n = _lib.lib.vmm_gif_scan(buf, len(buf), C.byref(info), frames, max_frames)
+    n = _lib.lib.vmm_gif_scan(buf, len(buf), 1 if pil_compat else 0, C.byref(info), frames, max_frames)
     if n < 0:
         raise _lib.VmmError(_lib.lib.vmm_last_error().decode())
     if n > max_frames:
-        return scan_gif(buf, n)
+        return scan_gif(buf, n, pil_compat)
     arr = np.frombuffer(frames, dtype=GIF_FRAME_DTYPE, count=n).copy()
     return (int(info.width), int(info.height)), arr
 
@@ -48,7 +50,7 @@ assert GIF_FRAME_DTYPE.itemsize == C.sizeof(_lib.GifFrame) == 32
 
 
 def decode_gifs(blobs: Sequence[bytes], frames_per_file: Optional[int], size_hw: Tuple[int, int], device, names: Optional[Sequence[str]] = None,
-                chunk_bytes: int = 1 << 30) -> Tuple[torch.Tensor, torch.Tensor]:
+                chunk_bytes: int = 1 << 30, pil_compat: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """Decode GIF files on the device: (u8 (n_files, frames_per_file, H, W) luminance, int32 (n_files,) frames each file holds, capped
     at frames_per_file; None = the largest frame count among the files).  Launched in chunks of about `chunk_bytes` of workspace."""
     H, W = size_hw
@@ -56,7 +58,7 @@ def decode_gifs(blobs: Sequence[bytes], frames_per_file: Optional[int], size_hw:
     tables: List[np.ndarray] = []
     for i, blob in enumerate(blobs):
         try:
-            (w, h), fr = scan_gif(blob)
+            (w, h), fr = scan_gif(blob, pil_compat=pil_compat)
         except _lib.VmmError as e:
             raise _lib.VmmError(f"{label(i)}: {e}") from None
         if (h, w) != (H, W):
@@ -141,7 +143,7 @@ def item_tables(ds: Dataset):
 class DeviceDataset:
     """Decoded dataset resident in HBM; `batch(indices)` is one kernel launch.  See the module docstring."""
 
-    def __init__(self, ds: Dataset, device="cuda", max_frames: Optional[int] = None):
+    def __init__(self, ds: Dataset, device="cuda", max_frames: Optional[int] = None, pil_compat: bool = True):
         if not isinstance(ds, Dataset):
             raise TypeError("DeviceDataset wraps a videometamaterials_b200.dataset.Dataset")
         if ds.horizontal_flip:
@@ -163,7 +165,7 @@ class DeviceDataset:
                 blobs.append(f.read())
         # an item uses at most num_frames frames of a file (cast_num_frames); without force_num_frames, all the frames the files hold
         fpf = int(max_frames) if max_frames is not None else (max(int(ds.num_frames), 1) if ds.force_num_frames else None)
-        u8, counts = decode_gifs(blobs, fpf, (S, S), self.device, names)
+        u8, counts = decode_gifs(blobs, fpf, (S, S), self.device, names, pil_compat=pil_compat)
         fpf = u8.shape[1]
         self.u8 = u8.view(n, len(planes), fpf, S, S)
         cnt = counts.view(n, len(planes))

@@ -5,9 +5,10 @@ Reference: VDDP = denoising_diffusion_pytorch/video_denoising_diffusion_pytorch.
 
 The nn.Module tree exists only to own parameters under the reference's names (so checkpoints load both
 ways); the arithmetic is issued block by block through `blocks.py` onto the C ABI.
-Only the shipped configuration is implemented (per_frame_cond=True -> 'self-stacked' attention with 11
-per-frame tokens, cond_to_time='add', use_temporal_attention_cond=True, padding_mode='zeros'); the
-ablation branches, several of which are broken upstream, raise NotImplementedError.
+Implemented: the shipped configuration (per_frame_cond=True -> 'self-stacked' attention with 11 per-frame tokens) with every
+value of padding_mode, use_temporal_attention_cond and cond_to_time ('add' | 'concat') of the config surface; the
+per_frame_cond=False ablation branches (CNN / GRU signal embedding, cross-attention), several of which are broken upstream
+(SURVEY.md section 2), raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -128,9 +129,8 @@ class Unet3D(nn.Module):
             unsupported.append("per_frame_cond=False (ablation path)")
         if cond_att_GRU:
             unsupported.append("cond_att_GRU=True")
-        if not use_temporal_attention_cond:
-            unsupported.append("use_temporal_attention_cond=False")
-        if cond_to_time != 'add':
+        if cond_to_time not in ('add', 'concat'):
+            # (the reference silently drops the label from the time embedding for any other string, VDDP:786-790)
             unsupported.append(f"cond_to_time={cond_to_time!r}")
         if padding_mode not in ('zeros', 'circular', 'circular_1d'):
             raise ValueError(f"unknown padding_mode {padding_mode!r}")
@@ -190,7 +190,8 @@ class Unet3D(nn.Module):
         # both circular upsamplers of the reference hold their transposed conv as `.conv_transpose` (VDDP:181, 204)
         up = lambda d: (nn.ConvTranspose3d(d, d, (1, 4, 4), (1, 2, 2), (0, 1, 1)) if padding_mode == 'zeros'
                         else _Holder(conv_transpose=nn.ConvTranspose3d(d, d, (1, 4, 4), (1, 2, 2), (0, 1, 1))))
-        rbc = partial(rb, time_emb_dim=time_dim)
+        # VDDP:666: with 'concat' every ResnetBlock MLP reads time embedding | label embedding
+        rbc = partial(rb, time_emb_dim=time_dim * 2 if cond_to_time == 'concat' else time_dim)
         lin = lambda d: _residual_prenorm(d, _LinearAttention(d, attn_heads, 32, time_dim), False)
         for ind, (di, do) in enumerate(in_out):
             last = ind >= n_res - 1
