@@ -61,6 +61,8 @@ def main(argv=None):
     ap.add_argument('--targets', default=None, help='target curves (default: <root>/data/target_responses.csv)')
     ap.add_argument('--wandb-username', default=None)
     ap.add_argument('--preload-data', action='store_true', help='decode the whole GIF dataset into host memory before training')
+    ap.add_argument('--device-dataset', action='store_true',
+                    help='decode the training GIFs on the GPU once and serve every batch from HBM (device_dataset.py); default: host Dataset + DataLoader')
     ap.add_argument('--synthetic-data', action='store_true', help='train on in-memory random clips when the data folders are absent')
     args = ap.parse_args(argv)
 
@@ -96,7 +98,8 @@ def main(argv=None):
                       train_lr=config['learning_rate'], save_and_sample_every=args.save_and_sample_every, train_num_steps=args.train_steps,
                       ema_decay=0.995, log=True, null_cond_prob=0.1, per_frame_cond=config['per_frame_cond'],
                       reference_frame=config['reference_frame'], run_name=args.run_name, accelerator=accelerator,
-                      wandb_username=args.wandb_username, preload_data=args.preload_data, synthetic_data=args.synthetic_data)
+                      wandb_username=args.wandb_username, preload_data=args.preload_data, synthetic_data=args.synthetic_data,
+                      device_dataset=args.device_dataset)
     trainer.train(load_model_step=load_step, num_samples=3, num_preds=args.num_preds)
     trainer.eval_target(args.targets or root + 'data/target_responses.csv', guidance_scale=args.guidance_scale, num_preds=args.num_preds)
     return 0

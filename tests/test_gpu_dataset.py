@@ -159,7 +159,7 @@ def test_trainer_trains_from_the_device_dataset(tmp_path, monkeypatch):
                        device_dataset=device_dataset)
 
     tr = make(True)
-    assert tr.dds is not None and tr.dds.u8.shape == (6, 5, 11, 16, 16)
+    assert tr.dds is not None and tr.dds.u8.shape == (6, 4, 11, 16, 16)      # topo + the three selected fields
     x, cond = next(tr.dl)
     assert x.is_cuda and x.shape == (2, 3, 11, 16, 16) and cond.shape == (2, 11) and cond.is_cuda
     # the batch is made of the host Dataset's items

@@ -647,10 +647,23 @@ extern "C" int vmm_gn_silu_bwd(const void* x, const void* dy, void* dx, int fmt,
   uint16_t* op = static_cast<uint16_t*>(dx);
   const bool gs8 = ((C / groups) % 8) == 0;
   const dim3 grid(gn_grid_x(nvec, B, C, 2, 2), B);     // measured: 4 vectors in flight x 2 CTAs / SM beats 2 x 3 and 2 x 4 (108 / 123 / 123 us, level 0)
+  // The reduce pass ends in 2 C global atomics per CTA onto the B x 2 C partial sums: at the small levels (C = 256 / 512, a few MB per
+  // launch) 74 CTAs per sample spent ~35 us mostly in those contended atomics (ncu launch list, round 2: 35 us at 12 x 12 against 22 us at
+  // 48 x 48).  Give every thread at least `min_vec` vectors there, i.e. fewer CTAs per sample.
+  static const int min_vec = [] { const char* e = getenv("VMM_GN_REDUCE_MIN_VEC"); return e ? atoi(e) : 16; }();
+  dim3 grid_r = grid;
+  if (min_vec > 0) {
+    int m = 1;
+    while ((static_cast<long long>(m) * 2048) % C) ++m;
+    long long want = nvec / (256LL * min_vec);
+    want = want / m * m;
+    if (want < m) want = m;
+    if (want < static_cast<long long>(grid.x)) grid_r.x = static_cast<unsigned int>(want);
+  }
   const size_t sm_r = (static_cast<size_t>(2) * C + 2 * groups) * sizeof(float), sm_a = static_cast<size_t>(C) * sizeof(float);
 #define GN_BWD(F, G8)                                                                                                                    \
   do {                                                                                                                                   \
-    gn_silu_bwd_reduce_kernel<F, G8, 4, 2><<<grid, 256, sm_r, stream>>>(xp, dp, pix, C, groups, stats, gamma, beta, scale_shift, eps, act, \
+    gn_silu_bwd_reduce_kernel<F, G8, 4, 2><<<grid_r, 256, sm_r, stream>>>(xp, dp, pix, C, groups, stats, gamma, beta, scale_shift, eps, act, \
                                                                         part, counter, gm, dgamma, dbeta, dscale_shift);                 \
     count_launch();                                                                                                                      \
     gn_silu_bwd_apply_kernel<F, G8, 4, 2><<<grid, 256, sm_a, stream>>>(xp, dp, op, pix, C, groups, stats, gamma, beta, scale_shift, eps,  \
