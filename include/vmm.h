@@ -204,7 +204,10 @@ int vmm_sattn_bwd(const void* qkv, const float* ekv, const void* aout, const voi
  * vmm_cfg_x0     : eps = null + (cond - null) * w (VDDP:728), x0 = sr*x - srm1*eps (VDDP:920-924);
  *                  eps_cl is fp32 channels-last [(2)B][F*H*W][C].
  * vmm_abs_quantile: s[b] = max(quantile(|v_b|), floor) with torch.quantile's linear interpolation between the
- *                  k-th and (k+1)-th order statistics (VDDP:941-947); exact radix select, one CTA per sample.
+ *                  k-th and (k+1)-th order statistics (VDDP:941-947); exact 4-pass 8-bit radix select.  With a workspace of
+ *                  vmm_abs_quantile_workspace(B) bytes (zeroed by the call, in stream order) and n >= 65536 every pass is
+ *                  one launch over the whole GPU (4 histogram launches + 1 that counts / finds the neighbour and
+ *                  writes s); with workspace == NULL or small n one CTA per sample does everything in one launch.
  * vmm_posterior_step: clamp(x0,-s,s)/s (skipped when s == NULL), posterior mean (VDDP:926-933), + sig[b]*noise (VDDP:963).
  * vmm_axpby      : out = ca*a + cb*b + cc  (DDIM update VDDP:1014-1016, unnormalize_img VDDP:1112).
  * vmm_adam_ema_step: torch.optim.Adam (VDDP:1481) over a flat arena + EMA (VDDP:121-129); ema_mode 0 none,
@@ -216,7 +219,9 @@ int vmm_loss(const float* pred, const float* target, float* loss_sum, void* dpre
              int l2, float grad_scale, void* stream);
 int vmm_cfg_x0(const float* x, const float* eps_cl, int has_null, float w, const float* sr, const float* srm1, float* x0,
                float* eps_out, int B, int C, int F, int H, int W, void* stream);
-int vmm_abs_quantile(const float* v, int B, long long n, long long k, float frac, float floor_val, float* s_out, void* stream);
+size_t vmm_abs_quantile_workspace(int B);
+int vmm_abs_quantile(const float* v, int B, long long n, long long k, float frac, float floor_val, float* s_out, void* workspace,
+                     size_t workspace_bytes, void* stream);
 int vmm_posterior_step(const float* x0, const float* x, const float* noise, const float* s, const float* c1, const float* c2,
                        const float* sig, float* out, int B, long long per, void* stream);
 int vmm_axpby(const float* a, const float* b, float ca, float cb, float cc, float* out, long long n, void* stream);

@@ -228,6 +228,38 @@ def test_quantile_edge_cases(ops):
         assert torch.equal(s, want), (n, s, want)
 
 
+@pytest.mark.parametrize("B,n", [(4, 304128), (1, 65536), (3, 70001), (8, 304128), (2, 1_200_000)])
+def test_quantile_multi_cta_path_is_exact(ops, B, n):
+    """n >= 65536: every radix pass is one launch over the whole GPU (csrc/sampler.cu quantile_hist_kernel / quantile_final_kernel).
+    Bit-equal to torch.quantile for heavy-tailed values, massive ties, constants, a sample of zeros, several quantiles, and equal to the
+    one-CTA kernel (workspace == NULL)."""
+    from videometamaterials_b200 import _lib
+    from videometamaterials_b200.diffusion import quantile_rank
+    torch.manual_seed(n + B)
+    v = torch.randn(B, n, device="cuda") * torch.exp(2 * torch.randn(B, 1, device="cuda"))
+    if B > 1:
+        v[1] = torch.round(v[1] * 4) / 4                       # a few dozen distinct values
+    if B > 2:
+        v[2] = 0.75
+    if B > 3:
+        v[3] = 0.0
+    for q in (0.9, 0.5, 0.999, 0.0, 1.0):
+        k, frac = quantile_rank(n, q)
+        s = torch.empty(B, device="cuda")
+        ops.abs_quantile(v, B, n, k, frac, 0.0, s)
+        want = torch.quantile(v.abs(), q, dim=-1)
+        assert torch.equal(s, want), (q, s, want)
+        s1 = torch.empty(B, device="cuda")
+        _lib.check(_lib.lib.vmm_abs_quantile(v.data_ptr(), B, n, k, frac, 0.0, s1.data_ptr(), None, 0, ops.stream_ptr()))
+        assert torch.equal(s1, want)
+    # the floor of the dynamic threshold (VDDP:947) and back-to-back calls on one workspace
+    k, frac = quantile_rank(n, 0.9)
+    s = torch.empty(B, device="cuda")
+    for _ in range(3):
+        ops.abs_quantile(v, B, n, k, frac, 1.0, s)
+    assert torch.equal(s, torch.quantile(v.abs(), 0.9, dim=-1).clamp(min=1.0))
+
+
 def test_adam_ema_step_matches_oracle(ops):
     """vmm_adam_ema_step (one launch over the flat arena) against the oracle's restatement of torch.optim.Adam + the reference's
     EMA (VDDP:116-129, 1633-1639; the oracle is pinned to torch.optim.Adam in tests/test_cpu_oracle.py), through the copy phase

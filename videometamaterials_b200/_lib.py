@@ -93,7 +93,7 @@ class VmmError(RuntimeError):
     pass
 
 
-ABI_VERSION = 4          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
+ABI_VERSION = 5          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
 
 
 def _load() -> C.CDLL:
@@ -159,7 +159,8 @@ _SIGNATURES = {
     "vmm_prep_input": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "vmm_loss": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "vmm_cfg_x0": [_P, _P, _I, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "vmm_abs_quantile": [_P, _I, _L, _L, _F, _F, _P, _P],
+    "vmm_abs_quantile_workspace": [_I],
+    "vmm_abs_quantile": [_P, _I, _L, _L, _F, _F, _P, _P, _Z, _P],
     "vmm_posterior_step": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _P],
     "vmm_axpby": [_P, _P, _F, _F, _F, _P, _L, _P],
     "vmm_gather_cast": [_P, _P, _P, _L, _I, _P],
@@ -168,7 +169,7 @@ _SIGNATURES = {
     "vmm_gif_decode": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "vmm_dataset_items": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
 }
-_RESTYPES = {"vmm_gn_silu_bwd_workspace": C.c_size_t, "vmm_ftattn_workspace": C.c_size_t, "vmm_cond_workspace": C.c_size_t,
+_RESTYPES = {"vmm_abs_quantile_workspace": C.c_size_t, "vmm_gn_silu_bwd_workspace": C.c_size_t, "vmm_ftattn_workspace": C.c_size_t, "vmm_cond_workspace": C.c_size_t,
              "vmm_flattn_workspace": C.c_size_t}
 for _name, _args in _SIGNATURES.items():
     _fn = getattr(lib, _name)     # AttributeError here == the .so is stale: rebuild it

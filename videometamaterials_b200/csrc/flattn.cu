@@ -171,48 +171,41 @@ __global__ void __launch_bounds__(256, 1) flattn_ctx_kernel(const __grid_constan
       tma_load_4d(xs, &p.xmap, &ctl->x_full, 0, (t + 1) * 128, bf, 0);
     }
     __syncwarp();
-    // ---- K^T rows of this thread's head-dim: max over the tile's pixels, then w = exp(k - max)
-    float m_t = -1e30f;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float v[32];
-      tmem_ld32f(lane_taddr + static_cast<uint32_t>(g * 128 + c * 32), v);
+    // ---- K^T rows of this thread's head-dim: max over the tile's pixels, then w = exp(k - max).  The four 32-column TMEM loads of a
+    // row are issued back to back and waited for once, and the row stays in registers for both passes (one CTA of 256 threads per SM:
+    // registers are plentiful; the earlier form read the row twice, one load + wait at a time)
+    float m_t = -1e30f, z_t = 0.f;
+    {
+      float kv[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32f(lane_taddr + static_cast<uint32_t>(g * 128 + c * 32), kv + 32 * c);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) m_t = fmaxf(m_t, v[j]);
-    }
-    float z_t = 0.f;
-    uint8_t* wrow = wt + g * 32768 + row * 128;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float v[32];
-      tmem_ld32f(lane_taddr + static_cast<uint32_t>(g * 128 + c * 32), v);
-      tmem_ld_wait();
+      for (int j = 0; j < 128; ++j) m_t = fmaxf(m_t, kv[j]);
+      uint8_t* wrow = wt + g * 32768 + row * 128;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = __expf(v[j] - m_t);
-        z_t += v[j];
-      }
+      for (int cc = 0; cc < 16; ++cc) {     // 8 pixels per 16-byte chunk: k-block cc >> 3, chunk cc & 7
+        float e[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {        // 8 pixels per 16-byte chunk; pixel index c * 32 + j * 8
-        const int cc = c * 4 + j;          // chunk of the 128-pixel row: k-block cc >> 3, chunk cc & 7
-        const uint4 u = make_uint4(pack2_h16(v[8 * j], v[8 * j + 1], FMT), pack2_h16(v[8 * j + 2], v[8 * j + 3], FMT),
-                                   pack2_h16(v[8 * j + 4], v[8 * j + 5], FMT), pack2_h16(v[8 * j + 6], v[8 * j + 7], FMT));
+        for (int j = 0; j < 8; ++j) {
+          e[j] = __expf(kv[8 * cc + j] - m_t);
+          z_t += e[j];
+        }
+        const uint4 u = make_uint4(pack2_h16(e[0], e[1], FMT), pack2_h16(e[2], e[3], FMT), pack2_h16(e[4], e[5], FMT), pack2_h16(e[6], e[7], FMT));
         *reinterpret_cast<uint4*>(wrow + (cc >> 3) * 16384 + (((cc & 7) ^ (row & 7)) << 4)) = u;
       }
     }
     // ---- V rows of this thread's pixel: 128 columns of the group as an MN-major B tile [pixel][64 e] x 2
-    uint8_t* vrow = vt + g * 32768 + row * 128;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float v[32];
-      tmem_ld32f(lane_taddr + static_cast<uint32_t>(256 + g * 128 + c * 32), v);
-      tmem_ld_wait();
+    {
+      float vv[128];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cc = c * 4 + j;
-        const uint4 u = make_uint4(pack2_h16(v[8 * j], v[8 * j + 1], FMT), pack2_h16(v[8 * j + 2], v[8 * j + 3], FMT),
-                                   pack2_h16(v[8 * j + 4], v[8 * j + 5], FMT), pack2_h16(v[8 * j + 6], v[8 * j + 7], FMT));
+      for (int c = 0; c < 4; ++c) tmem_ld32f(lane_taddr + static_cast<uint32_t>(256 + g * 128 + c * 32), vv + 32 * c);
+      tmem_ld_wait();
+      uint8_t* vrow = vt + g * 32768 + row * 128;
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) {
+        const uint4 u = make_uint4(pack2_h16(vv[8 * cc], vv[8 * cc + 1], FMT), pack2_h16(vv[8 * cc + 2], vv[8 * cc + 3], FMT),
+                                   pack2_h16(vv[8 * cc + 4], vv[8 * cc + 5], FMT), pack2_h16(vv[8 * cc + 6], vv[8 * cc + 7], FMT));
         *reinterpret_cast<uint4*>(vrow + (cc >> 3) * 16384 + (((cc & 7) ^ (row & 7)) << 4)) = u;
       }
     }
@@ -406,30 +399,35 @@ __global__ void __launch_bounds__(256, 1) flattn_out_kernel(const __grid_constan
       tma_load_4d(xs, &p.xmap, &ctl->x_full, 0, (t + 1) * 128, bf, 0);
     }
     __syncwarp();
-    // ---- q rows: softmax over each head's 32 values, x scale -> A tile [pixel][256 d] (4 k-blocks)
-#pragma unroll 1
-    for (int hh = 0; hh < 4; ++hh) {
-      float v[32];
-      tmem_ld32f(lane_taddr + static_cast<uint32_t>(half * 128 + hh * 32), v);
+    // ---- q rows: softmax over each head's 32 values, x scale -> A tile [pixel][256 d] (4 k-blocks); the four heads of this thread's
+    // half are loaded from TMEM back to back and waited for once
+    {
+      float qv[128];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) tmem_ld32f(lane_taddr + static_cast<uint32_t>(half * 128 + hh * 32), qv + 32 * hh);
       tmem_ld_wait();
-      float mx = v[0];
 #pragma unroll
-      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-      float sum = 0.f;
+      for (int hh = 0; hh < 4; ++hh) {
+        float* v = qv + 32 * hh;
+        float mx = v[0];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = __expf(v[j] - mx);
-        sum += v[j];
-      }
-      const float inv = p.scale / sum;
-      const int col0 = half * 128 + hh * 32;             // d column
-      uint8_t* base = qt + (col0 >> 6) * 16384 + row * 128;
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+        float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cc = ((col0 & 63) >> 3) + j;
-        const uint4 u = make_uint4(pack2_h16(v[8 * j] * inv, v[8 * j + 1] * inv, FMT), pack2_h16(v[8 * j + 2] * inv, v[8 * j + 3] * inv, FMT),
-                                   pack2_h16(v[8 * j + 4] * inv, v[8 * j + 5] * inv, FMT), pack2_h16(v[8 * j + 6] * inv, v[8 * j + 7] * inv, FMT));
-        *reinterpret_cast<uint4*>(base + ((cc ^ (row & 7)) << 4)) = u;
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __expf(v[j] - mx);
+          sum += v[j];
+        }
+        const float inv = p.scale / sum;
+        const int col0 = half * 128 + hh * 32;             // d column
+        uint8_t* base = qt + (col0 >> 6) * 16384 + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cc = ((col0 & 63) >> 3) + j;
+          const uint4 u = make_uint4(pack2_h16(v[8 * j] * inv, v[8 * j + 1] * inv, FMT), pack2_h16(v[8 * j + 2] * inv, v[8 * j + 3] * inv, FMT),
+                                     pack2_h16(v[8 * j + 4] * inv, v[8 * j + 5] * inv, FMT), pack2_h16(v[8 * j + 6] * inv, v[8 * j + 7] * inv, FMT));
+          *reinterpret_cast<uint4*>(base + ((cc ^ (row & 7)) << 4)) = u;
+        }
       }
     }
     tc_fence_before();
@@ -452,19 +450,23 @@ __global__ void __launch_bounds__(256, 1) flattn_out_kernel(const __grid_constan
     mbar_wait(&ctl->m2_full, it & 1);
     tc_fence_after();
     // ---- attention rows (x 1 / (h w)) over the same tile: A operand of to_out
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float v[32];
-      tmem_ld32f(lane_taddr + static_cast<uint32_t>(256 + half * 128 + c * 32), v);
-      tmem_ld_wait();
-      const int col0 = half * 128 + c * 32;
-      uint8_t* base = qt + (col0 >> 6) * 16384 + row * 128;
+    {
+      float av[128];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cc = ((col0 & 63) >> 3) + j;
-        const uint4 u = make_uint4(pack2_h16(v[8 * j] * inv_hw, v[8 * j + 1] * inv_hw, FMT), pack2_h16(v[8 * j + 2] * inv_hw, v[8 * j + 3] * inv_hw, FMT),
-                                   pack2_h16(v[8 * j + 4] * inv_hw, v[8 * j + 5] * inv_hw, FMT), pack2_h16(v[8 * j + 6] * inv_hw, v[8 * j + 7] * inv_hw, FMT));
-        *reinterpret_cast<uint4*>(base + ((cc ^ (row & 7)) << 4)) = u;
+      for (int c = 0; c < 4; ++c) tmem_ld32f(lane_taddr + static_cast<uint32_t>(256 + half * 128 + c * 32), av + 32 * c);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float* v = av + 32 * c;
+        const int col0 = half * 128 + c * 32;
+        uint8_t* base = qt + (col0 >> 6) * 16384 + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cc = ((col0 & 63) >> 3) + j;
+          const uint4 u = make_uint4(pack2_h16(v[8 * j] * inv_hw, v[8 * j + 1] * inv_hw, FMT), pack2_h16(v[8 * j + 2] * inv_hw, v[8 * j + 3] * inv_hw, FMT),
+                                     pack2_h16(v[8 * j + 4] * inv_hw, v[8 * j + 5] * inv_hw, FMT), pack2_h16(v[8 * j + 6] * inv_hw, v[8 * j + 7] * inv_hw, FMT));
+          *reinterpret_cast<uint4*>(base + ((cc ^ (row & 7)) << 4)) = u;
+        }
       }
     }
     tc_fence_before();

@@ -207,6 +207,148 @@ __global__ void __launch_bounds__(1024) abs_quantile_kernel(const float* __restr
   }
 }
 
+// The same selection spread over the whole GPU (one launch per pass; the single CTA per sample above took 494 us for 4 x 304 128
+// values, 5 % of a guided sampling step, on 4 of 148 SMs).  hist[b][pass][256] lives in a caller-provided workspace zeroed by the entry
+// point.  A CTA of pass p first replays the bucket choices of passes 0 .. p-1 from their finished histograms (p scans of 256 counters),
+// then counts its slice of the sample among the values that match the prefix.
+__device__ __forceinline__ void quantile_replay(const unsigned int* __restrict__ hist_b, int passes, unsigned int k, unsigned int* s_hist,
+                                                unsigned int& prefix, unsigned int& rank) {
+  __shared__ unsigned int s_sel[2];
+  prefix = 0;
+  rank = k;
+  for (int q = 0; q < passes; ++q) {
+    const int shift = 24 - 8 * q;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = __ldcg(hist_b + q * 256 + i);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // lane l owns buckets 8 l .. 8 l + 7: warp scan of the lane sums, then the bucket inside the lane
+      unsigned int c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c[j] = s_hist[threadIdx.x * 8 + j];
+        sum += c[j];
+      }
+      unsigned int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (threadIdx.x >= static_cast<unsigned int>(o)) incl += t;
+      }
+      const unsigned int excl = incl - sum;
+      const bool mine = excl <= rank && rank < incl;
+      const unsigned int any = __ballot_sync(0xffffffffu, mine);
+      if (any == 0) {                       // rank beyond the counted values (cannot happen for k < n): last bucket, as the one-CTA kernel
+        if (threadIdx.x == 31) {
+          s_sel[0] = prefix | (255u << shift);
+          s_sel[1] = rank - incl;
+        }
+      } else if (mine) {
+        unsigned int acc = excl;
+        int bsel = 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (acc + c[j] > rank) { bsel = j; break; }
+          acc += c[j];
+        }
+        s_sel[0] = prefix | (static_cast<unsigned int>(threadIdx.x * 8 + bsel) << shift);
+        s_sel[1] = rank - acc;
+      }
+    }
+    __syncthreads();
+    prefix = s_sel[0];
+    rank = s_sel[1];
+    __syncthreads();
+  }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(512) quantile_hist_kernel(const float* __restrict__ v, long long n, unsigned int k, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int s_hist[256];
+  const int b = blockIdx.y;
+  const float* vb = v + static_cast<long long>(b) * n;
+  unsigned int* hist_b = hist + static_cast<size_t>(b) * 4 * 256;
+  unsigned int prefix, rank;
+  quantile_replay(hist_b, PASS, k, s_hist, prefix, rank);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  constexpr int shift = 24 - 8 * PASS;
+  constexpr unsigned int mask_hi = PASS == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long i0 = per * blockIdx.x, i1 = min(i0 + per, n);
+  for (long long base = i0; base < i1; base += blockDim.x) {
+    const long long i = base + threadIdx.x;
+    unsigned int u = 0;
+    bool ok = false;
+    if (i < i1) {
+      u = __float_as_uint(fabsf(vb[i]));
+      ok = (u & mask_hi) == prefix;
+    }
+    const unsigned int live = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const unsigned int bkt = (u >> shift) & 0xFF;
+      const unsigned int peers = __match_any_sync(live, bkt);
+      if ((threadIdx.x & 31) == static_cast<unsigned int>(__ffs(peers) - 1)) atomicAdd(&s_hist[bkt], __popc(peers));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(hist_b + PASS * 256 + i, s_hist[i]);
+}
+
+// tail[b] = {count of values <= v_k, bits of the smallest value > v_k, CTAs done, -}; the last CTA of a sample writes s_out[b]
+__global__ void __launch_bounds__(512) quantile_final_kernel(const float* __restrict__ v, long long n, unsigned int k, float frac, float floor_val,
+                                                             const unsigned int* __restrict__ hist, unsigned int* __restrict__ tail,
+                                                             float* __restrict__ s_out) {
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int red[16];
+  __shared__ float redf[16];
+  __shared__ int s_last;
+  const int b = blockIdx.y;
+  const float* vb = v + static_cast<long long>(b) * n;
+  unsigned int prefix, rank;
+  quantile_replay(hist + static_cast<size_t>(b) * 4 * 256, 4, k, s_hist, prefix, rank);
+  const float vk = __uint_as_float(prefix);
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long i0 = per * blockIdx.x, i1 = min(i0 + per, n);
+  unsigned int cnt = 0;
+  float nxt = 3.4e38f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const float a = fabsf(vb[i]);
+    if (a <= vk) ++cnt;
+    else nxt = fminf(nxt, a);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    nxt = fminf(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = cnt;
+    redf[threadIdx.x >> 5] = nxt;
+  }
+  __syncthreads();
+  unsigned int* tb = tail + static_cast<size_t>(b) * 4;
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w) {
+      cnt += red[w];
+      nxt = fminf(nxt, redf[w]);
+    }
+    atomicAdd(tb, cnt);
+    atomicMax(tb + 1, ~__float_as_uint(nxt));      // complemented bits: a larger word is a smaller (non-negative) value, and the zeroed workspace means "none yet"
+    __threadfence();
+    s_last = atomicAdd(tb + 2, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  const unsigned int count_le_total = __ldcg(tb);
+  const unsigned int nb = __ldcg(tb + 1);
+  const float nx = nb ? __uint_as_float(~nb) : 3.4e38f;
+  const float vk1 = (count_le_total > k + 1u || static_cast<long long>(k) + 1 >= n) ? vk : nx;
+  const float d = vk1 - vk;
+  const float q = frac < 0.5f ? vk + frac * d : vk1 - d * (1.f - frac);     // torch.lerp
+  s_out[b] = fmaxf(q, floor_val);
+}
+
 //   x0c = clamp(x0, -s, s) / s ; mean = c1[b] x0c + c2[b] x ; out = mean + sig[b] * noise      VDDP:951, 926-933, 963
 // sig[b] = (t > 0) * exp(0.5 * posterior_log_variance_clipped[t]) is prepared by the caller from the schedule.
 __global__ void posterior_kernel(const float* __restrict__ x0, const float* __restrict__ x, const float* __restrict__ noise,
@@ -297,10 +439,38 @@ extern "C" int vmm_cfg_x0(const float* x, const float* eps_cl, int has_null, flo
   return check_launch("vmm_cfg_x0");
 }
 
-extern "C" int vmm_abs_quantile(const float* v, int B, long long n, long long k, float frac, float floor_val, float* s_out, void* stream) {
-  if (!v || !s_out || n < 1 || k < 0 || k >= n) return set_error(VMM_ERR_ARG, "vmm_abs_quantile: bad arguments");
-  abs_quantile_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(v, n, k, frac, floor_val, s_out);
-  count_launch();
+extern "C" size_t vmm_abs_quantile_workspace(int B) {
+  return B > 0 ? static_cast<size_t>(B) * (4 * 256 + 4) * sizeof(unsigned int) : 0;
+}
+
+extern "C" int vmm_abs_quantile(const float* v, int B, long long n, long long k, float frac, float floor_val, float* s_out, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (!v || !s_out || B < 1 || n < 1 || k < 0 || k >= n) return set_error(VMM_ERR_ARG, "vmm_abs_quantile: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // small samples (or no workspace): one CTA per sample does all four passes; otherwise every pass is spread over the whole GPU
+  if (!workspace || n < 65536) {
+    abs_quantile_kernel<<<B, 1024, 0, st>>>(v, n, k, frac, floor_val, s_out);
+    count_launch();
+    return check_launch("vmm_abs_quantile");
+  }
+  if (n >= (1LL << 32)) return set_error(VMM_ERR_UNSUPPORTED, "vmm_abs_quantile: more than 2^32 elements per sample");
+  if (workspace_bytes < vmm_abs_quantile_workspace(B)) return set_error(VMM_ERR_ARG, "vmm_abs_quantile: workspace too small");
+  cudaError_t e = cudaMemsetAsync(workspace, 0, vmm_abs_quantile_workspace(B), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "vmm_abs_quantile: memset");
+  unsigned int* hist = static_cast<unsigned int*>(workspace);
+  unsigned int* tail = hist + static_cast<size_t>(B) * 4 * 256;
+  // CTAs per sample: the whole GPU over the B samples, at least 2048 elements per CTA
+  int gx = (num_sms() + B - 1) / B;
+  const long long max_gx = (n + 2047) / 2048;
+  if (gx > max_gx) gx = static_cast<int>(max_gx);
+  if (gx < 1) gx = 1;
+  const dim3 grid(gx, B);
+  quantile_hist_kernel<0><<<grid, 512, 0, st>>>(v, n, static_cast<unsigned int>(k), hist);
+  quantile_hist_kernel<1><<<grid, 512, 0, st>>>(v, n, static_cast<unsigned int>(k), hist);
+  quantile_hist_kernel<2><<<grid, 512, 0, st>>>(v, n, static_cast<unsigned int>(k), hist);
+  quantile_hist_kernel<3><<<grid, 512, 0, st>>>(v, n, static_cast<unsigned int>(k), hist);
+  quantile_final_kernel<<<grid, 512, 0, st>>>(v, n, static_cast<unsigned int>(k), frac, floor_val, hist, tail, s_out);
+  for (int i = 0; i < 5; ++i) count_launch();
   return check_launch("vmm_abs_quantile");
 }
 

@@ -476,8 +476,17 @@ def cfg_x0(x, eps_cl, has_null, w, sr, srm1, x0, eps_out, B, C_, F_, H, W):
                          stream_ptr()), "vmm_cfg_x0")
 
 
+_quantile_ws = {}
+
+
 def abs_quantile(v, B, n, k, frac, floor_val, s_out):
-    check(lib.vmm_abs_quantile(_p(v), B, n, k, frac, floor_val, _p(s_out), stream_ptr()), "vmm_abs_quantile")
+    # per-(device, batch) workspace of the multi-CTA selection (4 x 256 counters per sample), created on first use and zeroed by the library
+    # in stream order on every call; one buffer per key is enough because calls on a device are stream-ordered
+    key = (v.device, int(B))
+    ws = _quantile_ws.get(key)
+    if ws is None:
+        ws = _quantile_ws[key] = torch.empty(max(int(lib.vmm_abs_quantile_workspace(B)), 16), dtype=torch.uint8, device=v.device)
+    check(lib.vmm_abs_quantile(_p(v), B, n, k, frac, floor_val, _p(s_out), _p(ws), ws.numel(), stream_ptr()), "vmm_abs_quantile")
 
 
 def posterior_step(x0, x, noise, s, c1, c2, sig, out, B, per):
