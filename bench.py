@@ -467,7 +467,9 @@ def run_own(args):
     others = {"tattn_fwd": mem_kernel(["tattn_fwd"]), "tattn_bwd": mem_kernel(["tattn_bwd"]), "tattn_fused_fwd": mem_kernel(["ftattn_fwd"]),
               "lattn_fwd": mem_kernel(["lattn_fwd"]), "lattn_bwd": mem_kernel(["lattn_bwd"]),
               "sattn": mem_kernel(["sattn_fwd", "sattn_bwd"]), "groupnorm": mem_kernel(["gn_silu_fwd", "gn_silu_bwd"]),
-              "layernorm": mem_kernel(["ln_fwd", "ln_bwd"])}
+              "layernorm": mem_kernel(["ln_fwd", "ln_bwd"]),
+              # fused to_qkv data + weight gradient of the 64-channel levels (csrc/qkvbwd.cu): tcgen05, bound by the one read of d(qkv)
+              "qkv_bwd_fused": mem_kernel(["qkv_bwd"])}
     roof = {"bound": "tensor", "kernel": "vmm::cgemm_kernel (all launches of a step)", "achieved": achieved, "peak": pk["tflops_sustained"],
             "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
             "traffic_note": "average DRAM bytes per launch, ncu (profiles/r1_gemm_dram.json); algorithmic_bytes_per_launch = operands read once + output written once",

@@ -300,6 +300,11 @@ typedef struct {
 } vmm_wgrad_params;
 
 int vmm_wgrad(const vmm_wgrad_params* p, void* stream);
+/* Both consumers of an attention block's d(qkv) rows at a 64-channel level in one pass over them (autograd of to_qkv, VDDP:437 / 336):
+ *   dxn[row][c] = sum_k dqkv[row][k] * W[k][c]   (16-bit, [rows][64]);      dw[k][c] += sum_row dqkv[row][k] * xn[row][c]   (fp32 [768][64])
+ * dqkv: [rows][768] 16-bit; xn: [rows][64] 16-bit (the to_qkv input); wd: W^T packed K-major [64][768] 16-bit (the data-gradient pack
+ * vmm_cgemm takes for the same product).  Equivalent to one vmm_cgemm + one vmm_wgrad launch that each stream dqkv from HBM. */
+int vmm_qkv_bwd(const void* dqkv, const void* xn, const void* wd, void* dxn, float* dw, long long rows, int fmt, void* stream);
 int vmm_colsum(const void* x, long long rows, int n, long long ld, int fmt, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------

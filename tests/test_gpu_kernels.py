@@ -228,6 +228,33 @@ def test_quantile_edge_cases(ops):
         assert torch.equal(s, want), (n, s, want)
 
 
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("rows", [148 * 128, 148 * 128 * 3 + 77, 811008 // 8])
+def test_fused_qkv_backward(ops, dt, rows):
+    """vmm_qkv_bwd (csrc/qkvbwd.cu: dxn = dqkv W and dW += dqkv^T xn in one pass over dqkv, two shared-memory descriptors on the same tile)
+    against fp32 torch and against the two launches it replaces (vmm_cgemm + vmm_wgrad); ragged last tile; dW accumulates."""
+    torch.manual_seed(rows % 1000)
+    dqkv = (torch.randn(rows, 768, device="cuda") * 0.5).to(dt)
+    xn = torch.randn(rows, 64, device="cuda").to(dt)
+    w = (torch.randn(768, 64, device="cuda") * 0.1)
+    wd = ops.pack_linear(w.t(), dt)                      # [64][768] K-major, the data-gradient pack of blocks.pack_all
+    dxn = torch.empty(rows, 64, device="cuda", dtype=dt)
+    dw0 = torch.randn(768, 64, device="cuda")
+    dw = dw0.clone()
+    ops.qkv_bwd(dqkv, xn, wd, dxn, dw)
+    torch.cuda.synchronize()
+    want_dx = dqkv.float() @ wd.float()[:64].t()
+    want_dw = dqkv.float().t() @ xn.float()
+    assert rel(dxn, want_dx) < (3e-3 if dt == torch.float16 else 6e-3)
+    assert rel(dw - dw0, want_dw) < 2e-3
+    # the two-kernel path on the same inputs
+    dxn2 = torch.empty_like(dxn)
+    dw2 = dw0.clone()
+    ops.linear_rows([dqkv], wd, 64, dxn2)
+    ops.wgrad_linear(dqkv, [xn], dw2)
+    assert rel(dxn, dxn2) < 1e-3 and rel(dw - dw0, dw2 - dw0) < 1e-3
+
+
 @pytest.mark.parametrize("B,n", [(4, 304128), (1, 65536), (3, 70001), (8, 304128), (2, 1_200_000)])
 def test_quantile_multi_cta_path_is_exact(ops, B, n):
     """n >= 65536: every radix pass is one launch over the whole GPU (csrc/sampler.cu quantile_hist_kernel / quantile_final_kernel).

@@ -206,8 +206,12 @@ class AttnBlockFn(torch.autograd.Function):
             ops.sattn_bwd(qkv, ekv, ao, dao, lse, dqkv, dekv, B * Fr, H * W, heads)
         # to_qkv
         dxn = torch.empty_like(xn)
-        ops.linear_rows([dqkv], P[pre + "qkv.wd"], Cc, dxn)
-        ops.wgrad_linear(dqkv, [xn], sd[pre + "to_qkv.weight"].grad)
+        if ops.qkv_bwd_eligible(_flat(dqkv), _flat(xn)):
+            # 64-channel levels: one pass over the 768-wide gradient rows for both products (csrc/qkvbwd.cu)
+            ops.qkv_bwd(_flat(dqkv), _flat(xn), P[pre + "qkv.wd"], _flat(dxn), sd[pre + "to_qkv.weight"].grad)
+        else:
+            ops.linear_rows([dqkv], P[pre + "qkv.wd"], Cc, dxn)
+            ops.wgrad_linear(dqkv, [xn], sd[pre + "to_qkv.weight"].grad)
         # PreNorm + the Residual skip
         norm_pre = pre[: pre.index("fn.fn.") + 3]
         gamma = sd[norm_pre + "norm.gamma"]

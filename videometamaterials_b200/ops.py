@@ -550,6 +550,24 @@ def wgrad(a_views: Sequence[torch.Tensor], b_views: Sequence[torch.Tensor], taps
         _prof_end("wgrad" + tag, 2.0 * bf * oh * ow * n * sum(tp[4] for tp in taps), e0, nbytes)
 
 
+def qkv_bwd(dqkv2d: torch.Tensor, xn2d: torch.Tensor, wd: torch.Tensor, dxn2d: torch.Tensor, dw: torch.Tensor) -> None:
+    """dxn = dqkv @ W and dW += dqkv^T @ xn of a to_qkv projection with 64 input channels, reading dqkv once (csrc/qkvbwd.cu)."""
+    _require_cuda(dqkv2d, xn2d, wd, dxn2d, dw)
+    rows = dqkv2d.shape[0]
+    assert dqkv2d.shape[1] == 768 and xn2d.shape == (rows, 64) and dxn2d.shape == (rows, 64) and wd.shape == (64, 768) and dw.numel() == 768 * 64
+    assert dqkv2d.is_contiguous() and xn2d.is_contiguous() and dxn2d.is_contiguous() and wd.is_contiguous() and dw.is_contiguous() and dw.dtype == torch.float32
+    e0 = _prof_begin()
+    check(lib.vmm_qkv_bwd(_p(dqkv2d), _p(xn2d), _p(wd), _p(dxn2d), _p(dw), rows, fmt_of(dqkv2d), stream_ptr()), "vmm_qkv_bwd")
+    _prof_end("qkv_bwd", 4.0 * rows * 768 * 64, e0, nbytes=rows * (768 + 64 + 64) * 2.0)
+
+
+def qkv_bwd_eligible(dqkv2d: torch.Tensor, xn2d: torch.Tensor) -> bool:
+    return FUSED_QKV_BWD and dqkv2d.shape[1] == 768 and xn2d.shape[1] == 64 and dqkv2d.shape[0] >= 128 * 148
+
+
+FUSED_QKV_BWD = os.environ.get("VMM_FUSED_QKV_BWD", "1") != "0"
+
+
 def colsum(x2d: torch.Tensor, out: torch.Tensor) -> None:
     """out[n] (fp32, accumulated) += sum over rows of x2d[:, n]."""
     rows, n = x2d.shape
