@@ -305,6 +305,11 @@ int vmm_wgrad(const vmm_wgrad_params* p, void* stream);
  * dqkv: [rows][768] 16-bit; xn: [rows][64] 16-bit (the to_qkv input); wd: W^T packed K-major [64][768] 16-bit (the data-gradient pack
  * vmm_cgemm takes for the same product).  Equivalent to one vmm_cgemm + one vmm_wgrad launch that each stream dqkv from HBM. */
 int vmm_qkv_bwd(const void* dqkv, const void* xn, const void* wd, void* dxn, float* dw, long long rows, int fmt, void* stream);
+/* The same with the PreNorm + Residual in front of to_qkv folded into the epilogue (VDDP:245-264, 131-137; what vmm_ln_bwd computes from
+ * the stored dxn rows): dx[row] = LayerNorm'(x[row]; gamma)(dxn[row]) + dres[row] (16-bit [rows][64]), dgamma[c] += sum_row dxn[row][c] * xhat[row][c].
+ * x: the block input, dres: the gradient arriving over the residual connection.  dxn never reaches HBM. */
+int vmm_qkv_ln_bwd(const void* dqkv, const void* xn, const void* wd, const void* x, const void* dres, const float* gamma, float eps, void* dx,
+                   float* dw, float* dgamma, long long rows, int fmt, void* stream);
 int vmm_colsum(const void* x, long long rows, int n, long long ld, int fmt, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -37,3 +37,18 @@ t2 = timed(two)
 t1 = timed(lambda: ops.qkv_bwd(dqkv, xn, wd, dxn, dw))
 nbytes = rows * (768 + 64 + 64) * 2
 print(f"two launches {t2:.0f} us | fused {t1:.0f} us ({nbytes / t1 / 1e3:.0f} GB/s of dqkv + xn read + dxn written once)")
+x = torch.randn(rows, 64, device="cuda").to(dt)
+dres = torch.randn(rows, 64, device="cuda").to(dt)
+gamma = torch.ones(64, device="cuda")
+dx = torch.empty_like(x)
+dg = torch.zeros(64, device="cuda")
+
+
+def three():
+    two()
+    ops.ln_bwd(x, dxn, dres, dx, gamma, dg)
+
+
+t3 = timed(three)
+t4 = timed(lambda: ops.qkv_ln_bwd(dqkv, xn, wd, x, dres, gamma, dx, dw, dg))
+print(f"with the LayerNorm backward: three launches {t3:.0f} us | fused {t4:.0f} us ({rows * (768 + 4 * 64) * 2 / t4 / 1e3:.0f} GB/s)")

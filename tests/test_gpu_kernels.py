@@ -253,6 +253,24 @@ def test_fused_qkv_backward(ops, dt, rows):
     ops.linear_rows([dqkv], wd, 64, dxn2)
     ops.wgrad_linear(dqkv, [xn], dw2)
     assert rel(dxn, dxn2) < 1e-3 and rel(dw - dw0, dw2 - dw0) < 1e-3
+    # LayerNorm form: dx = LN'(x)(dxn) + dres and dgamma in the epilogue, against vmm_ln_bwd on the stored rows and against fp32 autograd
+    x = torch.randn(rows, 64, device="cuda").to(dt)
+    dres = torch.randn(rows, 64, device="cuda").to(dt)
+    gamma = torch.rand(64, device="cuda") + 0.5
+    dx = torch.empty_like(x)
+    dw3, dg = dw0.clone(), torch.zeros(64, device="cuda")
+    ops.qkv_ln_bwd(dqkv, xn, wd, x, dres, gamma, dx, dw3, dg)
+    dx2, dg2 = torch.empty_like(x), torch.zeros(64, device="cuda")
+    ops.ln_bwd(x, dxn2, dres, dx2, gamma, dg2)
+    torch.cuda.synchronize()
+    assert rel(dw3 - dw0, want_dw) < 2e-3
+    xf = x.float().requires_grad_(True)
+    gf = gamma.clone().requires_grad_(True)
+    y = (xf - xf.mean(1, keepdim=True)) / (xf.var(1, unbiased=False, keepdim=True) + 1e-5).sqrt() * gf
+    y.backward(want_dx)
+    assert rel(dx, xf.grad + dres.float()) < (3e-3 if dt == torch.float16 else 8e-3)
+    assert rel(dg, gf.grad) < 3e-3
+    assert rel(dx, dx2) < 6e-3 and rel(dg, dg2) < 3e-3      # (the two-launch path rounds dxn to 16 bits in between)
 
 
 @pytest.mark.parametrize("B,n", [(4, 304128), (1, 65536), (3, 70001), (8, 304128), (2, 1_200_000)])

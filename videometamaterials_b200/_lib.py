@@ -93,7 +93,7 @@ class VmmError(RuntimeError):
     pass
 
 
-ABI_VERSION = 6          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
+ABI_VERSION = 7          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
 
 
 def _load() -> C.CDLL:
@@ -137,6 +137,7 @@ _SIGNATURES = {
     "vmm_wgrad": [C.POINTER(WgradParams), _P],
     "vmm_colsum": [_P, _L, _I, _L, _I, _P, _P],
     "vmm_qkv_bwd": [_P, _P, _P, _P, _P, _L, _I, _P],
+    "vmm_qkv_ln_bwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _L, _I, _P],
     "vmm_gn_silu_fwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P],
     "vmm_gn_silu_bwd_workspace": [_I, _I, _I],
     "vmm_gn_silu_bwd": [_P, _P, _P, _I, _I, _L, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _Z, _P],

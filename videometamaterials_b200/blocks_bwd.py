@@ -205,18 +205,23 @@ class AttnBlockFn(torch.autograd.Function):
             (lse,) = extra
             ops.sattn_bwd(qkv, ekv, ao, dao, lse, dqkv, dekv, B * Fr, H * W, heads)
         # to_qkv
-        dxn = torch.empty_like(xn)
-        if ops.qkv_bwd_eligible(_flat(dqkv), _flat(xn)):
-            # 64-channel levels: one pass over the 768-wide gradient rows for both products (csrc/qkvbwd.cu)
-            ops.qkv_bwd(_flat(dqkv), _flat(xn), P[pre + "qkv.wd"], _flat(dxn), sd[pre + "to_qkv.weight"].grad)
-        else:
-            ops.linear_rows([dqkv], P[pre + "qkv.wd"], Cc, dxn)
-            ops.wgrad_linear(dqkv, [xn], sd[pre + "to_qkv.weight"].grad)
-        # PreNorm + the Residual skip
         norm_pre = pre[: pre.index("fn.fn.") + 3]
         gamma = sd[norm_pre + "norm.gamma"]
         dx = torch.empty_like(x)
-        ops.ln_bwd(_flat(x), dxn, d2, _flat(dx), gamma.reshape(-1), gamma.grad.reshape(-1))
+        if ops.qkv_bwd_eligible(_flat(dqkv), _flat(xn)) and ops.FUSED_QKV_LN_BWD:
+            # 64-channel levels: ONE pass over the 768-wide gradient rows for the data gradient and the weight gradient of to_qkv, with the
+            # PreNorm backward + the Residual skip in the epilogue (csrc/qkvbwd.cu): dxn never reaches HBM
+            ops.qkv_ln_bwd(_flat(dqkv), _flat(xn), P[pre + "qkv.wd"], _flat(x), d2, gamma.reshape(-1), _flat(dx), sd[pre + "to_qkv.weight"].grad,
+                           gamma.grad.reshape(-1))
+        else:
+            dxn = torch.empty_like(xn)
+            if ops.qkv_bwd_eligible(_flat(dqkv), _flat(xn)):
+                ops.qkv_bwd(_flat(dqkv), _flat(xn), P[pre + "qkv.wd"], _flat(dxn), sd[pre + "to_qkv.weight"].grad)
+            else:
+                ops.linear_rows([dqkv], P[pre + "qkv.wd"], Cc, dxn)
+                ops.wgrad_linear(dqkv, [xn], sd[pre + "to_qkv.weight"].grad)
+            # PreNorm + the Residual skip
+            ops.ln_bwd(_flat(x), dxn, d2, _flat(dx), gamma.reshape(-1), gamma.grad.reshape(-1))
         if env.cond is not None:
             return None, None, None, dx, None, None, None
         return None, None, None, dx, dekv, dbias, None

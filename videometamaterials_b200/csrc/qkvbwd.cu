@@ -28,11 +28,17 @@ constexpr int QB_SMEM = QB_OFF_CTL + 256 + 1024;
 
 struct QbDev {
   CUtensorMap dqmap, xmap, wmap;
-  uint16_t* dxn;
+  uint16_t* dxn;          // plain form: the data gradient rows; LayerNorm form: dx (gradient of the block input)
   float* dw;
   long long rows;
   int tiles;
   uint32_t idesc_w, idesc_d;
+  // LayerNorm form (the PreNorm + Residual in front of to_qkv, VDDP:245-264, 131-137): dx = LN'(x; gamma)(dxn) + dres, dgamma += sum dxn * xhat
+  const uint16_t* x;
+  const uint16_t* dres;
+  const float* gamma;
+  float* dgamma;
+  float eps;
 };
 
 struct __align__(8) QbCtl {
@@ -44,7 +50,7 @@ struct __align__(8) QbCtl {
   uint32_t pad;
 };
 
-template <int FMT>
+template <int FMT, bool LN>
 __global__ void __launch_bounds__(256, 1) qkv_bwd_kernel(const __grid_constant__ QbDev p) {
   extern __shared__ uint8_t qb_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(qb_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -52,7 +58,9 @@ __global__ void __launch_bounds__(256, 1) qkv_bwd_kernel(const __grid_constant__
   uint8_t* ring = smem + QB_OFF_RING;
   uint8_t* xsm = smem + QB_OFF_XN;
   QbCtl* ctl = reinterpret_cast<QbCtl*>(smem + QB_OFF_CTL);
+  __shared__ float s_gamma[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (LN && threadIdx.x < 64) s_gamma[threadIdx.x] = __ldg(p.gamma + threadIdx.x);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.dqmap);
     tma_prefetch_desc(&p.xmap);
@@ -165,9 +173,22 @@ __global__ void __launch_bounds__(256, 1) qkv_bwd_kernel(const __grid_constant__
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float dg[LN ? 64 : 1];
+    if (LN) {
+#pragma unroll
+      for (int c = 0; c < 64; ++c) dg[c] = 0.f;
+    }
     int it = 0;
     for (int t = t0; t < t1; ++t, ++it) {
       const int db = it & 1;
+      const long long r = static_cast<long long>(t) * 128 + row;
+      const bool live = r < p.rows;
+      uint4 xr[LN ? 8 : 1];
+      if (LN) {                       // the row of the block input, requested before the accumulator is waited for
+        const uint4* xp = reinterpret_cast<const uint4*>(p.x + (live ? r : 0) * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xr[j] = live ? __ldg(xp + j) : make_uint4(0u, 0u, 0u, 0u);
+      }
       mbar_wait(&ctl->dfull[db], (it >> 1) & 1);
       tc_fence_after();
       float v[64];
@@ -176,8 +197,59 @@ __global__ void __launch_bounds__(256, 1) qkv_bwd_kernel(const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&ctl->dempty[db]);          // the accumulator is in registers: the next tile but one may overwrite it
-      const long long r = static_cast<long long>(t) * 128 + row;
-      if (r < p.rows) {
+      if (LN) {
+        // channel LayerNorm backward of this row (one thread = one position = 64 channels), as vmm_ln_bwd computes it
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xr);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 f = unpack2_h16(xw[j], FMT);
+          sum += f.x + f.y;
+        }
+        const float mean = sum * (1.f / 64.f);
+        float qq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 f = unpack2_h16(xw[j], FMT);
+          qq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+        }
+        const float rstd = rsqrtf(qq * (1.f / 64.f) + p.eps);
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 f = unpack2_h16(xw[j], FMT);
+          const float xh0 = (f.x - mean) * rstd, xh1 = (f.y - mean) * rstd;
+          dg[2 * j] += v[2 * j] * xh0;
+          dg[2 * j + 1] += v[2 * j + 1] * xh1;
+          const float g0 = v[2 * j] * s_gamma[2 * j], g1 = v[2 * j + 1] * s_gamma[2 * j + 1];
+          v[2 * j] = g0;
+          v[2 * j + 1] = g1;
+          a1 += g0 + g1;
+          a2 += g0 * xh0 + g1 * xh1;
+        }
+        a1 *= (1.f / 64.f);
+        a2 *= (1.f / 64.f);
+        if (live) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.dres + r * 64);
+          uint4* dst = reinterpret_cast<uint4*>(p.dxn + r * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 rr = __ldg(rp + j);
+            const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int c = 8 * j + 2 * u;
+              const float2 f = unpack2_h16(xw[4 * j + u], FMT);
+              const float2 d2 = unpack2_h16(rw[u], FMT);
+              const float o0 = rstd * (v[c] - a1 - (f.x - mean) * rstd * a2) + d2.x;
+              const float o1 = rstd * (v[c + 1] - a1 - (f.y - mean) * rstd * a2) + d2.y;
+              o[u] = pack2_h16(o0, o1, FMT);
+            }
+            dst[j] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      } else if (live) {
         uint4* dst = reinterpret_cast<uint4*>(p.dxn + r * 64);     // one 128-byte line per thread
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -202,6 +274,18 @@ __global__ void __launch_bounds__(256, 1) qkv_bwd_kernel(const __grid_constant__
                          : "memory");
         }
       }
+      if (LN) {
+        // every MMA has completed (accw_full): the stage ring is free.  [128 rows][64 + 1] partials -> one global add per channel
+        float* red = reinterpret_cast<float*>(ring);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) red[row * 65 + c] = dg[c];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (row < 64) {
+          float acc = 0.f;
+          for (int rr = 0; rr < 128; ++rr) acc += red[rr * 65 + row];
+          atomicAdd(p.dgamma + row, acc);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -216,12 +300,15 @@ __global__ void __launch_bounds__(256, 1) qkv_bwd_kernel(const __grid_constant__
 
 using namespace vmm;
 
-extern "C" int vmm_qkv_bwd(const void* dqkv, const void* xn, const void* wd, void* dxn, float* dw, long long rows, int fmt, void* stream_) {
-  if (!dqkv || !xn || !wd || !dxn || !dw || rows < 1) return set_error(VMM_ERR_ARG, "vmm_qkv_bwd: bad arguments");
+static int qkv_bwd_launch(const void* dqkv, const void* xn, const void* wd, void* out, float* dw, long long rows, int fmt, const void* x,
+                          const void* dres, const float* gamma, float* dgamma, float eps, bool ln, cudaStream_t stream, const char* who) {
+  if (!dqkv || !xn || !wd || !out || !dw || rows < 1) return set_error(VMM_ERR_ARG, "vmm_qkv_bwd: bad arguments");
+  if (ln && (!x || !dres || !gamma || !dgamma)) return set_error(VMM_ERR_ARG, "vmm_qkv_ln_bwd: null pointer");
   if (fmt != VMM_FMT_F16 && fmt != VMM_FMT_BF16) return set_error(VMM_ERR_ARG, "vmm_qkv_bwd: bad fmt");
   if (rows >= (1LL << 31)) return set_error(VMM_ERR_UNSUPPORTED, "vmm_qkv_bwd: more than 2^31 rows");
-  if ((reinterpret_cast<uintptr_t>(dw) & 15) || (reinterpret_cast<uintptr_t>(dxn) & 15)) return set_error(VMM_ERR_ARG, "vmm_qkv_bwd: dw / dxn must be 16-byte aligned");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if ((reinterpret_cast<uintptr_t>(dw) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (reinterpret_cast<uintptr_t>(dres) & 15))
+    return set_error(VMM_ERR_ARG, "vmm_qkv_bwd: pointers must be 16-byte aligned");
   QbDev d;
   memset(&d, 0, sizeof(d));
   const CUtensorMapDataType dt = fmt == VMM_FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -246,26 +333,46 @@ extern "C" int vmm_qkv_bwd(const void* dqkv, const void* xn, const void* wd, voi
     int rc = encode_tensor_map(&d.wmap, dt, 2, wd, gdim, gstr, box, true);
     if (rc) return rc;
   }
-  d.dxn = static_cast<uint16_t*>(dxn);
+  d.dxn = static_cast<uint16_t*>(out);
   d.dw = dw;
   d.rows = rows;
   d.tiles = static_cast<int>((rows + 127) / 128);
   d.idesc_w = make_idesc_f16(128, 64, fmt, 1, 1);
   d.idesc_d = make_idesc_f16(128, 64, fmt, 0, 0);
+  d.x = static_cast<const uint16_t*>(x);
+  d.dres = static_cast<const uint16_t*>(dres);
+  d.gamma = gamma;
+  d.dgamma = dgamma;
+  d.eps = eps;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(qkv_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, QB_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(qkv_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QB_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(qkv_bwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qkv_bwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qkv_bwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qkv_bwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QB_SMEM);
     if (e != cudaSuccess) return set_cuda_error(e, "vmm_qkv_bwd: cudaFuncSetAttribute");
     attr_set = true;
   }
   const int sms = num_sms();
   if (sms <= 0) return set_error(VMM_ERR_CUDA, "vmm_qkv_bwd: no CUDA device");
   const int grid = d.tiles < sms ? d.tiles : sms;
-  if (fmt == VMM_FMT_F16)
-    qkv_bwd_kernel<0><<<grid, 256, QB_SMEM, stream>>>(d);
-  else
-    qkv_bwd_kernel<1><<<grid, 256, QB_SMEM, stream>>>(d);
+  if (fmt == VMM_FMT_F16) {
+    if (ln) qkv_bwd_kernel<0, true><<<grid, 256, QB_SMEM, stream>>>(d);
+    else qkv_bwd_kernel<0, false><<<grid, 256, QB_SMEM, stream>>>(d);
+  } else {
+    if (ln) qkv_bwd_kernel<1, true><<<grid, 256, QB_SMEM, stream>>>(d);
+    else qkv_bwd_kernel<1, false><<<grid, 256, QB_SMEM, stream>>>(d);
+  }
   count_launch();
-  return check_launch("vmm_qkv_bwd");
+  return check_launch(who);
+}
+
+extern "C" int vmm_qkv_bwd(const void* dqkv, const void* xn, const void* wd, void* dxn, float* dw, long long rows, int fmt, void* stream_) {
+  return qkv_bwd_launch(dqkv, xn, wd, dxn, dw, rows, fmt, nullptr, nullptr, nullptr, nullptr, 0.f, false, static_cast<cudaStream_t>(stream_),
+                        "vmm_qkv_bwd");
+}
+
+extern "C" int vmm_qkv_ln_bwd(const void* dqkv, const void* xn, const void* wd, const void* x, const void* dres, const float* gamma, float eps,
+                              void* dx, float* dw, float* dgamma, long long rows, int fmt, void* stream_) {
+  return qkv_bwd_launch(dqkv, xn, wd, dx, dw, rows, fmt, x, dres, gamma, dgamma, eps, true, static_cast<cudaStream_t>(stream_), "vmm_qkv_ln_bwd");
 }

@@ -561,11 +561,27 @@ def qkv_bwd(dqkv2d: torch.Tensor, xn2d: torch.Tensor, wd: torch.Tensor, dxn2d: t
     _prof_end("qkv_bwd", 4.0 * rows * 768 * 64, e0, nbytes=rows * (768 + 64 + 64) * 2.0)
 
 
+def qkv_ln_bwd(dqkv2d, xn2d, wd, x2d, dres2d, gamma, dx2d, dw, dgamma, eps=1e-5) -> None:
+    """qkv_bwd with the LayerNorm backward + residual add of the block in its epilogue: dx = LN'(x)(dqkv @ W) + dres, dgamma += ..., dW += ..."""
+    _require_cuda(dqkv2d, xn2d, wd, x2d, dres2d, dx2d, dw, dgamma)
+    rows = dqkv2d.shape[0]
+    assert dqkv2d.shape[1] == 768 and xn2d.shape == (rows, 64) and x2d.shape == (rows, 64) and dres2d.shape == (rows, 64) and dx2d.shape == (rows, 64)
+    assert wd.shape == (64, 768) and dw.numel() == 768 * 64 and gamma.numel() == 64 and dgamma.numel() == 64
+    for t in (dqkv2d, xn2d, wd, x2d, dres2d, dx2d, dw, gamma, dgamma):
+        assert t.is_contiguous()
+    assert dw.dtype == torch.float32 and gamma.dtype == torch.float32 and dgamma.dtype == torch.float32
+    e0 = _prof_begin()
+    check(lib.vmm_qkv_ln_bwd(_p(dqkv2d), _p(xn2d), _p(wd), _p(x2d), _p(dres2d), _p(gamma), eps, _p(dx2d), _p(dw), _p(dgamma), rows,
+                             fmt_of(dqkv2d), stream_ptr()), "vmm_qkv_ln_bwd")
+    _prof_end("qkv_bwd", 4.0 * rows * 768 * 64, e0, nbytes=rows * (768 + 4 * 64) * 2.0)
+
+
 def qkv_bwd_eligible(dqkv2d: torch.Tensor, xn2d: torch.Tensor) -> bool:
     return FUSED_QKV_BWD and dqkv2d.shape[1] == 768 and xn2d.shape[1] == 64 and dqkv2d.shape[0] >= 128 * 148
 
 
 FUSED_QKV_BWD = os.environ.get("VMM_FUSED_QKV_BWD", "1") != "0"
+FUSED_QKV_LN_BWD = os.environ.get("VMM_FUSED_QKV_LN_BWD", "1") != "0"
 
 
 def colsum(x2d: torch.Tensor, out: torch.Tensor) -> None:
