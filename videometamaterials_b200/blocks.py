@@ -504,6 +504,29 @@ def _flat(x: Tensor) -> Tensor:
     return x.reshape(-1, x.shape[-1])
 
 
+class _StatsPool:
+    """GroupNorm statistics buffers (fp64 sum / sum of squares per sample and group, accumulated by the conv epilogue) of one network
+    pass: ONE zero fill at the start of the pass instead of one small fill kernel per convolution (38 per forward)."""
+    buf: Optional[Tensor] = None
+    used = 0
+
+
+def begin_stats_pool(n: int, B: int, groups: int, device) -> None:
+    _StatsPool.buf = torch.zeros(n, B, groups, 2, dtype=torch.float64, device=device)
+    _StatsPool.used = 0
+
+
+def _stats(B: int, groups: int, device) -> Tensor:
+    buf = _StatsPool.buf
+    if buf is not None and _StatsPool.used < buf.shape[0] and buf.shape[1:3] == (B, groups) and buf.device == device:
+        _StatsPool.used += 1
+        # an independent tensor on the pool's storage (not an autograd view: the blocks save their statistics for backward, and views of one
+        # base would share a version counter)
+        per = B * groups * 2
+        return torch.empty(0, dtype=buf.dtype, device=device).set_(buf.untyped_storage(), (_StatsPool.used - 1) * per, (B, groups, 2))
+    return torch.zeros(B, groups, 2, dtype=torch.float64, device=device)
+
+
 def resnet_fwd(P, sd, pre: str, xs: Sequence[Tensor], ss: Optional[Tensor], groups: int, mode: str = "zeros"):
     """ResnetBlock VDDP:299-311 on an implicit channel-concat of xs; `mode` = the padding mode of the two 3x3 convs."""
     B, Fr, H, W, _ = xs[0].shape
@@ -512,13 +535,13 @@ def resnet_fwd(P, sd, pre: str, xs: Sequence[Tensor], ss: Optional[Tensor], grou
     xv = [ops.as_bfhwc(x) for x in xs]
     pix = Fr * H * W
     h1 = torch.empty(B, Fr, H, W, cout, dtype=dt, device=dev)
-    st1 = torch.zeros(B, groups, 2, dtype=torch.float64, device=dev)
+    st1 = _stats(B, groups, dev)
     ops.conv3x3(xv, P[pre + "block1.w"], cout, h1, mode=mode, bias=sd[pre + "block1.proj.bias"], gn_stats=st1, gn_group=cout // groups,
                 frames_per_sample=Fr)
     a1 = torch.empty_like(h1)
     ops.gn_silu_fwd(h1, a1, st1, sd[pre + "block1.norm.weight"], sd[pre + "block1.norm.bias"], ss, B, pix, cout, groups)
     h2 = torch.empty_like(h1)
-    st2 = torch.zeros(B, groups, 2, dtype=torch.float64, device=dev)
+    st2 = _stats(B, groups, dev)
     ops.conv3x3([ops.as_bfhwc(a1)], P[pre + "block2.w"], cout, h2, mode=mode, bias=sd[pre + "block2.proj.bias"], gn_stats=st2,
                 gn_group=cout // groups, frames_per_sample=Fr)
     out = torch.empty_like(h1)
@@ -634,6 +657,7 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
     g, heads, pm = model.groups, model.heads, model.padding_mode
     frames = x.shape[2]
     ss, ekv, bias, rot = conditioning(model, time, cond, null_mask, frames)
+    begin_stats_pool(2 * len(resnet_names(model)), x.shape[0], g, x.device)
     tkv = (lambda q: ekv[q]) if model.use_temporal_attention_cond else (lambda q: None)      # VDDP:792-795
     h, _ = init_fwd(P, sd, model, x.float(), noise, qcoef)
     h, _ = attn_block_fwd(P, sd, "init_temporal_attn.fn.fn.fn.", "temporal", h, None, bias, rot, heads, keep=False)

@@ -374,6 +374,7 @@ def _trunk(model, x0: Tensor, noise: Optional[Tensor], qcoef, t: Tensor, cond: T
     L = len(model.dim_mults)
     frames = x0.shape[2]
     ss, ekv, bias, rot, env.cond = blocks.conditioning_state(model, t, cond, null_mask, frames)
+    blocks.begin_stats_pool(2 * len(blocks.resnet_names(model)), x0.shape[0], model.groups, x0.device)
     tkv = (lambda q: ekv[q]) if model.use_temporal_attention_cond else (lambda q: None)      # VDDP:792-795
     anchor = torch.zeros(1, device=x0.device, requires_grad=True)
     a, c, s = qcoef if qcoef is not None else (None, None, None)
