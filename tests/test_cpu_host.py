@@ -218,10 +218,12 @@ def test_main_config_wiring(golden_dir, tmp_path):
     assert (diffusion.image_size, diffusion.num_frames, diffusion.channels) == (96, 11, 3)
     _, ddim = main.build_model(dict(cfg, sampling_timesteps=250))
     assert ddim.is_ddim_sampling
-    for key, val in (("per_frame_cond", False), ("unet_cond_to_time", "concat"),
-                     ("unet_cond_att_GRU", True), ("unet_temporal_att_cond", False)):
+    for key, val in (("per_frame_cond", False), ("unet_cond_to_time", "multiply"), ("unet_cond_att_GRU", True)):
         with pytest.raises(NotImplementedError):
             main.build_model(dict(cfg, **{key: val}))
+    # the other switches of the config surface build (their arithmetic is checked against the reference-pinned oracle elsewhere)
+    m2, _ = main.build_model(dict(cfg, unet_cond_to_time="concat", unet_temporal_att_cond=False, unet_dim=16))
+    assert m2.downs[0][0].mlp[1].weight.shape == (32, 128) and not m2.use_temporal_attention_cond
     bad = tmp_path / "model.yaml"
     bad.write_text(yaml.dump({k: v for k, v in cfg.items() if k != "unet_dim"}))
     with pytest.raises(KeyError):
