@@ -50,7 +50,7 @@ assert GIF_FRAME_DTYPE.itemsize == C.sizeof(_lib.GifFrame) == 32
 
 
 def decode_gifs(blobs: Sequence[bytes], frames_per_file: Optional[int], size_hw: Tuple[int, int], device, names: Optional[Sequence[str]] = None,
-                chunk_bytes: int = 1 << 30, pil_compat: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+                chunk_bytes: int = 1 << 30, pil_compat: bool = True, timing: Optional[list] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Decode GIF files on the device: (u8 (n_files, frames_per_file, H, W) luminance, int32 (n_files,) frames each file holds, capped
     at frames_per_file; None = the largest frame count among the files).  Launched in chunks of about `chunk_bytes` of workspace."""
     H, W = size_hw
@@ -89,9 +89,16 @@ def decode_gifs(blobs: Sequence[bytes], frames_per_file: Optional[int], size_hw:
         d_fr = torch.from_numpy(fr.view(np.uint8).reshape(-1).copy()).to(device)
         d_ws = torch.empty(ws_total, dtype=torch.uint8, device=device)
         d_err = torch.zeros(1, dtype=torch.int32, device=device)
+        if timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(_lib.lib.vmm_gif_decode(d_bytes.data_ptr(), d_fofs.data_ptr(), d_begin.data_ptr(), d_fr.data_ptr(), i1 - i0, len(fr),
                                            frames_per_file, H, W, d_ws.data_ptr(), out[i0:i1].data_ptr(), d_err.data_ptr(), ops.stream_ptr()),
                    "vmm_gif_decode")
+        if timing is not None:
+            e1.record()
+            torch.cuda.synchronize()
+            timing.append(e0.elapsed_time(e1))          # ms of the two decode kernels of this chunk
         bad = int(d_err.item())         # the read-back also keeps this chunk's buffers alive until its kernels are done
         if bad:
             raise _lib.VmmError(f"vmm_gif_decode: {bad} frame(s) with a short or invalid LZW stream in {label(i0)} .. {label(i1 - 1)}")
