@@ -333,7 +333,9 @@ int vmm_colsum(const void* x, long long rows, int n, long long ld, int fmt, floa
  * (n_files + 1 entries), frame_begin[i] .. frame_begin[i+1] = its rows in `frames` (n_files + 1 entries,
  * frame_begin[n_files] = n_frames_total; the tables vmm_gif_scan produced, copied to the device).
  * Kernel 1 (one warp per frame) walks the sub-block chain and decodes the LZW stream into `index_ws`
- * (sum of w*h over all frames bytes; vmm_gif_frame.px_ofs = the frame's offset in it).  Kernel 2 (one CTA per
+ * (vmm_gif_frame.px_ofs = the frame's offset in it; multiples of 16 get 16-byte stores).  max_frame_px = the largest w*h in
+ * `frames` (the caller has the table on the host): up to 12 288 pixels a frame's index stream is built in shared memory and
+ * written out once; <= 0 or larger frames decode in global memory.  Kernel 2 (one CTA per
  * file) composites the frames in order on the logical screen (frame rectangle, interlace, transparency, disposal
  * 0 / 1 / 2) and writes out[file][frame][H][W] 8-bit luminance = ITU-R 601-2 luma of the palette colour, which is
  * what PIL's convert('L') returns for every frame of such a file.  Every file has the logical screen H x W and at
@@ -373,8 +375,8 @@ typedef struct {
 #define VMM_GIF_PIL_COMPAT 1 /* reproduce Pillow's handling of a palette that arrives while the image is still in mode 'L' (above) */
 int vmm_gif_scan(const uint8_t* file, size_t nbytes, int flags, vmm_gif_info* info, vmm_gif_frame* frames, int max_frames);
 int vmm_gif_decode(const uint8_t* files, const uint64_t* file_ofs, const int32_t* frame_begin, const vmm_gif_frame* frames,
-                   int n_files, int n_frames_total, int frames_per_file, int H, int W, uint8_t* index_ws, uint8_t* out, int32_t* err,
-                   void* stream);
+                   int n_files, int n_frames_total, int frames_per_file, int H, int W, int max_frame_px, uint8_t* index_ws, uint8_t* out,
+                   int32_t* err, void* stream);
 int vmm_dataset_items(const uint8_t* u8, const int64_t* index, int n, int n_planes, int topo_plane, int n_ch,
                       const int32_t* ch_plane, const int32_t* ch_has_range, const float* sample_rng, const float* global_rng,
                       const int32_t* sample_frames, int frames, int frames_out, int hw, float* out, void* stream);

@@ -222,6 +222,8 @@ def corpus(seed: int = 0):
 
     save('L_noise_96x96x11', grey(96, 96, 11))                                   # the dataset's own format (interlaced by PIL's default)
     save('L_noise_not_interlaced', grey(96, 96, 3), interlace=False)
+    save('L_noise_128x128', grey(128, 128, 3))                                   # above the shared-memory decode limit of the kernel: global-memory form
+    save('L_boxes_160x120', drifting(120, 160, 4))
     save('L_boxes', drifting(64, 80, 6))
     save('L_smooth', [Image.fromarray((np.add.outer(np.arange(96), np.arange(96)) * (k + 1) % 256).astype(np.uint8), 'L') for k in range(4)])
     save('L_binary_mask', [Image.fromarray(((rng.random((96, 96)) > 0.3) * 255).astype(np.uint8), 'L') for _ in range(11)])

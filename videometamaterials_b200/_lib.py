@@ -93,7 +93,7 @@ class VmmError(RuntimeError):
     pass
 
 
-ABI_VERSION = 7          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
+ABI_VERSION = 8          # must equal vmm_abi_version() of the loaded library (bumped whenever a params struct or signature changes)
 
 
 def _load() -> C.CDLL:
@@ -168,7 +168,7 @@ _SIGNATURES = {
     "vmm_gather_cast": [_P, _P, _P, _L, _I, _P],
     "vmm_adam_ema_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _I, _F, _P],
     "vmm_gif_scan": [_P, _Z, _I, C.POINTER(GifInfo), C.POINTER(GifFrame), _I],
-    "vmm_gif_decode": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "vmm_gif_decode": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "vmm_dataset_items": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
 }
 _RESTYPES = {"vmm_abs_quantile_workspace": C.c_size_t, "vmm_gn_silu_bwd_workspace": C.c_size_t, "vmm_ftattn_workspace": C.c_size_t, "vmm_cond_workspace": C.c_size_t,

@@ -96,5 +96,5 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const 
 }  // namespace vmm
 
 extern "C" const char* vmm_last_error(void) { return vmm::error_buffer(); }
-extern "C" int vmm_abi_version(void) { return 7; }
+extern "C" int vmm_abi_version(void) { return 8; }
 extern "C" uint64_t vmm_launch_count(void) { return vmm::g_launches.load(); }

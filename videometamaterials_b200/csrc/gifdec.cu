@@ -11,6 +11,8 @@
 //   gif_compose_kernel one CTA per file: frames in order on the logical screen (rectangle, interlace, transparency, disposal 0/1/2),
 //                      palette colour -> ITU-R 601-2 luma as PIL's convert('L') computes it ((19595 R + 38470 G + 7471 B + 32768) >> 16)
 //   dataset_items_kernel  gather + u8/255 -> sample range -> void pixels -> global range, every operation separately rounded
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vmm {
@@ -19,6 +21,7 @@ static_assert(sizeof(vmm_gif_frame) == 32, "vmm_gif_frame layout (mirrored by ct
 static constexpr uint32_t GIF_NO_PALETTE = 0xffffffffu;
 static constexpr int GIF_MAX_FRAME_PX = 1 << 19;   // offset field of a dictionary word
 static constexpr int GIF_WARPS = 8;                // warps (= frames in flight) per CTA: 8 x 16 KB of dictionary
+static constexpr int GIF_SMEM_PX = 12288;          // frames up to this many pixels (96 x 96 = 9216) are decoded into shared memory
 
 // ----------------------------------------------------------------------------------------------------------------------------
 // LZW
@@ -40,12 +43,16 @@ struct GifByteReader {
   }
 };
 
+// SMEM_OUT: the index stream of the frame is built in shared memory (every decoded string is a copy from earlier output: a global-memory
+// round trip per code otherwise, ~300 clocks where shared memory takes ~30) and written out once with 16-byte stores.
+template <bool SMEM_OUT>
 __global__ void __launch_bounds__(GIF_WARPS * 32) gif_lzw_kernel(const uint8_t* __restrict__ files, const uint64_t* __restrict__ file_ofs,
                                                                  const int32_t* __restrict__ frame_begin, const vmm_gif_frame* __restrict__ frames,
                                                                  int n_files, int n_frames_total, uint8_t* ws, int32_t* err) {
   extern __shared__ uint32_t gif_dict_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* dict = gif_dict_smem + warp * 4096;
+  uint8_t* sm_out = reinterpret_cast<uint8_t*>(gif_dict_smem + GIF_WARPS * 4096) + warp * GIF_SMEM_PX;
   const int warps_total = gridDim.x * GIF_WARPS;
   for (int fi = blockIdx.x * GIF_WARPS + warp; fi < n_frames_total; fi += warps_total) {
     // file of this frame: last i with frame_begin[i] <= fi
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(GIF_WARPS * 32) gif_lzw_kernel(const uint8_t* 
     rd.p = fr.data_ofs;
     rd.rem = 0;
     rd.ended = false;
-    uint8_t* out = ws + fr.px_ofs;
+    uint8_t* out = SMEM_OUT ? sm_out : ws + fr.px_ofs;
     const uint32_t npx = static_cast<uint32_t>(fr.w) * fr.h;
     const uint32_t m = fr.min_code, clear = 1u << m, eoi = clear + 1;
     uint32_t next = clear + 2, size = m + 1, bitbuf = 0, nbits = 0, pos = 0, prev_off = 0, prev_len = 0;
@@ -121,6 +128,17 @@ __global__ void __launch_bounds__(GIF_WARPS * 32) gif_lzw_kernel(const uint8_t* 
       if (lane == 0) atomicAdd(err, 1);
     }
     __syncwarp();
+    if (SMEM_OUT) {
+      uint8_t* dst = ws + fr.px_ofs;
+      if ((fr.px_ofs & 15u) == 0) {
+        const uint32_t n16 = npx >> 4;
+        for (uint32_t j = lane; j < n16; j += 32) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(sm_out)[j];
+        for (uint32_t j = (n16 << 4) + lane; j < npx; j += 32) dst[j] = sm_out[j];
+      } else {
+        for (uint32_t j = lane; j < npx; j += 32) dst[j] = sm_out[j];
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -351,24 +369,31 @@ extern "C" int vmm_gif_scan(const uint8_t* f, size_t n, int flags, vmm_gif_info*
 }
 
 extern "C" int vmm_gif_decode(const uint8_t* files, const uint64_t* file_ofs, const int32_t* frame_begin, const vmm_gif_frame* frames,
-                              int n_files, int n_frames_total, int frames_per_file, int H, int W, uint8_t* index_ws, uint8_t* out, int32_t* err,
-                              void* stream) {
+                              int n_files, int n_frames_total, int frames_per_file, int H, int W, int max_frame_px, uint8_t* index_ws, uint8_t* out,
+                              int32_t* err, void* stream) {
   using namespace vmm;
   if (!files || !file_ofs || !frame_begin || !frames || !index_ws || !out || !err) return set_error(VMM_ERR_ARG, "vmm_gif_decode: null argument");
   if (n_files <= 0 || n_frames_total <= 0 || frames_per_file <= 0 || H <= 0 || W <= 0) return set_error(VMM_ERR_ARG, "vmm_gif_decode: bad sizes");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static bool attr_set = false;
-  const size_t smem = static_cast<size_t>(GIF_WARPS) * 4096 * sizeof(uint32_t);
+  const size_t smem_dict = static_cast<size_t>(GIF_WARPS) * 4096 * sizeof(uint32_t);
+  const size_t smem_all = smem_dict + static_cast<size_t>(GIF_WARPS) * GIF_SMEM_PX;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gif_lzw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(gif_lzw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_dict));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gif_lzw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_all));
     if (e != cudaSuccess) return set_cuda_error(e, "vmm_gif_decode: cudaFuncSetAttribute");
     attr_set = true;
   }
+  static const bool no_smem_out = getenv("VMM_GIF_NO_SMEM_OUT") != nullptr;
+  const bool smem_out = !no_smem_out && max_frame_px > 0 && max_frame_px <= GIF_SMEM_PX;     // max_frame_px <= 0: unknown, global-memory form
   const int sms = num_sms();
   if (sms <= 0) return set_error(VMM_ERR_CUDA, "vmm_gif_decode: no CUDA device");
   const unsigned int want = ceil_div(n_frames_total, GIF_WARPS);
   const unsigned int grid1 = want < static_cast<unsigned int>(sms) ? want : static_cast<unsigned int>(sms);     // one CTA (128 KB of dictionaries) per SM
-  gif_lzw_kernel<<<grid1, GIF_WARPS * 32, smem, st>>>(files, file_ofs, frame_begin, frames, n_files, n_frames_total, index_ws, err);
+  if (smem_out)
+    gif_lzw_kernel<true><<<grid1, GIF_WARPS * 32, smem_all, st>>>(files, file_ofs, frame_begin, frames, n_files, n_frames_total, index_ws, err);
+  else
+    gif_lzw_kernel<false><<<grid1, GIF_WARPS * 32, smem_dict, st>>>(files, file_ofs, frame_begin, frames, n_files, n_frames_total, index_ws, err);
   count_launch();
   int rc = check_launch("gif_lzw_kernel");
   if (rc) return rc;

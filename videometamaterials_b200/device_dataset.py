@@ -76,7 +76,7 @@ def decode_gifs(blobs: Sequence[bytes], frames_per_file: Optional[int], size_hw:
         begin[1:] = np.cumsum([len(t) for t in tables[i0:i1]])
         px = fr["w"].astype(np.int64) * fr["h"].astype(np.int64)
         ofs = np.zeros(len(fr), dtype=np.int64)
-        ofs[1:] = np.cumsum(px)[:-1]
+        ofs[1:] = np.cumsum((px + 15) // 16 * 16)[:-1]          # 16-byte aligned index streams (vector stores in the decode kernel)
         ws_total = int(ofs[-1] + px[-1])
         if ws_total >= 1 << 32:
             raise _lib.VmmError("decode_gifs: more than 4 GiB of decode workspace in one chunk; lower chunk_bytes")
@@ -93,7 +93,7 @@ def decode_gifs(blobs: Sequence[bytes], frames_per_file: Optional[int], size_hw:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         _lib.check(_lib.lib.vmm_gif_decode(d_bytes.data_ptr(), d_fofs.data_ptr(), d_begin.data_ptr(), d_fr.data_ptr(), i1 - i0, len(fr),
-                                           frames_per_file, H, W, d_ws.data_ptr(), out[i0:i1].data_ptr(), d_err.data_ptr(), ops.stream_ptr()),
+                                           frames_per_file, H, W, int(px.max()), d_ws.data_ptr(), out[i0:i1].data_ptr(), d_err.data_ptr(), ops.stream_ptr()),
                    "vmm_gif_decode")
         if timing is not None:
             e1.record()
