@@ -646,6 +646,9 @@ def final_fwd(P, sd, model, x: Tensor):
 # ------------------------------------------------------------------------------------------------
 # whole network, inference form (no autograd)      VDDP:730-821
 # ------------------------------------------------------------------------------------------------
+SHARED_STEM = os.environ.get("VMM_SHARED_STEM", "1") != "0"      # guided sampling: the label-free stem once for both halves of the batch
+
+
 @torch.no_grad()
 def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor, cond: Tensor, null_mask: Tensor) -> Tensor:
     """x fp32 (b, c, f, h, w) -> eps fp32 channels-last (b, f, h, w, c)."""
@@ -657,10 +660,15 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
     g, heads, pm = model.groups, model.heads, model.padding_mode
     frames = x.shape[2]
     ss, ekv, bias, rot = conditioning(model, time, cond, null_mask, frames)
-    begin_stats_pool(2 * len(resnet_names(model)), x.shape[0], g, x.device)
+    begin_stats_pool(2 * len(resnet_names(model)), time.shape[0], g, x.device)
     tkv = (lambda q: ekv[q]) if model.use_temporal_attention_cond else (lambda q: None)      # VDDP:792-795
     h, _ = init_fwd(P, sd, model, x.float(), noise, qcoef)
     h, _ = attn_block_fwd(P, sd, "init_temporal_attn.fn.fn.fn.", "temporal", h, None, bias, rot, heads, keep=False)
+    if time.shape[0] == 2 * x.shape[0]:
+        # guided sampling (VDDP:715-728): the conditional and the unconditional pass see the same x, and nothing up to here depends on the
+        # time step or the label (init_conv VDDP:742, init_temporal_attn without tokens VDDP:743), so this stem runs ONCE for both halves of
+        # the batch; per-sample arithmetic is unchanged
+        h = torch.cat((h, h))
     r = h
     skips = []
     for i in range(L):

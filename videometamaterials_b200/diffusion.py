@@ -114,7 +114,10 @@ class GaussianDiffusion(nn.Module):
             mask = torch.zeros(b, dtype=torch.bool, device=x.device)
             return blocks.unet_forward(self.denoise_fn, x, None, None, t, cond, mask), False
         mask = torch.cat((torch.zeros(b, dtype=torch.bool, device=x.device), torch.ones(b, dtype=torch.bool, device=x.device)))
-        eps = blocks.unet_forward(self.denoise_fn, torch.cat((x, x)), None, None, torch.cat((t, t)), torch.cat((cond, cond)), mask)
+        # x is passed ONCE: blocks.unet_forward runs the label-free stem (init_conv + init_temporal_attn) on b samples and duplicates its
+        # output for the 2b conditional | unconditional rows (VMM_SHARED_STEM=0: the stem on the duplicated input, as before)
+        xin = x if blocks.SHARED_STEM else torch.cat((x, x))
+        eps = blocks.unet_forward(self.denoise_fn, xin, None, None, torch.cat((t, t)), torch.cat((cond, cond)), mask)
         return eps, True
 
     def _p_sample_core(self, x, t, cond, guidance_scale, noise, clip_denoised=True):

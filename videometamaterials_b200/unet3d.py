@@ -274,7 +274,8 @@ class Unet3D(nn.Module):
             return self.forward(*args, null_cond_prob=0., **kwargs)
         b = x.shape[0]
         mask = torch.cat((torch.zeros(b, dtype=torch.bool, device=x.device), torch.ones(b, dtype=torch.bool, device=x.device)))
-        eps = self._forward_masked(torch.cat((x, x)), torch.cat((time, time)), torch.cat((cond, cond)), mask)
+        xin = x if (blocks.SHARED_STEM and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))) else torch.cat((x, x))
+        eps = self._forward_masked(xin, torch.cat((time, time)), torch.cat((cond, cond)), mask)
         logits, null_logits = eps[:b], eps[b:]
         return null_logits + (logits - null_logits) * guidance_scale
 
