@@ -135,6 +135,17 @@ def run_case(name):
             ms = e0.elapsed_time(e1) / 10
             fl = 2.0 * bf * h * h * n * 9 * cin
             print(f"  perf conv3x3 bf={bf} {h}x{h} {cin}->{n}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s")
+            if name == "perf1":     # where does the tile time go: the same launch without the GroupNorm statistics / without bias and statistics
+                for label, kw in (("no gn_stats", dict(bias=bias)), ("no bias, no gn_stats", dict())):
+                    for _ in range(3):
+                        ops.conv3x3([x], wp, n, out, **kw)
+                    e0.record()
+                    for _ in range(10):
+                        ops.conv3x3([x], wp, n, out, **kw)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms2 = e0.elapsed_time(e1) / 10
+                    print(f"    {label}: {ms2 * 1e3:.1f} us  {fl / ms2 / 1e9:.1f} TFLOP/s")
         return True
     return cases[name]()
 

@@ -987,6 +987,10 @@ extern "C" int vmm_cgemm(const vmm_cgemm_params* hp, void* stream_) {
   d.tx_bytes = d.stage_bytes;
   int stages = (smem_budget - static_cast<int>(bres_bytes)) / static_cast<int>(d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* e = getenv("VMM_CGEMM_STAGES")) {      // experiment knob: cap the ring depth
+    const int cap = atoi(e);
+    if (cap >= 2 && cap < stages) stages = cap;
+  }
   if (stages < 2) return set_error(VMM_ERR_UNSUPPORTED, "vmm_cgemm: tile too large for shared memory");
   d.stages = stages;
   d.acc_stride = (BN + 31) / 32 * 32;
