@@ -114,3 +114,29 @@ def test_device_dataset_has_no_host_path():
     from videometamaterials_b200.device_dataset import DeviceDataset
     with pytest.raises(TypeError):
         DeviceDataset(object())
+
+
+def test_device_loader_order_logic_without_a_device():
+    """DeviceLoader's index bookkeeping (host logic only; a stand-in dataset records the index batches): RandomSampler's draw for one
+    rank, disjoint strided shares of one permutation padded by wrapping for two, a new permutation per pass, drop_last."""
+    from videometamaterials_b200.device_dataset import DeviceLoader
+
+    class Stub:
+        def __len__(self):
+            return 7
+
+        def batch(self, idx):
+            return idx.tolist(), None
+
+    g = torch.Generator().manual_seed(11)
+    dl = DeviceLoader(Stub(), 3, True, False, g, 0, 1)
+    first = [b for b, _ in dl]
+    assert [len(b) for b in first] == [3, 3, 1] and sum(first, []) == torch.randperm(7, generator=torch.Generator().manual_seed(11)).tolist()
+    assert sorted(sum([b for b, _ in dl], [])) == list(range(7))
+    assert [b for b, _ in DeviceLoader(Stub(), 4, False, False, None, 0, 1)] == [[0, 1, 2, 3], [4, 5, 6]]
+    assert len(DeviceLoader(Stub(), 3, True, True, None, 0, 1)) == 2
+    r0 = sum([b for b, _ in DeviceLoader(Stub(), 2, True, False, None, 0, 2)], [])
+    r1 = sum([b for b, _ in DeviceLoader(Stub(), 2, True, False, None, 1, 2)], [])
+    assert len(r0) == len(r1) == 4 and sorted(set(r0 + r1)) == list(range(7)) and len(set(r0) & set(r1)) <= 1      # 8 slots for 7 samples: one wraps
+    e0 = DeviceLoader(Stub(), 2, True, False, None, 0, 2)
+    assert sum([b for b, _ in e0], []) != sum([b for b, _ in e0], [])                                               # reshuffled every pass

@@ -42,14 +42,41 @@ class _DeviceLoader:
             self.sampler.set_epoch(self.epoch)
             self.epoch += 1
         n_batches = len(self.loader)
+        # On a CUDA device the copy of batch i + 1 is issued on a copy stream when batch i is handed out, so that it runs under the
+        # step that consumes batch i (the compute stream only waits for the copy's event: no host synchronisation).
+        side = self.device.type == "cuda" and torch.cuda.is_available()
+        if side and getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        pending = None
         for i, batch in enumerate(self.loader):
             # accelerate's GradientState: on the last batch of a sharded loader `remainder` = the number of genuine samples in the
             # gathered global batch (the DistributedSampler pads every rank's shard to equal length with repeated samples)
-            self.remainder = -1
+            rem = -1
             if self.sampler is not None and i == n_batches - 1 and self.total is not None and self.loader.batch_size:
-                self.remainder = self.total % (self.loader.batch_size * self.sampler.num_replicas)
-            yield self._to_device(batch)
+                rem = self.total % (self.loader.batch_size * self.sampler.num_replicas)
+            if side:
+                with torch.cuda.stream(self._copy_stream):
+                    dev_batch = self._to_device(batch)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+            else:
+                dev_batch, ev = self._to_device(batch), None
+            if pending is not None:
+                yield self._hand_out(*pending)
+            pending = (dev_batch, ev, rem)
+        if pending is not None:
+            yield self._hand_out(*pending)
         self.remainder = -1
+
+    def _hand_out(self, batch, ev, rem):
+        self.remainder = rem
+        if ev is not None:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            for t in (batch if isinstance(batch, (list, tuple)) else (batch,)):
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(cur)          # allocated on the copy stream, consumed on the compute stream
+        return batch
 
     def _to_device(self, batch):
         if isinstance(batch, (list, tuple)):
