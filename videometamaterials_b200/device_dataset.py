@@ -28,7 +28,7 @@ from . import ops
 from .dataset import _LAYOUT, Dataset
 
 
-def scan_gif(buf: bytes, max_frames: int = 4096, pil_compat: bool = True) -> Tuple[Tuple[int, int], np.ndarray]:
+def scan_gif(buf: bytes, max_frames: int = 64, pil_compat: bool = True) -> Tuple[Tuple[int, int], np.ndarray]:
     """Frame table of one GIF file (host; `vmm_gif_scan`): ((width, height), structured array of vmm_gif_frame rows).
     pil_compat: reproduce Pillow's decode of a palette that arrives while the image is still in mode 'L' (include/vmm.h), so that the
     planes equal what the reference's `gif_to_tensor` reads; False maps every frame through its own palette."""
@@ -83,7 +83,7 @@ def decode_gifs(blobs: Sequence[bytes], frames_per_file: Optional[int], size_hw:
         fr["px_ofs"] = ofs.astype(np.uint32)
         fofs = np.zeros(i1 - i0 + 1, dtype=np.int64)
         fofs[1:] = np.cumsum([len(b) for b in blobs[i0:i1]])
-        d_bytes = torch.frombuffer(bytearray(b"".join(blobs[i0:i1])), dtype=torch.uint8).to(device)
+        d_bytes = torch.from_numpy(np.concatenate([np.frombuffer(b, dtype=np.uint8) for b in blobs[i0:i1]])).to(device)      # one host copy
         d_fofs = torch.from_numpy(fofs).to(device)
         d_begin = torch.from_numpy(begin).to(device)
         d_fr = torch.from_numpy(fr.view(np.uint8).reshape(-1).copy()).to(device)
