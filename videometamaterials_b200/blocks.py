@@ -646,6 +646,25 @@ def final_fwd(P, sd, model, x: Tensor):
 # ------------------------------------------------------------------------------------------------
 # whole network, inference form (no autograd)      VDDP:730-821
 # ------------------------------------------------------------------------------------------------
+SIDE_COND = os.environ.get("VMM_SIDE_COND", "1") != "0"            # inference: the conditioning kernel on a side stream under the stem
+_SIDE_STREAMS: Dict[str, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _stem_tables(model, frames: int, device):
+    c = model.__dict__.get("_vmm_stem_tables")
+    if c is not None and c[0] == (model._packed_key, frames, str(device)):
+        return c[1], c[2]
+    return None
+
+
 SHARED_STEM = os.environ.get("VMM_SHARED_STEM", "1") != "0"      # guided sampling: the label-free stem once for both halves of the batch
 
 
@@ -659,11 +678,29 @@ def unet_forward(model, x: Tensor, noise: Optional[Tensor], qcoef, time: Tensor,
     L = len(model.dim_mults)
     g, heads, pm = model.groups, model.heads, model.padding_mode
     frames = x.shape[2]
-    ss, ekv, bias, rot = conditioning(model, time, cond, null_mask, frames)
+    # The stem (init_conv + init_temporal_attn) needs only the position bias and the rotary tables from the conditioning path, and those
+    # depend on the parameters alone: they are kept from an earlier pass with the same weights, so that the conditioning kernel of THIS pass
+    # (time MLP, tokens, every block's scale / shift and keys / values: ~160 us on ~70 CTAs) runs on a side stream under the stem.
+    on_dev = SIDE_COND and x.is_cuda and torch.cuda.is_available()
+    tables = _stem_tables(model, frames, x.device) if (on_dev and cond_kernel_eligible(model, time, cond)) else None
+    if tables is not None:
+        cur, side = torch.cuda.current_stream(x.device), _side_stream(x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ss, ekv, bias, rot = conditioning(model, time, cond, null_mask, frames)
+        bias0, rot0 = tables
+    else:
+        ss, ekv, bias, rot = conditioning(model, time, cond, null_mask, frames)
+        bias0, rot0 = bias, rot
+        if on_dev and not torch.cuda.is_current_stream_capturing():
+            model.__dict__["_vmm_stem_tables"] = ((model._packed_key, frames, str(x.device)), bias.clone(), rot.clone())
     begin_stats_pool(2 * len(resnet_names(model)), time.shape[0], g, x.device)
     tkv = (lambda q: ekv[q]) if model.use_temporal_attention_cond else (lambda q: None)      # VDDP:792-795
     h, _ = init_fwd(P, sd, model, x.float(), noise, qcoef)
-    h, _ = attn_block_fwd(P, sd, "init_temporal_attn.fn.fn.fn.", "temporal", h, None, bias, rot, heads, keep=False)
+    h, _ = attn_block_fwd(P, sd, "init_temporal_attn.fn.fn.fn.", "temporal", h, None, bias0, rot0, heads, keep=False)
+    if tables is not None:
+        cur.wait_stream(side)
+        bias.record_stream(cur)          # one flat buffer behind ss / ekv / bias / rot, allocated on the side stream, consumed on this one
     if time.shape[0] == 2 * x.shape[0]:
         # guided sampling (VDDP:715-728): the conditional and the unconditional pass see the same x, and nothing up to here depends on the
         # time step or the label (init_conv VDDP:742, init_temporal_attn without tokens VDDP:743), so this stem runs ONCE for both halves of
