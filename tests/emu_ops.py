@@ -142,6 +142,21 @@ def ln_bwd(x2d, dy2d, dres2d, dx2d, gamma, dgamma, eps=1e-5):
     dgamma += g_.grad
 
 
+def qkv_bwd(dqkv2d, xn2d, wd, dxn2d, dw):
+    """vmm_qkv_bwd: dxn = dqkv @ W (W^T arrives packed K-major as wd [C][768]) and dW += dqkv^T @ xn."""
+    dq = dqkv2d.float()
+    dxn2d.copy_((dq @ wd.float()[: xn2d.shape[1]].t()).to(dxn2d.dtype))
+    dw += (dq.t() @ xn2d.float()).reshape(dw.shape)
+
+
+def qkv_ln_bwd(dqkv2d, xn2d, wd, x2d, dres2d, gamma, dx2d, dw, dgamma, eps=1e-5):
+    """vmm_qkv_ln_bwd: the same, with the PreNorm backward + residual add applied to the (unrounded) dxn rows."""
+    dq = dqkv2d.float()
+    dxn = dq @ wd.float()[: xn2d.shape[1]].t()
+    dw += (dq.t() @ xn2d.float()).reshape(dw.shape)
+    ln_bwd(x2d, dxn, dres2d, dx2d, gamma, dgamma, eps)
+
+
 def _unturn(x, rot):
     """Inverse of _turn (rotation by the negative angle)."""
     return _turn(x, torch.stack((rot[..., 0], -rot[..., 1]), dim=-1))
@@ -233,7 +248,7 @@ def install_training(monkeypatch, ops):
     """Forward and backward wrappers (everything blocks_bwd.training_loss launches)."""
     install(monkeypatch, ops)
     monkeypatch.setattr(ops, "wgrad", emu_cgemm.wgrad)
-    for name in ("colsum", "gn_silu_bwd", "ln_bwd", "tattn_bwd", "lattn_bwd", "sattn_bwd", "loss_fwd_bwd"):
+    for name in ("colsum", "gn_silu_bwd", "ln_bwd", "tattn_bwd", "lattn_bwd", "sattn_bwd", "loss_fwd_bwd", "qkv_bwd", "qkv_ln_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
 
 

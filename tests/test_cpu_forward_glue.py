@@ -99,6 +99,52 @@ def test_training_glue_matches_oracle_gradients(monkeypatch, channels, mults, l2
         assert worst[0] < 1e-4, (pre_rot, worst)            # measured 3e-6 .. 4e-6 over 126 / 196 / 266 parameter tensors
 
 
+@pytest.mark.parametrize("ln_form", [True, False])
+def test_training_glue_through_the_fused_qkv_backward(monkeypatch, ln_form):
+    """The 64-channel branch of AttnBlockFn.backward (one fused launch for the to_qkv data gradient + weight gradient, with or without the
+    PreNorm backward in its epilogue, csrc/qkvbwd.cu) wired with the right operands: a dim-64 network on the CPU contract statements, the
+    row-count threshold of the branch lowered, against the oracle's loss and every parameter gradient."""
+    from oracle import vdm_oracle as O
+    from videometamaterials_b200 import Unet3D, blocks, blocks_bwd, ops
+    emu_ops.install_training(monkeypatch, ops)
+    monkeypatch.setattr(ops, "qkv_bwd_eligible", lambda dq, xn: dq.shape[1] == 768 and xn.shape[1] == 64)
+    monkeypatch.setattr(ops, "FUSED_QKV_LN_BWD", ln_form)
+    used = []
+    for name in ("qkv_bwd", "qkv_ln_bwd"):
+        fn = getattr(ops, name)
+        monkeypatch.setattr(ops, name, (lambda f, n: (lambda *a, **k: (used.append(n), f(*a, **k))[1]))(fn, name))
+    cfg = O.UnetCfg(dim=64, dim_mults=(1,))
+    sd = O.synthetic_state_dict(cfg, seed=15)
+    model = Unet3D(dim=64, dim_mults=(1,), channels=3, attn_heads=8, attn_dim_head=32, use_sparse_linear_attn=True, resnet_groups=8,
+                   cond_bias=True, cond_attention='self-stacked', use_temporal_attention_cond=True, cond_to_time='add', per_frame_cond=True)
+    model.load_state_dict(sd)
+    model.compute_dtype, model._packed = torch.float32, None
+    g = torch.Generator().manual_seed(4)
+    b, size = 2, 8
+    x01 = torch.rand(b, 3, 11, size, size, generator=g)
+    cond = torch.rand(b, 11, generator=g) * 2 - 1
+    t = torch.tensor([2, 6])
+    noise = torch.randn(b, 3, 11, size, size, generator=g)
+    mask = torch.tensor([False, True])
+    S = O.schedule(8)
+    P = {k: v.clone().requires_grad_(v.is_floating_point() and "freqs" not in k) for k, v in sd.items()}
+    want = O.p_losses(P, cfg, S, x01, t, cond, noise, mask)
+    want.backward()
+    blocks_bwd.get_arena(model).zero_grad()
+    a, s = S["sqrt_alphas_cumprod"][t].contiguous(), S["sqrt_one_minus_alphas_cumprod"][t].contiguous()
+    loss = blocks_bwd.training_loss(model, (x01 * 2 - 1).as_subclass(_ClaimsCuda), noise, (a, None, s), t, cond, mask)
+    loss.backward()
+    assert used and set(used) == {"qkv_ln_bwd" if ln_form else "qkv_bwd"} and len(used) == 7      # init, downs.0.{2,3}, mid spatial + temporal, ups.0.{2,3}: every attention block of a one-level dim-64 network
+    assert abs(float(loss.detach()) - float(want.detach())) < 1e-5 * float(want.detach())
+    worst = (0.0, None)
+    for k, p in model.named_parameters():
+        ref = P[k].grad
+        if ref is None or float(ref.norm()) == 0.0:
+            continue
+        worst = max(worst, (float((p.grad - ref).norm() / ref.norm()), k))
+    assert worst[0] < 1e-4, worst
+
+
 class _Replay:
     """torch.randn / randn_like return a recorded list of tensors, in call order (as the GPU sampling tests do)."""
 
