@@ -140,3 +140,30 @@ def test_device_loader_order_logic_without_a_device():
     assert len(r0) == len(r1) == 4 and sorted(set(r0 + r1)) == list(range(7)) and len(set(r0) & set(r1)) <= 1      # 8 slots for 7 samples: one wraps
     e0 = DeviceLoader(Stub(), 2, True, False, None, 0, 2)
     assert sum([b for b, _ in e0], []) != sum([b for b, _ in e0], [])                                               # reshuffled every pass
+
+
+def test_decode_files_pass_by_pass_assembles_one_tensor():
+    """decode_files reads / decodes / releases a large file list in passes (host logic; the decode and the file reads are stand-ins here):
+    same result as one pass, every file read exactly once, the per-file frame counts in file order."""
+    from videometamaterials_b200.device_dataset import decode_files
+    names = [f"f{i}" for i in range(23)]
+    reads = []
+
+    def read(nm):
+        reads.append(nm)
+        return bytes([int(nm[1:])])
+
+    def decode(blobs, fpf, size_hw, device, nms, pil_compat=True):
+        assert [bytes([int(n[1:])]) for n in nms] == list(blobs)
+        out = torch.stack([torch.full((fpf,) + tuple(size_hw), b[0], dtype=torch.uint8) for b in blobs])
+        return out, torch.tensor([b[0] % 5 for b in blobs], dtype=torch.int32)
+
+    whole, c_whole = decode_files(names, 3, (2, 2), "cpu", files_per_pass=100, decode=decode, read=read)
+    assert reads == names
+    reads.clear()
+    parts, c_parts = decode_files(names, 3, (2, 2), "cpu", files_per_pass=5, decode=decode, read=read)
+    assert reads == names and torch.equal(parts, whole) and torch.equal(c_parts, c_whole) and parts.shape == (23, 3, 2, 2)
+    assert [int(parts[i, 0, 0, 0]) for i in range(23)] == list(range(23))
+    reads.clear()
+    every, _ = decode_files(names, None, (2, 2), "cpu", files_per_pass=5, decode=lambda b, f, s, d, n, pil_compat=True: decode(b, 3, s, d, n), read=read)
+    assert reads == names and torch.equal(every, whole)          # no frame count given: one pass over everything

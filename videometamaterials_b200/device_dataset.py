@@ -115,6 +115,31 @@ def decode_gifs(blobs: Sequence[bytes], frames_per_file: Optional[int], size_hw:
     return out, counts
 
 
+def _read_file(name: str) -> bytes:
+    with open(name, 'rb') as f:
+        return f.read()
+
+
+def decode_files(names: Sequence[str], frames_per_file: Optional[int], size_hw: Tuple[int, int], device, pil_compat: bool = True,
+                 files_per_pass: int = 8192, decode=None, read=_read_file) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`decode_gifs` over files on disk.  Up to `files_per_pass` files are held in host memory at a time (a 96 x 96 x 11 noise GIF is
+    ~115 KB, so the default keeps under 1 GB of file bytes resident; the real data set has tens of thousands of samples x 4-5 files):
+    larger sets are read, decoded and released pass by pass into one output tensor.  Without a frame count (`frames_per_file=None`: the
+    largest count among ALL files decides the layout) everything is read at once."""
+    decode = decode if decode is not None else decode_gifs
+    if frames_per_file is None or len(names) <= files_per_pass:
+        return decode([read(nm) for nm in names], frames_per_file, size_hw, device, names, pil_compat=pil_compat)
+    out, counts = None, torch.zeros(len(names), dtype=torch.int32)
+    for i0 in range(0, len(names), files_per_pass):
+        part = names[i0:i0 + files_per_pass]
+        o, c = decode([read(nm) for nm in part], frames_per_file, size_hw, device, part, pil_compat=pil_compat)
+        if out is None:
+            out = torch.empty((len(names),) + tuple(o.shape[1:]), dtype=o.dtype, device=o.device)
+        out[i0:i0 + len(part)].copy_(o)
+        counts[i0:i0 + len(part)] = c
+    return out, counts
+
+
 def item_tables(ds: Dataset):
     """The tables `vmm_dataset_items` needs, from a host Dataset: (planes, ch_plane, ch_has_range, sample_rng (n, c, 2) fp32,
     global_rng (c, 2) fp32).  Host arithmetic only.  The reference's fp32 image tensor meets float64 0-dim range tensors (VDDP:1340-1358):
@@ -150,7 +175,7 @@ def item_tables(ds: Dataset):
 class DeviceDataset:
     """Decoded dataset resident in HBM; `batch(indices)` is one kernel launch.  See the module docstring."""
 
-    def __init__(self, ds: Dataset, device="cuda", max_frames: Optional[int] = None, pil_compat: bool = True):
+    def __init__(self, ds: Dataset, device="cuda", max_frames: Optional[int] = None, pil_compat: bool = True, files_per_pass: int = 8192):
         if not isinstance(ds, Dataset):
             raise TypeError("DeviceDataset wraps a videometamaterials_b200.dataset.Dataset")
         if ds.horizontal_flip:
@@ -166,13 +191,9 @@ class DeviceDataset:
         S = ds.image_size
         # 1 + 2: file bytes -> device -> decoded planes
         names = [str(ds.paths[sub][i]) for i in range(n) for sub in planes]
-        blobs = []
-        for name in names:
-            with open(name, 'rb') as f:
-                blobs.append(f.read())
         # an item uses at most num_frames frames of a file (cast_num_frames); without force_num_frames, all the frames the files hold
         fpf = int(max_frames) if max_frames is not None else (max(int(ds.num_frames), 1) if ds.force_num_frames else None)
-        u8, counts = decode_gifs(blobs, fpf, (S, S), self.device, names, pil_compat=pil_compat)
+        u8, counts = decode_files(names, fpf, (S, S), self.device, pil_compat=pil_compat, files_per_pass=files_per_pass)
         fpf = u8.shape[1]
         self.u8 = u8.view(n, len(planes), fpf, S, S)
         cnt = counts.view(n, len(planes))
