@@ -485,7 +485,9 @@ def abs_quantile(v, B, n, k, frac, floor_val, s_out):
     key = (v.device, int(B))
     ws = _quantile_ws.get(key)
     if ws is None:
-        ws = _quantile_ws[key] = torch.empty(max(int(lib.vmm_abs_quantile_workspace(B)), 16), dtype=torch.uint8, device=v.device)
+        ws = torch.empty(max(int(lib.vmm_abs_quantile_workspace(B)), 16), dtype=torch.uint8, device=v.device)
+        if not torch.cuda.is_current_stream_capturing():
+            _quantile_ws[key] = ws          # (a buffer created during a graph capture belongs to that graph's pool: it is not kept for others)
     check(lib.vmm_abs_quantile(_p(v), B, n, k, frac, floor_val, _p(s_out), _p(ws), ws.numel(), stream_ptr()), "vmm_abs_quantile")
 
 
