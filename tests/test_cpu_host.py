@@ -24,6 +24,16 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib.vmm_abi_version() == _lib.ABI_VERSION
 
 
+def test_host_side_entry_points_answer_without_a_device():
+    """Workspace-size queries and the GIF container scan are host code: they work (and are exercised) on a machine without a GPU."""
+    from videometamaterials_b200 import _lib
+    assert int(_lib.lib.vmm_abs_quantile_workspace(4)) == 4 * (4 * 256 + 4) * 4 and int(_lib.lib.vmm_abs_quantile_workspace(0)) == 0
+    assert int(_lib.lib.vmm_gn_silu_bwd_workspace(8, 64, 8)) > 0
+    info = _lib.GifInfo()
+    assert _lib.lib.vmm_gif_scan(b"not a gif at all", 16, 1, ctypes.byref(info), None, 0) == -1
+    assert b"not a GIF" in _lib.lib.vmm_last_error()
+
+
 def test_compute_call_without_gpu_fails_loudly():
     from videometamaterials_b200 import Unet3D, ops
     if torch.cuda.is_available():
